@@ -1,0 +1,261 @@
+"""TEST INFRASTRUCTURE ONLY -- pins ``oracle/tpspp_oracle.py`` against the unmodified
+reference and writes the committed fixtures under ``tests/golden/``.
+
+Run in the build container (needs ``/root/reference``):
+
+    python -m oracle.make_golden            # check + (re)write tests/golden/*.npz
+    python -m oracle.make_golden --check    # check only
+
+What is pinned (reference file:line in brackets):
+
+* constants ``hat_C``/``P_hat``/``P`` of TPS++ and ``inv_delta_C``/``P_hat`` of the classical
+  generator, bit-for-bit against the reference buffers [tps_pp.py:353-366, tps_preprocessor.py:176-187]
+* ``tpspp_grid`` / ``classical_grid`` against ``build_P_prime`` [tps_pp.py:481-496, tps_preprocessor.py:270-282]
+* numpy ``grid_sample`` and its backward against ``F.grid_sample`` + autograd (what the reference calls)
+* every head stage and the whole ``TPS_PP.forward`` against the reference module holding the same
+  ``trained_like_state`` weights (fp32 and its ``.double()`` twin) [tps_pp.py:564-625]
+* the reference's own ctor-time initial state under ``torch.manual_seed(0)`` (shape/keys + checksum)
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ref_loader as rl
+from . import tpspp_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def _mx(a, b):
+    a = a.detach().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))))
+
+
+def check(name, err, tol):
+    ok = err <= tol
+    print(f"  [{'ok' if ok else 'FAIL'}] {name}: {err:.3e} (tol {tol:.1e})")
+    if not ok:
+        raise SystemExit(f"oracle not pinned: {name}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--check', action='store_true')
+    args = ap.parse_args()
+    torch.set_num_threads(8)
+    ref = rl.load_reference()
+    os.makedirs(GOLD, exist_ok=True)
+
+    # ---- constants ---------------------------------------------------------
+    print('constants')
+    m = rl.build_quiet(ref.TPS_PP, seed=0)
+    c = O.tpspp_constants()
+    check('hat_C bit-exact', _mx(m.atten_tps.hat_C, c['hat_C']), 0.0)
+    check('P_hat bit-exact', _mx(m.atten_tps.P_hat, c['P_hat']), 0.0)
+    check('P bit-exact', _mx(torch.tensor(m.atten_tps.P).float(), c['P']), 0.0)
+    init_sd = {k: v.clone() for k, v in m.state_dict().items()}
+    check('init bias lattice', _mx(init_sd['TPE.localization_fc2.bias'],
+                                   O.tpspp_init_bias().reshape(-1).astype(np.float32)), 0.0)
+    gold_const = dict(tpspp_hat_C=c['hat_C'], tpspp_P_hat=c['P_hat'], tpspp_P=c['P'])
+    for f, rs in ((20, (32, 100)), (20, (64, 256)), (40, (64, 256)), (6, (8, 12))):
+        g = ref.GridGenerator(f, rs)
+        cc = O.classical_constants(f, rs)
+        check(f'classical F={f} {rs} inv_delta_C', _mx(g.inv_delta_C, cc['inv_delta_C']), 0.0)
+        check(f'classical F={f} {rs} P_hat', _mx(g.P_hat, cc['P_hat']), 0.0)
+        if rs[1] <= 100:
+            gold_const[f'classical_F{f}_{rs[0]}x{rs[1]}_inv_delta_C'] = cc['inv_delta_C']
+            gold_const[f'classical_F{f}_{rs[0]}x{rs[1]}_P_hat'] = cc['P_hat']
+    # init-state digest: keys, shapes, per-tensor sum -- pins the drop-in module's ctor
+    gold_const['init_keys'] = np.array(list(init_sd.keys()))
+    gold_const['init_sums'] = np.array([float(v.double().sum()) for v in init_sd.values()])
+    gold_const['init_abs_sums'] = np.array([float(v.double().abs().sum()) for v in init_sd.values()])
+
+    # ---- grid generator + sampler (warp only) ------------------------------
+    print('warp (TPS++)')
+    B = 3
+    rs = np.random.RandomState(11)
+    cp = O.smooth_c_prime(O.tpspp_init_bias(), B, seed=7, amp=0.05)
+    score = np.tanh(0.5 * rs.standard_normal((B, 1024, 32))).astype(np.float32)
+    fg = rs.standard_normal((B, 64, 32, 128)).astype(np.float32)
+    x = rs.standard_normal((B, 64, 16, 64)).astype(np.float32)
+    at = m.atten_tps
+    with torch.no_grad():
+        ref_grid32 = at.build_P_prime(torch.from_numpy(cp), torch.from_numpy(score), 'cpu').numpy()
+    g64 = O.tpspp_grid(cp, score, c['hat_C'], c['P'], c['P_hat'], dtype=np.float64)
+    g32 = O.tpspp_grid(cp, score, c['hat_C'], c['P'], c['P_hat'], dtype=np.float32)
+    check('grid fp64-oracle vs ref fp32 (ref noise floor)', _mx(g64, ref_grid32), 1e-4)
+    check('grid fp32-oracle vs ref fp32', _mx(g32, ref_grid32), 1e-4)
+    # fp64 twin of the reference arithmetic (buffers are the fp32-rounded ones, App. B)
+    hat64 = torch.from_numpy(c['hat_C']).double(); ph64 = torch.from_numpy(c['P_hat']).double()
+    P64 = torch.from_numpy(c['P']).double()
+    s64 = torch.from_numpy(score).double(); cp64 = torch.from_numpy(cp).double()
+    phi = torch.cat([torch.ones(B, 1024, 1, dtype=torch.float64), P64[None].repeat(B, 1, 1),
+                     ph64[None] * (s64 * 0.5 + 1)], 2)
+    Tm = torch.bmm(hat64[None].repeat(B, 1, 1), torch.cat([cp64, torch.zeros(B, 3, 2, dtype=torch.float64)], 1))
+    ref_grid64 = torch.bmm(phi, Tm).numpy()
+    check('grid fp64-oracle vs ref fp64 twin', _mx(g64, ref_grid64), 1e-12)
+    print(f'    ref fp32 vs ref fp64 grid: {_mx(ref_grid32, ref_grid64):.3e}; '
+          f'grid range x[{g64[..., 0].min():.3f},{g64[..., 0].max():.3f}] y[{g64[..., 1].min():.3f},{g64[..., 1].max():.3f}]')
+
+    tg = torch.from_numpy(ref_grid32).reshape(B, 16, 64, 2)
+    ref_out = F.grid_sample(torch.from_numpy(fg), tg, padding_mode='border', align_corners=True).numpy()
+    ref_mp = F.grid_sample(torch.from_numpy(x), tg, padding_mode='border', align_corners=True).numpy()
+    o_out = O.grid_sample(fg, tg.numpy(), dtype=np.float32)
+    o_mp = O.grid_sample(x, tg.numpy(), dtype=np.float32)
+    check('sampler numpy fp32 vs ATen fp32 (feat_grid)', _mx(o_out, ref_out), 2e-6)
+    check('sampler numpy fp32 vs ATen fp32 (x)', _mx(o_mp, ref_mp), 2e-6)
+    tg64 = torch.from_numpy(ref_grid64).reshape(B, 16, 64, 2)
+    ref_out64 = F.grid_sample(torch.from_numpy(fg).double(), tg64, padding_mode='border', align_corners=True).numpy()
+    check('sampler numpy fp64 vs ATen fp64', _mx(O.grid_sample(fg, tg64.numpy(), dtype=np.float64), ref_out64), 1e-12)
+
+    # backward of the warp through autograd of the reference ops (fp64)
+    print('warp backward (fp64)')
+    Bb = 2
+    fgt = torch.from_numpy(fg[:Bb]).double().requires_grad_(True)
+    xt = torch.from_numpy(x[:Bb]).double().requires_grad_(True)
+    cpt = torch.from_numpy(cp[:Bb]).double().requires_grad_(True)
+    st_ = torch.from_numpy(score[:Bb]).double().requires_grad_(True)
+    phi = torch.cat([torch.ones(Bb, 1024, 1, dtype=torch.float64), P64[None].repeat(Bb, 1, 1),
+                     ph64[None] * (st_ * 0.5 + 1)], 2)
+    Tm = torch.bmm(hat64[None].repeat(Bb, 1, 1), torch.cat([cpt, torch.zeros(Bb, 3, 2, dtype=torch.float64)], 1))
+    gr = torch.bmm(phi, Tm).reshape(Bb, 16, 64, 2)
+    o1 = F.grid_sample(fgt, gr, padding_mode='border', align_corners=True)
+    o2 = F.grid_sample(xt, gr, padding_mode='border', align_corners=True)
+    go1 = rs.standard_normal(o1.shape); go2 = rs.standard_normal(o2.shape)
+    (o1 * torch.from_numpy(go1)).sum().backward(retain_graph=True)
+    (o2 * torch.from_numpy(go2)).sum().backward()
+    gsrc1, gg1 = O.grid_sample_backward(fg[:Bb], gr.detach().numpy(), go1, dtype=np.float64)
+    gsrc2, gg2 = O.grid_sample_backward(x[:Bb], gr.detach().numpy(), go2, dtype=np.float64)
+    dC, ds = O.tpspp_grid_backward((gg1 + gg2).reshape(Bb, 1024, 2), cp[:Bb], score[:Bb],
+                                   c['hat_C'], c['P'], c['P_hat'], dtype=np.float64)
+    check('d feat_grid', _mx(gsrc1, fgt.grad), 1e-10)
+    check('d x', _mx(gsrc2, xt.grad), 1e-10)
+    check('d C\' (rel)', _mx(dC, cpt.grad) / max(1.0, float(cpt.grad.abs().max())), 1e-10)
+    check('d pc_score (rel)', _mx(ds, st_.grad) / max(1.0, float(st_.grad.abs().max())), 1e-10)
+
+    np.savez_compressed(
+        os.path.join(GOLD, 'warp_tpspp.npz'),
+        c_prime=cp, pc_score=score.astype(np.float16).astype(np.float32) if False else score,
+        seed_note=np.array('fg,x = RandomState(11) after score; see oracle/make_golden.py'),
+        ref_grid32=ref_grid32, ref_grid64=ref_grid64.astype(np.float64),
+        ref_out_ch=ref_out[:, ::8].copy(), ref_mp_ch=ref_mp[:, ::8].copy(),
+        ref_out64_ch=ref_out64[:, ::8].copy(),
+        fg_ch=fg[:, ::8].copy(), x_ch=x[:, ::8].copy()) if not args.check else None
+
+    # ---- classical warp ------------------------------------------------------
+    print('warp (classical)')
+    gold_cl = {}
+    for f, rsz, ch in ((20, (32, 100), 3), (6, (8, 12), 1)):
+        gen = ref.GridGenerator(f, rsz)
+        cc = O.classical_constants(f, rsz)
+        Bc = 2
+        cpc = O.smooth_c_prime(O.classical_init_bias(f), Bc, seed=5, amp=0.1, centre=0.0)
+        img = rs.standard_normal((Bc, ch) + rsz).astype(np.float32)
+        with torch.no_grad():
+            rg = gen.build_P_prime(torch.from_numpy(cpc), 'cpu')
+            ro = F.grid_sample(torch.from_numpy(img), rg.reshape(Bc, rsz[0], rsz[1], 2),
+                               padding_mode='border', align_corners=True).numpy()
+        og, = [O.classical_grid(cpc, cc['inv_delta_C'], cc['P_hat'], dtype=np.float64)]
+        check(f'classical F={f} grid vs ref fp32', _mx(og, rg), 2e-5)
+        oo = O.grid_sample(img, rg.numpy().reshape(Bc, rsz[0], rsz[1], 2), dtype=np.float32)
+        check(f'classical F={f} sample vs ATen', _mx(oo, ro), 2e-6)
+        gold_cl[f'F{f}_c_prime'] = cpc; gold_cl[f'F{f}_img'] = img
+        gold_cl[f'F{f}_ref_grid32'] = rg.numpy(); gold_cl[f'F{f}_ref_out'] = ro
+    if not args.check:
+        np.savez_compressed(os.path.join(GOLD, 'warp_classical.npz'), **gold_cl)
+
+    # ---- whole module with trained-like weights --------------------------------
+    print('TPS_PP.forward (trained-like weights)')
+    sd = O.trained_like_state(seed=3)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    Bm = 2
+    xi, o0, o1_ = O.synthetic_tpspp_inputs(Bm, seed=0)
+    with torch.no_grad():
+        r32 = m(torch.from_numpy(xi), [torch.from_numpy(o0), torch.from_numpy(o1_)])
+        # internals via the reference's own submodules
+        f0 = m.down0(torch.from_numpy(o0)); f1 = m.down1(torch.from_numpy(o1_)); f2 = m.down2(torch.from_numpy(xi))
+        fcat = torch.cat((m.down0_1(f0), m.down1_1(f1), f2), 1)
+        fgrid = m.grid(f0, f1, f2)
+        lg = m.MSFA(fcat)
+        cp_ref, sc_ref = m.TPE(lg['en_feat'], lg['de_feat'])
+    o32 = O.tps_pp_forward(sd, xi, [o0, o1_], dtype=torch.float32)
+    o64 = O.tps_pp_forward(sd, xi, [o0, o1_], dtype=torch.float64)
+    check('feat_cat', _mx(o32['feat_cat'], fcat), 1e-5)
+    check('feat_grid', _mx(o32['feat_grid'], fgrid), 1e-5)
+    check('en_feat', _mx(o32['en_feat'], lg['en_feat']), 1e-5)
+    check('de_feat', _mx(o32['de_feat'], lg['de_feat']), 1e-5)
+    check("C'", _mx(o32['control_point'], cp_ref), 1e-6)
+    check('pc_score', _mx(o32['pc_score'], sc_ref), 1e-5)
+    check('pc_score (r32 dict)', _mx(o32['pc_score'], r32['pc_score']), 1e-5)
+    e_o = _mx(o32['output'], r32['output']); e_m = _mx(o32['mp_img'], r32['mp_img'])
+    print(f'    output |oracle32-ref32| {e_o:.3e}, mp_img {e_m:.3e}; '
+          f'|oracle64-ref32| {_mx(o64["output"], r32["output"]):.3e} / {_mx(o64["mp_img"], r32["mp_img"]):.3e}')
+    check('output oracle fp32 vs ref fp32 (F6 noise floor)', e_o, 5e-3)
+    check('mp_img oracle fp32 vs ref fp32 (F6 noise floor)', e_m, 1e-2)
+    # fp64 twin of the reference module itself (App. B): double() + recomputed double grid
+    m64 = rl.build_quiet(ref.TPS_PP, seed=0)
+    m64.load_state_dict(sd, strict=True)
+    m64 = m64.double().eval()
+    with torch.no_grad():
+        x64 = torch.from_numpy(xi).double()
+        f0 = m64.down0(torch.from_numpy(o0).double()); f1 = m64.down1(torch.from_numpy(o1_).double()); f2 = m64.down2(x64)
+        fcat = torch.cat((m64.down0_1(f0), m64.down1_1(f1), f2), 1)
+        fgrid64 = m64.grid(f0, f1, f2)
+        lg = m64.MSFA(fcat)
+        cp64r, sc64r = m64.TPE(lg['en_feat'], lg['de_feat'])
+        Bq = Bm
+        phi = torch.cat([torch.ones(Bq, 1024, 1, dtype=torch.float64), P64[None].repeat(Bq, 1, 1),
+                         m64.atten_tps.P_hat[None] * (sc64r * 0.5 + 1)], 2)
+        Tm = torch.bmm(m64.atten_tps.hat_C[None].repeat(Bq, 1, 1),
+                       torch.cat([cp64r, torch.zeros(Bq, 3, 2, dtype=torch.float64)], 1))
+        gr64 = torch.bmm(phi, Tm)
+        out64r = F.grid_sample(fgrid64, gr64.reshape(Bq, 16, 64, 2), padding_mode='border', align_corners=True)
+        mp64r = F.grid_sample(x64, gr64.reshape(Bq, 16, 64, 2), padding_mode='border', align_corners=True)
+    check("C' oracle64 vs ref64", _mx(o64['control_point'], cp64r), 1e-12)
+    check('pc_score oracle64 vs ref64', _mx(o64['pc_score'], sc64r), 1e-12)
+    check('grid oracle64 vs ref64', _mx(o64['grid'], gr64), 1e-10)
+    check('output oracle64 vs ref64', _mx(o64['output'], out64r), 1e-9)
+    check('mp_img oracle64 vs ref64', _mx(o64['mp_img'], mp64r), 1e-9)
+    print(f'    ref32 vs ref64: C\' {_mx(r32["output"]*0+0, 0):.0e} output {_mx(r32["output"], out64r):.3e} '
+          f'mp_img {_mx(r32["mp_img"], mp64r):.3e} pc_score {_mx(r32["pc_score"], sc64r):.3e} '
+          f'C\' {_mx(cp_ref, cp64r):.3e}')
+    if not args.check:
+        np.savez_compressed(
+            os.path.join(GOLD, 'tpspp_forward.npz'),
+            state_seed=np.array(3), input_seed=np.array(0), batch=np.array(Bm),
+            ref32_control_point=cp_ref.numpy(), ref64_control_point=cp64r.numpy(),
+            ref32_pc_score=r32['pc_score'].numpy().astype(np.float32),
+            ref64_pc_score=sc64r.numpy().astype(np.float32),
+            ref64_grid=gr64.numpy(),
+            ref32_output=r32['output'].numpy(), ref64_output=out64r.numpy().astype(np.float32),
+            ref32_mp_img=r32['mp_img'].numpy(), ref64_mp_img=mp64r.numpy().astype(np.float32),
+            ref32_feat_grid_ch=fgrid.numpy()[:, ::16].copy(),
+            ref32_en_feat=o32['en_feat'].numpy() * 0 + lg['en_feat'].float().numpy(),
+            ref32_de_feat_ch=lg['de_feat'].float().numpy()[:, ::16].copy(),
+            state_digest=np.array([float(v.double().abs().sum()) for v in sd.values()]))
+        np.savez_compressed(os.path.join(GOLD, 'constants.npz'), **gold_const)
+
+    # ---- classical full module ------------------------------------------------
+    print('TPSPreprocessor.forward')
+    tp = rl.build_quiet(ref.TPSPreprocessor, seed=0, num_fiducial=20, img_size=(32, 100),
+                        rectified_img_size=(32, 100), num_img_channel=1).eval()
+    img = rs.standard_normal((2, 1, 32, 100)).astype(np.float32)
+    with torch.no_grad():
+        ro = tp(torch.from_numpy(img))
+        rc = tp.LocalizationNetwork(torch.from_numpy(img))
+    sdc = tp.state_dict()
+    oc = O.classical_localization(sdc, torch.from_numpy(img))
+    check("classical C'", _mx(oc, rc), 1e-6)
+    print('all oracle checks passed' + ('' if args.check else f'; fixtures written to {GOLD}'))
+
+
+if __name__ == '__main__':
+    main()
