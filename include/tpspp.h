@@ -1,0 +1,154 @@
+/*
+ * tpspp.h -- C ABI of libtpspp.so: the B200-native (sm_100a) TPS++ rectifier hot path.
+ *
+ * This is the drop-in boundary for the path  TPS_PP.forward / TPSPreprocessor.forward
+ * of simplify23/TPS_PP (an MMOCR 0.4.0 fork).  The reference is pure Python/PyTorch and has
+ * no FFI of its own; every entry point below names the reference code it replaces
+ * (paths relative to mmocr/models/textrecog/ in the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise
+ *   - the caller owns every buffer, including the workspace; the library never allocates
+ *     device memory and never synchronises the host with the device
+ *   - all work is enqueued on the given stream; calls are re-entrant per stream
+ *   - return value: 0 = ok, negative = error (TPSPP_E_*); tpspp_last_error() gives a
+ *     thread-local human readable message.  No C++ exception crosses this boundary.
+ *   - tensors are dense row-major ("contiguous" NCHW); feature dtype is fp32 unless
+ *     cfg.feat_dtype says bf16; coordinates, scores and control points are always fp32
+ */
+#ifndef TPSPP_H_
+#define TPSPP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPSPP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TPSPP_API __attribute__((visibility("default")))
+#else
+#define TPSPP_API
+#endif
+
+typedef struct CUstream_st* tpspp_stream_t; /* == cudaStream_t */
+
+enum {
+  TPSPP_OK = 0,
+  TPSPP_E_INVALID = -1,     /* bad argument / unsupported shape */
+  TPSPP_E_CUDA = -2,        /* a CUDA runtime call failed (message has the cudaError) */
+  TPSPP_E_UNSUPPORTED = -3, /* requested variant cannot run this configuration */
+  TPSPP_E_NO_DEVICE = -4    /* no sm_100 device */
+};
+
+enum { TPSPP_F32 = 0, TPSPP_BF16 = 1 };
+
+/* Which Phi the grid generator uses. */
+enum {
+  /* TPS++ : Phi[b,p,:] = [1, P_p, P_hat[p,:] * (1 + theta * pc_score[b,p,:])]
+   *         backbones/tps_pp/tps_pp.py:467-479 (P_hat_score_process), P_hat is [n, F]        */
+  TPSPP_MODE_ATTENTION = 0,
+  /* RARE  : Phi[p,:] = P_hat[p,:] with P_hat already [n, F+3] = [1, P, rbf]
+   *         preprocessor/tps_preprocessor.py:255-268,270-282                                  */
+  TPSPP_MODE_CLASSICAL = 1
+};
+
+/* Kernel variant selection (0 lets the library choose; the others are for tests/bench). */
+enum {
+  TPSPP_VARIANT_AUTO = 0,
+  TPSPP_VARIANT_GENERIC = 1, /* one thread per output pixel, direct global gathers            */
+  TPSPP_VARIANT_STAGED = 2   /* persistent CTAs, TMA bulk-copied source planes in shared mem  */
+};
+
+/* Geometry of one fused warp call.  src1/out1 are the optional second sampled tensor
+ * (TPS_PP samples feat_grid and batch_img with the same grid: tps_pp.py:606-615).          */
+typedef struct tpspp_warp_cfg {
+  int32_t batch;          /* B                                                              */
+  int32_t channels0;      /* C of src0 / out0                                               */
+  int32_t src0_h, src0_w; /* source plane of src0                                           */
+  int32_t channels1;      /* C of src1 / out1, 0 when there is no second tensor             */
+  int32_t src1_h, src1_w;
+  int32_t out_h, out_w;   /* rectified size (Hr, Wr); n = Hr*Wr                             */
+  int32_t num_fiducial;   /* F                                                              */
+  int32_t mode;           /* TPSPP_MODE_*                                                   */
+  float theta;            /* 0.5 in the reference ("thela", tps_pp.py:341)                  */
+  int32_t feat_dtype;     /* TPSPP_F32 | TPSPP_BF16 (dtype of src0/src1/out0/out1)          */
+  int32_t variant;        /* TPSPP_VARIANT_*                                                */
+} tpspp_warp_cfg;
+
+TPSPP_API int tpspp_version(void);
+TPSPP_API const char* tpspp_last_error(void);
+
+/* Number of SMs of the current device and the cubin architecture that was loaded (e.g. 100). */
+TPSPP_API int tpspp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Bytes of scratch the forward / backward calls need for this cfg (may be 0). */
+TPSPP_API size_t tpspp_warp_workspace_bytes(const tpspp_warp_cfg* cfg);
+
+/*
+ * Fused TPS grid generator + bilinear grid_sample (border padding, align_corners=True).
+ *
+ * Replaces, in one launch and without materialising Phi, T or the grid in HBM:
+ *   Attention_Enhanced_TPS.build_P_prime + P_hat_score_process  (tps_pp.py:467-496)
+ *   the reshape and both F.grid_sample calls of TPS_PP.forward   (tps_pp.py:601-615)
+ * and for TPSPP_MODE_CLASSICAL
+ *   GridGenerator.build_P_prime + F.grid_sample of TPSPreprocessor.forward
+ *                                                     (tps_preprocessor.py:72-83,270-282)
+ *
+ *   src0        [B, C0, H0, W0]           feature map that is rectified ("feat_grid")
+ *   src1        [B, C1, H1, W1] or NULL   second tensor sampled with the same grid ("batch_img")
+ *   c_prime     [B, F, 2]      fp32       predicted control points C'
+ *   pc_score    [B, n, F]      fp32       attention scores (ATTENTION mode) or NULL
+ *   P_hat       ATTENTION: [n, F] rbf columns;  CLASSICAL: [n, F+3]           (module buffer)
+ *   P           [n, 2] fp32 target pixel centres (ATTENTION mode; tps_pp.py:472) or NULL
+ *   inv_delta_C [F+3, F+3] fp32 (module buffer "hat_C" / "inv_delta_C")
+ *   out0        [B, C0, Hr, Wr]
+ *   out1        [B, C1, Hr, Wr] or NULL
+ *   grid_out    [B, n, 2] fp32 or NULL -- optional copy of the sampling grid (tests only;
+ *               the generic variant writes it, the staged variant rejects a non-NULL value)
+ *
+ * Arithmetic: T and Phi.T are evaluated in fp64 from the fp32 inputs and the source
+ * coordinates / bilinear weights are derived in fp64; the four taps are blended in fp32 in
+ * ATen's order (nw, ne, sw, se).
+ */
+TPSPP_API int tpspp_warp_fwd(const tpspp_warp_cfg* cfg, const void* src0, const void* src1,
+                   const float* c_prime, const float* pc_score, const float* P_hat,
+                   const float* P, const float* inv_delta_C, void* out0, void* out1,
+                   float* grid_out, void* workspace, tpspp_stream_t stream);
+
+/*
+ * Bilinear sampler alone, for a caller-provided grid [B, Hr, Wr, 2] (x, y in [-1, 1]).
+ * Bit-compatible restatement of torch's grid_sampler_2d CUDA kernel for
+ * (bilinear, border, align_corners=True) -- the call at tps_pp.py:606-615 and
+ * tps_preprocessor.py:79-83 -- in fp32 coordinate arithmetic.  Uses cfg geometry fields only.
+ */
+TPSPP_API int tpspp_sample_fwd(const tpspp_warp_cfg* cfg, const void* src0, const void* src1,
+                     const float* grid, void* out0, void* out1, tpspp_stream_t stream);
+
+/*
+ * Backward of tpspp_warp_fwd (autograd of tps_pp.py:481-496,606-615 /
+ * tps_preprocessor.py:72-83).  Recomputes the grid instead of saving it.
+ *
+ *   gout0/gout1  upstream gradients of out0/out1 (gout1 may be NULL)
+ *   gsrc0/gsrc1  [like src0/src1] written (not accumulated); NULL skips that gradient
+ *   g_c_prime    [B, F, 2] written; NULL skips
+ *   g_pc_score   [B, n, F] written (ATTENTION mode); NULL skips
+ *   workspace    >= tpspp_warp_workspace_bytes(cfg)
+ */
+TPSPP_API int tpspp_warp_bwd(const tpspp_warp_cfg* cfg, const void* src0, const void* src1,
+                   const float* c_prime, const float* pc_score, const float* P_hat,
+                   const float* P, const float* inv_delta_C, const void* gout0,
+                   const void* gout1, void* gsrc0, void* gsrc1, float* g_c_prime,
+                   float* g_pc_score, void* workspace, tpspp_stream_t stream);
+
+/* Number of kernel launches the most recent call on this host thread enqueued
+ * (bench.py uses it to report gpu_launches). */
+TPSPP_API int tpspp_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPSPP_H_ */

@@ -1,0 +1,123 @@
+"""CPU: the drop-in boundary -- registries, ctor contracts, state_dict layout, the C-ABI library
+loads and exports every symbol include/tpspp.h declares.  No compute calls (no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import tps_pp_b200 as T
+from tps_pp_b200 import _native, constants as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    header = open(os.path.join(ROOT, "include", "tpspp.h")).read()
+    declared = re.findall(r"TPSPP_API\s+[\w\s\*]+?\b(tpspp_\w+)\s*\(", header)
+    assert len(declared) >= 8
+    for name in declared:
+        assert hasattr(native_lib, name), f"libtpspp.so does not export {name}"
+    assert set(declared) == set(_native.exported_symbols())
+    assert native_lib.tpspp_version() == 1
+
+
+def test_cfg_struct_matches_header():
+    header = open(os.path.join(ROOT, "include", "tpspp.h")).read()
+    body = re.search(r"typedef struct tpspp_warp_cfg \{(.*?)\} tpspp_warp_cfg;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+    assert names == [f[0] for f in _native.WarpCfg._fields_]
+
+
+def test_workspace_query_is_host_only(native_lib):
+    import ctypes
+    cfg = _native.WarpCfg(256, 64, 32, 128, 64, 16, 64, 16, 64, 32, 0, 0.5, 0, 0)
+    nbytes = native_lib.tpspp_warp_workspace_bytes(ctypes.byref(cfg))
+    assert nbytes >= 256 * 1024 * 2 * 4
+    bad = _native.WarpCfg(1, 0, 32, 128, 0, 0, 0, 16, 64, 32, 0, 0.5, 0, 0)
+    assert native_lib.tpspp_warp_workspace_bytes(ctypes.byref(bad)) == 0
+    assert b"src0 geometry" in native_lib.tpspp_last_error()
+
+
+def test_registry_builds_reference_names():
+    m = T.build_backbone(dict(type="TPS_PP"))
+    assert isinstance(m, T.TPS_PP)
+    p = T.build_preprocessor(dict(type="TPSPreprocessor", num_fiducial=20, img_size=(32, 100),
+                                  rectified_img_size=(32, 100), num_img_channel=3))
+    assert isinstance(p, T.TPSPreprocessor)
+    with pytest.raises(KeyError):
+        T.build_backbone(dict(type="NoSuchThing"))
+
+
+def test_ctor_contracts_like_reference_tests():
+    # tests/test_models/test_ocr_preprocessor.py:10-17 of the reference
+    with pytest.raises(AssertionError):
+        T.TPSPreprocessor(num_fiducial=-1)
+    with pytest.raises(AssertionError):
+        T.TPSPreprocessor(img_size=32)
+    with pytest.raises(AssertionError):
+        T.TPSPreprocessor(rectified_img_size=100)
+    with pytest.raises(AssertionError):
+        T.TPSPreprocessor(num_img_channel="bgr")
+    with pytest.raises(AssertionError):
+        T.TPS_PP(img_size=[16, 64])
+    with pytest.raises(AssertionError):
+        T.TPS_PP(rectified_img_size=64)
+    pre = T.BasePreprocessor()
+    pre.init_weights()
+    x = torch.randn(1, 1, 32, 100)
+    assert pre(x).shape == x.shape
+
+
+def test_state_dict_layout_and_init_match_reference(golden):
+    g = golden("constants.npz")
+    torch.manual_seed(0)
+    m = T.TPS_PP()
+    m.init_weights()
+    sd = m.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["init_keys"]]
+    assert len(sd) == 60 and sum(p.numel() for p in m.parameters()) == 546597
+    sums = np.array([float(v.double().sum()) for v in sd.values()])
+    abss = np.array([float(v.double().abs().sum()) for v in sd.values()])
+    assert np.array_equal(sums, g["init_sums"]) and np.array_equal(abss, g["init_abs_sums"])
+    assert float(sd["TPE.localization_fc2.weight"].abs().max()) == 0.0
+
+
+def test_constants_match_reference_buffers(golden):
+    g = golden("constants.npz")
+    hat, ph, p, _ = K.attention_tps_buffers((2, 16), (16, 64))
+    assert np.array_equal(hat, g["tpspp_hat_C"]) and np.array_equal(ph, g["tpspp_P_hat"]) and np.array_equal(p, g["tpspp_P"])
+    for f, rs in ((20, (32, 100)), (6, (8, 12))):
+        inv, pc, _ = K.classical_tps_buffers(f, rs)
+        assert np.array_equal(inv, g[f"classical_F{f}_{rs[0]}x{rs[1]}_inv_delta_C"])
+        assert np.array_equal(pc, g[f"classical_F{f}_{rs[0]}x{rs[1]}_P_hat"])
+    c = T.TPSPreprocessor(20, (32, 100), (32, 100), 1)
+    keys = list(c.state_dict().keys())
+    assert "GridGenerator.inv_delta_C" in keys and "GridGenerator.P_hat" in keys
+    assert "LocalizationNetwork.conv.13.running_var" in keys and "LocalizationNetwork.localization_fc2.bias" in keys
+
+
+def test_no_cpu_fallback():
+    m = T.TPS_PP()
+    x = torch.randn(1, 64, 16, 64)
+    o = torch.randn(1, 32, 32, 128)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x, [o, o])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        T.TPSPreprocessor()(torch.randn(1, 1, 32, 100))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "tps_pp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text.replace("# oracle", ""), f"{fn} mentions the oracle"

@@ -1,0 +1,146 @@
+"""GPU: the drop-in modules (TPS_PP, TPSPreprocessor) against reference vectors and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import tps_pp_b200 as T
+from oracle import tpspp_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def mx(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))))
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def test_tps_pp_forward_vs_reference_golden(golden, native_lib):
+    """Three-tier parity of the whole module: control points 1e-4 (north_star), pc_score,
+    and pixels against the reference's fp64 twin with the reference's own fp32 error as the floor."""
+    g = golden("tpspp_forward.npz")
+    sd = O.trained_like_state(int(g["state_seed"]))
+    m = T.TPS_PP().to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    x, o0, o1 = O.synthetic_tpspp_inputs(int(g["batch"]), int(g["input_seed"]))
+    with torch.no_grad():
+        r = m(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
+    assert set(r.keys()) == {"output", "logits", "mp_img", "pc_score"} and r["logits"] is None
+    assert r["output"].shape == (2, 64, 16, 64) and r["mp_img"].shape == (2, 64, 16, 64)
+    assert r["pc_score"].shape == (2, 1024, 32)
+    assert mx(r["pc_score"], g["ref64_pc_score"]) <= 5e-5
+    floor_o = mx(g["ref32_output"], g["ref64_output"])
+    floor_m = mx(g["ref32_mp_img"], g["ref64_mp_img"])
+    e_o, e_m = mx(r["output"], g["ref64_output"]), mx(r["mp_img"], g["ref64_mp_img"])
+    print(f"output |ours-ref64|={e_o:.3e} (ref32-ref64 floor {floor_o:.3e}); mp_img {e_m:.3e} (floor {floor_m:.3e})")
+    assert e_o <= max(1e-5, 4 * floor_o)
+    assert e_m <= max(1e-5, 4 * floor_m)
+
+
+def test_tps_pp_head_control_points(golden, native_lib):
+    g = golden("tpspp_forward.npz")
+    sd = O.trained_like_state(int(g["state_seed"]))
+    m = T.TPS_PP().to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    x, o0, o1 = O.synthetic_tpspp_inputs(int(g["batch"]), int(g["input_seed"]))
+    with torch.no_grad():
+        fg, cp, sc = m.head(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
+    assert mx(cp, g["ref64_control_point"]) <= 1e-4          # north_star tolerance
+    assert mx(cp, g["ref32_control_point"]) <= 1e-6
+    assert mx(fg[:, ::16], g["ref32_feat_grid_ch"]) <= 5e-5
+
+
+def test_tps_pp_random_init_matches_oracle(native_lib):
+    """Stock initialisation (fc2.weight == 0): C' is the bias lattice, F5 coordinate quirk included."""
+    torch.manual_seed(0)
+    m = T.TPS_PP().to(DEV).eval()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    x, o0, o1 = O.synthetic_tpspp_inputs(2, 5)
+    with torch.no_grad():
+        r = m(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
+    r64 = O.tps_pp_forward(sd, x, [o0, o1], dtype=torch.float64, sampler="numpy")
+    r32 = O.tps_pp_forward(sd, x, [o0, o1], dtype=torch.float32)
+    floor = mx(r32["output"], r64["output"])
+    assert mx(r["output"], r64["output"]) <= max(1e-5, 4 * floor)
+    assert mx(r["mp_img"], r64["mp_img"]) <= max(1e-5, 4 * mx(r32["mp_img"], r64["mp_img"]))
+
+
+def test_tps_pp_autograd_reaches_every_parameter(native_lib):
+    """Training contract: grads flow to batch_img, outs[*] and every parameter."""
+    sd = O.trained_like_state(3)
+    m = T.TPS_PP().to(DEV)
+    m.load_state_dict(sd, strict=True)
+    x, o0, o1 = O.synthetic_tpspp_inputs(2, 1)
+    tx = torch.from_numpy(x).to(DEV).requires_grad_()
+    t0 = torch.from_numpy(o0).to(DEV).requires_grad_()
+    t1 = torch.from_numpy(o1).to(DEV).requires_grad_()
+    r = m(tx, [t0, t1])
+    r["output"].square().mean().backward()
+    for name, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    assert tx.grad is not None and t0.grad is not None and t1.grad is not None
+    # against the oracle's torch-CPU autograd in fp64
+    m64 = {k: v.double() for k, v in sd.items()}
+    px = torch.from_numpy(x).double().requires_grad_()
+    import torch.nn.functional as F
+    st = {k: v.clone().requires_grad_(v.is_floating_point() and not k.startswith("atten_tps")) for k, v in m64.items()}
+
+    def run():
+        feat_cat, feat_grid = O.down_stage(st, px, torch.from_numpy(o0).double(), torch.from_numpy(o1).double())
+        en, de = O.msfa(st, feat_cat)
+        cp, score, _ = O.tpe(st, en, de)
+        c = O.tpspp_constants()
+        hat = torch.from_numpy(c["hat_C"]).double(); ph = torch.from_numpy(c["P_hat"]).double(); P = torch.from_numpy(c["P"]).double()
+        B = cp.shape[0]
+        phi = torch.cat([torch.ones(B, 1024, 1, dtype=torch.float64), P[None].repeat(B, 1, 1), ph[None] * (score * 0.5 + 1)], 2)
+        Tm = torch.bmm(hat[None].repeat(B, 1, 1), torch.cat([cp, torch.zeros(B, 3, 2, dtype=torch.float64)], 1))
+        grid = torch.bmm(phi, Tm).reshape(B, 16, 64, 2)
+        return F.grid_sample(feat_grid, grid, padding_mode="border", align_corners=True)
+
+    # _t() in the oracle detaches; patch it for this differentiable run
+    orig = O._t
+    O._t = lambda state, key, dtype: state[key]
+    try:
+        run().square().mean().backward()
+    finally:
+        O._t = orig
+    for name, p in m.named_parameters():
+        ref = st[name].grad
+        scale = max(float(ref.abs().max()), 1e-12)
+        assert mx(p.grad, ref) <= 2e-3 * scale + 1e-9, name
+    assert mx(tx.grad, px.grad) <= 2e-3 * float(px.grad.abs().max())
+
+
+def test_tps_preprocessor_like_reference_test(native_lib):
+    """reference tests/test_models/test_ocr_preprocessor.py:19-29 (shape contract), on the GPU."""
+    pre = T.TPSPreprocessor(num_fiducial=20, img_size=(32, 100), rectified_img_size=(32, 100), num_img_channel=1)
+    pre.init_weights()
+    pre.train()
+    pre = pre.to(DEV)
+    out = pre(torch.randn(1, 1, 32, 100, device=DEV))
+    assert out.shape == torch.Size([1, 1, 32, 100])
+
+
+def test_tps_preprocessor_vs_oracle(native_lib):
+    torch.manual_seed(0)
+    pre = T.TPSPreprocessor(20, (32, 100), (32, 100), 3).to(DEV).eval()
+    with torch.no_grad():
+        pre.LocalizationNetwork.localization_fc2.weight.normal_(0, 1e-2)
+    sd = {k: v.detach().cpu() for k, v in pre.state_dict().items()}
+    img = np.random.RandomState(0).standard_normal((3, 3, 32, 100)).astype(np.float32)
+    with torch.no_grad():
+        out = pre(torch.from_numpy(img).to(DEV))
+        cp = pre.localize(torch.from_numpy(img).to(DEV))
+    cpo = O.classical_localization(sd, torch.from_numpy(img))
+    assert mx(cp, cpo) <= 1e-4
+    cc = O.classical_constants(20, (32, 100))
+    o64, _ = O.classical_warp(img, cp.cpu().numpy(), cc, (32, 100), dtype=np.float64)
+    assert mx(out, o64) <= 1e-5

@@ -1,0 +1,90 @@
+"""ctypes binding of libtpspp.so (C ABI declared in include/tpspp.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a
+``RuntimeError`` is raised -- the product path never routes through PyTorch/CPU code.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("TPSPP_LIB", os.path.join(_HERE, "libtpspp.so"))
+
+OK = 0
+F32, BF16 = 0, 1
+MODE_ATTENTION, MODE_CLASSICAL = 0, 1
+VARIANT_AUTO, VARIANT_GENERIC, VARIANT_STAGED = 0, 1, 2
+
+
+class WarpCfg(Structure):
+    """Mirror of ``tpspp_warp_cfg`` (include/tpspp.h)."""
+    _fields_ = [
+        ("batch", c_int32), ("channels0", c_int32), ("src0_h", c_int32), ("src0_w", c_int32),
+        ("channels1", c_int32), ("src1_h", c_int32), ("src1_w", c_int32),
+        ("out_h", c_int32), ("out_w", c_int32), ("num_fiducial", c_int32), ("mode", c_int32),
+        ("theta", c_float), ("feat_dtype", c_int32), ("variant", c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "tpspp_version": (c_int, []),
+    "tpspp_last_error": (c_char_p, []),
+    "tpspp_last_launch_count": (c_int, []),
+    "tpspp_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "tpspp_warp_workspace_bytes": (c_size_t, [POINTER(WarpCfg)]),
+    "tpspp_warp_fwd": (c_int, [POINTER(WarpCfg)] + [c_void_p] * 12),
+    "tpspp_sample_fwd": (c_int, [POINTER(WarpCfg)] + [c_void_p] * 6),
+    "tpspp_warp_bwd": (c_int, [POINTER(WarpCfg)] + [c_void_p] * 15),
+}
+_OPTIONAL = {}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names every build of the library must export (tests check this without a GPU)."""
+    return sorted(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"libtpspp.so not found at {LIB_PATH}: build it with `python -m tps_pp_b200.build` "
+                "(there is no CPU/PyTorch fallback for the TPS++ hot path)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in {**_SIGNATURES, **_OPTIONAL}.items():
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                if name in _OPTIONAL:
+                    continue
+                raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild it")
+            fn.restype = res
+            fn.argtypes = args
+        if handle.tpspp_version() != 1:
+            raise RuntimeError("libtpspp ABI version mismatch; rebuild it")
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().tpspp_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def last_launch_count() -> int:
+    return int(lib().tpspp_last_launch_count())
+
+
+def device_info():
+    sm, maj, mi = c_int(0), c_int(0), c_int(0)
+    check(lib().tpspp_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mi)), "tpspp_device_info")
+    return sm.value, maj.value, mi.value

@@ -1,0 +1,87 @@
+"""Drop-in ``TPSPreprocessor`` / ``BasePreprocessor`` (registry ``PREPROCESSOR``).
+
+Interface kept from the reference (preprocessor/tps_preprocessor.py:24-85,
+preprocessor/base_preprocessor.py:7-12): ctor kwargs ``num_fiducial=20, img_size=(32,100),
+rectified_img_size=(32,100), num_img_channel=1, init_cfg=None`` with its five asserts,
+``forward(batch_img[B,C,H,W]) -> Tensor[B,C,Hr,Wr]``, state_dict keys
+``LocalizationNetwork.conv.{0,4,8,12}.weight``, BN ``{1,5,9,13}.*``,
+``LocalizationNetwork.localization_fc1.0.*``, ``LocalizationNetwork.localization_fc2.*`` and the
+buffers ``GridGenerator.inv_delta_C`` / ``GridGenerator.P_hat``.
+
+The grid generator + sampler is the fused native kernel (classical mode).  The localisation conv
+stack stays a cuDNN library op (not on the named hot path).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from . import constants as K
+from . import functional as TF
+from .rectifier import _BaseModule
+from .registry import PREPROCESSOR
+
+
+@PREPROCESSOR.register_module()
+class BasePreprocessor(_BaseModule):
+    """Identity preprocessor (base_preprocessor.py:7-12)."""
+
+    def forward(self, x, **kwargs):
+        return x
+
+
+def _localization_convs(cin: int) -> nn.Sequential:
+    layers = []
+    chans = (cin, 64, 128, 256, 512)
+    for i in range(4):
+        layers += [nn.Conv2d(chans[i], chans[i + 1], 3, 1, 1, bias=False), nn.BatchNorm2d(chans[i + 1]), nn.ReLU(True)]
+        layers.append(nn.MaxPool2d(2, 2) if i < 3 else nn.AdaptiveAvgPool2d(1))
+    return nn.Sequential(*layers)
+
+
+@PREPROCESSOR.register_module()
+class TPSPreprocessor(BasePreprocessor):
+    def __init__(self, num_fiducial=20, img_size=(32, 100), rectified_img_size=(32, 100),
+                 num_img_channel=1, init_cfg=None):
+        super().__init__(init_cfg=init_cfg)
+        assert isinstance(num_fiducial, int)
+        assert num_fiducial > 0
+        assert isinstance(img_size, tuple)
+        assert isinstance(rectified_img_size, tuple)
+        assert isinstance(num_img_channel, int)
+        self.num_fiducial = num_fiducial
+        self.img_size = img_size
+        self.rectified_img_size = rectified_img_size
+        self.num_img_channel = num_img_channel
+
+        loc = nn.Module()
+        self.add_module("LocalizationNetwork", loc)
+        loc.add_module("conv", _localization_convs(num_img_channel))
+        loc.add_module("localization_fc1", nn.Sequential(nn.Linear(512, 256), nn.ReLU(True)))
+        loc.add_module("localization_fc2", nn.Linear(256, num_fiducial * 2))
+        with torch.no_grad():
+            loc.localization_fc2.weight.fill_(0)
+            loc.localization_fc2.bias.copy_(torch.from_numpy(K.classical_init_bias(num_fiducial)).float().view(-1))
+
+        inv_dc, p_hat, _ = K.classical_tps_buffers(num_fiducial, rectified_img_size)
+        gen = nn.Module()
+        self.add_module("GridGenerator", gen)
+        gen.register_buffer("inv_delta_C", torch.from_numpy(inv_dc))
+        gen.register_buffer("P_hat", torch.from_numpy(p_hat))
+        self.warp_variant = N.VARIANT_AUTO
+
+    def localize(self, batch_img: torch.Tensor) -> torch.Tensor:
+        """C' [B,F,2] (tps_preprocessor.py:143-156)."""
+        loc = self.LocalizationNetwork
+        feats = loc.conv(batch_img).view(batch_img.size(0), -1)
+        return loc.localization_fc2(loc.localization_fc1(feats)).view(batch_img.size(0), self.num_fiducial, 2)
+
+    def forward(self, batch_img: torch.Tensor, **kwargs) -> torch.Tensor:
+        if not batch_img.is_cuda:
+            raise RuntimeError("tps_pp_b200.TPSPreprocessor runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        c_prime = self.localize(batch_img)
+        gen = self.GridGenerator
+        out, _ = TF.tps_warp(batch_img, None, c_prime.float(), None, gen.P_hat, None, gen.inv_delta_C,
+                             self.rectified_img_size, N.MODE_CLASSICAL, 0.0, self.warp_variant)
+        return out

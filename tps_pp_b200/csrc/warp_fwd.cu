@@ -1,0 +1,397 @@
+// Fused TPS grid generator + bilinear grid_sample, forward.
+//
+// Replaces Attention_Enhanced_TPS.build_P_prime / P_hat_score_process and both
+// F.grid_sample calls of TPS_PP.forward (reference backbones/tps_pp/tps_pp.py:467-496,
+// 601-615) and GridGenerator.build_P_prime + F.grid_sample of TPSPreprocessor.forward
+// (preprocessor/tps_preprocessor.py:72-83,270-282).
+//
+// Two kernels:
+//   warp_fwd_generic_kernel  any geometry / mode / dtype: one thread per output pixel,
+//                            fp64 grid in registers, direct global gathers.
+//   warp_fwd_staged_kernel   the TPS++ geometry (F=32, n<=1024, fp32): persistent CTAs own a
+//                            contiguous range of (image, channel) planes; a producer lane
+//                            streams whole source planes into a shared-memory ring with
+//                            cp.async.bulk (TMA engine) + mbarriers, 8 consumer warps gather
+//                            the 4 bilinear taps from shared memory and write coalesced rows.
+//                            The sampling grid lives in shared memory / registers only.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace tpspp {
+
+// MODE: 0 attention, 1 classical, 2 explicit grid (sampler only, ATen fp32 coordinate math)
+template <typename FT, int MODE>
+__global__ void __launch_bounds__(256) warp_fwd_generic_kernel(WarpParams p, int cchunk) {
+  extern __shared__ double Tsm[];
+  const int b = blockIdx.y;
+  if (MODE != 2) {
+    compute_T(p, b, Tsm, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= p.n) return;
+
+  Taps t0, t1;
+  if (MODE == 2) {
+    const float gx = __ldg(p.grid_in + ((size_t)b * p.n + pix) * 2);
+    const float gy = __ldg(p.grid_in + ((size_t)b * p.n + pix) * 2 + 1);
+    t0 = make_taps<float>(gx, gy, p.W0, p.H0);
+    if (p.C1 > 0) t1 = make_taps<float>(gx, gy, p.W1, p.H1);
+  } else {
+    double gx, gy;
+    pixel_grid<MODE>(p, Tsm, b, pix, gx, gy);
+    if (p.grid_out != nullptr && blockIdx.z == 0) {
+      p.grid_out[((size_t)b * p.n + pix) * 2] = (float)gx;
+      p.grid_out[((size_t)b * p.n + pix) * 2 + 1] = (float)gy;
+    }
+    t0 = make_taps<double>(gx, gy, p.W0, p.H0);
+    if (p.C1 > 0) t1 = make_taps<double>(gx, gy, p.W1, p.H1);
+  }
+
+  const int cb = blockIdx.z * cchunk;
+  {
+    const int ce = min(p.C0, cb + cchunk);
+    const size_t plane = (size_t)p.H0 * p.W0;
+    const FT* src = (const FT*)p.src0 + ((size_t)b * p.C0 + cb) * plane + t0.off;
+    FT* out = (FT*)p.out0 + ((size_t)b * p.C0 + cb) * p.n + pix;
+#pragma unroll 4
+    for (int c = cb; c < ce; ++c, src += plane, out += p.n) {
+      const float r = blend4(ldf(src), ldf(src + t0.dx), ldf(src + t0.dy), ldf(src + t0.dy + t0.dx), t0.w);
+      stf(out, r);
+    }
+  }
+  if (p.C1 > 0) {
+    const int ce = min(p.C1, cb + cchunk);
+    const size_t plane = (size_t)p.H1 * p.W1;
+    const FT* src = (const FT*)p.src1 + ((size_t)b * p.C1 + cb) * plane + t1.off;
+    FT* out = (FT*)p.out1 + ((size_t)b * p.C1 + cb) * p.n + pix;
+#pragma unroll 4
+    for (int c = cb; c < ce; ++c, src += plane, out += p.n) {
+      const float r = blend4(ldf(src), ldf(src + t1.dx), ldf(src + t1.dy), ldf(src + t1.dy + t1.dx), t1.w);
+      stf(out, r);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// staged persistent kernel
+// ------------------------------------------------------------------------------------------
+constexpr int ST_CONSUMER_WARPS = 8;
+constexpr int ST_CONSUMERS = ST_CONSUMER_WARPS * 32;  // 256
+constexpr int ST_THREADS = ST_CONSUMERS + 32;         // + producer warp
+constexpr int ST_PPT = 4;                             // output pixels per consumer thread
+constexpr int ST_MAX_N = ST_CONSUMERS * ST_PPT;       // 1024
+constexpr int ST_F = 32;
+constexpr int ST_K = ST_F + 3;
+constexpr int ST_MAX_STAGES = 8;
+
+struct StagedArgs {
+  WarpParams p;
+  int nstages;
+  int planes_total;       // B * C
+  uint32_t s0_bytes;      // bytes of one src0 plane
+  uint32_t s1_bytes;      // bytes of one src1 plane (0 if !DUAL)
+  uint32_t stage_bytes;   // 128B-aligned s0+s1
+};
+
+struct StagedSmemTail {   // lives after the stage ring and the grid
+  double T[2 * ST_K];
+  uint64_t full[ST_MAX_STAGES];
+  uint64_t empty[ST_MAX_STAGES];
+};
+
+template <bool DUAL>
+__global__ void __launch_bounds__(ST_THREADS, 2) warp_fwd_staged_kernel(StagedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const WarpParams& p = a.p;
+  unsigned char* ring = smem;
+  double2* gridsm = reinterpret_cast<double2*>(smem + (size_t)a.nstages * a.stage_bytes);
+  StagedSmemTail* tail = reinterpret_cast<StagedSmemTail*>(gridsm + ST_MAX_N);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = p.C0;
+  const int p_begin = (int)(((long long)blockIdx.x * a.planes_total) / gridDim.x);
+  const int p_end = (int)(((long long)(blockIdx.x + 1) * a.planes_total) / gridDim.x);
+
+  if (tid == 0) {
+    for (int s = 0; s < a.nstages; ++s) {
+      mbar_init(&tail->full[s], 1);
+      mbar_init(&tail->empty[s], ST_CONSUMER_WARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == ST_CONSUMER_WARPS) {
+    // ===== producer: one lane streams whole planes through the ring =====
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();   // every source byte is read exactly once
+      const unsigned char* g0 = (const unsigned char*)p.src0;
+      const unsigned char* g1 = (const unsigned char*)p.src1;
+      int it = 0;
+      for (int plane = p_begin; plane < p_end; ++plane, ++it) {
+        const int s = it % a.nstages;
+        const uint32_t ph = (uint32_t)((it / a.nstages) & 1);
+        mbar_wait(&tail->empty[s], ph ^ 1u);
+        unsigned char* dst = ring + (size_t)s * a.stage_bytes;
+        mbar_arrive_expect_tx(&tail->full[s], a.s0_bytes + a.s1_bytes);
+        bulk_g2s(dst, g0 + (size_t)plane * a.s0_bytes, a.s0_bytes, &tail->full[s], pol);
+        if (DUAL) bulk_g2s(dst + a.s0_bytes, g1 + (size_t)plane * a.s1_bytes, a.s1_bytes, &tail->full[s], pol);
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int n = p.n;
+  const int kq = (lane & 7) * 4;     // this lane's 4 rbf columns in the grid phase
+  int it = 0;
+  int plane = p_begin;
+  while (plane < p_end) {
+    const int b = plane / C;
+    const int c_begin = plane - b * C;
+    const int c_end = min(C, c_begin + (p_end - plane));
+
+    named_bar_sync(1, ST_CONSUMERS);  // everyone is done with the previous image's T / grid
+    compute_T(p, b, tail->T, tid, ST_CONSUMERS);
+    named_bar_sync(1, ST_CONSUMERS);
+
+    // ---- grid phase: 8 lanes per pixel, 4 pixels per warp step, coalesced float4 loads ----
+    {
+      double tx[4], ty[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        tx[i] = tail->T[2 * (3 + kq + i)];
+        ty[i] = tail->T[2 * (3 + kq + i) + 1];
+      }
+      const double th = (double)p.theta;
+      const float* sbase = p.score + (size_t)b * n * ST_F;
+      const int pix0 = warp * (ST_MAX_N / ST_CONSUMER_WARPS) + (lane >> 3);
+#pragma unroll 4
+      for (int step = 0; step < ST_MAX_N / ST_CONSUMER_WARPS / 4; ++step) {
+        const int pix = pix0 + step * 4;
+        const bool ok = pix < n;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), h4 = s4;
+        if (ok) {
+          s4 = __ldg(reinterpret_cast<const float4*>(sbase + (size_t)pix * ST_F + kq));
+          h4 = __ldg(reinterpret_cast<const float4*>(p.P_hat + (size_t)pix * ST_F + kq));
+        }
+        const double f0 = (double)h4.x * (1.0 + th * (double)s4.x);
+        const double f1 = (double)h4.y * (1.0 + th * (double)s4.y);
+        const double f2 = (double)h4.z * (1.0 + th * (double)s4.z);
+        const double f3 = (double)h4.w * (1.0 + th * (double)s4.w);
+        double ax = fma(f3, tx[3], fma(f2, tx[2], fma(f1, tx[1], f0 * tx[0])));
+        double ay = fma(f3, ty[3], fma(f2, ty[2], fma(f1, ty[1], f0 * ty[0])));
+#pragma unroll
+        for (int m = 1; m < 8; m <<= 1) {
+          ax += shfl_xor_f64(ax, m);
+          ay += shfl_xor_f64(ay, m);
+        }
+        if (ok && (lane & 7) == 0) {
+          const double px = (double)__ldg(p.P + 2 * pix), py = (double)__ldg(p.P + 2 * pix + 1);
+          const double gx = tail->T[0] + px * tail->T[2] + py * tail->T[4] + ax;
+          const double gy = tail->T[1] + px * tail->T[3] + py * tail->T[5] + ay;
+          gridsm[pix] = make_double2(gx, gy);
+        }
+      }
+    }
+    named_bar_sync(1, ST_CONSUMERS);
+
+    // ---- per-thread taps for its 4 pixels (pixel = tid + 256*j: neighbouring lanes sample
+    //      neighbouring source columns, which keeps shared-memory bank conflicts low) ----
+    Taps t0[ST_PPT], t1[ST_PPT];
+#pragma unroll
+    for (int j = 0; j < ST_PPT; ++j) {
+      const int pix = tid + ST_CONSUMERS * j;
+      double2 g = make_double2(0.0, 0.0);
+      if (pix < n) g = gridsm[pix];
+      t0[j] = make_taps<double>(g.x, g.y, p.W0, p.H0);
+      if (DUAL) t1[j] = make_taps<double>(g.x, g.y, p.W1, p.H1);
+    }
+
+    // ---- channel loop over the ring ----
+    for (int c = c_begin; c < c_end; ++c, ++it) {
+      const int s = it % a.nstages;
+      const uint32_t ph = (uint32_t)((it / a.nstages) & 1);
+      mbar_wait(&tail->full[s], ph);
+      const float* s0 = reinterpret_cast<const float*>(ring + (size_t)s * a.stage_bytes);
+      const float* s1 = reinterpret_cast<const float*>(ring + (size_t)s * a.stage_bytes + a.s0_bytes);
+      float* o0 = (float*)p.out0 + ((size_t)b * C + c) * n;
+      float* o1 = (float*)p.out1 + ((size_t)b * C + c) * n;
+      float r0[ST_PPT], r1[ST_PPT];
+#pragma unroll
+      for (int j = 0; j < ST_PPT; ++j) {
+        const float* q = s0 + t0[j].off;
+        r0[j] = blend4(q[0], q[t0[j].dx], q[t0[j].dy], q[t0[j].dy + t0[j].dx], t0[j].w);
+        if (DUAL) {
+          const float* r = s1 + t1[j].off;
+          r1[j] = blend4(r[0], r[t1[j].dx], r[t1[j].dy], r[t1[j].dy + t1[j].dx], t1[j].w);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->empty[s]);   // the stage may be refilled
+#pragma unroll
+      for (int j = 0; j < ST_PPT; ++j) {
+        const int pix = tid + ST_CONSUMERS * j;
+        if (pix < n) {
+          __stcs(o0 + pix, r0[j]);
+          if (DUAL) __stcs(o1 + pix, r1[j]);
+        }
+      }
+    }
+    plane += (c_end - c_begin);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static size_t staged_fixed_smem() { return (size_t)ST_MAX_N * sizeof(double2) + sizeof(StagedSmemTail) + 128; }
+
+// returns nstages (0 = not eligible)
+static int staged_plan(const tpspp_warp_cfg* cfg, uint32_t* s0, uint32_t* s1, uint32_t* stage) {
+  if (cfg->mode != TPSPP_MODE_ATTENTION || cfg->num_fiducial != ST_F) return 0;
+  if (cfg->feat_dtype != TPSPP_F32) return 0;
+  const int n = cfg->out_h * cfg->out_w;
+  if (n > ST_MAX_N) return 0;
+  if (cfg->channels1 != 0 && cfg->channels1 != cfg->channels0) return 0;
+  const size_t b0 = (size_t)cfg->src0_h * cfg->src0_w * 4;
+  const size_t b1 = cfg->channels1 ? (size_t)cfg->src1_h * cfg->src1_w * 4 : 0;
+  if (b0 % 16 || b1 % 16) return 0;
+  const size_t st = (b0 + b1 + 127) / 128 * 128;
+  const size_t per_cta_two = (232448 / 2) - 1024;   // two CTAs per SM
+  const size_t per_cta_one = 232448 - 1024;
+  size_t avail = per_cta_two > staged_fixed_smem() ? per_cta_two - staged_fixed_smem() : 0;
+  int ns = (int)(avail / st);
+  if (ns < 3) {
+    avail = per_cta_one > staged_fixed_smem() ? per_cta_one - staged_fixed_smem() : 0;
+    ns = (int)(avail / st);
+  }
+  if (ns > ST_MAX_STAGES) ns = ST_MAX_STAGES;
+  if (ns < 2) return 0;
+  *s0 = (uint32_t)b0; *s1 = (uint32_t)b1; *stage = (uint32_t)st;
+  return ns;
+}
+
+static int launch_staged(const tpspp_warp_cfg* cfg, const WarpParams& p, cudaStream_t stream) {
+  StagedArgs a;
+  a.p = p;
+  a.nstages = staged_plan(cfg, &a.s0_bytes, &a.s1_bytes, &a.stage_bytes);
+  if (a.nstages == 0) {
+    set_error("staged warp variant does not support this configuration "
+              "(needs attention mode, F=32, n<=1024, fp32, C1 in {0,C0}, planes that fit shared memory)");
+    return TPSPP_E_UNSUPPORTED;
+  }
+  if (p.grid_out != nullptr) {
+    set_error("staged warp variant keeps the grid on chip; grid_out must be NULL");
+    return TPSPP_E_UNSUPPORTED;
+  }
+  if (((uintptr_t)p.src0 & 15) || ((uintptr_t)p.src1 & 15) || ((uintptr_t)p.score & 15) ||
+      ((uintptr_t)p.P_hat & 15)) {
+    set_error("staged warp variant needs 16-byte aligned src/pc_score/P_hat pointers");
+    return TPSPP_E_UNSUPPORTED;
+  }
+  a.planes_total = p.B * p.C0;
+  const size_t smem = (size_t)a.nstages * a.stage_bytes + staged_fixed_smem();
+  const bool dual = p.C1 > 0;
+  auto kern = dual ? warp_fwd_staged_kernel<true> : warp_fwd_staged_kernel<false>;
+  TPSPP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int ctas_per_sm = 0;
+  TPSPP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, ST_THREADS, smem));
+  if (ctas_per_sm < 1) {
+    set_error("staged warp kernel does not fit on an SM (smem %zu)", smem);
+    return TPSPP_E_UNSUPPORTED;
+  }
+  int grid = sm_count() * ctas_per_sm;
+  if (grid > a.planes_total) grid = a.planes_total;
+  kern<<<grid, ST_THREADS, smem, stream>>>(a);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
+template <typename FT>
+static int launch_generic_t(const WarpParams& p, int mode, cudaStream_t stream) {
+  const int maxc = p.C0 > p.C1 ? p.C0 : p.C1;
+  // enough CTAs to fill the machine a few times over, without shredding the channel loop
+  const int tiles = (p.n + 255) / 256;
+  int zsplit = 1;
+  const long long want = 4LL * sm_count();
+  while ((long long)tiles * p.B * zsplit < want && zsplit < maxc && zsplit < 16) zsplit *= 2;
+  const int cchunk = (maxc + zsplit - 1) / zsplit;
+  zsplit = (maxc + cchunk - 1) / cchunk;
+  dim3 grid(tiles, p.B, zsplit);
+  const size_t smem = (size_t)2 * p.K * sizeof(double);
+  if (mode == 0) warp_fwd_generic_kernel<FT, 0><<<grid, 256, smem, stream>>>(p, cchunk);
+  else if (mode == 1) warp_fwd_generic_kernel<FT, 1><<<grid, 256, smem, stream>>>(p, cchunk);
+  else warp_fwd_generic_kernel<FT, 2><<<grid, 256, smem, stream>>>(p, cchunk);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
+static int launch_generic(const tpspp_warp_cfg* cfg, const WarpParams& p, int mode, cudaStream_t stream) {
+  TPSPP_REQUIRE(p.B <= 65535, "batch %d exceeds the generic kernel's grid.y limit (65535)", p.B);
+  if (cfg->feat_dtype == TPSPP_BF16) return launch_generic_t<__nv_bfloat16>(p, mode, stream);
+  return launch_generic_t<float>(p, mode, stream);
+}
+
+void fill_params(const tpspp_warp_cfg* cfg, WarpParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->B = cfg->batch; p->C0 = cfg->channels0; p->H0 = cfg->src0_h; p->W0 = cfg->src0_w;
+  p->C1 = cfg->channels1; p->H1 = cfg->src1_h; p->W1 = cfg->src1_w;
+  p->n = cfg->out_h * cfg->out_w; p->F = cfg->num_fiducial; p->K = cfg->num_fiducial + 3;
+  p->mode = cfg->mode; p->theta = cfg->theta;
+}
+
+}  // namespace tpspp
+
+using namespace tpspp;
+
+extern "C" int tpspp_warp_fwd(const tpspp_warp_cfg* cfg, const void* src0, const void* src1,
+                              const float* c_prime, const float* pc_score, const float* P_hat,
+                              const float* P, const float* inv_delta_C, void* out0, void* out1,
+                              float* grid_out, void* workspace, tpspp_stream_t stream) {
+  (void)workspace;
+  reset_launch_count();
+  int rc = validate_cfg(cfg);
+  if (rc != TPSPP_OK) return rc;
+  TPSPP_REQUIRE(src0 && out0 && c_prime && P_hat && inv_delta_C, "tpspp_warp_fwd: null required pointer");
+  TPSPP_REQUIRE((cfg->channels1 == 0) == (src1 == nullptr) && (cfg->channels1 == 0) == (out1 == nullptr),
+                "tpspp_warp_fwd: src1/out1 must be given exactly when channels1 > 0");
+  if (cfg->mode == TPSPP_MODE_ATTENTION)
+    TPSPP_REQUIRE(pc_score && P, "tpspp_warp_fwd: attention mode needs pc_score and P");
+  if (cfg->batch == 0) return TPSPP_OK;
+  WarpParams p;
+  fill_params(cfg, &p);
+  p.src0 = src0; p.src1 = src1; p.c_prime = c_prime; p.score = pc_score; p.P_hat = P_hat; p.P = P;
+  p.hatC = inv_delta_C; p.out0 = out0; p.out1 = out1; p.grid_out = grid_out;
+  cudaStream_t st = (cudaStream_t)stream;
+  int variant = cfg->variant;
+  if (variant == TPSPP_VARIANT_AUTO) {
+    uint32_t a, b, c;
+    const bool aligned = !(((uintptr_t)src0 | (uintptr_t)src1 | (uintptr_t)pc_score | (uintptr_t)P_hat) & 15);
+    variant = (grid_out == nullptr && aligned && staged_plan(cfg, &a, &b, &c) > 0) ? TPSPP_VARIANT_STAGED
+                                                                                  : TPSPP_VARIANT_GENERIC;
+  }
+  if (variant == TPSPP_VARIANT_STAGED) return launch_staged(cfg, p, st);
+  if (variant == TPSPP_VARIANT_GENERIC) return launch_generic(cfg, p, cfg->mode, st);
+  set_error("tpspp_warp_fwd: unknown variant %d", cfg->variant);
+  return TPSPP_E_INVALID;
+}
+
+extern "C" int tpspp_sample_fwd(const tpspp_warp_cfg* cfg, const void* src0, const void* src1,
+                                const float* grid, void* out0, void* out1, tpspp_stream_t stream) {
+  reset_launch_count();
+  int rc = validate_cfg(cfg);
+  if (rc != TPSPP_OK) return rc;
+  TPSPP_REQUIRE(src0 && out0 && grid, "tpspp_sample_fwd: null required pointer");
+  TPSPP_REQUIRE((cfg->channels1 == 0) == (src1 == nullptr) && (cfg->channels1 == 0) == (out1 == nullptr),
+                "tpspp_sample_fwd: src1/out1 must be given exactly when channels1 > 0");
+  if (cfg->batch == 0) return TPSPP_OK;
+  WarpParams p;
+  fill_params(cfg, &p);
+  p.src0 = src0; p.src1 = src1; p.grid_in = grid; p.out0 = out0; p.out1 = out1;
+  return launch_generic(cfg, p, 2, (cudaStream_t)stream);
+}

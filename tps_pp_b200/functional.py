@@ -1,0 +1,157 @@
+"""Autograd-aware Python entry points over the C ABI (include/tpspp.h).
+
+``tps_warp``      fused grid generator + bilinear sampling (reference tps_pp.py:481-496,601-615;
+                  tps_preprocessor.py:72-83,270-282)
+``grid_sample_border`` the sampler alone for an explicit grid (ATen-compatible fp32 coordinates)
+
+Tensors must live on a CUDA device; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_DT = {torch.float32: N.F32, torch.bfloat16: N.BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(name: str, t: Optional[torch.Tensor], dtype=None):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"tps_pp_b200: `{name}` must be a CUDA tensor (the TPS++ hot path has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"tps_pp_b200: `{name}` must be {dtype}, got {t.dtype}")
+
+
+def _cfg(src0, src1, out_size, num_fiducial, mode, theta, variant) -> N.WarpCfg:
+    if src0.dtype not in _DT:
+        raise RuntimeError(f"tps_pp_b200: unsupported feature dtype {src0.dtype} (fp32 or bf16)")
+    if src1 is not None and src1.dtype != src0.dtype:
+        raise RuntimeError("tps_pp_b200: src0/src1 dtype mismatch")
+    b, c0, h0, w0 = src0.shape
+    c1, h1, w1 = (src1.shape[1:] if src1 is not None else (0, 0, 0))
+    return N.WarpCfg(b, c0, h0, w0, c1, h1, w1, int(out_size[0]), int(out_size[1]), int(num_fiducial),
+                     int(mode), float(theta), _DT[src0.dtype], int(variant))
+
+
+class _TpsWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src0, src1, c_prime, pc_score, P_hat, P, inv_delta_C, out_size, mode, theta, variant):
+        _require_cuda("src0", src0)
+        _require_cuda("src1", src1)
+        _require_cuda("c_prime", c_prime, torch.float32)
+        _require_cuda("pc_score", pc_score, torch.float32)
+        for nm, t in (("P_hat", P_hat), ("P", P), ("inv_delta_C", inv_delta_C)):
+            _require_cuda(nm, t, torch.float32)
+        src0 = src0.contiguous()
+        src1 = src1.contiguous() if src1 is not None else None
+        c_prime = c_prime.contiguous()
+        pc_score = pc_score.contiguous() if pc_score is not None else None
+        P_hat = P_hat.contiguous(); inv_delta_C = inv_delta_C.contiguous()
+        P = P.contiguous() if P is not None else None
+        b, f = c_prime.shape[0], c_prime.shape[1]
+        n = out_size[0] * out_size[1]
+        if c_prime.shape != (src0.shape[0], f, 2):
+            raise RuntimeError(f"tps_pp_b200: c_prime must be [B,F,2], got {tuple(c_prime.shape)}")
+        k_cols = f if mode == N.MODE_ATTENTION else f + 3
+        if P_hat.shape != (n, k_cols):
+            raise RuntimeError(f"tps_pp_b200: P_hat must be [{n},{k_cols}], got {tuple(P_hat.shape)}")
+        if inv_delta_C.shape != (f + 3, f + 3):
+            raise RuntimeError(f"tps_pp_b200: inv_delta_C must be [{f + 3},{f + 3}]")
+        if mode == N.MODE_ATTENTION:
+            if pc_score is None or pc_score.shape != (b, n, f):
+                raise RuntimeError(f"tps_pp_b200: pc_score must be [{b},{n},{f}]")
+            if P is None or P.shape != (n, 2):
+                raise RuntimeError(f"tps_pp_b200: P must be [{n},2]")
+        cfg = _cfg(src0, src1, out_size, f, mode, theta, variant)
+        out0 = torch.empty((b, src0.shape[1], out_size[0], out_size[1]), dtype=src0.dtype, device=src0.device)
+        out1 = (torch.empty((b, src1.shape[1], out_size[0], out_size[1]), dtype=src1.dtype, device=src1.device)
+                if src1 is not None else None)
+        with torch.cuda.device(src0.device):
+            N.check(N.lib().tpspp_warp_fwd(ctypes.byref(cfg), _ptr(src0), _ptr(src1), _ptr(c_prime), _ptr(pc_score),
+                                           _ptr(P_hat), _ptr(P), _ptr(inv_delta_C), _ptr(out0), _ptr(out1),
+                                           None, None, _stream(src0)), "tpspp_warp_fwd")
+        ctx.save_for_backward(src0, src1, c_prime, pc_score, P_hat, P, inv_delta_C)
+        ctx.cfg_args = (out_size, mode, theta)
+        return out0, out1
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        src0, src1, c_prime, pc_score, P_hat, P, inv_delta_C = ctx.saved_tensors
+        out_size, mode, theta = ctx.cfg_args
+        f = c_prime.shape[1]
+        cfg = _cfg(src0, src1, out_size, f, mode, theta, N.VARIANT_AUTO)
+        need = ctx.needs_input_grad
+        if g0 is None:
+            g0 = torch.zeros((src0.shape[0], src0.shape[1]) + tuple(out_size), dtype=src0.dtype, device=src0.device)
+        g0 = g0.contiguous()
+        g1 = g1.contiguous() if (g1 is not None and src1 is not None) else None
+        gsrc0 = torch.empty_like(src0) if need[0] else None
+        gsrc1 = torch.empty_like(src1) if (src1 is not None and need[1] and g1 is not None) else None
+        gcp = torch.empty_like(c_prime) if need[2] else None
+        gsc = torch.empty_like(pc_score) if (pc_score is not None and need[3]) else None
+        with torch.cuda.device(src0.device):
+            nbytes = int(N.lib().tpspp_warp_workspace_bytes(ctypes.byref(cfg)))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=src0.device)
+            N.check(N.lib().tpspp_warp_bwd(ctypes.byref(cfg), _ptr(src0), _ptr(src1), _ptr(c_prime), _ptr(pc_score),
+                                           _ptr(P_hat), _ptr(P), _ptr(inv_delta_C), _ptr(g0), _ptr(g1),
+                                           _ptr(gsrc0), _ptr(gsrc1), _ptr(gcp), _ptr(gsc), _ptr(ws), _stream(src0)),
+                    "tpspp_warp_bwd")
+        if src1 is not None and need[1] and gsrc1 is None:
+            gsrc1 = torch.zeros_like(src1)
+        return gsrc0, gsrc1, gcp, gsc, None, None, None, None, None, None, None
+
+
+def tps_warp(src0: torch.Tensor, src1: Optional[torch.Tensor], c_prime: torch.Tensor,
+             pc_score: Optional[torch.Tensor], P_hat: torch.Tensor, P: Optional[torch.Tensor],
+             inv_delta_C: torch.Tensor, out_size: Tuple[int, int], mode: int = N.MODE_ATTENTION,
+             theta: float = 0.5, variant: int = N.VARIANT_AUTO):
+    """Fused ``build_P_prime`` + ``grid_sample`` (x2).  Returns ``(out0, out1_or_None)``."""
+    return _TpsWarp.apply(src0, src1, c_prime, pc_score, P_hat, P, inv_delta_C, tuple(out_size), mode, theta, variant)
+
+
+def tps_grid(c_prime, pc_score, P_hat, P, inv_delta_C, out_size, mode=N.MODE_ATTENTION, theta=0.5):
+    """Debug/test helper: the sampling grid [B,n,2] as the fused kernel computes it (generic variant)."""
+    b, f = c_prime.shape[:2]
+    dummy = torch.zeros((b, 1, 1, 1), dtype=torch.float32, device=c_prime.device)
+    cfg = _cfg(dummy, None, out_size, f, mode, theta, N.VARIANT_GENERIC)
+    n = out_size[0] * out_size[1]
+    grid = torch.empty((b, n, 2), dtype=torch.float32, device=c_prime.device)
+    out = torch.empty((b, 1) + tuple(out_size), dtype=torch.float32, device=c_prime.device)
+    with torch.cuda.device(c_prime.device):
+        N.check(N.lib().tpspp_warp_fwd(ctypes.byref(cfg), _ptr(dummy), None, _ptr(c_prime.contiguous()),
+                                       _ptr(pc_score.contiguous() if pc_score is not None else None),
+                                       _ptr(P_hat.contiguous()), _ptr(P.contiguous() if P is not None else None),
+                                       _ptr(inv_delta_C.contiguous()), _ptr(out), None, _ptr(grid), None,
+                                       _stream(dummy)), "tpspp_warp_fwd")
+    return grid
+
+
+def grid_sample_border(src0: torch.Tensor, grid: torch.Tensor, src1: Optional[torch.Tensor] = None):
+    """``F.grid_sample(src, grid, padding_mode='border', align_corners=True)`` for one or two sources
+    (forward only; the differentiable path is :func:`tps_warp`)."""
+    _require_cuda("src0", src0); _require_cuda("src1", src1); _require_cuda("grid", grid, torch.float32)
+    src0 = src0.contiguous(); grid = grid.contiguous()
+    src1 = src1.contiguous() if src1 is not None else None
+    b, hr, wr, two = grid.shape
+    if two != 2 or b != src0.shape[0]:
+        raise RuntimeError("tps_pp_b200: grid must be [B,Hr,Wr,2]")
+    cfg = _cfg(src0, src1, (hr, wr), 1, N.MODE_CLASSICAL, 0.0, N.VARIANT_GENERIC)
+    out0 = torch.empty((b, src0.shape[1], hr, wr), dtype=src0.dtype, device=src0.device)
+    out1 = torch.empty((b, src1.shape[1], hr, wr), dtype=src1.dtype, device=src1.device) if src1 is not None else None
+    with torch.cuda.device(src0.device):
+        N.check(N.lib().tpspp_sample_fwd(ctypes.byref(cfg), _ptr(src0), _ptr(src1), _ptr(grid), _ptr(out0),
+                                         _ptr(out1), _stream(src0)), "tpspp_sample_fwd")
+    return (out0, out1) if src1 is not None else out0

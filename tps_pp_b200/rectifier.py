@@ -1,0 +1,237 @@
+"""Drop-in ``TPS_PP`` (registry ``BACKBONES``): the attention-enhanced TPS rectifier.
+
+Interface kept from the reference (backbones/tps_pp/tps_pp.py:499-625):
+
+* ctor kwargs/defaults ``img_size=(16,64), rectified_img_size=(16,64), num_img_channel=64,
+  point_size=(2,16), p_stride=2, visual_point=False, init_cfg=None`` and the two tuple asserts
+  (:505-516)
+* ``forward(batch_img[B,64,h,w], outs=[o0,o1]) -> dict(output, logits=None, mp_img, pc_score)``
+  (:564-625); called by the backbone at backbones/resnet_v2_large.py:183-191
+* ``state_dict`` keys/shapes so reference checkpoints load with strict=True;
+  parameters are created in the reference's construction order with the same initialisers, so
+  ``torch.manual_seed(s); TPS_PP()`` yields the reference's initial weights.
+
+The architecture is not the reference's module tree: parameters hang off passive containers and
+``forward`` is a flat pipeline of stages, each of which is a native sm_100a kernel (through the C
+ABI, :mod:`tps_pp_b200.functional`) or -- until its kernel lands -- a cuDNN/cuBLAS library op.
+``self.native_stages`` says which is which.  All tensors must be CUDA tensors; there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native as N
+from . import constants as K
+from . import functional as TF
+from .registry import BACKBONES
+
+
+def _attach(root: nn.Module, path: str, leaf: nn.Module) -> nn.Module:
+    """Hang ``leaf`` at dotted ``path`` under ``root`` creating passive containers on the way."""
+    parts = path.split(".")
+    cur = root
+    for name in parts[:-1]:
+        nxt = cur._modules.get(name)
+        if nxt is None:
+            nxt = nn.Module()
+            cur.add_module(name, nxt)
+        cur = nxt
+    cur.add_module(parts[-1], leaf)
+    return leaf
+
+
+class _BaseModule(nn.Module):
+    """The slice of mmcv ``BaseModule`` the recogniser relies on (``init_cfg`` + ``init_weights``)."""
+
+    def __init__(self, init_cfg=None):
+        super().__init__()
+        self.init_cfg = init_cfg
+
+    def init_weights(self):
+        # the reference's TPS_PP has no init_cfg: mmcv's BaseModule.init_weights() leaves the
+        # constructor initialisation untouched
+        return None
+
+
+@BACKBONES.register_module()
+class TPS_PP(_BaseModule):
+    def __init__(self, img_size=(16, 64), rectified_img_size=(16, 64), num_img_channel=64,
+                 point_size=(2, 16), p_stride=2, visual_point=False, init_cfg=None):
+        super().__init__(init_cfg=init_cfg)
+        assert isinstance(img_size, tuple)
+        assert isinstance(rectified_img_size, tuple)
+        self.visual_point = visual_point
+        self.img_size = img_size
+        self.rectified_img_size = rectified_img_size
+        self.point_size = point_size
+        self.num_img_channel = num_img_channel
+        self.num_fiducial = point_size[0] * point_size[1]
+        self.p_stride = p_stride
+        self.scale = num_img_channel ** -0.5          # tps_pp.py:247
+        self.theta = 0.5                              # tps_pp.py:341
+        c = num_img_channel
+        f = self.num_fiducial
+        hh, ww = img_size
+
+        def conv(path, cin, cout, k, bias=True):
+            return _attach(self, path, nn.Conv2d(cin, cout, k, bias=bias))
+
+        def lin(path, cin, cout, bias=True):
+            return _attach(self, path, nn.Linear(cin, cout, bias=bias))
+
+        # ---- creation order == reference construction order (RNG parity) -------------------
+        # MSFA (tps_pp.py:94-119, num_map=3 -> 3c input channels)
+        conv("MSFA.conv.k_encoder.0.conv", 3 * c, 64, 3)
+        for i in (1, 2, 3):
+            conv(f"MSFA.conv.k_encoder.{i}.conv", 64, 64, 3)
+        conv("MSFA.conv.atten.channel_attention.shared_MLP.0", 64, 64 // 16, 1, bias=False)
+        conv("MSFA.conv.atten.channel_attention.shared_MLP.2", 64 // 16, 64, 1, bias=False)
+        conv("MSFA.conv.atten.spatial_attention.conv2d", 2, 1, 3)
+        for i in (0, 1, 2):
+            conv(f"MSFA.conv.k_decoder.{i}.1.conv", 64, 64, 3)
+        conv("MSFA.conv.k_decoder.3.1.conv", 64, c, 3)
+        # TPE (tps_pp.py:253-285)
+        lin("TPE.p_linear.0", c, 32); lin("TPE.p_linear.1", 32, 128)
+        lin("TPE.feat_linear.0", c, 32); lin("TPE.feat_linear.1", 32, 128)
+        _attach(self, "TPE.atten.0.norm1", nn.LayerNorm([hh, ww]))
+        lin("TPE.atten.0.attn.mlp_h.0", hh + f, hh + 1, bias=False)
+        lin("TPE.atten.0.attn.mlp_w.0", ww + f, ww + 1, bias=False)
+        lin("TPE.atten.0.attn.proj", c, c)
+        _attach(self, "TPE.atten.0.norm2", nn.LayerNorm([hh, ww]))
+        lin("TPE.atten.0.mlp.fc1", c, 4 * c); lin("TPE.atten.0.mlp.fc2", 4 * c, c)
+        lin("TPE.localization_fc1.0", c, 256); lin("TPE.localization_fc1.2", 256, 2)
+        fc2 = lin("TPE.localization_fc2", 2 * f, 2 * f)
+        with torch.no_grad():
+            fc2.weight.fill_(0)
+            fc2.bias.copy_(torch.from_numpy(K.attention_init_bias(point_size)).float().view(-1))
+        # down* (tps_pp.py:538-548)
+        conv("down0.conv", 32, c, 1); conv("down1.conv", 32, c, 1); conv("down2.conv", 64, c, 1)
+        conv("down0_1.conv", c, c, 3); conv("down1_1.conv", c, c, 3)
+        conv("down_feat.conv", 3 * c, c, 1)
+        # constants (tps_pp.py:353-366); P is a plain attribute in the reference (re-uploaded
+        # every forward at :472) -- here a non-persistent buffer so state_dict keys stay identical
+        hat_c, p_hat, p, _ = K.attention_tps_buffers(point_size, rectified_img_size)
+        holder = nn.Module()
+        self.add_module("atten_tps", holder)
+        holder.register_buffer("hat_C", torch.from_numpy(hat_c))
+        holder.register_buffer("P_hat", torch.from_numpy(p_hat))
+        holder.register_buffer("P", torch.from_numpy(p), persistent=False)
+
+        self.warp_variant = N.VARIANT_AUTO
+        self.warp_events = None     # bench hook: list that receives (start, end) CUDA events around the warp
+        self.native_stages = {"warp": True, "down": False, "msfa": False, "tpe": False, "score": False}
+
+    # ------------------------------------------------------------------ stages
+    def _p(self, name: str) -> torch.Tensor:
+        return self.get_parameter(name)
+
+    def _conv_relu(self, prefix: str, x, stride=1, padding=0):
+        return F.relu(F.conv2d(x, self._p(prefix + ".conv.weight"), self._p(prefix + ".conv.bias"),
+                               stride=stride, padding=padding))
+
+    def _down(self, x, o0, o1):
+        """tps_pp.py:581-585 (+ :560-562)."""
+        f0 = self._conv_relu("down0", o0)
+        f1 = self._conv_relu("down1", o1)
+        f2 = self._conv_relu("down2", x)
+        feat_cat = torch.cat((self._conv_relu("down0_1", f0, 2, 1), self._conv_relu("down1_1", f1, 2, 1), f2), dim=1)
+        up = F.interpolate(f2, scale_factor=2, mode="nearest")
+        feat_grid = self._conv_relu("down_feat", torch.cat((f0, f1, up), dim=1))
+        return feat_cat, feat_grid
+
+    def _cbam(self, x):
+        """tps_pp.py:27-82."""
+        w0 = self._p("MSFA.conv.atten.channel_attention.shared_MLP.0.weight")
+        w2 = self._p("MSFA.conv.atten.channel_attention.shared_MLP.2.weight")
+        pooled = torch.cat([x.mean(dim=(2, 3), keepdim=True), x.amax(dim=(2, 3), keepdim=True)], dim=0)
+        z = F.conv2d(F.relu(F.conv2d(pooled, w0)), w2)
+        b = x.shape[0]
+        out = torch.sigmoid(z[:b] + z[b:]) * x
+        sp = torch.cat([out.mean(dim=1, keepdim=True), out.amax(dim=1, keepdim=True)], dim=1)
+        gate = F.conv2d(sp, self._p("MSFA.conv.atten.spatial_attention.conv2d.weight"),
+                        self._p("MSFA.conv.atten.spatial_attention.conv2d.bias"), padding=1)
+        return torch.sigmoid(gate) * out
+
+    def _msfa(self, feat_cat):
+        """tps_pp.py:156-169."""
+        strides = (1, 2, self.p_stride, (2, 1))
+        skips = []
+        k = feat_cat
+        for i, s in enumerate(strides):
+            k = self._conv_relu(f"MSFA.conv.k_encoder.{i}", k, s, 1)
+            skips.append(k)
+        en_feat = skips[-1]
+        k = self._cbam(en_feat)
+        for i, sc in enumerate(((2, 1), self.p_stride, 2, 1)):
+            if sc != 1:
+                k = F.interpolate(k, scale_factor=sc, mode="nearest")
+            k = self._conv_relu(f"MSFA.conv.k_decoder.{i}.1", k, 1, 1)
+            if i < 3:
+                k = k + skips[2 - i]
+        return en_feat, k
+
+    def _dgab(self, x, en):
+        """DGAB.py:39-55,74-77.  x [B,C,H,W]; en [B,F,C]."""
+        pre = "TPE.atten.0."
+        h, w = x.shape[2], x.shape[3]
+        u = F.layer_norm(x, (h, w), self._p(pre + "norm1.weight"), self._p(pre + "norm1.bias"))
+        yt = en.transpose(1, 2)
+        lw = F.linear(torch.cat([u.mean(2), yt], 2), self._p(pre + "attn.mlp_w.0.weight"))
+        lh = F.linear(torch.cat([u.mean(3), yt], 2), self._p(pre + "attn.mlp_h.0.weight"))
+        v_w = lw[:, :, :-1].softmax(dim=-1).unsqueeze(2) * lw[:, :, -1, None, None]
+        v_h = lh[:, :, :-1].softmax(dim=-1).unsqueeze(3) * lh[:, :, -1, None, None]
+        a = u * (v_h + v_w)
+        x = x + F.linear(a, self._p(pre + "attn.proj.weight"), self._p(pre + "attn.proj.bias"))
+        v = F.layer_norm(x, (h, w), self._p(pre + "norm2.weight"), self._p(pre + "norm2.bias"))
+        v = F.linear(F.gelu(F.linear(v, self._p(pre + "mlp.fc1.weight"), self._p(pre + "mlp.fc1.bias"))),
+                     self._p(pre + "mlp.fc2.weight"), self._p(pre + "mlp.fc2.bias"))
+        return x + v
+
+    def _tpe(self, en_feat, de_feat):
+        """tps_pp.py:315-325 and :293-312."""
+        b = en_feat.shape[0]
+        en = en_feat.flatten(2).transpose(1, 2)
+        de = self._dgab(de_feat, en)
+        z = F.relu(F.linear(F.relu(F.linear(en, self._p("TPE.localization_fc1.0.weight"), self._p("TPE.localization_fc1.0.bias"))),
+                            self._p("TPE.localization_fc1.2.weight"), self._p("TPE.localization_fc1.2.bias")))
+        c_prime = F.linear(z.reshape(b, -1), self._p("TPE.localization_fc2.weight"),
+                           self._p("TPE.localization_fc2.bias")).view(b, self.num_fiducial, 2)
+        p1 = F.linear(F.linear(en, self._p("TPE.p_linear.0.weight"), self._p("TPE.p_linear.0.bias")),
+                      self._p("TPE.p_linear.1.weight"), self._p("TPE.p_linear.1.bias"))
+        feat = de.flatten(2).transpose(1, 2)
+        f = F.linear(F.linear(feat, self._p("TPE.feat_linear.0.weight"), self._p("TPE.feat_linear.0.bias")),
+                     self._p("TPE.feat_linear.1.weight"), self._p("TPE.feat_linear.1.bias"))
+        score = torch.tanh(torch.bmm(f, p1.transpose(1, 2)) * self.scale)
+        return c_prime, score
+
+    # ------------------------------------------------------------------ forward
+    def head(self, batch_img: torch.Tensor, outs: Sequence[torch.Tensor]):
+        """Everything before the warp: -> (feat_grid, C' [B,F,2], pc_score [B,n,F])."""
+        feat_cat, feat_grid = self._down(batch_img, outs[0], outs[1])
+        en_feat, de_feat = self._msfa(feat_cat)
+        c_prime, score = self._tpe(en_feat, de_feat)
+        return feat_grid, c_prime, score
+
+    def forward(self, batch_img: torch.Tensor, outs: Sequence[torch.Tensor], **kwargs) -> Dict[str, Optional[torch.Tensor]]:
+        if not batch_img.is_cuda:
+            raise RuntimeError("tps_pp_b200.TPS_PP runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        if outs is None or len(outs) < 2:
+            raise RuntimeError("TPS_PP.forward needs outs=[stem_out, layer1_out] (tps_pp.py:580-585)")
+        feat_grid, c_prime, score = self.head(batch_img, outs)
+        at = self.atten_tps
+        # fp32 island: control points, scores and the TPS solve never run below fp32
+        ev = None
+        if self.warp_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        output, mp_img = TF.tps_warp(feat_grid, batch_img, c_prime.float(), score.float(), at.P_hat, at.P, at.hat_C,
+                                     self.rectified_img_size, N.MODE_ATTENTION, self.theta, self.warp_variant)
+        if ev is not None:
+            ev[1].record()
+            self.warp_events.append(ev)
+        return {"output": output, "logits": None, "mp_img": mp_img, "pc_score": score}
