@@ -45,6 +45,18 @@ def _attach(root: nn.Module, path: str, leaf: nn.Module) -> nn.Module:
     return leaf
 
 
+class _matmul_fp32:
+    """Context: cuBLAS matmuls in true fp32 (torch.backends.cuda.matmul.allow_tf32 = False)."""
+
+    def __enter__(self):
+        self._prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self._prev
+        return False
+
+
 class _BaseModule(nn.Module):
     """The slice of mmcv ``BaseModule`` the recogniser relies on (``init_cfg`` + ``init_weights``)."""
 
@@ -212,9 +224,11 @@ class TPS_PP(_BaseModule):
     # ------------------------------------------------------------------ forward
     def head(self, batch_img: torch.Tensor, outs: Sequence[torch.Tensor]):
         """Everything before the warp: -> (feat_grid, C' [B,F,2], pc_score [B,n,F])."""
-        feat_cat, feat_grid = self._down(batch_img, outs[0], outs[1])
-        en_feat, de_feat = self._msfa(feat_cat)
-        c_prime, score = self._tpe(en_feat, de_feat)
+        # library stages must not drop to TF32: C' feeds a solve that amplifies rounding 1e2-1e3x (SURVEY F6)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False), _matmul_fp32():
+            feat_cat, feat_grid = self._down(batch_img, outs[0], outs[1])
+            en_feat, de_feat = self._msfa(feat_cat)
+            c_prime, score = self._tpe(en_feat, de_feat)
         return feat_grid, c_prime, score
 
     def forward(self, batch_img: torch.Tensor, outs: Sequence[torch.Tensor], **kwargs) -> Dict[str, Optional[torch.Tensor]]:
