@@ -144,6 +144,63 @@ TPSPP_API int tpspp_warp_bwd(const tpspp_warp_cfg* cfg, const void* src0, const 
                    const void* gout1, void* gsrc0, void* gsrc1, float* g_c_prime,
                    float* g_pc_score, void* workspace, tpspp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Control-point attention head: everything in TPS_PP.forward before the warp
+ * (tps_pp.py:581-594): down0/1/2, down0_1/1_1, grid()/down_feat, MSFA encoder/CBAM/decoder,
+ * TPE (DGAB, localization_fc1/2 -> C', p_linear/feat_linear + tanh(QK^T/8) -> pc_score).
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  TPSPP_HEAD_FP32 = 0,  /* CUDA-core fp32 FMAs everywhere (parity mode)                          */
+  TPSPP_HEAD_TC = 1     /* tcgen05 tensor cores for the dense contractions       */
+};
+
+typedef struct tpspp_head_cfg {
+  int32_t batch;            /* B                                                                 */
+  int32_t height, width;    /* of batch_img (16, 64); outs are 2x that; width must be 64         */
+  int32_t point_h, point_w; /* control-point lattice (2, 16)                                     */
+  int32_t p_stride;         /* stride of the third MSFA encoder conv (2)                         */
+  int32_t precision;        /* TPSPP_HEAD_*                                                      */
+} tpspp_head_cfg;
+
+/* Index of each learnable tensor in the `params` pointer table = state_dict order of the
+ * reference module (tps_pp.py:94-119,253-285,538-548).                      */
+enum {
+  TPSPP_P_ENC0_W = 0, TPSPP_P_ENC0_B, TPSPP_P_ENC1_W, TPSPP_P_ENC1_B, TPSPP_P_ENC2_W, TPSPP_P_ENC2_B,
+  TPSPP_P_ENC3_W, TPSPP_P_ENC3_B, TPSPP_P_CBAM_MLP0_W, TPSPP_P_CBAM_MLP2_W, TPSPP_P_CBAM_SP_W,
+  TPSPP_P_CBAM_SP_B, TPSPP_P_DEC0_W, TPSPP_P_DEC0_B, TPSPP_P_DEC1_W, TPSPP_P_DEC1_B, TPSPP_P_DEC2_W,
+  TPSPP_P_DEC2_B, TPSPP_P_DEC3_W, TPSPP_P_DEC3_B, TPSPP_P_PLIN0_W, TPSPP_P_PLIN0_B, TPSPP_P_PLIN1_W,
+  TPSPP_P_PLIN1_B, TPSPP_P_FLIN0_W, TPSPP_P_FLIN0_B, TPSPP_P_FLIN1_W, TPSPP_P_FLIN1_B,
+  TPSPP_P_NORM1_W, TPSPP_P_NORM1_B, TPSPP_P_MLP_H_W, TPSPP_P_MLP_W_W, TPSPP_P_PROJ_W, TPSPP_P_PROJ_B,
+  TPSPP_P_NORM2_W, TPSPP_P_NORM2_B, TPSPP_P_FC1_W, TPSPP_P_FC1_B, TPSPP_P_FC2_W, TPSPP_P_FC2_B,
+  TPSPP_P_LOC1A_W, TPSPP_P_LOC1A_B, TPSPP_P_LOC1B_W, TPSPP_P_LOC1B_B, TPSPP_P_LOC2_W, TPSPP_P_LOC2_B,
+  TPSPP_P_DOWN0_W, TPSPP_P_DOWN0_B, TPSPP_P_DOWN1_W, TPSPP_P_DOWN1_B, TPSPP_P_DOWN2_W, TPSPP_P_DOWN2_B,
+  TPSPP_P_DOWN0_1_W, TPSPP_P_DOWN0_1_B, TPSPP_P_DOWN1_1_W, TPSPP_P_DOWN1_1_B, TPSPP_P_DOWNFEAT_W,
+  TPSPP_P_DOWNFEAT_B, TPSPP_P_COUNT
+};
+
+/* Intermediates kept in the workspace (float offsets via tpspp_head_workspace_offsets; tests and
+ * the backward pass read them). */
+enum {
+  TPSPP_WS_F0 = 0, TPSPP_WS_F1, TPSPP_WS_F2, TPSPP_WS_A0, TPSPP_WS_A1, TPSPP_WS_E0, TPSPP_WS_E1,
+  TPSPP_WS_E2, TPSPP_WS_E3 /* en_feat, pre-CBAM */, TPSPP_WS_CBAM, TPSPP_WS_D0, TPSPP_WS_D1, TPSPP_WS_D2,
+  TPSPP_WS_DE /* de_feat */, TPSPP_WS_X1, TPSPP_WS_V, TPSPP_WS_DE2 /* de_feat after DGAB */,
+  TPSPP_WS_P1 /* p_linear(en) [B,F,128] */, TPSPP_WS_COUNT
+};
+
+TPSPP_API size_t tpspp_head_workspace_bytes(const tpspp_head_cfg* cfg);
+/* offsets[TPSPP_WS_COUNT] in BYTES from the workspace base (host call) */
+TPSPP_API int tpspp_head_workspace_offsets(const tpspp_head_cfg* cfg, size_t* offsets);
+
+/*
+ * x [B,64,h,w], o0/o1 [B,32,2h,2w] fp32 NCHW; params: HOST array of TPSPP_P_COUNT DEVICE pointers.
+ * Outputs: feat_grid [B,64,2h,2w] (tps_pp.py:585), c_prime [B,F,2] (tps_pp.py:321-323),
+ *          pc_score [B,h*w,F] (tps_pp.py:324).  workspace: 256-byte aligned,
+ *          >= tpspp_head_workspace_bytes(cfg).
+ */
+TPSPP_API int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const float* o0, const float* o1,
+                             const float* const* params, float* feat_grid, float* c_prime,
+                             float* pc_score, void* workspace, tpspp_stream_t stream);
+
 /* Number of kernel launches the most recent call on this host thread enqueued
  * (bench.py uses it to report gpu_launches). */
 TPSPP_API int tpspp_last_launch_count(void);

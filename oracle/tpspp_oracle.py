@@ -559,3 +559,52 @@ def synthetic_tpspp_inputs(batch: int, seed: int = 0, h: int = 16, w: int = 64):
     o0 = rs.standard_normal((batch, 32, 2 * h, 2 * w)).astype(np.float32)
     o1 = rs.standard_normal((batch, 32, 2 * h, 2 * w)).astype(np.float32)
     return x, o0, o1
+
+
+def head_intermediates(state, x, outs, dtype=torch.float32, p_stride=2):
+    """Every intermediate of the head, named like the native workspace slots (include/tpspp.h TPSPP_WS_*),
+    computed with the same stage functions as :func:`tps_pp_forward` (tps_pp.py:581-594, 156-169;
+    DGAB.py:39-55,74-77)."""
+    x = torch.as_tensor(x).to(dtype); o0 = torch.as_tensor(outs[0]).to(dtype); o1 = torch.as_tensor(outs[1]).to(dtype)
+    r = {}
+    r['f0'] = _conv_relu(state, 'down0', o0)
+    r['f1'] = _conv_relu(state, 'down1', o1)
+    r['f2'] = _conv_relu(state, 'down2', x)
+    r['a0'] = _conv_relu(state, 'down0_1', r['f0'], 2, 1)
+    r['a1'] = _conv_relu(state, 'down1_1', r['f1'], 2, 1)
+    up = F.interpolate(r['f2'], scale_factor=2, mode='nearest')
+    r['feat_grid'] = _conv_relu(state, 'down_feat', torch.cat((r['f0'], r['f1'], up), dim=1))
+    k = torch.cat((r['a0'], r['a1'], r['f2']), dim=1)
+    for i, s in enumerate([1, 2, p_stride, (2, 1)]):
+        k = _conv_relu(state, f'MSFA.conv.k_encoder.{i}', k, s, 1)
+        r[f'e{i}'] = k
+    k = cbam(state, 'MSFA.conv.atten', r['e3'])
+    r['cbam'] = k
+    skips = [r['e2'], r['e1'], r['e0']]
+    for i, sc in enumerate([(2, 1), p_stride, 2, 1]):
+        if sc != 1:
+            k = F.interpolate(k, scale_factor=sc, mode='nearest')
+        k = _conv_relu(state, f'MSFA.conv.k_decoder.{i}.1', k, 1, 1)
+        if i < 3:
+            k = k + skips[i]
+            r[f'd{i}'] = k
+    r['de'] = k
+    # DGAB split at the same points as the native kernels
+    pre = 'TPE.atten.0'
+    en = r['e3'].flatten(2).transpose(1, 2)
+    h, w = k.shape[2], k.shape[3]
+    u = F.layer_norm(k, (h, w), _t(state, pre + '.norm1.weight', dtype), _t(state, pre + '.norm1.bias', dtype))
+    yt = en.transpose(1, 2)
+    lw = F.linear(torch.cat([u.mean(2), yt], 2), _t(state, pre + '.attn.mlp_w.0.weight', dtype))
+    lh = F.linear(torch.cat([u.mean(3), yt], 2), _t(state, pre + '.attn.mlp_h.0.weight', dtype))
+    v_w = lw[:, :, :-1].softmax(dim=-1).unsqueeze(2)
+    v_h = lh[:, :, :-1].softmax(dim=-1).unsqueeze(3)
+    a = v_h * u * lh[:, :, -1].unsqueeze(-1).unsqueeze(-1) + v_w * u * lw[:, :, -1].unsqueeze(-1).unsqueeze(-1)
+    r['x1'] = k + _linear(state, pre + '.attn.proj', a)
+    r['v'] = F.layer_norm(r['x1'], (h, w), _t(state, pre + '.norm2.weight', dtype), _t(state, pre + '.norm2.bias', dtype))
+    r['de2'] = r['x1'] + _linear(state, pre + '.mlp.fc2', F.gelu(_linear(state, pre + '.mlp.fc1', r['v'])))
+    r['p1'] = _linear(state, 'TPE.p_linear.1', _linear(state, 'TPE.p_linear.0', en))
+    cp, score, de2 = tpe(state, r['e3'], r['de'], scale=x.shape[1] ** -0.5)
+    r['c_prime'] = cp
+    r['pc_score'] = score
+    return r

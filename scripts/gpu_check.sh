@@ -10,6 +10,7 @@ import os, torch
 print("cores", os.cpu_count(), "torch", torch.__version__, "cuda", torch.cuda.is_available(), torch.cuda.get_device_name(0))
 PY
 echo "== pytest -m gpu (warp)"; timeout 900 python -m pytest tests/test_warp_gpu.py -q -m gpu --timeout=300 -x --no-header -rA 2>&1 | tail -60 | tee gpurun_out/pytest_warp.log
+echo "== pytest -m gpu (head)"; timeout 900 python -m pytest tests/test_head_gpu.py -q -m gpu --timeout=300 --no-header -rA -s 2>&1 | tail -80 | tee gpurun_out/pytest_head.log
 echo "== pytest -m gpu (module)"; timeout 900 python -m pytest tests/test_module_gpu.py -q -m gpu --timeout=300 --no-header -rA -s 2>&1 | tail -60 | tee gpurun_out/pytest_module.log
 if [ "$mode" = quick ]; then exit 0; fi
 echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -20 | tee gpurun_out/smoke.log

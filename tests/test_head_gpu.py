@@ -1,0 +1,114 @@
+"""GPU: the native control-point attention head (tpspp_head_fwd) stage by stage against the oracle.
+
+Every stage is fp32 CUDA-core arithmetic; the acceptance rule is "as close to the fp64 twin as the reference's
+own fp32 path is" (SURVEY F6): err(ours, ref64) <= 4 * err(ref32, ref64) + 1e-6 * scale."""
+import numpy as np
+import pytest
+import torch
+
+import tps_pp_b200 as T
+from oracle import tpspp_oracle as O
+from tps_pp_b200 import _native as N
+from tps_pp_b200 import functional as TF
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def mx(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))))
+
+
+def _run_native(sd, x, o0, o1):
+    m = T.TPS_PP().to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        fg, cp, sc, ws = TF.head_forward(torch.from_numpy(x).to(DEV), torch.from_numpy(o0).to(DEV),
+                                         torch.from_numpy(o1).to(DEV), list(m.parameters()), (2, 16), 2)
+    torch.cuda.synchronize()
+    b = x.shape[0]
+    cfg = TF.head_cfg(b, 16, 64, (2, 16), 2)
+    off = TF.head_workspace_offsets(cfg)
+    shapes = dict(f0=(b, 64, 32, 128), f1=(b, 64, 32, 128), f2=(b, 64, 16, 64), a0=(b, 64, 16, 64), a1=(b, 64, 16, 64),
+                  e0=(b, 64, 16, 64), e1=(b, 64, 8, 32), e2=(b, 64, 4, 16), e3=(b, 64, 2, 16), cbam=(b, 64, 2, 16),
+                  d0=(b, 64, 4, 16), d1=(b, 64, 8, 32), d2=(b, 64, 16, 64), de=(b, 64, 16, 64), x1=(b, 64, 16, 64),
+                  v=(b, 64, 16, 64), de2=(b, 64, 16, 64), p1=(b, 32, 128))
+    got = {}
+    for name, shp in shapes.items():
+        n = int(np.prod(shp))
+        got[name] = ws[off[name]: off[name] + 4 * n].view(torch.float32).view(shp).cpu()
+    got.update(feat_grid=fg.cpu(), c_prime=cp.cpu(), pc_score=sc.cpu())
+    return got, m
+
+
+@pytest.mark.parametrize("batch,seed", [(2, 0), (5, 11)])
+def test_head_stages_vs_oracle(native_lib, batch, seed):
+    sd = O.trained_like_state(3)
+    x, o0, o1 = O.synthetic_tpspp_inputs(batch, seed)
+    got, _ = _run_native(sd, x, o0, o1)
+    r32 = O.head_intermediates(sd, x, [o0, o1], dtype=torch.float32)
+    r64 = O.head_intermediates(sd, x, [o0, o1], dtype=torch.float64)
+    report = []
+    for name in ["f0", "f1", "f2", "a0", "a1", "feat_grid", "e0", "e1", "e2", "e3", "cbam", "d0", "d1", "d2", "de",
+                 "x1", "v", "de2", "p1", "c_prime", "pc_score"]:
+        scale = float(r64[name].abs().max())
+        floor = mx(r32[name], r64[name])
+        err = mx(got[name], r64[name])
+        report.append(f"{name:10s} |ours-ref64|={err:.2e} |ref32-ref64|={floor:.2e} scale={scale:.2f}")
+        assert err <= 4 * floor + 1e-6 * max(scale, 1.0), "\n".join(report)
+    print("\n".join(report))
+    assert mx(got["c_prime"], r64["c_prime"]) <= 1e-4            # north_star tolerance for control points
+
+
+def test_head_stock_init_and_module_path(native_lib, golden):
+    """Whole module through the native head (inference) against the reference vectors."""
+    g = golden("tpspp_forward.npz")
+    sd = O.trained_like_state(int(g["state_seed"]))
+    m = T.TPS_PP().to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    x, o0, o1 = O.synthetic_tpspp_inputs(int(g["batch"]), int(g["input_seed"]))
+    with torch.no_grad():
+        r = m(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
+    with torch.no_grad():
+        assert all(m.native_stages.values())
+    assert m._last_head_launches >= 18
+    floor_o = mx(g["ref32_output"], g["ref64_output"]); floor_m = mx(g["ref32_mp_img"], g["ref64_mp_img"])
+    e_o = mx(r["output"], g["ref64_output"]); e_m = mx(r["mp_img"], g["ref64_mp_img"])
+    print(f"native head: output |ours-ref64|={e_o:.3e} (floor {floor_o:.3e}); mp_img {e_m:.3e} (floor {floor_m:.3e})")
+    assert e_o <= max(1e-5, 4 * floor_o) and e_m <= max(1e-5, 4 * floor_m)
+    assert mx(r["pc_score"], g["ref64_pc_score"]) <= 5e-5
+    # stock init (fc2.weight == 0): C' must be exactly the bias lattice
+    torch.manual_seed(0)
+    m2 = T.TPS_PP().to(DEV).eval()
+    with torch.no_grad():
+        fg, cp, sc = m2.head(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
+    assert torch.equal(cp, m2.get_parameter("TPE.localization_fc2.bias").view(1, 32, 2).expand(cp.shape[0], -1, -1))
+
+
+def test_head_native_equals_library_path(native_lib):
+    sd = O.trained_like_state(3)
+    m = T.TPS_PP().to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    x, o0, o1 = (torch.from_numpy(t).to(DEV) for t in O.synthetic_tpspp_inputs(3, 2))
+    with torch.no_grad():
+        m.head_impl = "native"
+        a = m.head(x, [o0, o1])
+        m.head_impl = "library"
+        b = m.head(x, [o0, o1])
+    assert mx(a[0], b[0]) <= 1e-4 and mx(a[1], b[1]) <= 1e-6 and mx(a[2], b[2]) <= 1e-4
+
+
+def test_head_rejects_bad_geometry(native_lib):
+    import ctypes
+    cfg = TF.head_cfg(1, 16, 50, (2, 16), 2)
+    assert N.lib().tpspp_head_workspace_bytes(ctypes.byref(cfg)) == 0
+    assert "width 64" in N.last_error()
+    m = T.TPS_PP().to(DEV).eval()
+    m.head_impl = "native"
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            m(torch.zeros(1, 64, 16, 50, device=DEV), [torch.zeros(1, 32, 32, 100, device=DEV)] * 2)
+    with pytest.raises(RuntimeError, match="no backward"):
+        m(torch.zeros(1, 64, 16, 64, device=DEV, requires_grad=True), [torch.zeros(1, 32, 32, 128, device=DEV)] * 2)

@@ -28,6 +28,18 @@ class WarpCfg(Structure):
     ]
 
 
+class HeadCfg(Structure):
+    """Mirror of ``tpspp_head_cfg`` (include/tpspp.h)."""
+    _fields_ = [
+        ("batch", c_int32), ("height", c_int32), ("width", c_int32), ("point_h", c_int32), ("point_w", c_int32),
+        ("p_stride", c_int32), ("precision", c_int32),
+    ]
+
+
+HEAD_FP32, HEAD_TC = 0, 1
+P_COUNT = 58
+WS_NAMES = ("f0", "f1", "f2", "a0", "a1", "e0", "e1", "e2", "e3", "cbam", "d0", "d1", "d2", "de", "x1", "v", "de2", "p1")
+
 _SIGNATURES = {
     "tpspp_version": (c_int, []),
     "tpspp_last_error": (c_char_p, []),
@@ -37,6 +49,10 @@ _SIGNATURES = {
     "tpspp_warp_fwd": (c_int, [POINTER(WarpCfg)] + [c_void_p] * 12),
     "tpspp_sample_fwd": (c_int, [POINTER(WarpCfg)] + [c_void_p] * 6),
     "tpspp_warp_bwd": (c_int, [POINTER(WarpCfg)] + [c_void_p] * 15),
+    "tpspp_head_workspace_bytes": (c_size_t, [POINTER(HeadCfg)]),
+    "tpspp_head_workspace_offsets": (c_int, [POINTER(HeadCfg), POINTER(c_size_t)]),
+    "tpspp_head_fwd": (c_int, [POINTER(HeadCfg), c_void_p, c_void_p, c_void_p, POINTER(c_void_p),
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 _OPTIONAL = {}
 

@@ -1,0 +1,885 @@
+// Control-point attention head of TPS_PP, forward, fp32 on CUDA cores (parity mode).
+//
+// Reference being replaced (backbones/tps_pp/tps_pp.py unless noted):
+//   down0/1/2, down0_1/1_1, grid()/down_feat        :538-548,560-562,581-585   -> conv_ffma_kernel
+//   Encoder_Decoder_Feature_Extractor.forward       :156-169                   -> conv_ffma_kernel (+skip)
+//   CBAM / ChannelAttention / SpatialAttention      :27-82                     -> cbam_kernel
+//   DGAB.forward / DGAB_Block.forward (DGAB.py:39-55,74-77), LayerNorm(H,W)    -> dgab_plane_kernel
+//   Mlp.forward (DGAB.py:17-23) + residual                                     -> dgab_mlp_kernel
+//   localization_fc1/fc2 -> C' (:321-323), p_linear (:305)                     -> loc_p1_kernel
+//   feat_linear + atten_score = tanh(f p1^T * 64^-0.5) (:293-312)              -> score_kernel
+//
+// All tensors NCHW fp32 exactly as the reference holds them.  Every conv here has 64 output
+// channels; conv_ffma_kernel is an implicit GEMM (M = B*Ho*Wo pixels, N = 64, K = Cin*KH*KW) with
+// up to three concatenated input tensors, optional nearest up-sampling of each input
+// (nn.Upsample in the decoder / grid()), stride, zero padding, bias + ReLU and the decoder's
+// skip add fused -- torch.cat / Upsample never materialise.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace tpspp {
+
+// =====================================================================================
+// implicit-GEMM convolution, 64 output channels, fp32 FFMA
+// =====================================================================================
+struct ConvSrc {
+  const float* ptr;
+  int C, H, W, uh, uw;   // stored size and integer nearest-upsample factors (1 or 2)
+};
+struct ConvArgs {
+  ConvSrc src[3];
+  const float* weight;   // [64][Ctot][KS][KS]
+  const float* bias;     // [64]
+  const float* skip;     // [B,64,Ho,Wo] added after the ReLU, or null
+  float* out;            // [B,64,Ho,Wo]
+  int B, Ho, Wo, Ctot, sh, sw, pad;
+};
+
+constexpr int CV_TM = 128;   // output pixels per CTA
+constexpr int CV_KC = 32;    // K chunk
+constexpr int CV_WLD = 68;   // padded leading dim of the weight chunk (floats)
+constexpr int CV_SMEM = (2 * CV_KC * CV_TM + 2 * CV_KC * CV_WLD) * 4;
+
+template <int KS>
+__global__ void __launch_bounds__(256, 2) conv_ffma_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                           // [2][CV_KC][CV_TM]
+  float* Ws = smem + 2 * CV_KC * CV_TM;       // [2][CV_KC][CV_WLD]
+  constexpr int TAPS = KS * KS;
+  const int tid = threadIdx.x;
+  const int HoWo = a.Ho * a.Wo;
+  const long long Mtot = (long long)a.B * HoWo;
+  const long long m_base = (long long)blockIdx.x * CV_TM;
+  const int Ktot = a.Ctot * TAPS;
+  const int nchunks = (Ktot + CV_KC - 1) / CV_KC;
+
+  // loader role: one output pixel per thread (lp), k rows lk0, lk0+2, ...
+  const int lp = tid & (CV_TM - 1), lk0 = tid >> 7;
+  const long long lm = m_base + lp;
+  const bool lvalid = lm < Mtot;
+  int lb = 0, iy0 = 0, ix0 = 0;
+  if (lvalid) {
+    lb = (int)(lm / HoWo);
+    const int r = (int)(lm - (long long)lb * HoWo);
+    const int oy = r / a.Wo, ox = r - oy * a.Wo;
+    iy0 = oy * a.sh - a.pad;
+    ix0 = ox * a.sw - a.pad;
+  }
+  const int wk = tid & 31, wc0 = tid >> 5;
+
+  float ra[16], rw[8];
+  auto load_chunk = [&](int chunk) {
+    const int k0 = chunk * CV_KC;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = k0 + lk0 + 2 * i;
+      float v = 0.f;
+      if (lvalid && k < Ktot) {
+        const int cin = k / TAPS, tap = k - cin * TAPS;
+        const int dy = tap / KS, dx = tap - dy * KS;
+        int s = 0, c = cin;
+        if (c >= a.src[0].C) {
+          c -= a.src[0].C; s = 1;
+          if (c >= a.src[1].C) { c -= a.src[1].C; s = 2; }
+        }
+        // select by value (no dynamic indexing of the kernel parameter struct -> no local-memory copy)
+        const float* sp = s == 0 ? a.src[0].ptr : (s == 1 ? a.src[1].ptr : a.src[2].ptr);
+        const int SC = s == 0 ? a.src[0].C : (s == 1 ? a.src[1].C : a.src[2].C);
+        const int SH = s == 0 ? a.src[0].H : (s == 1 ? a.src[1].H : a.src[2].H);
+        const int SW = s == 0 ? a.src[0].W : (s == 1 ? a.src[1].W : a.src[2].W);
+        const int uh = s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh);
+        const int uw = s == 0 ? a.src[0].uw : (s == 1 ? a.src[1].uw : a.src[2].uw);
+        const int iy = iy0 + dy, ix = ix0 + dx;
+        if (iy >= 0 && ix >= 0 && iy < SH * uh && ix < SW * uw) {
+          const int sy = (uh == 2) ? (iy >> 1) : iy, sx = (uw == 2) ? (ix >> 1) : ix;
+          v = __ldg(sp + (((size_t)lb * SC + c) * SH + sy) * SW + sx);
+        }
+      }
+      ra[i] = v;
+    }
+    const int k = k0 + wk;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rw[i] = (k < Ktot) ? __ldg(a.weight + (size_t)(wc0 + 8 * i) * Ktot + k) : 0.f;
+  };
+  auto store_chunk = [&](int buf) {
+    float* Ab = As + buf * CV_KC * CV_TM;
+    float* Wb = Ws + buf * CV_KC * CV_WLD;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Ab[(lk0 + 2 * i) * CV_TM + lp] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Wb[wk * CV_WLD + wc0 + 8 * i] = rw[i];
+  };
+
+  const int tx = tid & 15, ty = tid >> 4;     // 16 pixel-quads x 16 cout-quads
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  load_chunk(0);
+  store_chunk(0);
+  __syncthreads();
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) load_chunk(ch + 1);
+    const float* Ab = As + buf * CV_KC * CV_TM;
+    const float* Wb = Ws + buf * CV_KC * CV_WLD;
+#pragma unroll
+    for (int kk = 0; kk < CV_KC; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(Ab + kk * CV_TM + tx * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(Ab + kk * CV_TM + 64 + tx * 4);
+      const float4 w = *reinterpret_cast<const float4*>(Wb + kk * CV_WLD + ty * 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(av[i], wv[j], acc[i][j]);
+    }
+    if (ch + 1 < nchunks) store_chunk(buf ^ 1);
+    __syncthreads();
+  }
+
+  // epilogue: bias, ReLU, optional skip, NCHW float4 stores (4 consecutive pixels per store)
+#pragma unroll
+  for (int pg = 0; pg < 2; ++pg) {
+    const long long m0 = m_base + pg * 64 + tx * 4;
+    if (m0 >= Mtot) continue;
+    const int b = (int)(m0 / HoWo);
+    const int rem = (int)(m0 - (long long)b * HoWo);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = ty * 4 + j;
+      const float bs = __ldg(a.bias + co);
+      float4 v;
+      v.x = fmaxf(acc[pg * 4 + 0][j] + bs, 0.f);
+      v.y = fmaxf(acc[pg * 4 + 1][j] + bs, 0.f);
+      v.z = fmaxf(acc[pg * 4 + 2][j] + bs, 0.f);
+      v.w = fmaxf(acc[pg * 4 + 3][j] + bs, 0.f);
+      const size_t o = ((size_t)b * 64 + co) * HoWo + rem;
+      if (a.skip != nullptr) {
+        const float4 sk = __ldg(reinterpret_cast<const float4*>(a.skip + o));
+        v.x += sk.x; v.y += sk.y; v.z += sk.z; v.w += sk.w;
+      }
+      *reinterpret_cast<float4*>(a.out + o) = v;
+    }
+  }
+}
+
+// =====================================================================================
+// CBAM on the [64, P] control-point map (P = py*px <= 64), one CTA per image
+// =====================================================================================
+__global__ void __launch_bounds__(256) cbam_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                    const float* __restrict__ w0, const float* __restrict__ w2,
+                                                    const float* __restrict__ spw, const float* __restrict__ spb,
+                                                    int py, int px) {
+  __shared__ float xs[64][65];
+  __shared__ float avg[64], mxv[64], hid[2][4], gate[64];
+  __shared__ float spm[2][66];   // [mean|max][p]
+  __shared__ float sg[64];
+  const int P = py * px;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* xb = x + (size_t)b * 64 * P;
+  for (int i = tid; i < 64 * P; i += 256) xs[i / P][i % P] = __ldg(xb + i);
+  __syncthreads();
+  if (tid < 64) {
+    float s = 0.f, m = -INFINITY;
+    for (int p = 0; p < P; ++p) { s += xs[tid][p]; m = fmaxf(m, xs[tid][p]); }
+    avg[tid] = s / (float)P;
+    mxv[tid] = m;
+  }
+  __syncthreads();
+  if (tid < 8) {
+    const int which = tid >> 2, j = tid & 3;
+    const float* v = which ? mxv : avg;
+    float s = 0.f;
+    for (int c = 0; c < 64; ++c) s = __fmaf_rn(__ldg(w0 + j * 64 + c), v[c], s);
+    hid[which][j] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float sa = 0.f, sm = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      sa = __fmaf_rn(__ldg(w2 + tid * 4 + j), hid[0][j], sa);
+      sm = __fmaf_rn(__ldg(w2 + tid * 4 + j), hid[1][j], sm);
+    }
+    gate[tid] = 1.f / (1.f + expf(-(sa + sm)));
+  }
+  __syncthreads();
+  for (int i = tid; i < 64 * P; i += 256) xs[i / P][i % P] *= gate[i / P];
+  __syncthreads();
+  if (tid < P) {
+    float s = 0.f, m = -INFINITY;
+    for (int c = 0; c < 64; ++c) { s += xs[c][tid]; m = fmaxf(m, xs[c][tid]); }
+    spm[0][tid] = s / 64.f;
+    spm[1][tid] = m;
+  }
+  __syncthreads();
+  if (tid < P) {
+    const int y = tid / px, xx = tid - y * px;
+    float s = __ldg(spb);
+    for (int ch = 0; ch < 2; ++ch)
+      for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx) {
+          const int yy = y + dy - 1, xc = xx + dx - 1;
+          if (yy >= 0 && yy < py && xc >= 0 && xc < px)
+            s = __fmaf_rn(__ldg(spw + (ch * 3 + dy) * 3 + dx), spm[ch][yy * px + xc], s);
+        }
+    sg[tid] = 1.f / (1.f + expf(-s));
+  }
+  __syncthreads();
+  float* ob = out + (size_t)b * 64 * P;
+  for (int i = tid; i < 64 * P; i += 256) ob[i] = xs[i / P][i % P] * sg[i % P];
+}
+
+// =====================================================================================
+// localisation head (C') and p_linear(en) -> p1, one CTA per image
+// =====================================================================================
+struct LocArgs {
+  const float* e3;   // [B,64,F]
+  const float *wa, *ba, *wb, *bb, *wc, *bc;      // loc1.0 [256,64], loc1.2 [2,256], loc2 [2F,2F]
+  const float *wp0, *bp0, *wp1, *bp1;            // p_linear.0 [32,64], p_linear.1 [128,32]
+  float* c_prime;    // [B,F,2]
+  float* p1;         // [B,F,128]
+  int F;
+};
+
+__global__ void __launch_bounds__(256) loc_p1_kernel(LocArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int F = a.F, b = blockIdx.x, tid = threadIdx.x;
+  float* en = sm;                 // [F][65]
+  float* z1 = en + F * 65;        // [F][256]
+  float* z2 = z1 + F * 256;       // [2F]
+  float* t1 = z2 + 2 * F;         // [F][33]
+  for (int i = tid; i < 64 * F; i += 256) {
+    const int c = i / F, k = i - c * F;
+    en[k * 65 + c] = __ldg(a.e3 + (size_t)b * 64 * F + i);
+  }
+  __syncthreads();
+  {  // z1[k][m] = relu(Wa[m,:] . en[k,:] + ba[m]), m = tid
+    float w[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) w[c] = __ldg(a.wa + tid * 64 + c);
+    const float bs = __ldg(a.ba + tid);
+    for (int k = 0; k < F; ++k) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) s = __fmaf_rn(w[c], en[k * 65 + c], s);
+      z1[k * 256 + tid] = fmaxf(s + bs, 0.f);
+    }
+  }
+  // t1[k][q] = Wp0[q,:] . en[k,:] + bp0[q]
+  for (int o = tid; o < F * 32; o += 256) {
+    const int k = o >> 5, q = o & 31;
+    float s = 0.f;
+    for (int c = 0; c < 64; ++c) s = __fmaf_rn(__ldg(a.wp0 + q * 64 + c), en[k * 65 + c], s);
+    t1[k * 33 + q] = s + __ldg(a.bp0 + q);
+  }
+  __syncthreads();
+  // z2[k*2+j] = relu(Wb[j,:] . z1[k,:] + bb[j]) : 8 lanes per output
+  for (int o0 = (tid >> 3); o0 < 2 * F; o0 += 32) {
+    const int k = o0 >> 1, j = o0 & 1, l = tid & 7;
+    float s = 0.f;
+    for (int m = l; m < 256; m += 8) s = __fmaf_rn(__ldg(a.wb + j * 256 + m), z1[k * 256 + m], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (l == 0) z2[o0] = fmaxf(s + __ldg(a.bb + j), 0.f);
+  }
+  // p1[k][r] = Wp1[r,:] . t1[k,:] + bp1[r]
+  for (int o = tid; o < F * 128; o += 256) {
+    const int k = o >> 7, r = o & 127;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) s = __fmaf_rn(__ldg(a.wp1 + r * 32 + q), t1[k * 33 + q], s);
+    a.p1[((size_t)b * F + k) * 128 + r] = s + __ldg(a.bp1 + r);
+  }
+  __syncthreads();
+  if (tid < 2 * F) {
+    float s = 0.f;
+    for (int i = 0; i < 2 * F; ++i) s = __fmaf_rn(__ldg(a.wc + tid * 2 * F + i), z2[i], s);
+    a.c_prime[(size_t)b * 2 * F + tid] = s + __ldg(a.bc + tid);
+  }
+}
+
+// =====================================================================================
+// DGAB part 1, one CTA per (image, channel) plane [H, 64]:
+//   u = LN1(x); gates from axial means + control-point features; a = u*(v_h*h_last + v_w*w_last);
+//   x1 = x + proj_W(a); v = LN2(x1)
+// =====================================================================================
+struct DgabArgs {
+  const float* x;     // de_feat [B,64,H,64]
+  const float* e3;    // [B,64,F]  (y^T[b,c,:] is exactly this plane)
+  const float *n1w, *n1b, *n2w, *n2b;   // [H,64]
+  const float *wh, *ww;                 // mlp_h [H+1, H+F], mlp_w [65, 64+F]
+  const float *wp, *bp;                 // proj [64,64]
+  float* x1;          // [B,64,H,64]
+  float* v;           // [B,64,H,64]
+  int H, F;
+};
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+constexpr int DG_MAXH = 32;
+
+__global__ void __launch_bounds__(256) dgab_plane_kernel(DgabArgs a) {
+  __shared__ float us[DG_MAXH][64];
+  __shared__ float as[DG_MAXH][64];
+  __shared__ float wpT[64][65];
+  __shared__ float colm[64], rowm[DG_MAXH], yt[64], lw[65], lh[DG_MAXH + 1], vw[64], vh[DG_MAXH];
+  __shared__ float red[8];
+  const int H = a.H, F = a.F, tid = threadIdx.x;
+  const int n = H * 64;
+  const size_t plane = (size_t)blockIdx.x * n;
+  const int per = n / 256;     // H/4 elements per thread (H multiple of 4)
+  float xv[DG_MAXH / 4];
+  // proj weight transposed into shared memory
+  for (int i = tid; i < 4096; i += 256) wpT[i & 63][i >> 6] = __ldg(a.wp + i);
+  if (tid < F) yt[tid] = __ldg(a.e3 + (size_t)blockIdx.x * F + tid);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < DG_MAXH / 4; ++i)
+    if (i < per) { xv[i] = __ldg(a.x + plane + tid + 256 * i); s += xv[i]; }
+  const float mean = block_sum_256(s, red) / (float)n;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < DG_MAXH / 4; ++i)
+    if (i < per) { const float d = xv[i] - mean; q = __fmaf_rn(d, d, q); }
+  const float rstd = rsqrtf(block_sum_256(q, red) / (float)n + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < DG_MAXH / 4; ++i)
+    if (i < per) {
+      const int idx = tid + 256 * i;
+      us[idx >> 6][idx & 63] = (xv[i] - mean) * rstd * __ldg(a.n1w + idx) + __ldg(a.n1b + idx);
+    }
+  __syncthreads();
+  if (tid < 64) {
+    float t = 0.f;
+    for (int h = 0; h < H; ++h) t += us[h][tid];
+    colm[tid] = t / (float)H;
+  } else if (tid < 64 + H) {
+    const int h = tid - 64;
+    float t = 0.f;
+    for (int w = 0; w < 64; ++w) t += us[h][w];
+    rowm[h] = t / 64.f;
+  }
+  __syncthreads();
+  if (tid < 65) {            // mlp_w : [65, 64+F] . [colmean ; y]
+    const float* r = a.ww + (size_t)tid * (64 + F);
+    float t = 0.f;
+    for (int i = 0; i < 64; ++i) t = __fmaf_rn(__ldg(r + i), colm[i], t);
+    for (int i = 0; i < F; ++i) t = __fmaf_rn(__ldg(r + 64 + i), yt[i], t);
+    lw[tid] = t;
+  } else if (tid >= 96 && tid < 96 + H + 1) {   // mlp_h : [H+1, H+F] . [rowmean ; y]
+    const int j = tid - 96;
+    const float* r = a.wh + (size_t)j * (H + F);
+    float t = 0.f;
+    for (int i = 0; i < H; ++i) t = __fmaf_rn(__ldg(r + i), rowm[i], t);
+    for (int i = 0; i < F; ++i) t = __fmaf_rn(__ldg(r + H + i), yt[i], t);
+    lh[j] = t;
+  }
+  __syncthreads();
+  if (tid < 32) {            // softmax over the 64 width logits
+    const float v0 = lw[tid], v1 = lw[tid + 32];
+    float m = fmaxf(v0, v1);
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    const float e0 = expf(v0 - m), e1 = expf(v1 - m);
+    float t = e0 + e1;
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
+    vw[tid] = e0 / t;
+    vw[tid + 32] = e1 / t;
+  } else if (tid < 64) {     // softmax over the H height logits
+    const int l = tid - 32;
+    const float v0 = l < H ? lh[l] : -INFINITY;
+    float m = v0;
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    const float e0 = l < H ? expf(v0 - m) : 0.f;
+    float t = e0;
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
+    if (l < H) vh[l] = e0 / t;
+  }
+  __syncthreads();
+  {
+    const float hl = lh[H], wl = lw[64];
+#pragma unroll
+    for (int i = 0; i < DG_MAXH / 4; ++i)
+      if (i < per) {
+        const int idx = tid + 256 * i, h = idx >> 6, w = idx & 63;
+        const float u = us[h][w];
+        as[h][w] = (vh[h] * u) * hl + (vw[w] * u) * wl;   // same association as DGAB.py:50
+      }
+  }
+  __syncthreads();
+  // proj over the width axis + residual; thread -> column j = tid&63, rows (tid>>6) + 4*i
+  float o[DG_MAXH / 4];
+  {
+    const int j = tid & 63, h0 = tid >> 6;
+    const float bs = __ldg(a.bp + j);
+#pragma unroll
+    for (int i = 0; i < DG_MAXH / 4; ++i) o[i] = 0.f;
+    for (int w = 0; w < 64; ++w) {
+      const float wv = wpT[w][j];
+#pragma unroll
+      for (int i = 0; i < DG_MAXH / 4; ++i)
+        if (i < per) o[i] = __fmaf_rn(as[h0 + 4 * i][w], wv, o[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < DG_MAXH / 4; ++i)
+      if (i < per) o[i] = xv[i] + (o[i] + bs);    // idx = tid + 256*i  <->  (h0+4i, j): same element as xv[i]
+  }
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < DG_MAXH / 4; ++i)
+    if (i < per) { a.x1[plane + tid + 256 * i] = o[i]; s2 += o[i]; }
+  const float mean2 = block_sum_256(s2, red) / (float)n;
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < DG_MAXH / 4; ++i)
+    if (i < per) { const float d = o[i] - mean2; q2 = __fmaf_rn(d, d, q2); }
+  const float rstd2 = rsqrtf(block_sum_256(q2, red) / (float)n + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < DG_MAXH / 4; ++i)
+    if (i < per) {
+      const int idx = tid + 256 * i;
+      a.v[plane + idx] = (o[i] - mean2) * rstd2 * __ldg(a.n2w + idx) + __ldg(a.n2b + idx);
+    }
+}
+
+// =====================================================================================
+// DGAB part 2: x2 = x1 + fc2(GELU(fc1(v))) over the width axis; rows = (b, c, h), K = 64
+// =====================================================================================
+struct MlpArgs {
+  const float* v;     // [R,64]
+  const float* x1;    // [R,64]
+  const float *w1, *b1, *w2, *b2;   // fc1 [256,64], fc2 [64,256]
+  float* out;         // [R,64]
+  long long R;
+};
+constexpr int ML_SMEM = (64 * 128 + 64 * 128 + 64 * CV_WLD + 64 * CV_WLD) * 4;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(256, 2) dgab_mlp_kernel(MlpArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                    // [64 k][128 rows]
+  float* Hs = As + 64 * 128;           // [64 m][128 rows]
+  float* W1s = Hs + 64 * 128;          // [64 k][68]  (m within chunk)
+  float* W2s = W1s + 64 * CV_WLD;      // [64 m][68]  (j)
+  const int tid = threadIdx.x;
+  const long long r_base = (long long)blockIdx.x * 128;
+  {  // input tile, transposed: thread -> row lp, float4 along k
+    const int lp = tid & 127, k40 = tid >> 7;
+    const long long r = r_base + lp;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k4 = k40 + 2 * i;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < a.R) t = __ldg(reinterpret_cast<const float4*>(a.v + r * 64 + k4 * 4));
+      As[(k4 * 4 + 0) * 128 + lp] = t.x;
+      As[(k4 * 4 + 1) * 128 + lp] = t.y;
+      As[(k4 * 4 + 2) * 128 + lp] = t.z;
+      As[(k4 * 4 + 3) * 128 + lp] = t.w;
+    }
+  }
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int hc = 0; hc < 4; ++hc) {
+    {  // weight chunks: W1s[k][mm] = fc1.w[hc*64+mm][k];  W2s[mm][j] = fc2.w[j][hc*64+mm]
+      const int c = tid & 63, r0 = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int rr = r0 + 4 * i;
+        W1s[c * CV_WLD + rr] = __ldg(a.w1 + (size_t)(hc * 64 + rr) * 64 + c);
+        W2s[c * CV_WLD + rr] = __ldg(a.w2 + (size_t)rr * 256 + hc * 64 + c);
+      }
+    }
+    __syncthreads();
+    float hacc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hacc[i][j] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(As + k * 128 + tx * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(As + k * 128 + 64 + tx * 4);
+      const float4 w = *reinterpret_cast<const float4*>(W1s + k * CV_WLD + ty * 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hacc[i][j] = __fmaf_rn(av[i], wv[j], hacc[i][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float bs = __ldg(a.b1 + hc * 64 + ty * 4 + j);
+      float4 h0, h1;
+      h0.x = gelu_erf(hacc[0][j] + bs); h0.y = gelu_erf(hacc[1][j] + bs);
+      h0.z = gelu_erf(hacc[2][j] + bs); h0.w = gelu_erf(hacc[3][j] + bs);
+      h1.x = gelu_erf(hacc[4][j] + bs); h1.y = gelu_erf(hacc[5][j] + bs);
+      h1.z = gelu_erf(hacc[6][j] + bs); h1.w = gelu_erf(hacc[7][j] + bs);
+      *reinterpret_cast<float4*>(Hs + (ty * 4 + j) * 128 + tx * 4) = h0;
+      *reinterpret_cast<float4*>(Hs + (ty * 4 + j) * 128 + 64 + tx * 4) = h1;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int m = 0; m < 64; ++m) {
+      const float4 a0 = *reinterpret_cast<const float4*>(Hs + m * 128 + tx * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(Hs + m * 128 + 64 + tx * 4);
+      const float4 w = *reinterpret_cast<const float4*>(W2s + m * CV_WLD + ty * 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.b2 + ty * 4));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long r = r_base + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
+    if (r >= a.R) continue;
+    const float4 res = __ldg(reinterpret_cast<const float4*>(a.x1 + r * 64 + ty * 4));
+    float4 o;
+    o.x = res.x + (acc[i][0] + b2.x); o.y = res.y + (acc[i][1] + b2.y);
+    o.z = res.z + (acc[i][2] + b2.z); o.w = res.w + (acc[i][3] + b2.w);
+    *reinterpret_cast<float4*>(a.out + r * 64 + ty * 4) = o;
+  }
+}
+
+// =====================================================================================
+// score head: pc_score[b,p,k] = tanh(scale * f[p,:] . p1[b,k,:]),
+//   f = feat_linear.1(feat_linear.0(de2[b,:,p]))           (tps_pp.py:303-308, 293-299)
+// one CTA per (image, 128 consecutive pixels); F <= 32
+// =====================================================================================
+struct ScoreArgs {
+  const float* de2;   // [B,64,n]
+  const float* p1;    // [B,F,128]
+  const float *wf0, *bf0, *wf1, *bf1;   // [32,64], [128,32]
+  float* score;       // [B,n,F]
+  int n, F;
+  float scale;
+};
+constexpr int SC_SMEM = (64 * 128 + 32 * 128 + 128 * 128 + 64 * 36 + 32 * 132 + 128 * 36) * 4;
+
+__global__ void __launch_bounds__(256, 1) score_kernel(ScoreArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                    // [64 c][128 px]
+  float* T1 = As + 64 * 128;           // [32 q][128 px]
+  float* Fs = T1 + 32 * 128;           // [128 r][128 px]
+  float* W0 = Fs + 128 * 128;          // [64 c][36]  (q)
+  float* W1 = W0 + 64 * 36;            // [32 q][132] (r)
+  float* P1 = W1 + 32 * 132;           // [128 r][36] (k)
+  const int tid = threadIdx.x, b = blockIdx.y, p0 = blockIdx.x * 128;
+  const int n = a.n, F = a.F;
+  for (int i = tid; i < 64 * 128; i += 256) {
+    const int c = i >> 7, px = i & 127;
+    As[i] = (p0 + px < n) ? __ldg(a.de2 + ((size_t)b * 64 + c) * n + p0 + px) : 0.f;
+  }
+  for (int i = tid; i < 32 * 64; i += 256) W0[(i & 63) * 36 + (i >> 6)] = __ldg(a.wf0 + i);       // wf0[q][c]
+  for (int i = tid; i < 128 * 32; i += 256) W1[(i & 31) * 132 + (i >> 5)] = __ldg(a.wf1 + i);     // wf1[r][q]
+  for (int i = tid; i < 128 * 32; i += 256) {
+    const int k = i >> 7, r = i & 127;
+    P1[r * 36 + k] = (k < F) ? __ldg(a.p1 + ((size_t)b * F + k) * 128 + r) : 0.f;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  {  // t1[px][q]: 8 px x 2 q per thread
+    float acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+      const float4 a0 = *reinterpret_cast<const float4*>(As + c * 128 + tx * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(As + c * 128 + 64 + tx * 4);
+      const float2 w = *reinterpret_cast<const float2*>(W0 + c * 36 + ty * 2);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = __fmaf_rn(av[i], w.x, acc[i][0]);
+        acc[i][1] = __fmaf_rn(av[i], w.y, acc[i][1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float bs = __ldg(a.bf0 + ty * 2 + j);
+      *reinterpret_cast<float4*>(T1 + (ty * 2 + j) * 128 + tx * 4) =
+          make_float4(acc[0][j] + bs, acc[1][j] + bs, acc[2][j] + bs, acc[3][j] + bs);
+      *reinterpret_cast<float4*>(T1 + (ty * 2 + j) * 128 + 64 + tx * 4) =
+          make_float4(acc[4][j] + bs, acc[5][j] + bs, acc[6][j] + bs, acc[7][j] + bs);
+    }
+  }
+  __syncthreads();
+  {  // f[px][r]: 8 px x 8 r per thread
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < 32; ++q) {
+      const float4 a0 = *reinterpret_cast<const float4*>(T1 + q * 128 + tx * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(T1 + q * 128 + 64 + tx * 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(W1 + q * 132 + ty * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(W1 + q * 132 + ty * 8 + 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(av[i], wv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bs = __ldg(a.bf1 + ty * 8 + j);
+      *reinterpret_cast<float4*>(Fs + (ty * 8 + j) * 128 + tx * 4) =
+          make_float4(acc[0][j] + bs, acc[1][j] + bs, acc[2][j] + bs, acc[3][j] + bs);
+      *reinterpret_cast<float4*>(Fs + (ty * 8 + j) * 128 + 64 + tx * 4) =
+          make_float4(acc[4][j] + bs, acc[5][j] + bs, acc[6][j] + bs, acc[7][j] + bs);
+    }
+  }
+  __syncthreads();
+  {  // s[px][k]: 8 px x 2 k per thread, K = 128
+    float acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+#pragma unroll 8
+    for (int r = 0; r < 128; ++r) {
+      const float4 a0 = *reinterpret_cast<const float4*>(Fs + r * 128 + tx * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(Fs + r * 128 + 64 + tx * 4);
+      const float2 w = *reinterpret_cast<const float2*>(P1 + r * 36 + ty * 2);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = __fmaf_rn(av[i], w.x, acc[i][0]);
+        acc[i][1] = __fmaf_rn(av[i], w.y, acc[i][1]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int px = p0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
+      if (px >= n) continue;
+      float* o = a.score + ((size_t)b * n + px) * F;
+      const int k = ty * 2;
+      if (k < F) o[k] = tanhf(acc[i][0] * a.scale);
+      if (k + 1 < F) o[k + 1] = tanhf(acc[i][1] * a.scale);
+    }
+  }
+}
+
+// =====================================================================================
+// host orchestration
+// =====================================================================================
+struct HeadDims {
+  int B, h, w, H2, W2, F, py, px, ps;
+  int h1, w1, h2, w2;   // after enc1 / enc2
+};
+
+static int head_dims(const tpspp_head_cfg* c, HeadDims* d) {
+  TPSPP_REQUIRE(c != nullptr, "head cfg is NULL");
+  TPSPP_REQUIRE(c->batch >= 0, "batch must be >= 0");
+  TPSPP_REQUIRE(c->width == 64, "TPS_PP head needs feature-map width 64 (DGAB linear layers act on the width axis; "
+                                "reference DGAB.py:36,52 -- SURVEY F4), got %d", c->width);
+  TPSPP_REQUIRE(c->height >= 8 && c->height <= DG_MAXH && c->height % 8 == 0, "height must be a multiple of 8 in [8,%d]", DG_MAXH);
+  TPSPP_REQUIRE(c->p_stride == 1 || c->p_stride == 2, "p_stride must be 1 or 2");
+  d->B = c->batch; d->h = c->height; d->w = c->width; d->H2 = 2 * c->height; d->W2 = 2 * c->width;
+  d->ps = c->p_stride;
+  d->h1 = d->h / 2; d->w1 = d->w / 2;
+  d->h2 = d->h1 / d->ps; d->w2 = d->w1 / d->ps;
+  d->py = d->h2 / 2; d->px = d->w2;
+  d->F = d->py * d->px;
+  TPSPP_REQUIRE(d->py == c->point_h && d->px == c->point_w,
+                "point_size (%d,%d) must equal the MSFA encoder's output lattice (%d,%d) (SURVEY F4)", c->point_h,
+                c->point_w, d->py, d->px);
+  TPSPP_REQUIRE(d->F <= 32 && d->F % 2 == 0, "num_fiducial must be even and <= 32 for the score kernel (got %d)", d->F);
+  TPSPP_REQUIRE(c->precision == TPSPP_HEAD_FP32 || c->precision == TPSPP_HEAD_TC, "unknown precision %d", c->precision);
+  return TPSPP_OK;
+}
+
+static void head_offsets(const HeadDims& d, size_t* off, size_t* total) {
+  const size_t B = d.B;
+  size_t sz[TPSPP_WS_COUNT];
+  const size_t big = B * 64 * d.H2 * d.W2, mid = B * 64 * d.h * d.w;
+  sz[TPSPP_WS_F0] = big; sz[TPSPP_WS_F1] = big; sz[TPSPP_WS_F2] = mid; sz[TPSPP_WS_A0] = mid; sz[TPSPP_WS_A1] = mid;
+  sz[TPSPP_WS_E0] = mid; sz[TPSPP_WS_E1] = B * 64 * d.h1 * d.w1; sz[TPSPP_WS_E2] = B * 64 * d.h2 * d.w2;
+  sz[TPSPP_WS_E3] = B * 64 * d.F; sz[TPSPP_WS_CBAM] = B * 64 * d.F; sz[TPSPP_WS_D0] = sz[TPSPP_WS_E2];
+  sz[TPSPP_WS_D1] = sz[TPSPP_WS_E1]; sz[TPSPP_WS_D2] = mid; sz[TPSPP_WS_DE] = mid; sz[TPSPP_WS_X1] = mid;
+  sz[TPSPP_WS_V] = mid; sz[TPSPP_WS_DE2] = mid; sz[TPSPP_WS_P1] = B * d.F * 128;
+  size_t cur = 0;
+  for (int i = 0; i < TPSPP_WS_COUNT; ++i) {
+    off[i] = cur;
+    cur += (sz[i] * sizeof(float) + 255) / 256 * 256;
+  }
+  *total = cur + 256;
+}
+
+static ConvSrc mk_src(const float* p, int C, int H, int W, int uh = 1, int uw = 1) {
+  ConvSrc s; s.ptr = p; s.C = C; s.H = H; s.W = W; s.uh = uh; s.uw = uw; return s;
+}
+
+static int run_conv(int KS, ConvSrc s0, ConvSrc s1, ConvSrc s2, const float* w, const float* bias, const float* skip,
+                    float* out, int B, int Ho, int Wo, int sh, int sw, cudaStream_t st) {
+  ConvArgs a;
+  a.src[0] = s0; a.src[1] = s1; a.src[2] = s2;
+  a.weight = w; a.bias = bias; a.skip = skip; a.out = out;
+  a.B = B; a.Ho = Ho; a.Wo = Wo; a.Ctot = s0.C + s1.C + s2.C; a.sh = sh; a.sw = sw; a.pad = (KS == 3) ? 1 : 0;
+  const long long M = (long long)B * Ho * Wo;
+  const unsigned grid = (unsigned)((M + CV_TM - 1) / CV_TM);
+  if (KS == 1) conv_ffma_kernel<1><<<grid, 256, CV_SMEM, st>>>(a);
+  else conv_ffma_kernel<3><<<grid, 256, CV_SMEM, st>>>(a);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
+static int head_attrs_once() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (done_dev == dev) return TPSPP_OK;
+  TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM));
+  TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM));
+  TPSPP_CHECK_CUDA(cudaFuncSetAttribute(dgab_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM));
+  TPSPP_CHECK_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+  TPSPP_CHECK_CUDA(cudaFuncSetAttribute(loc_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  done_dev = dev;
+  return TPSPP_OK;
+}
+
+}  // namespace tpspp
+
+using namespace tpspp;
+
+extern "C" size_t tpspp_head_workspace_bytes(const tpspp_head_cfg* cfg) {
+  HeadDims d;
+  if (head_dims(cfg, &d) != TPSPP_OK) return 0;
+  size_t off[TPSPP_WS_COUNT], total;
+  head_offsets(d, off, &total);
+  return total;
+}
+
+extern "C" int tpspp_head_workspace_offsets(const tpspp_head_cfg* cfg, size_t* offsets) {
+  HeadDims d;
+  int rc = head_dims(cfg, &d);
+  if (rc != TPSPP_OK) return rc;
+  TPSPP_REQUIRE(offsets != nullptr, "offsets is NULL");
+  size_t total;
+  head_offsets(d, offsets, &total);
+  return TPSPP_OK;
+}
+
+extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const float* o0, const float* o1,
+                              const float* const* P, float* feat_grid, float* c_prime, float* pc_score,
+                              void* workspace, tpspp_stream_t stream) {
+  reset_launch_count();
+  HeadDims d;
+  int rc = head_dims(cfg, &d);
+  if (rc != TPSPP_OK) return rc;
+  TPSPP_REQUIRE(x && o0 && o1 && P && feat_grid && c_prime && pc_score && workspace, "tpspp_head_fwd: null pointer");
+  TPSPP_REQUIRE(((uintptr_t)workspace & 255) == 0, "tpspp_head_fwd: workspace must be 256-byte aligned");
+  for (int i = 0; i < TPSPP_P_COUNT; ++i) TPSPP_REQUIRE(P[i] != nullptr, "tpspp_head_fwd: params[%d] is NULL", i);
+  if (d.B == 0) return TPSPP_OK;
+  rc = head_attrs_once();
+  if (rc != TPSPP_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t off[TPSPP_WS_COUNT], total;
+  head_offsets(d, off, &total);
+  auto W = [&](int i) { return reinterpret_cast<float*>((char*)workspace + off[i]); };
+  const ConvSrc none = mk_src(nullptr, 0, 1, 1);
+  const int B = d.B, h = d.h, w = d.w, H2 = d.H2, W2 = d.W2;
+
+#define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != TPSPP_OK) return rc; } while (0)
+  // down0/1/2 (tps_pp.py:581-583)
+  RUN(1, mk_src(o0, 32, H2, W2), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), B, H2, W2, 1, 1, st);
+  RUN(1, mk_src(o1, 32, H2, W2), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), B, H2, W2, 1, 1, st);
+  RUN(1, mk_src(x, 64, h, w), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), B, h, w, 1, 1, st);
+  // down0_1 / down1_1: 3x3 stride 2 (tps_pp.py:584)
+  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), B, h, w, 2, 2, st);
+  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), B, h, w, 2, 2, st);
+  // grid(): down_feat(cat(f0, f1, up2(f2))) (tps_pp.py:560-562,585)
+  RUN(1, mk_src(W(TPSPP_WS_F0), 64, H2, W2), mk_src(W(TPSPP_WS_F1), 64, H2, W2), mk_src(W(TPSPP_WS_F2), 64, h, w, 2, 2),
+      P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, B, H2, W2, 1, 1, st);
+  // MSFA encoder (tps_pp.py:158-160): cat(a0, a1, f2) -> e0 -> e1 -> e2 -> e3
+  RUN(3, mk_src(W(TPSPP_WS_A0), 64, h, w), mk_src(W(TPSPP_WS_A1), 64, h, w), mk_src(W(TPSPP_WS_F2), 64, h, w),
+      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), B, h, w, 1, 1, st);
+  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), B, d.h1, d.w1, 2, 2, st);
+  RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), B, d.h2, d.w2, d.ps, d.ps, st);
+  RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), B, d.py, d.px, 2, 1, st);
+  // CBAM on the deepest map (tps_pp.py:163)
+  cbam_kernel<<<B, 256, 0, st>>>(W(TPSPP_WS_E3), W(TPSPP_WS_CBAM), P[TPSPP_P_CBAM_MLP0_W], P[TPSPP_P_CBAM_MLP2_W],
+                                 P[TPSPP_P_CBAM_SP_W], P[TPSPP_P_CBAM_SP_B], d.py, d.px);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  // decoder (tps_pp.py:165-168): upsample + conv + skip
+  RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), B, d.h2, d.w2, 1, 1, st);
+  RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), B, d.h1, d.w1, 1, 1, st);
+  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), B, h, w, 1, 1, st);
+  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), B, h, w, 1, 1, st);
+#undef RUN
+  // localisation + p_linear (tps_pp.py:321-323, 305)
+  {
+    LocArgs a;
+    a.e3 = W(TPSPP_WS_E3);
+    a.wa = P[TPSPP_P_LOC1A_W]; a.ba = P[TPSPP_P_LOC1A_B]; a.wb = P[TPSPP_P_LOC1B_W]; a.bb = P[TPSPP_P_LOC1B_B];
+    a.wc = P[TPSPP_P_LOC2_W]; a.bc = P[TPSPP_P_LOC2_B];
+    a.wp0 = P[TPSPP_P_PLIN0_W]; a.bp0 = P[TPSPP_P_PLIN0_B]; a.wp1 = P[TPSPP_P_PLIN1_W]; a.bp1 = P[TPSPP_P_PLIN1_B];
+    a.c_prime = c_prime; a.p1 = W(TPSPP_WS_P1); a.F = d.F;
+    const size_t smem = (size_t)(d.F * 65 + d.F * 256 + 2 * d.F + d.F * 33) * sizeof(float);
+    loc_p1_kernel<<<B, 256, smem, st>>>(a);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+  }
+  // DGAB (DGAB.py:74-77)
+  {
+    DgabArgs a;
+    a.x = W(TPSPP_WS_DE); a.e3 = W(TPSPP_WS_E3);
+    a.n1w = P[TPSPP_P_NORM1_W]; a.n1b = P[TPSPP_P_NORM1_B]; a.n2w = P[TPSPP_P_NORM2_W]; a.n2b = P[TPSPP_P_NORM2_B];
+    a.wh = P[TPSPP_P_MLP_H_W]; a.ww = P[TPSPP_P_MLP_W_W]; a.wp = P[TPSPP_P_PROJ_W]; a.bp = P[TPSPP_P_PROJ_B];
+    a.x1 = W(TPSPP_WS_X1); a.v = W(TPSPP_WS_V); a.H = h; a.F = d.F;
+    dgab_plane_kernel<<<B * 64, 256, 0, st>>>(a);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+    MlpArgs m;
+    m.v = W(TPSPP_WS_V); m.x1 = W(TPSPP_WS_X1); m.w1 = P[TPSPP_P_FC1_W]; m.b1 = P[TPSPP_P_FC1_B];
+    m.w2 = P[TPSPP_P_FC2_W]; m.b2 = P[TPSPP_P_FC2_B]; m.out = W(TPSPP_WS_DE2); m.R = (long long)B * 64 * h;
+    dgab_mlp_kernel<<<(unsigned)((m.R + 127) / 128), 256, ML_SMEM, st>>>(m);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+  }
+  // attention score (tps_pp.py:303-312)
+  {
+    ScoreArgs a;
+    a.de2 = W(TPSPP_WS_DE2); a.p1 = W(TPSPP_WS_P1);
+    a.wf0 = P[TPSPP_P_FLIN0_W]; a.bf0 = P[TPSPP_P_FLIN0_B]; a.wf1 = P[TPSPP_P_FLIN1_W]; a.bf1 = P[TPSPP_P_FLIN1_B];
+    a.score = pc_score; a.n = h * w; a.F = d.F; a.scale = 0.125f;   // 64^-0.5 (tps_pp.py:247)
+    dim3 grid((a.n + 127) / 128, B);
+    score_kernel<<<grid, 256, SC_SMEM, st>>>(a);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+  }
+  return TPSPP_OK;
+}

@@ -155,3 +155,54 @@ def grid_sample_border(src0: torch.Tensor, grid: torch.Tensor, src1: Optional[to
         N.check(N.lib().tpspp_sample_fwd(ctypes.byref(cfg), _ptr(src0), _ptr(src1), _ptr(grid), _ptr(out0),
                                          _ptr(out1), _stream(src0)), "tpspp_sample_fwd")
     return (out0, out1) if src1 is not None else out0
+
+
+# ----------------------------------------------------------------------------- head
+def head_cfg(batch, height, width, point_size, p_stride, precision=N.HEAD_FP32) -> N.HeadCfg:
+    return N.HeadCfg(int(batch), int(height), int(width), int(point_size[0]), int(point_size[1]), int(p_stride),
+                     int(precision))
+
+
+def head_workspace_offsets(cfg: N.HeadCfg):
+    """{name: byte offset} of the intermediates inside the head workspace (tests / backward)."""
+    arr = (ctypes.c_size_t * len(N.WS_NAMES))()
+    N.check(N.lib().tpspp_head_workspace_offsets(ctypes.byref(cfg), arr), "tpspp_head_workspace_offsets")
+    return dict(zip(N.WS_NAMES, [int(v) for v in arr]))
+
+
+def head_forward(x: torch.Tensor, o0: torch.Tensor, o1: torch.Tensor, params, point_size, p_stride,
+                 precision=N.HEAD_FP32, workspace: Optional[torch.Tensor] = None):
+    """Native control-point attention head (reference tps_pp.py:581-594), inference only (no autograd).
+
+    ``params``: the module's parameters in state_dict order (58 fp32 CUDA tensors).
+    Returns ``(feat_grid, c_prime, pc_score, workspace)``."""
+    for nm, t in (("batch_img", x), ("outs[0]", o0), ("outs[1]", o1)):
+        _require_cuda(nm, t, torch.float32)
+    x = x.contiguous(); o0 = o0.contiguous(); o1 = o1.contiguous()
+    b, c, h, w = x.shape
+    if c != 64 or o0.shape != (b, 32, 2 * h, 2 * w) or o1.shape != (b, 32, 2 * h, 2 * w):
+        raise RuntimeError(f"tps_pp_b200: TPS_PP expects batch_img [B,64,h,w] and outs 2x[B,32,2h,2w]; got "
+                           f"{tuple(x.shape)}, {tuple(o0.shape)}, {tuple(o1.shape)}")
+    params = list(params)
+    if len(params) != N.P_COUNT:
+        raise RuntimeError(f"tps_pp_b200: expected {N.P_COUNT} parameter tensors, got {len(params)}")
+    table = (ctypes.c_void_p * N.P_COUNT)()
+    for i, p in enumerate(params):
+        _require_cuda(f"param[{i}]", p, torch.float32)
+        if not p.is_contiguous():
+            raise RuntimeError(f"tps_pp_b200: param[{i}] must be contiguous")
+        table[i] = p.data_ptr()
+    cfg = head_cfg(b, h, w, point_size, p_stride, precision)
+    f = point_size[0] * point_size[1]
+    with torch.cuda.device(x.device):
+        nbytes = int(N.lib().tpspp_head_workspace_bytes(ctypes.byref(cfg)))
+        if nbytes == 0 and b > 0:
+            raise RuntimeError("tpspp_head_workspace_bytes failed: " + N.last_error())
+        if workspace is None or workspace.numel() < nbytes or workspace.device != x.device:
+            workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+        feat_grid = torch.empty((b, 64, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+        c_prime = torch.empty((b, f, 2), dtype=torch.float32, device=x.device)
+        score = torch.empty((b, h * w, f), dtype=torch.float32, device=x.device)
+        N.check(N.lib().tpspp_head_fwd(ctypes.byref(cfg), _ptr(x), _ptr(o0), _ptr(o1), table, _ptr(feat_grid),
+                                       _ptr(c_prime), _ptr(score), _ptr(workspace), _stream(x)), "tpspp_head_fwd")
+    return feat_grid, c_prime, score, workspace

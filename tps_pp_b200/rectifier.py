@@ -136,7 +136,12 @@ class TPS_PP(_BaseModule):
 
         self.warp_variant = N.VARIANT_AUTO
         self.warp_events = None     # bench hook: list that receives (start, end) CUDA events around the warp
-        self.native_stages = {"warp": True, "down": False, "msfa": False, "tpe": False, "score": False}
+        # "auto": native kernels whenever autograd is not recording (inference); the library-op head is kept
+        # for training, where its backward comes from torch autograd (the warp's backward is native either way)
+        self.head_impl = "auto"
+        self.head_precision = N.HEAD_FP32
+        self._head_ws = None
+        self._last_head_launches = 0
 
     # ------------------------------------------------------------------ stages
     def _p(self, name: str) -> torch.Tensor:
@@ -222,8 +227,30 @@ class TPS_PP(_BaseModule):
         return c_prime, score
 
     # ------------------------------------------------------------------ forward
+    @property
+    def native_stages(self):
+        nat = self._use_native_head(None)
+        return {"warp": True, "down": nat, "msfa": nat, "cbam": nat, "dgab": nat, "localization": nat, "score": nat}
+
+    def _use_native_head(self, batch_img) -> bool:
+        if self.head_impl == "native":
+            return True
+        if self.head_impl == "library":
+            return False
+        return not torch.is_grad_enabled()
+
     def head(self, batch_img: torch.Tensor, outs: Sequence[torch.Tensor]):
         """Everything before the warp: -> (feat_grid, C' [B,F,2], pc_score [B,n,F])."""
+        if self._use_native_head(batch_img):
+            if torch.is_grad_enabled() and (batch_img.requires_grad or any(p.requires_grad for p in self.parameters())):
+                raise RuntimeError("tps_pp_b200: head_impl='native' has no backward yet; use torch.no_grad() or "
+                                   "head_impl='auto'/'library' for training")
+            fg, cp, sc, self._head_ws = TF.head_forward(batch_img, outs[0], outs[1], list(self.parameters()),
+                                                        self.point_size, self.p_stride, self.head_precision,
+                                                        self._head_ws)
+            self._last_head_launches = N.last_launch_count()
+            return fg, cp, sc
+        self._last_head_launches = 0
         # library stages must not drop to TF32: C' feeds a solve that amplifies rounding 1e2-1e3x (SURVEY F6)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False), _matmul_fp32():
             feat_cat, feat_grid = self._down(batch_img, outs[0], outs[1])
