@@ -9,10 +9,14 @@ python - <<'PY' > gpurun_out/env.txt 2>&1
 import os, torch
 print("cores", os.cpu_count(), "torch", torch.__version__, "cuda", torch.cuda.is_available(), torch.cuda.get_device_name(0))
 PY
+if [ "$mode" != head ]; then
 echo "== pytest -m gpu (warp)"; timeout 900 python -m pytest tests/test_warp_gpu.py -q -m gpu --timeout=300 -x --no-header -rA 2>&1 | tail -60 | tee gpurun_out/pytest_warp.log
-echo "== pytest -m gpu (head)"; timeout 900 python -m pytest tests/test_head_gpu.py -q -m gpu --timeout=300 --no-header -rA -s 2>&1 | tail -80 | tee gpurun_out/pytest_head.log
+fi
+echo "== pytest -m gpu (head)"; timeout 400 python -m pytest tests/test_head_gpu.py -q -m gpu --timeout=300 --no-header -rA -s 2>&1 | tail -80 | tee gpurun_out/pytest_head.log
+[ "$mode" = head ] && exit 0
 echo "== pytest -m gpu (module)"; timeout 900 python -m pytest tests/test_module_gpu.py -q -m gpu --timeout=300 --no-header -rA -s 2>&1 | tail -60 | tee gpurun_out/pytest_module.log
 if [ "$mode" = quick ]; then exit 0; fi
+if [ "$mode" = head ]; then exit 0; fi
 echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -20 | tee gpurun_out/smoke.log
 echo "== bench"; timeout 900 python bench.py --steps 20 --warmup 5 2>&1 | tail -5 | tee gpurun_out/bench.log
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -3 | tee gpurun_out/bench_ref.log

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Training-step timing of the rectifier (BASELINE config 3, rectifier part): forward + backward +
+one flat-bucket NCCL all-reduce + Adam, batch 128 per GPU.  NRTR itself is out of scope, so
+the loss is a synthetic regression on `output`.  Launch: python scripts/train_step_bench.py  or
+python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/train_step_bench.py"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tps_pp_b200 as T  # noqa: E402
+from tps_pp_b200 import parallel as PAR  # noqa: E402
+from bench import _trained_like_  # noqa: E402
+
+
+def main():
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, steps, warm = 128, 10, 3
+    m = T.TPS_PP().to(dev).train()
+    _trained_like_(m)
+    bucket = PAR.GradBucket(m.parameters())
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)      # schedule_adam_step_12e.py:1
+    g = torch.Generator(device=dev).manual_seed(rank)
+    x = torch.randn((B, 64, 16, 64), device=dev, generator=g)
+    o0 = torch.randn((B, 32, 32, 128), device=dev, generator=g)
+    o1 = torch.randn((B, 32, 32, 128), device=dev, generator=g)
+    tgt = torch.randn((B, 64, 16, 64), device=dev, generator=g)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t_total = t_ar = 0.0
+    for it in range(warm + steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        bucket.zero()
+        r = m(x, [o0, o1])
+        loss = (r["output"] - tgt).square().mean()
+        loss.backward()
+        ev[1].record()
+        bucket.all_reduce_mean()
+        ev[2].record()
+        opt.step()
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it >= warm:
+            t_total += ev[0].elapsed_time(ev[3]); t_ar += ev[1].elapsed_time(ev[2])
+    t = torch.tensor([t_total / steps, t_ar / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"metric": "tps_pp_train_step", "n_gpus": world, "batch_per_gpu": B, "ms_per_step": t[0].item(),
+                          "allreduce_ms": t[1].item(), "img_per_s": world * B / (t[0].item() * 1e-3),
+                          "grad_bucket_bytes": bucket.flat.numel() * 4, "loss": float(loss),
+                          "head": "library ops + autograd (fp32), warp fwd/bwd native"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

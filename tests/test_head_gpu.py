@@ -21,12 +21,12 @@ def mx(a, b):
     return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))))
 
 
-def _run_native(sd, x, o0, o1):
+def _run_native(sd, x, o0, o1, precision=N.HEAD_FP32):
     m = T.TPS_PP().to(DEV).eval()
     m.load_state_dict(sd, strict=True)
     with torch.no_grad():
         fg, cp, sc, ws = TF.head_forward(torch.from_numpy(x).to(DEV), torch.from_numpy(o0).to(DEV),
-                                         torch.from_numpy(o1).to(DEV), list(m.parameters()), (2, 16), 2)
+                                         torch.from_numpy(o1).to(DEV), list(m.parameters()), (2, 16), 2, precision)
     torch.cuda.synchronize()
     b = x.shape[0]
     cfg = TF.head_cfg(b, 16, 64, (2, 16), 2)
@@ -43,11 +43,13 @@ def _run_native(sd, x, o0, o1):
     return got, m
 
 
-@pytest.mark.parametrize("batch,seed", [(2, 0), (5, 11)])
-def test_head_stages_vs_oracle(native_lib, batch, seed):
+@pytest.mark.parametrize("batch,seed,precision", [(2, 0, N.HEAD_FP32), (5, 11, N.HEAD_FP32),
+                                                  (2, 0, N.HEAD_TC), (7, 11, N.HEAD_TC)])
+def test_head_stages_vs_oracle(native_lib, batch, seed, precision):
+    """precision TC = tcgen05 convolutions with 3xTF32 error compensation: same fp32-level acceptance rule."""
     sd = O.trained_like_state(3)
     x, o0, o1 = O.synthetic_tpspp_inputs(batch, seed)
-    got, _ = _run_native(sd, x, o0, o1)
+    got, _ = _run_native(sd, x, o0, o1, precision)
     r32 = O.head_intermediates(sd, x, [o0, o1], dtype=torch.float32)
     r64 = O.head_intermediates(sd, x, [o0, o1], dtype=torch.float64)
     report = []
@@ -57,7 +59,9 @@ def test_head_stages_vs_oracle(native_lib, batch, seed):
         floor = mx(r32[name], r64[name])
         err = mx(got[name], r64[name])
         report.append(f"{name:10s} |ours-ref64|={err:.2e} |ref32-ref64|={floor:.2e} scale={scale:.2f}")
-        assert err <= 4 * floor + 1e-6 * max(scale, 1.0), "\n".join(report)
+        # tensor-core accumulators truncate instead of rounding to nearest: ~K/8 * 2^-24 relative per layer
+        rel = 1e-6 if precision == N.HEAD_FP32 else 2e-5
+        assert err <= 4 * floor + rel * max(scale, 1.0), "\n".join(report)
     print("\n".join(report))
     assert mx(got["c_prime"], r64["c_prime"]) <= 1e-4            # north_star tolerance for control points
 
@@ -85,6 +89,26 @@ def test_head_stock_init_and_module_path(native_lib, golden):
     with torch.no_grad():
         fg, cp, sc = m2.head(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
     assert torch.equal(cp, m2.get_parameter("TPE.localization_fc2.bias").view(1, 32, 2).expand(cp.shape[0], -1, -1))
+
+
+def test_module_with_tensor_core_head_vs_reference_golden(native_lib, golden):
+    """End-to-end acceptance is the same for the tcgen05 (3xTF32) head as for the fp32 one."""
+    g = golden("tpspp_forward.npz")
+    sd = O.trained_like_state(int(g["state_seed"]))
+    m = T.TPS_PP().to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    m.head_precision = N.HEAD_TC
+    x, o0, o1 = O.synthetic_tpspp_inputs(int(g["batch"]), int(g["input_seed"]))
+    with torch.no_grad():
+        r = m(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
+        fg, cp, sc = m.head(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
+    floor_o = mx(g["ref32_output"], g["ref64_output"]); floor_m = mx(g["ref32_mp_img"], g["ref64_mp_img"])
+    e_o = mx(r["output"], g["ref64_output"]); e_m = mx(r["mp_img"], g["ref64_mp_img"])
+    print(f"TC head: output |ours-ref64|={e_o:.3e} (floor {floor_o:.3e}); mp_img {e_m:.3e} (floor {floor_m:.3e}); "
+          f"C' {mx(cp, g['ref64_control_point']):.2e}; pc_score {mx(r['pc_score'], g['ref64_pc_score']):.2e}")
+    assert e_o <= max(1e-5, 4 * floor_o) and e_m <= max(1e-5, 4 * floor_m)
+    assert mx(cp, g["ref64_control_point"]) <= 1e-4
+    assert mx(r["pc_score"], g["ref64_pc_score"]) <= 2e-4
 
 
 def test_head_native_equals_library_path(native_lib):

@@ -14,7 +14,7 @@
 // up to three concatenated input tensors, optional nearest up-sampling of each input
 // (nn.Upsample in the decoder / grid()), stride, zero padding, bias + ReLU and the decoder's
 // skip add fused -- torch.cat / Upsample never materialise.
-#include "common.cuh"
+#include "head.cuh"
 
 #include <string.h>
 
@@ -23,19 +23,6 @@ namespace tpspp {
 // =====================================================================================
 // implicit-GEMM convolution, 64 output channels, fp32 FFMA
 // =====================================================================================
-struct ConvSrc {
-  const float* ptr;
-  int C, H, W, uh, uw;   // stored size and integer nearest-upsample factors (1 or 2)
-};
-struct ConvArgs {
-  ConvSrc src[3];
-  const float* weight;   // [64][Ctot][KS][KS]
-  const float* bias;     // [64]
-  const float* skip;     // [B,64,Ho,Wo] added after the ReLU, or null
-  float* out;            // [B,64,Ho,Wo]
-  int B, Ho, Wo, Ctot, sh, sw, pad;
-};
-
 constexpr int CV_TM = 128;   // output pixels per CTA
 constexpr int CV_KC = 32;    // K chunk
 constexpr int CV_WLD = 68;   // padded leading dim of the weight chunk (floats)
@@ -720,6 +707,19 @@ static int head_dims(const tpspp_head_cfg* c, HeadDims* d) {
   return TPSPP_OK;
 }
 
+// the 14 convolutions in launch order: weight index, Cin total, kernel size
+struct ConvLayerDesc { int w_idx, Ctot, KS; };
+static const ConvLayerDesc kConvLayers[14] = {
+    {TPSPP_P_DOWN0_W, 32, 1},   {TPSPP_P_DOWN1_W, 32, 1},   {TPSPP_P_DOWN2_W, 64, 1},  {TPSPP_P_DOWN0_1_W, 64, 3},
+    {TPSPP_P_DOWN1_1_W, 64, 3}, {TPSPP_P_DOWNFEAT_W, 192, 1}, {TPSPP_P_ENC0_W, 192, 3}, {TPSPP_P_ENC1_W, 64, 3},
+    {TPSPP_P_ENC2_W, 64, 3},    {TPSPP_P_ENC3_W, 64, 3},    {TPSPP_P_DEC0_W, 64, 3},   {TPSPP_P_DEC1_W, 64, 3},
+    {TPSPP_P_DEC2_W, 64, 3},    {TPSPP_P_DEC3_W, 64, 3}};
+static size_t wprep_total_floats() {
+  size_t t = 0;
+  for (int i = 0; i < 14; ++i) t += conv_tc_wprep_floats(kConvLayers[i].Ctot, kConvLayers[i].KS);
+  return t;
+}
+
 static void head_offsets(const HeadDims& d, size_t* off, size_t* total) {
   const size_t B = d.B;
   size_t sz[TPSPP_WS_COUNT];
@@ -729,6 +729,7 @@ static void head_offsets(const HeadDims& d, size_t* off, size_t* total) {
   sz[TPSPP_WS_E3] = B * 64 * d.F; sz[TPSPP_WS_CBAM] = B * 64 * d.F; sz[TPSPP_WS_D0] = sz[TPSPP_WS_E2];
   sz[TPSPP_WS_D1] = sz[TPSPP_WS_E1]; sz[TPSPP_WS_D2] = mid; sz[TPSPP_WS_DE] = mid; sz[TPSPP_WS_X1] = mid;
   sz[TPSPP_WS_V] = mid; sz[TPSPP_WS_DE2] = mid; sz[TPSPP_WS_P1] = B * d.F * 128;
+  sz[TPSPP_WS_WPREP] = wprep_total_floats();
   size_t cur = 0;
   for (int i = 0; i < TPSPP_WS_COUNT; ++i) {
     off[i] = cur;
@@ -742,11 +743,12 @@ static ConvSrc mk_src(const float* p, int C, int H, int W, int uh = 1, int uw = 
 }
 
 static int run_conv(int KS, ConvSrc s0, ConvSrc s1, ConvSrc s2, const float* w, const float* bias, const float* skip,
-                    float* out, int B, int Ho, int Wo, int sh, int sw, cudaStream_t st) {
+                    float* out, int B, int Ho, int Wo, int sh, int sw, cudaStream_t st, const float* wprep = nullptr) {
   ConvArgs a;
   a.src[0] = s0; a.src[1] = s1; a.src[2] = s2;
   a.weight = w; a.bias = bias; a.skip = skip; a.out = out;
   a.B = B; a.Ho = Ho; a.Wo = Wo; a.Ctot = s0.C + s1.C + s2.C; a.sh = sh; a.sw = sw; a.pad = (KS == 3) ? 1 : 0;
+  if (wprep != nullptr && conv_tc_eligible(a, KS)) return run_conv_tc(KS, a, wprep, st);
   const long long M = (long long)B * Ho * Wo;
   const unsigned grid = (unsigned)((M + CV_TM - 1) / CV_TM);
   if (KS == 1) conv_ffma_kernel<1><<<grid, 256, CV_SMEM, st>>>(a);
@@ -799,6 +801,7 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   HeadDims d;
   int rc = head_dims(cfg, &d);
   if (rc != TPSPP_OK) return rc;
+  if (d.B == 0) return TPSPP_OK;
   TPSPP_REQUIRE(x && o0 && o1 && P && feat_grid && c_prime && pc_score && workspace, "tpspp_head_fwd: null pointer");
   TPSPP_REQUIRE(((uintptr_t)workspace & 255) == 0, "tpspp_head_fwd: workspace must be 256-byte aligned");
   for (int i = 0; i < TPSPP_P_COUNT; ++i) TPSPP_REQUIRE(P[i] != nullptr, "tpspp_head_fwd: params[%d] is NULL", i);
@@ -812,33 +815,48 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   const ConvSrc none = mk_src(nullptr, 0, 1, 1);
   const int B = d.B, h = d.h, w = d.w, H2 = d.H2, W2 = d.W2;
 
+  // tensor-core mode: one tiny launch re-lays every conv weight as its UMMA operand image (hi/lo split)
+  const float* wp[14];
+  for (int i = 0; i < 14; ++i) wp[i] = nullptr;
+  if (cfg->precision == TPSPP_HEAD_TC) {
+    WPrepLayer L[14];
+    float* cur = W(TPSPP_WS_WPREP);
+    for (int i = 0; i < 14; ++i) {
+      L[i].w = P[kConvLayers[i].w_idx]; L[i].out = cur; L[i].Ctot = kConvLayers[i].Ctot;
+      L[i].taps = kConvLayers[i].KS * kConvLayers[i].KS;
+      wp[i] = cur;
+      cur += conv_tc_wprep_floats(kConvLayers[i].Ctot, kConvLayers[i].KS);
+    }
+    rc = conv_tc_prepare_weights(L, 14, st);
+    if (rc != TPSPP_OK) return rc;
+  }
 #define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != TPSPP_OK) return rc; } while (0)
   // down0/1/2 (tps_pp.py:581-583)
-  RUN(1, mk_src(o0, 32, H2, W2), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), B, H2, W2, 1, 1, st);
-  RUN(1, mk_src(o1, 32, H2, W2), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), B, H2, W2, 1, 1, st);
-  RUN(1, mk_src(x, 64, h, w), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), B, h, w, 1, 1, st);
+  RUN(1, mk_src(o0, 32, H2, W2), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), B, H2, W2, 1, 1, st, wp[0]);
+  RUN(1, mk_src(o1, 32, H2, W2), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), B, H2, W2, 1, 1, st, wp[1]);
+  RUN(1, mk_src(x, 64, h, w), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), B, h, w, 1, 1, st, wp[2]);
   // down0_1 / down1_1: 3x3 stride 2 (tps_pp.py:584)
-  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), B, h, w, 2, 2, st);
-  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), B, h, w, 2, 2, st);
+  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), B, h, w, 2, 2, st, wp[3]);
+  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), B, h, w, 2, 2, st, wp[4]);
   // grid(): down_feat(cat(f0, f1, up2(f2))) (tps_pp.py:560-562,585)
   RUN(1, mk_src(W(TPSPP_WS_F0), 64, H2, W2), mk_src(W(TPSPP_WS_F1), 64, H2, W2), mk_src(W(TPSPP_WS_F2), 64, h, w, 2, 2),
-      P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, B, H2, W2, 1, 1, st);
+      P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, B, H2, W2, 1, 1, st, wp[5]);
   // MSFA encoder (tps_pp.py:158-160): cat(a0, a1, f2) -> e0 -> e1 -> e2 -> e3
   RUN(3, mk_src(W(TPSPP_WS_A0), 64, h, w), mk_src(W(TPSPP_WS_A1), 64, h, w), mk_src(W(TPSPP_WS_F2), 64, h, w),
-      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), B, h, w, 1, 1, st);
-  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), B, d.h1, d.w1, 2, 2, st);
-  RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), B, d.h2, d.w2, d.ps, d.ps, st);
-  RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), B, d.py, d.px, 2, 1, st);
+      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), B, h, w, 1, 1, st, wp[6]);
+  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), B, d.h1, d.w1, 2, 2, st, wp[7]);
+  RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), B, d.h2, d.w2, d.ps, d.ps, st, wp[8]);
+  RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), B, d.py, d.px, 2, 1, st, wp[9]);
   // CBAM on the deepest map (tps_pp.py:163)
   cbam_kernel<<<B, 256, 0, st>>>(W(TPSPP_WS_E3), W(TPSPP_WS_CBAM), P[TPSPP_P_CBAM_MLP0_W], P[TPSPP_P_CBAM_MLP2_W],
                                  P[TPSPP_P_CBAM_SP_W], P[TPSPP_P_CBAM_SP_B], d.py, d.px);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   // decoder (tps_pp.py:165-168): upsample + conv + skip
-  RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), B, d.h2, d.w2, 1, 1, st);
-  RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), B, d.h1, d.w1, 1, 1, st);
-  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), B, h, w, 1, 1, st);
-  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), B, h, w, 1, 1, st);
+  RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), B, d.h2, d.w2, 1, 1, st, wp[10]);
+  RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), B, d.h1, d.w1, 1, 1, st, wp[11]);
+  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), B, h, w, 1, 1, st, wp[12]);
+  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), B, h, w, 1, 1, st, wp[13]);
 #undef RUN
   // localisation + p_linear (tps_pp.py:321-323, 305)
   {

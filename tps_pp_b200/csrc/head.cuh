@@ -1,0 +1,35 @@
+// Shared declarations of the head kernels (fp32 FFMA path in head.cu, tcgen05 path in head_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tpspp {
+
+struct ConvSrc {
+  const float* ptr;
+  int C, H, W, uh, uw;   // stored size and integer nearest-upsample factors (1 or 2)
+};
+struct ConvArgs {
+  ConvSrc src[3];
+  const float* weight;   // [64][Ctot][KS][KS]
+  const float* bias;     // [64]
+  const float* skip;     // [B,64,Ho,Wo] added after the ReLU, or null
+  float* out;            // [B,64,Ho,Wo]
+  int B, Ho, Wo, Ctot, sh, sw, pad;
+};
+
+
+// tcgen05 implicit-GEMM convolution (head_tc.cu).  `wprep` is the layer's weight image produced by
+// conv_tc_prepare_weights (3xTF32 hi/lo split, UMMA core-matrix order).
+bool conv_tc_eligible(const ConvArgs& a, int KS);
+int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, cudaStream_t st);
+size_t conv_tc_wprep_floats(int Ctot, int KS);           // floats needed for one layer's image
+
+struct WPrepLayer {
+  const float* w;   // [64][Ctot][KS*KS]
+  float* out;
+  int Ctot, taps;
+};
+constexpr int WPREP_MAX_LAYERS = 16;
+int conv_tc_prepare_weights(const WPrepLayer* layers, int nlayers, cudaStream_t st);
+
+}  // namespace tpspp

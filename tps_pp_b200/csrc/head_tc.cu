@@ -1,0 +1,235 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for the TPS_PP head, 64 output channels.
+//
+// Same contract as conv_ffma_kernel (head.cu): up to three concatenated NCHW inputs, nearest
+// up-sampling, stride, zero padding, bias + ReLU (+ decoder skip) -- reference tps_pp.py:126-131,
+// 149-169, 538-548, 560-562, 581-585.  fp32 accuracy comes from 3xTF32 error compensation: every
+// fp32 operand is split into hi (the 19 bits the tf32 datapath reads) and lo = x - hi, and
+//   D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi      (fp32 accumulate in TMEM)
+// drops only the lo*lo term (2^-22 relative).
+//
+// Per CTA: a 128-pixel x 64-channel output tile; accumulator = 128 TMEM lanes x 64 fp32 columns.
+// K is ordered (tap, cin) and cut into chunks of 32: a chunk lies inside one filter tap and one input
+// tensor, so the im2col gather is 16 coalesced loads per thread.  All 256 threads stage chunk c+1
+// (split + core-matrix layout, 16-byte k-groups: [k/4][row][4]) while the tensor core runs chunk c
+// (2-deep ring, tcgen05.commit -> mbarrier releases a buffer); one thread issues the 12 MMAs of a chunk.
+#include "head.cuh"
+#include "tc.cuh"
+
+namespace tpspp {
+
+constexpr int TC_TM = 128, TC_KC = 32, TC_N = 64;
+constexpr int TC_A_BYTES = TC_TM * TC_KC * 4;               // 16 KB per part (hi / lo)
+constexpr int TC_B_BYTES = TC_N * TC_KC * 4;                // 8 KB per part
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 48 KB
+constexpr int TC_SMEM = 2 * TC_STAGE_BYTES + 64;
+constexpr int TC_TMEM_COLS = 64;
+
+struct ConvTcArgs {
+  ConvArgs c;
+  const float* wprep;   // [nchunks][hi|lo][8 k-groups][64 n][4]
+};
+
+template <int KS>
+__global__ void __launch_bounds__(256, 2) conv_tc_kernel(ConvTcArgs t) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TC_STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const ConvArgs& a = t.c;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int HoWo = a.Ho * a.Wo;
+  const long long Mtot = (long long)a.B * HoWo;
+  const long long m_base = (long long)blockIdx.x * TC_TM;
+  const int Ctot = a.Ctot;
+  const int nchunks = (Ctot * KS * KS) / TC_KC;
+
+  // loader role: pixel lp, 16-byte k-groups g0, g0+2, g0+4, g0+6 of every chunk
+  const int lp = tid & (TC_TM - 1), g0 = tid >> 7;
+  const long long lm = m_base + lp;
+  const bool lvalid = lm < Mtot;
+  int lb = 0, iy0 = 0, ix0 = 0;
+  if (lvalid) {
+    lb = (int)(lm / HoWo);
+    const int r = (int)(lm - (long long)lb * HoWo);
+    const int oy = r / a.Wo, ox = r - oy * a.Wo;
+    iy0 = oy * a.sh - a.pad;
+    ix0 = ox * a.sw - a.pad;
+  }
+  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, TC_N, 2);
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    // ---- chunk geometry: uniform over the CTA ----
+    const int k0 = ch * TC_KC;
+    const int tap = k0 / Ctot, cin0 = k0 - tap * Ctot;
+    const int dy = tap / KS, dx = tap - dy * KS;
+    int s = 0, c0 = cin0;
+    if (c0 >= a.src[0].C) {
+      c0 -= a.src[0].C; s = 1;
+      if (c0 >= a.src[1].C) { c0 -= a.src[1].C; s = 2; }
+    }
+    const float* sp = s == 0 ? a.src[0].ptr : (s == 1 ? a.src[1].ptr : a.src[2].ptr);
+    const int SC = s == 0 ? a.src[0].C : (s == 1 ? a.src[1].C : a.src[2].C);
+    const int SH = s == 0 ? a.src[0].H : (s == 1 ? a.src[1].H : a.src[2].H);
+    const int SW = s == 0 ? a.src[0].W : (s == 1 ? a.src[1].W : a.src[2].W);
+    const int uh = s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh);
+    const int uw = s == 0 ? a.src[0].uw : (s == 1 ? a.src[1].uw : a.src[2].uw);
+    // ---- gather this thread's 4 x 4 channels of its pixel ----
+    float4 v[4];
+    {
+      const int iy = iy0 + dy, ix = ix0 + dx;
+      const bool ok = lvalid && iy >= 0 && ix >= 0 && iy < SH * uh && ix < SW * uw;
+      const int sy = (uh == 2) ? (iy >> 1) : iy, sx = (uw == 2) ? (ix >> 1) : ix;
+      const size_t plane = (size_t)SH * SW;
+      const float* base = sp + ((size_t)lb * SC + c0) * plane + (size_t)(ok ? sy * SW + sx : 0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* q = base + (size_t)((g0 + 2 * i) * 4) * plane;
+        v[i] = ok ? make_float4(__ldg(q), __ldg(q + plane), __ldg(q + 2 * plane), __ldg(q + 3 * plane))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float4* wsrc = reinterpret_cast<const float4*>(t.wprep + (size_t)ch * (2 * TC_N * TC_KC));
+    float4 wv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wv[i] = __ldg(wsrc + tid + 256 * i);
+
+    // ---- the MMAs that read this buffer two chunks ago must have completed ----
+    if (ch >= 2) mbar_wait_bounded(&bars[buf], (uint32_t)(((ch >> 1) - 1) & 1));
+    unsigned char* st = smem + buf * TC_STAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 hi, lo;
+      split_tf32(v[i], hi, lo);
+      const int off = (g0 + 2 * i) * (TC_TM * 16) + lp * 16;
+      *reinterpret_cast<float4*>(st + off) = hi;
+      *reinterpret_cast<float4*>(st + TC_A_BYTES + off) = lo;
+    }
+    float4* wdst = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wdst[tid + 256 * i] = wv[i];
+    fence_proxy_async();     // generic-proxy stores -> visible to the tensor core's async proxy
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_A_BYTES;
+      const uint32_t b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+      for (int j = 0; j < TC_KC / 8; ++j) {       // one MMA = K 8 = two 16-byte k-groups
+        const uint64_t dah = umma_smem_desc(a_hi + j * 2 * (TC_TM * 16), TC_TM * 16, 128);
+        const uint64_t dal = umma_smem_desc(a_lo + j * 2 * (TC_TM * 16), TC_TM * 16, 128);
+        const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (TC_N * 16), TC_N * 16, 128);
+        const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (TC_N * 16), TC_N * 16, 128);
+        umma<2>(tmem_d, dal, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
+        umma<2>(tmem_d, dah, dbl, IDESC, 1u);
+        umma<2>(tmem_d, dah, dbh, IDESC, 1u);
+      }
+      umma_commit(&bars[buf]);
+    }
+  }
+  {
+    const int last = nchunks - 1;
+    mbar_wait_bounded(&bars[last & 1], (uint32_t)((last >> 1) & 1));
+    tc_fence_after();
+  }
+  // ---- epilogue: TMEM -> registers -> bias/ReLU/skip -> NCHW (lane = pixel: coalesced per channel) ----
+  {
+    const int wq = warp & 3, half = warp >> 2;
+    float acc[32];
+    tmem_ld32(tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * 32), acc);
+    const long long m = m_base + wq * 32 + lane;
+    if (m < Mtot) {
+      const int b = (int)(m / HoWo);
+      const int rem = (int)(m - (long long)b * HoWo);
+      const size_t o0 = ((size_t)b * 64 + half * 32) * HoWo + rem;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float r = fmaxf(acc[j] + __ldg(a.bias + half * 32 + j), 0.f);
+        const size_t o = o0 + (size_t)j * HoWo;
+        if (a.skip != nullptr) r += __ldg(a.skip + o);
+        a.out[o] = r;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, TC_TMEM_COLS);
+}
+
+// weight image: out[((ch*2 + part)*8 + kg)*256 + n*4 + j] with k = ch*32 + kg*4 + j = tap*Ctot + cin
+struct WPrepArgs {
+  WPrepLayer L[WPREP_MAX_LAYERS];
+  int n;
+};
+__global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
+  const WPrepLayer L = a.L[blockIdx.y];
+  const int Ktot = L.Ctot * L.taps;
+  const int total = 64 * Ktot;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int n = i / Ktot, k = i - n * Ktot;          // coalesced writes are not needed here (tiny)
+    const int tap = k / L.Ctot, cin = k - tap * L.Ctot;
+    const float w = __ldg(L.w + (size_t)n * Ktot + cin * L.taps + tap);
+    const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    const int ch = k >> 5, kg = (k >> 2) & 7, j = k & 3;
+    float* o = L.out + (size_t)ch * 4096 + kg * 256 + n * 4 + j;
+    o[0] = hi;
+    o[2048] = w - hi;
+  }
+}
+
+bool conv_tc_eligible(const ConvArgs& a, int KS) {
+  if (a.Ctot % TC_KC) return false;
+  for (int s = 0; s < 3; ++s)
+    if (a.src[s].C % TC_KC) return false;
+  (void)KS;
+  return true;
+}
+
+size_t conv_tc_wprep_floats(int Ctot, int KS) { return (size_t)2 * 64 * Ctot * KS * KS; }
+
+int conv_tc_prepare_weights(const WPrepLayer* layers, int nlayers, cudaStream_t st) {
+  TPSPP_REQUIRE(nlayers <= WPREP_MAX_LAYERS, "too many layers for wprep");
+  WPrepArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < nlayers; ++i) a.L[i] = layers[i];
+  a.n = nlayers;
+  dim3 grid(32, nlayers);
+  wprep_kernel<<<grid, 256, 0, st>>>(a);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
+int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, cudaStream_t st) {
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    attr_dev = dev;
+  }
+  ConvTcArgs t;
+  t.c = a;
+  t.wprep = wprep;
+  const long long M = (long long)a.B * a.Ho * a.Wo;
+  const unsigned grid = (unsigned)((M + TC_TM - 1) / TC_TM);
+  if (KS == 1) conv_tc_kernel<1><<<grid, 256, TC_SMEM, st>>>(t);
+  else conv_tc_kernel<3><<<grid, 256, TC_SMEM, st>>>(t);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
+}  // namespace tpspp

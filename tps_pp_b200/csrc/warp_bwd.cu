@@ -271,6 +271,7 @@ extern "C" int tpspp_warp_bwd(const tpspp_warp_cfg* cfg, const void* src0, const
   reset_launch_count();
   int rc = validate_cfg(cfg);
   if (rc != TPSPP_OK) return rc;
+  if (cfg->batch == 0) return TPSPP_OK;
   TPSPP_REQUIRE(src0 && gout0 && c_prime && P_hat && inv_delta_C && workspace,
                 "tpspp_warp_bwd: null required pointer");
   TPSPP_REQUIRE(((uintptr_t)workspace & 255) == 0, "tpspp_warp_bwd: workspace must be 256-byte aligned");

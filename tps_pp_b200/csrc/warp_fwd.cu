@@ -357,6 +357,7 @@ extern "C" int tpspp_warp_fwd(const tpspp_warp_cfg* cfg, const void* src0, const
   reset_launch_count();
   int rc = validate_cfg(cfg);
   if (rc != TPSPP_OK) return rc;
+  if (cfg->batch == 0) return TPSPP_OK;   // empty batch: nothing to do (pointers may be NULL)
   TPSPP_REQUIRE(src0 && out0 && c_prime && P_hat && inv_delta_C, "tpspp_warp_fwd: null required pointer");
   TPSPP_REQUIRE((cfg->channels1 == 0) == (src1 == nullptr) && (cfg->channels1 == 0) == (out1 == nullptr),
                 "tpspp_warp_fwd: src1/out1 must be given exactly when channels1 > 0");
@@ -386,6 +387,7 @@ extern "C" int tpspp_sample_fwd(const tpspp_warp_cfg* cfg, const void* src0, con
   reset_launch_count();
   int rc = validate_cfg(cfg);
   if (rc != TPSPP_OK) return rc;
+  if (cfg->batch == 0) return TPSPP_OK;
   TPSPP_REQUIRE(src0 && out0 && grid, "tpspp_sample_fwd: null required pointer");
   TPSPP_REQUIRE((cfg->channels1 == 0) == (src1 == nullptr) && (cfg->channels1 == 0) == (out1 == nullptr),
                 "tpspp_sample_fwd: src1/out1 must be given exactly when channels1 > 0");
