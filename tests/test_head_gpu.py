@@ -118,6 +118,7 @@ def test_head_native_equals_library_path(native_lib):
     x, o0, o1 = (torch.from_numpy(t).to(DEV) for t in O.synthetic_tpspp_inputs(3, 2))
     with torch.no_grad():
         m.head_impl = "native"
+        m.head_precision = N.HEAD_FP32
         a = m.head(x, [o0, o1])
         m.head_impl = "library"
         b = m.head(x, [o0, o1])

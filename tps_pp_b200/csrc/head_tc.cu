@@ -12,6 +12,7 @@
 // tensor, so the im2col gather is 16 coalesced loads per thread.  All 256 threads stage chunk c+1
 // (split + core-matrix layout, 16-byte k-groups: [k/4][row][4]) while the tensor core runs chunk c
 // (2-deep ring, tcgen05.commit -> mbarrier releases a buffer); one thread issues the 12 MMAs of a chunk.
+// Accumulators: 3 x (128 TMEM lanes x 64 fp32 columns), see the comment at the MMA issue.
 #include "head.cuh"
 #include "tc.cuh"
 
@@ -22,7 +23,7 @@ constexpr int TC_A_BYTES = TC_TM * TC_KC * 4;               // 16 KB per part (h
 constexpr int TC_B_BYTES = TC_N * TC_KC * 4;                // 8 KB per part
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 48 KB
 constexpr int TC_SMEM = 2 * TC_STAGE_BYTES + 64;
-constexpr int TC_TMEM_COLS = 64;
+constexpr int TC_TMEM_COLS = 256;   // 3 accumulators x 64 columns (power-of-two allocation)
 
 struct ConvTcArgs {
   ConvArgs c;
@@ -131,9 +132,13 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(ConvTcArgs t) {
         const uint64_t dal = umma_smem_desc(a_lo + j * 2 * (TC_TM * 16), TC_TM * 16, 128);
         const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (TC_N * 16), TC_N * 16, 128);
         const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (TC_N * 16), TC_N * 16, 128);
-        umma<2>(tmem_d, dal, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
-        umma<2>(tmem_d, dah, dbl, IDESC, 1u);
-        umma<2>(tmem_d, dah, dbh, IDESC, 1u);
+        // The tensor core truncates (does not round) when it adds into the fp32 accumulator, so the error grows
+        // with the number of accumulation steps.  Three accumulators keep that at fp32 level: hi*hi of even /
+        // odd chunks in D0 / D1 (half the steps at half the magnitude each) and the small lo*hi + hi*lo
+        // corrections in D2, summed with round-to-nearest in the epilogue.
+        umma<2>(tmem_d + 128, dal, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
+        umma<2>(tmem_d + 128, dah, dbl, IDESC, 1u);
+        umma<2>(tmem_d + (uint32_t)(buf * 64), dah, dbh, IDESC, (ch > 1 || j > 0) ? 1u : 0u);
       }
       umma_commit(&bars[buf]);
     }
@@ -146,8 +151,17 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(ConvTcArgs t) {
   // ---- epilogue: TMEM -> registers -> bias/ReLU/skip -> NCHW (lane = pixel: coalesced per channel) ----
   {
     const int wq = warp & 3, half = warp >> 2;
-    float acc[32];
-    tmem_ld32(tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * 32), acc);
+    float acc[32], part[32];
+    const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * 32);
+    tmem_ld32(taddr, acc);
+    tmem_ld32(taddr + 128, part);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += part[j];
+    if (nchunks > 1) {
+      tmem_ld32(taddr + 64, part);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] += part[j];
+    }
     const long long m = m_base + wq * 32 + lane;
     if (m < Mtot) {
       const int b = (int)(m / HoWo);

@@ -139,7 +139,8 @@ class TPS_PP(_BaseModule):
         # "auto": native kernels whenever autograd is not recording (inference); the library-op head is kept
         # for training, where its backward comes from torch autograd (the warp's backward is native either way)
         self.head_impl = "auto"
-        self.head_precision = N.HEAD_FP32
+        # tcgen05 3xTF32 convolutions (fp32-level accuracy); N.HEAD_FP32 = CUDA-core only
+        self.head_precision = N.HEAD_TC
         self._head_ws = None
         self._last_head_launches = 0
 
