@@ -36,9 +36,14 @@ def _run_native(sd, x, o0, o1, precision=N.HEAD_FP32):
                   d0=(b, 64, 4, 16), d1=(b, 64, 8, 32), d2=(b, 64, 16, 64), de=(b, 64, 16, 64), x1=(b, 64, 16, 64),
                   v=(b, 64, 16, 64), de2=(b, 64, 16, 64), p1=(b, 32, 128))
     got = {}
+    nhwc = {"f0", "f1", "f2", "a0", "a1", "e0", "e1", "e2", "d0", "d1", "d2"}    # internal channels-last slots
     for name, shp in shapes.items():
         n = int(np.prod(shp))
-        got[name] = ws[off[name]: off[name] + 4 * n].view(torch.float32).view(shp).cpu()
+        flat = ws[off[name]: off[name] + 4 * n].view(torch.float32)
+        if name in nhwc:
+            got[name] = flat.view(shp[0], shp[2], shp[3], shp[1]).permute(0, 3, 1, 2).contiguous().cpu()
+        else:
+            got[name] = flat.view(shp).cpu()
     got.update(feat_grid=fg.cpu(), c_prime=cp.cpu(), pc_score=sc.cpu())
     return got, m
 

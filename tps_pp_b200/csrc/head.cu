@@ -77,10 +77,12 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(ConvArgs a) {
         const int SW = s == 0 ? a.src[0].W : (s == 1 ? a.src[1].W : a.src[2].W);
         const int uh = s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh);
         const int uw = s == 0 ? a.src[0].uw : (s == 1 ? a.src[1].uw : a.src[2].uw);
+        const int nhwc = s == 0 ? a.src[0].nhwc : (s == 1 ? a.src[1].nhwc : a.src[2].nhwc);
         const int iy = iy0 + dy, ix = ix0 + dx;
         if (iy >= 0 && ix >= 0 && iy < SH * uh && ix < SW * uw) {
           const int sy = (uh == 2) ? (iy >> 1) : iy, sx = (uw == 2) ? (ix >> 1) : ix;
-          v = __ldg(sp + (((size_t)lb * SC + c) * SH + sy) * SW + sx);
+          v = nhwc ? __ldg(sp + (((size_t)lb * SH + sy) * SW + sx) * SC + c)
+                   : __ldg(sp + (((size_t)lb * SC + c) * SH + sy) * SW + sx);
         }
       }
       ra[i] = v;
@@ -129,7 +131,26 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(ConvArgs a) {
     __syncthreads();
   }
 
-  // epilogue: bias, ReLU, optional skip, NCHW float4 stores (4 consecutive pixels per store)
+  // epilogue: bias, ReLU, optional skip
+  if (a.out_nhwc) {          // [B,Ho,Wo,64]: one float4 = 4 output channels of a pixel
+    const float4 bs = __ldg(reinterpret_cast<const float4*>(a.bias + ty * 4));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long m = m_base + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
+      if (m >= Mtot) continue;
+      float4 v;
+      v.x = fmaxf(acc[i][0] + bs.x, 0.f); v.y = fmaxf(acc[i][1] + bs.y, 0.f);
+      v.z = fmaxf(acc[i][2] + bs.z, 0.f); v.w = fmaxf(acc[i][3] + bs.w, 0.f);
+      const size_t o = (size_t)m * 64 + ty * 4;
+      if (a.skip != nullptr) {
+        const float4 sk = __ldg(reinterpret_cast<const float4*>(a.skip + o));
+        v.x += sk.x; v.y += sk.y; v.z += sk.z; v.w += sk.w;
+      }
+      *reinterpret_cast<float4*>(a.out + o) = v;
+    }
+    return;
+  }
+  // NCHW float4 stores (4 consecutive pixels per store)
 #pragma unroll
   for (int pg = 0; pg < 2; ++pg) {
     const long long m0 = m_base + pg * 64 + tx * 4;
@@ -738,13 +759,15 @@ static void head_offsets(const HeadDims& d, size_t* off, size_t* total) {
   *total = cur + 256;
 }
 
-static ConvSrc mk_src(const float* p, int C, int H, int W, int uh = 1, int uw = 1) {
-  ConvSrc s; s.ptr = p; s.C = C; s.H = H; s.W = W; s.uh = uh; s.uw = uw; return s;
+static ConvSrc mk_src(const float* p, int C, int H, int W, int nhwc, int uh = 1, int uw = 1) {
+  ConvSrc s; s.ptr = p; s.C = C; s.H = H; s.W = W; s.uh = uh; s.uw = uw; s.nhwc = nhwc; return s;
 }
 
 static int run_conv(int KS, ConvSrc s0, ConvSrc s1, ConvSrc s2, const float* w, const float* bias, const float* skip,
-                    float* out, int B, int Ho, int Wo, int sh, int sw, cudaStream_t st, const float* wprep = nullptr) {
+                    float* out, int out_nhwc, int B, int Ho, int Wo, int sh, int sw, cudaStream_t st,
+                    const float* wprep = nullptr) {
   ConvArgs a;
+  a.out_nhwc = out_nhwc;
   a.src[0] = s0; a.src[1] = s1; a.src[2] = s2;
   a.weight = w; a.bias = bias; a.skip = skip; a.out = out;
   a.B = B; a.Ho = Ho; a.Wo = Wo; a.Ctot = s0.C + s1.C + s2.C; a.sh = sh; a.sw = sw; a.pad = (KS == 3) ? 1 : 0;
@@ -812,7 +835,8 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   size_t off[TPSPP_WS_COUNT], total;
   head_offsets(d, off, &total);
   auto W = [&](int i) { return reinterpret_cast<float*>((char*)workspace + off[i]); };
-  const ConvSrc none = mk_src(nullptr, 0, 1, 1);
+  const ConvSrc none = mk_src(nullptr, 0, 1, 1, 0);
+  constexpr int NCHW = 0, NHWC = 1;   // internal activations are channels-last; boundary tensors stay NCHW
   const int B = d.B, h = d.h, w = d.w, H2 = d.H2, W2 = d.W2;
 
   // tensor-core mode: one tiny launch re-lays every conv weight as its UMMA operand image (hi/lo split)
@@ -831,32 +855,32 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     if (rc != TPSPP_OK) return rc;
   }
 #define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != TPSPP_OK) return rc; } while (0)
-  // down0/1/2 (tps_pp.py:581-583)
-  RUN(1, mk_src(o0, 32, H2, W2), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), B, H2, W2, 1, 1, st, wp[0]);
-  RUN(1, mk_src(o1, 32, H2, W2), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), B, H2, W2, 1, 1, st, wp[1]);
-  RUN(1, mk_src(x, 64, h, w), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), B, h, w, 1, 1, st, wp[2]);
+  // down0/1/2 (tps_pp.py:581-583): NCHW boundary inputs -> channels-last intermediates
+  RUN(1, mk_src(o0, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), NHWC, B, H2, W2, 1, 1, st, wp[0]);
+  RUN(1, mk_src(o1, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), NHWC, B, H2, W2, 1, 1, st, wp[1]);
+  RUN(1, mk_src(x, 64, h, w, NCHW), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), NHWC, B, h, w, 1, 1, st, wp[2]);
   // down0_1 / down1_1: 3x3 stride 2 (tps_pp.py:584)
-  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), B, h, w, 2, 2, st, wp[3]);
-  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), B, h, w, 2, 2, st, wp[4]);
-  // grid(): down_feat(cat(f0, f1, up2(f2))) (tps_pp.py:560-562,585)
-  RUN(1, mk_src(W(TPSPP_WS_F0), 64, H2, W2), mk_src(W(TPSPP_WS_F1), 64, H2, W2), mk_src(W(TPSPP_WS_F2), 64, h, w, 2, 2),
-      P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, B, H2, W2, 1, 1, st, wp[5]);
+  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NHWC), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), NHWC, B, h, w, 2, 2, st, wp[3]);
+  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2, NHWC), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), NHWC, B, h, w, 2, 2, st, wp[4]);
+  // grid(): down_feat(cat(f0, f1, up2(f2))) (tps_pp.py:560-562,585) -> feat_grid in the boundary layout (warp input)
+  RUN(1, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NHWC), mk_src(W(TPSPP_WS_F1), 64, H2, W2, NHWC), mk_src(W(TPSPP_WS_F2), 64, h, w, NHWC, 2, 2),
+      P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, NCHW, B, H2, W2, 1, 1, st, wp[5]);
   // MSFA encoder (tps_pp.py:158-160): cat(a0, a1, f2) -> e0 -> e1 -> e2 -> e3
-  RUN(3, mk_src(W(TPSPP_WS_A0), 64, h, w), mk_src(W(TPSPP_WS_A1), 64, h, w), mk_src(W(TPSPP_WS_F2), 64, h, w),
-      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), B, h, w, 1, 1, st, wp[6]);
-  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), B, d.h1, d.w1, 2, 2, st, wp[7]);
-  RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), B, d.h2, d.w2, d.ps, d.ps, st, wp[8]);
-  RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), B, d.py, d.px, 2, 1, st, wp[9]);
+  RUN(3, mk_src(W(TPSPP_WS_A0), 64, h, w, NHWC), mk_src(W(TPSPP_WS_A1), 64, h, w, NHWC), mk_src(W(TPSPP_WS_F2), 64, h, w, NHWC),
+      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), NHWC, B, h, w, 1, 1, st, wp[6]);
+  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w, NHWC), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), NHWC, B, d.h1, d.w1, 2, 2, st, wp[7]);
+  RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1, NHWC), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), NHWC, B, d.h2, d.w2, d.ps, d.ps, st, wp[8]);
+  RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2, NHWC), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), NCHW, B, d.py, d.px, 2, 1, st, wp[9]);
   // CBAM on the deepest map (tps_pp.py:163)
   cbam_kernel<<<B, 256, 0, st>>>(W(TPSPP_WS_E3), W(TPSPP_WS_CBAM), P[TPSPP_P_CBAM_MLP0_W], P[TPSPP_P_CBAM_MLP2_W],
                                  P[TPSPP_P_CBAM_SP_W], P[TPSPP_P_CBAM_SP_B], d.py, d.px);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   // decoder (tps_pp.py:165-168): upsample + conv + skip
-  RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), B, d.h2, d.w2, 1, 1, st, wp[10]);
-  RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), B, d.h1, d.w1, 1, 1, st, wp[11]);
-  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), B, h, w, 1, 1, st, wp[12]);
-  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), B, h, w, 1, 1, st, wp[13]);
+  RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, NCHW, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), NHWC, B, d.h2, d.w2, 1, 1, st, wp[10]);
+  RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, NHWC, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), NHWC, B, d.h1, d.w1, 1, 1, st, wp[11]);
+  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, NHWC, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), NHWC, B, h, w, 1, 1, st, wp[12]);
+  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w, NHWC), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), NCHW, B, h, w, 1, 1, st, wp[13]);
 #undef RUN
   // localisation + p_linear (tps_pp.py:321-323, 305)
   {

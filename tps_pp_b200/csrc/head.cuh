@@ -7,6 +7,7 @@ namespace tpspp {
 struct ConvSrc {
   const float* ptr;
   int C, H, W, uh, uw;   // stored size and integer nearest-upsample factors (1 or 2)
+  int nhwc;              // 0: [B,C,H,W] (the reference's layout, used at the boundary), 1: [B,H,W,C] (internal)
 };
 struct ConvArgs {
   ConvSrc src[3];
@@ -15,6 +16,7 @@ struct ConvArgs {
   const float* skip;     // [B,64,Ho,Wo] added after the ReLU, or null
   float* out;            // [B,64,Ho,Wo]
   int B, Ho, Wo, Ctot, sh, sw, pad;
+  int out_nhwc;          // layout of out (and skip)
 };
 
 
