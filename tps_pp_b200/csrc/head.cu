@@ -342,131 +342,185 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 
 constexpr int DG_MAXH = 32;
 
-__global__ void __launch_bounds__(256) dgab_plane_kernel(DgabArgs a) {
-  __shared__ float us[DG_MAXH][64];
-  __shared__ float as[DG_MAXH][64];
-  __shared__ float wpT[64][65];
-  __shared__ float colm[64], rowm[DG_MAXH], yt[64], lw[65], lh[DG_MAXH + 1], vw[64], vh[DG_MAXH];
-  __shared__ float red[8];
+// dot product of a shared-memory weight row with a shared-memory vector, split over G consecutive lanes
+template <int G>
+__device__ __forceinline__ float group_dot(const float* row, const float* vec, int len, int part) {
+  float t = 0.f;
+  for (int i = part; i < len; i += G) t = __fmaf_rn(row[i], vec[i], t);
+#pragma unroll
+  for (int m = 1; m < G; m <<= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+  return t;
+}
+
+// Persistent: every CTA keeps the DGAB weights (proj^T, mlp_w, mlp_h, both LayerNorm affines) in shared
+// memory and walks planes blockIdx.x, blockIdx.x + gridDim.x, ...; the next plane's pixels are prefetched
+// into registers while the current one is processed.
+template <int PER>   // H/4 plane elements per thread
+__global__ void __launch_bounds__(256, 2) dgab_plane_kernel(DgabArgs a, int nplanes) {
+  extern __shared__ __align__(16) float dsm[];
   const int H = a.H, F = a.F, tid = threadIdx.x;
   const int n = H * 64;
-  const size_t plane = (size_t)blockIdx.x * n;
-  const int per = n / 256;     // H/4 elements per thread (H multiple of 4)
-  float xv[DG_MAXH / 4];
-  // proj weight transposed into shared memory
-  for (int i = tid; i < 4096; i += 256) wpT[i & 63][i >> 6] = __ldg(a.wp + i);
-  if (tid < F) yt[tid] = __ldg(a.e3 + (size_t)blockIdx.x * F + tid);
-  float s = 0.f;
+  const int LW = 64 + F + 1, LH = H + F + 1;        // padded row strides (conflict-free group_dot)
+  float* wpT = dsm;                      // [64][65]
+  float* wws = wpT + 64 * 65;            // [65][LW]
+  float* whs = wws + 65 * LW;            // [H+1][LH]
+  float* n1w = whs + (H + 1) * LH;       // [n] x4
+  float* n1b = n1w + n;
+  float* n2w = n1b + n;
+  float* n2b = n2w + n;
+  float* us = n2b + n;                   // [H][64]
+  float* as = us + n;                    // [H][64]
+  float* vecw = as + n;                  // [64+F] = colmean | y
+  float* vech = vecw + 64 + F;           // [H+F]  = rowmean | y
+  float* lw = vech + H + F;              // [65]
+  float* lh = lw + 65;                   // [H+1]
+  float* vw = lh + H + 1;                // [64]
+  float* vh = vw + 64;                   // [H]
+  float* red = vh + H;                   // [8]
+
+  for (int i = tid; i < 4096; i += 256) wpT[(i & 63) * 65 + (i >> 6)] = __ldg(a.wp + i);
+  for (int i = tid; i < 65 * (64 + F); i += 256) { const int r = i / (64 + F); wws[r * LW + (i - r * (64 + F))] = __ldg(a.ww + i); }
+  for (int i = tid; i < (H + 1) * (H + F); i += 256) { const int r = i / (H + F); whs[r * LH + (i - r * (H + F))] = __ldg(a.wh + i); }
+  for (int i = tid; i < n; i += 256) {
+    n1w[i] = __ldg(a.n1w + i); n1b[i] = __ldg(a.n1b + i); n2w[i] = __ldg(a.n2w + i); n2b[i] = __ldg(a.n2b + i);
+  }
+  const float bproj = __ldg(a.bp + (tid & 63));
+
+  float xn[PER];
+  int pl = blockIdx.x;
+  if (pl < nplanes) {
 #pragma unroll
-  for (int i = 0; i < DG_MAXH / 4; ++i)
-    if (i < per) { xv[i] = __ldg(a.x + plane + tid + 256 * i); s += xv[i]; }
-  const float mean = block_sum_256(s, red) / (float)n;
-  float q = 0.f;
+    for (int i = 0; i < PER; ++i)
+      xn[i] = __ldg(a.x + (size_t)pl * n + tid + 256 * i);
+  }
+  for (; pl < nplanes; pl += gridDim.x) {
+    const size_t plane = (size_t)pl * n;
+    float xv[PER];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < DG_MAXH / 4; ++i)
-    if (i < per) { const float d = xv[i] - mean; q = __fmaf_rn(d, d, q); }
-  const float rstd = rsqrtf(block_sum_256(q, red) / (float)n + 1e-5f);
+    for (int i = 0; i < PER; ++i)
+      { xv[i] = xn[i]; s += xv[i]; }
+    if (pl + (int)gridDim.x < nplanes) {      // prefetch the next plane of this CTA
 #pragma unroll
-  for (int i = 0; i < DG_MAXH / 4; ++i)
-    if (i < per) {
-      const int idx = tid + 256 * i;
-      us[idx >> 6][idx & 63] = (xv[i] - mean) * rstd * __ldg(a.n1w + idx) + __ldg(a.n1b + idx);
+      for (int i = 0; i < PER; ++i)
+        xn[i] = __ldg(a.x + (size_t)(pl + gridDim.x) * n + tid + 256 * i);
     }
-  __syncthreads();
-  if (tid < 64) {
-    float t = 0.f;
-    for (int h = 0; h < H; ++h) t += us[h][tid];
-    colm[tid] = t / (float)H;
-  } else if (tid < 64 + H) {
-    const int h = tid - 64;
-    float t = 0.f;
-    for (int w = 0; w < 64; ++w) t += us[h][w];
-    rowm[h] = t / 64.f;
-  }
-  __syncthreads();
-  if (tid < 65) {            // mlp_w : [65, 64+F] . [colmean ; y]
-    const float* r = a.ww + (size_t)tid * (64 + F);
-    float t = 0.f;
-    for (int i = 0; i < 64; ++i) t = __fmaf_rn(__ldg(r + i), colm[i], t);
-    for (int i = 0; i < F; ++i) t = __fmaf_rn(__ldg(r + 64 + i), yt[i], t);
-    lw[tid] = t;
-  } else if (tid >= 96 && tid < 96 + H + 1) {   // mlp_h : [H+1, H+F] . [rowmean ; y]
-    const int j = tid - 96;
-    const float* r = a.wh + (size_t)j * (H + F);
-    float t = 0.f;
-    for (int i = 0; i < H; ++i) t = __fmaf_rn(__ldg(r + i), rowm[i], t);
-    for (int i = 0; i < F; ++i) t = __fmaf_rn(__ldg(r + H + i), yt[i], t);
-    lh[j] = t;
-  }
-  __syncthreads();
-  if (tid < 32) {            // softmax over the 64 width logits
-    const float v0 = lw[tid], v1 = lw[tid + 32];
-    float m = fmaxf(v0, v1);
+    if (tid < F) { const float y = __ldg(a.e3 + (size_t)pl * F + tid); vecw[64 + tid] = y; vech[H + tid] = y; }
+    const float mean = block_sum_256(s, red) / (float)n;
+    float q = 0.f;
 #pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
-    const float e0 = expf(v0 - m), e1 = expf(v1 - m);
-    float t = e0 + e1;
+    for (int i = 0; i < PER; ++i)
+      { const float d = xv[i] - mean; q = __fmaf_rn(d, d, q); }
+    const float rstd = rsqrtf(block_sum_256(q, red) / (float)n + 1e-5f);
 #pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
-    vw[tid] = e0 / t;
-    vw[tid + 32] = e1 / t;
-  } else if (tid < 64) {     // softmax over the H height logits
-    const int l = tid - 32;
-    const float v0 = l < H ? lh[l] : -INFINITY;
-    float m = v0;
-#pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
-    const float e0 = l < H ? expf(v0 - m) : 0.f;
-    float t = e0;
-#pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
-    if (l < H) vh[l] = e0 / t;
-  }
-  __syncthreads();
-  {
-    const float hl = lh[H], wl = lw[64];
-#pragma unroll
-    for (int i = 0; i < DG_MAXH / 4; ++i)
-      if (i < per) {
-        const int idx = tid + 256 * i, h = idx >> 6, w = idx & 63;
-        const float u = us[h][w];
-        as[h][w] = (vh[h] * u) * hl + (vw[w] * u) * wl;   // same association as DGAB.py:50
+    for (int i = 0; i < PER; ++i)
+      {
+        const int idx = tid + 256 * i;
+        us[idx] = (xv[i] - mean) * rstd * n1w[idx] + n1b[idx];
       }
-  }
-  __syncthreads();
-  // proj over the width axis + residual; thread -> column j = tid&63, rows (tid>>6) + 4*i
-  float o[DG_MAXH / 4];
-  {
-    const int j = tid & 63, h0 = tid >> 6;
-    const float bs = __ldg(a.bp + j);
-#pragma unroll
-    for (int i = 0; i < DG_MAXH / 4; ++i) o[i] = 0.f;
-    for (int w = 0; w < 64; ++w) {
-      const float wv = wpT[w][j];
-#pragma unroll
-      for (int i = 0; i < DG_MAXH / 4; ++i)
-        if (i < per) o[i] = __fmaf_rn(as[h0 + 4 * i][w], wv, o[i]);
+    __syncthreads();
+    if (tid < 64) {
+      float t = 0.f;
+      for (int h = 0; h < H; ++h) t += us[h * 64 + tid];
+      vecw[tid] = t / (float)H;
+    } else if (tid < 64 + H) {
+      const int h = tid - 64;
+      float t = 0.f;
+      for (int w = 0; w < 64; ++w) t += us[h * 64 + w];
+      vech[h] = t / 64.f;
     }
-#pragma unroll
-    for (int i = 0; i < DG_MAXH / 4; ++i)
-      if (i < per) o[i] = xv[i] + (o[i] + bs);    // idx = tid + 256*i  <->  (h0+4i, j): same element as xv[i]
-  }
-  float s2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < DG_MAXH / 4; ++i)
-    if (i < per) { a.x1[plane + tid + 256 * i] = o[i]; s2 += o[i]; }
-  const float mean2 = block_sum_256(s2, red) / (float)n;
-  float q2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < DG_MAXH / 4; ++i)
-    if (i < per) { const float d = o[i] - mean2; q2 = __fmaf_rn(d, d, q2); }
-  const float rstd2 = rsqrtf(block_sum_256(q2, red) / (float)n + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < DG_MAXH / 4; ++i)
-    if (i < per) {
-      const int idx = tid + 256 * i;
-      a.v[plane + idx] = (o[i] - mean2) * rstd2 * __ldg(a.n2w + idx) + __ldg(a.n2b + idx);
+    __syncthreads();
+    {  // width logits 0..63: 4 lanes each;   then logit 64 and the H+1 height logits: 8 lanes each
+      const float t = group_dot<4>(wws + (tid >> 2) * LW, vecw, 64 + F, tid & 3);
+      if ((tid & 3) == 0) lw[tid >> 2] = t;
+      const int o = tid >> 3;                 // 0: lw[64]; 1..H+1: lh[o-1]
+      const bool act = o < H + 2;             // inactive groups run an empty loop: shuffles stay warp-uniform
+      const float* row = !act ? wws : (o == 0) ? (wws + 64 * LW) : (whs + (o - 1) * LH);
+      const float* vec = (o == 0) ? vecw : vech;
+      const float t2 = group_dot<8>(row, vec, !act ? 0 : (o == 0) ? 64 + F : H + F, tid & 7);
+      if (act && (tid & 7) == 0) { if (o == 0) lw[64] = t2; else lh[o - 1] = t2; }
     }
+    __syncthreads();
+    if (tid < 32) {            // softmax over the 64 width logits
+      const float v0 = lw[tid], v1 = lw[tid + 32];
+      float m = fmaxf(v0, v1);
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+      const float e0 = expf(v0 - m), e1 = expf(v1 - m);
+      float t = e0 + e1;
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
+      vw[tid] = e0 / t;
+      vw[tid + 32] = e1 / t;
+    } else if (tid < 64) {     // softmax over the H height logits
+      const int l = tid - 32;
+      const float v0 = l < H ? lh[l] : -INFINITY;
+      float m = v0;
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+      const float e0 = l < H ? expf(v0 - m) : 0.f;
+      float t = e0;
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
+      if (l < H) vh[l] = e0 / t;
+    }
+    __syncthreads();
+    {
+      const float hl = lh[H], wl = lw[64];
+#pragma unroll
+      for (int i = 0; i < PER; ++i)
+        {
+          const int idx = tid + 256 * i, h = idx >> 6, w = idx & 63;
+          const float u = us[idx];
+          as[idx] = (vh[h] * u) * hl + (vw[w] * u) * wl;   // same association as DGAB.py:50
+        }
+    }
+    __syncthreads();
+    // proj over the width axis + residual; thread -> column j = tid&63, rows (tid>>6) + 4*i
+    float o[PER];
+    {
+      const int j = tid & 63, h0 = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) o[i] = 0.f;
+#pragma unroll 2
+      for (int w = 0; w < 64; w += 4) {
+        const float w0 = wpT[(w + 0) * 65 + j], w1 = wpT[(w + 1) * 65 + j];
+        const float w2 = wpT[(w + 2) * 65 + j], w3 = wpT[(w + 3) * 65 + j];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const float4 av = *reinterpret_cast<const float4*>(as + (h0 + 4 * i) * 64 + w);   // warp-wide broadcast
+          o[i] = __fmaf_rn(av.x, w0, o[i]); o[i] = __fmaf_rn(av.y, w1, o[i]);
+          o[i] = __fmaf_rn(av.z, w2, o[i]); o[i] = __fmaf_rn(av.w, w3, o[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) o[i] = xv[i] + (o[i] + bproj);    // idx = tid + 256*i <-> (h0+4i, j)
+    }
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      { a.x1[plane + tid + 256 * i] = o[i]; s2 += o[i]; }
+    const float mean2 = block_sum_256(s2, red) / (float)n;
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      { const float d = o[i] - mean2; q2 = __fmaf_rn(d, d, q2); }
+    const float rstd2 = rsqrtf(block_sum_256(q2, red) / (float)n + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      {
+        const int idx = tid + 256 * i;
+        a.v[plane + idx] = (o[i] - mean2) * rstd2 * n2w[idx] + n2b[idx];
+      }
+    // the next iteration's first shared-memory writes (vecw/vech tails, us) are ordered behind the
+    // block_sum_256 barriers above, after every read of this plane's us / as / vw / vh
+  }
+}
+
+static size_t dgab_plane_smem(int H, int F) {
+  const int n = H * 64;
+  return sizeof(float) * (size_t)(64 * 65 + 65 * (64 + F + 1) + (H + 1) * (H + F + 1) + 6 * n + (64 + F) + (H + F) + 65 +
+                                  (H + 1) + 64 + H + 8 + 16);
 }
 
 // =====================================================================================
@@ -902,7 +956,18 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     a.n1w = P[TPSPP_P_NORM1_W]; a.n1b = P[TPSPP_P_NORM1_B]; a.n2w = P[TPSPP_P_NORM2_W]; a.n2b = P[TPSPP_P_NORM2_B];
     a.wh = P[TPSPP_P_MLP_H_W]; a.ww = P[TPSPP_P_MLP_W_W]; a.wp = P[TPSPP_P_PROJ_W]; a.bp = P[TPSPP_P_PROJ_B];
     a.x1 = W(TPSPP_WS_X1); a.v = W(TPSPP_WS_V); a.H = h; a.F = d.F;
-    dgab_plane_kernel<<<B * 64, 256, 0, st>>>(a);
+    {
+      const size_t smem = dgab_plane_smem(h, d.F);
+      auto kern = h == 8 ? dgab_plane_kernel<2> : h == 16 ? dgab_plane_kernel<4> : h == 24 ? dgab_plane_kernel<6>
+                                                                                            : dgab_plane_kernel<8>;
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      TPSPP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+      if (per_sm < 1) per_sm = 1;
+      int grid = sm_count() * per_sm;
+      if (grid > B * 64) grid = B * 64;
+      kern<<<grid, 256, smem, st>>>(a, B * 64);
+    }
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
     MlpArgs m;
