@@ -361,16 +361,16 @@ __global__ void __launch_bounds__(256, 2) dgab_plane_kernel(DgabArgs a, int npla
   const int H = a.H, F = a.F, tid = threadIdx.x;
   const int n = H * 64;
   const int LW = 64 + F + 1, LH = H + F + 1;        // padded row strides (conflict-free group_dot)
-  float* wpT = dsm;                      // [64][65]
-  float* wws = wpT + 64 * 65;            // [65][LW]
-  float* whs = wws + 65 * LW;            // [H+1][LH]
-  float* n1w = whs + (H + 1) * LH;       // [n] x4
+  float* as = dsm;                       // [H][64]   (float4 reads: keep the 16-byte aligned arrays first)
+  float* us = as + n;                    // [H][64]
+  float* n1w = us + n;                   // [n] x4
   float* n1b = n1w + n;
   float* n2w = n1b + n;
   float* n2b = n2w + n;
-  float* us = n2b + n;                   // [H][64]
-  float* as = us + n;                    // [H][64]
-  float* vecw = as + n;                  // [64+F] = colmean | y
+  float* wpT = n2b + n;                  // [64][65]
+  float* wws = wpT + 64 * 65;            // [65][LW]
+  float* whs = wws + 65 * LW;            // [H+1][LH]
+  float* vecw = whs + (H + 1) * LH;      // [64+F] = colmean | y
   float* vech = vecw + 64 + F;           // [H+F]  = rowmean | y
   float* lw = vech + H + F;              // [65]
   float* lh = lw + 65;                   // [H+1]
