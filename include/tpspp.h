@@ -185,7 +185,8 @@ enum {
   TPSPP_WS_E2, TPSPP_WS_E3 /* en_feat, pre-CBAM */, TPSPP_WS_CBAM, TPSPP_WS_D0, TPSPP_WS_D1, TPSPP_WS_D2,
   TPSPP_WS_DE /* de_feat */, TPSPP_WS_X1, TPSPP_WS_V, TPSPP_WS_DE2 /* de_feat after DGAB */,
   TPSPP_WS_P1 /* p_linear(en) [B,F,128] */,
-  TPSPP_WS_WPREP /* tensor-core weight images */, TPSPP_WS_COUNT
+  TPSPP_WS_WPREP /* tensor-core weight images */, TPSPP_WS_T1, TPSPP_WS_FS /* feat_linear outputs */,
+  TPSPP_WS_HID /* Mlp hidden */, TPSPP_WS_P1IMG /* per-image score weights */, TPSPP_WS_COUNT
 };
 
 TPSPP_API size_t tpspp_head_workspace_bytes(const tpspp_head_cfg* cfg);

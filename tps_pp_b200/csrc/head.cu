@@ -251,6 +251,7 @@ struct LocArgs {
   const float *wp0, *bp0, *wp1, *bp1;            // p_linear.0 [32,64], p_linear.1 [128,32]
   float* c_prime;    // [B,F,2]
   float* p1;         // [B,F,128]
+  float* p1img;      // [B][4 chunks][hi|lo][8 k-groups][32 rows][4] tensor-core operand image of p1, or null
   int F;
 };
 
@@ -302,7 +303,14 @@ __global__ void __launch_bounds__(256) loc_p1_kernel(LocArgs a) {
     float s = 0.f;
 #pragma unroll
     for (int q = 0; q < 32; ++q) s = __fmaf_rn(__ldg(a.wp1 + r * 32 + q), t1[k * 33 + q], s);
-    a.p1[((size_t)b * F + k) * 128 + r] = s + __ldg(a.bp1 + r);
+    const float pv = s + __ldg(a.bp1 + r);
+    a.p1[((size_t)b * F + k) * 128 + r] = pv;
+    if (a.p1img != nullptr) {      // B operand of the score GEMM: row n = control point k, K index = r
+      const float hi = __uint_as_float(__float_as_uint(pv) & 0xFFFFE000u);
+      float* o = a.p1img + (size_t)b * 8192 + (size_t)(r >> 5) * 2048 + ((r >> 2) & 7) * 128 + k * 4 + (r & 3);
+      o[0] = hi;
+      o[1024] = pv - hi;
+    }
   }
   __syncthreads();
   if (tid < 2 * F) {
@@ -783,15 +791,21 @@ static int head_dims(const tpspp_head_cfg* c, HeadDims* d) {
 }
 
 // the 14 convolutions in launch order: weight index, Cin total, kernel size
-struct ConvLayerDesc { int w_idx, Ctot, KS; };
-static const ConvLayerDesc kConvLayers[14] = {
-    {TPSPP_P_DOWN0_W, 32, 1},   {TPSPP_P_DOWN1_W, 32, 1},   {TPSPP_P_DOWN2_W, 64, 1},  {TPSPP_P_DOWN0_1_W, 64, 3},
-    {TPSPP_P_DOWN1_1_W, 64, 3}, {TPSPP_P_DOWNFEAT_W, 192, 1}, {TPSPP_P_ENC0_W, 192, 3}, {TPSPP_P_ENC1_W, 64, 3},
-    {TPSPP_P_ENC2_W, 64, 3},    {TPSPP_P_ENC3_W, 64, 3},    {TPSPP_P_DEC0_W, 64, 3},   {TPSPP_P_DEC1_W, 64, 3},
-    {TPSPP_P_DEC2_W, 64, 3},    {TPSPP_P_DEC3_W, 64, 3}};
+// plus the four linear layers the tensor-core engine runs as 1x1 convolutions over rows
+struct ConvLayerDesc { int w_idx, Ctot, KS, N, NT; };
+constexpr int kNumTcLayers = 18;
+enum { TCL_FLIN0 = 14, TCL_FLIN1 = 15, TCL_FC1 = 16, TCL_FC2 = 17 };
+static const ConvLayerDesc kConvLayers[kNumTcLayers] = {
+    {TPSPP_P_DOWN0_W, 32, 1, 64, 64},   {TPSPP_P_DOWN1_W, 32, 1, 64, 64},    {TPSPP_P_DOWN2_W, 64, 1, 64, 64},
+    {TPSPP_P_DOWN0_1_W, 64, 3, 64, 64}, {TPSPP_P_DOWN1_1_W, 64, 3, 64, 64},  {TPSPP_P_DOWNFEAT_W, 192, 1, 64, 64},
+    {TPSPP_P_ENC0_W, 192, 3, 64, 64},   {TPSPP_P_ENC1_W, 64, 3, 64, 64},     {TPSPP_P_ENC2_W, 64, 3, 64, 64},
+    {TPSPP_P_ENC3_W, 64, 3, 64, 64},    {TPSPP_P_DEC0_W, 64, 3, 64, 64},     {TPSPP_P_DEC1_W, 64, 3, 64, 64},
+    {TPSPP_P_DEC2_W, 64, 3, 64, 64},    {TPSPP_P_DEC3_W, 64, 3, 64, 64},
+    {TPSPP_P_FLIN0_W, 64, 1, 32, 32},   {TPSPP_P_FLIN1_W, 32, 1, 128, 64},   {TPSPP_P_FC1_W, 64, 1, 256, 64},
+    {TPSPP_P_FC2_W, 256, 1, 64, 64}};
 static size_t wprep_total_floats() {
   size_t t = 0;
-  for (int i = 0; i < 14; ++i) t += conv_tc_wprep_floats(kConvLayers[i].Ctot, kConvLayers[i].KS);
+  for (int i = 0; i < kNumTcLayers; ++i) t += conv_tc_wprep_floats(kConvLayers[i].Ctot, kConvLayers[i].KS, kConvLayers[i].N);
   return t;
 }
 
@@ -805,6 +819,10 @@ static void head_offsets(const HeadDims& d, size_t* off, size_t* total) {
   sz[TPSPP_WS_D1] = sz[TPSPP_WS_E1]; sz[TPSPP_WS_D2] = mid; sz[TPSPP_WS_DE] = mid; sz[TPSPP_WS_X1] = mid;
   sz[TPSPP_WS_V] = mid; sz[TPSPP_WS_DE2] = mid; sz[TPSPP_WS_P1] = B * d.F * 128;
   sz[TPSPP_WS_WPREP] = wprep_total_floats();
+  sz[TPSPP_WS_T1] = B * d.h * d.w * 32;          // feat_linear.0 output, rows x 32
+  sz[TPSPP_WS_FS] = B * d.h * d.w * 128;         // feat_linear.1 output, rows x 128
+  sz[TPSPP_WS_HID] = mid * 4;                    // Mlp hidden, rows x 256
+  sz[TPSPP_WS_P1IMG] = B * 8192;                 // per-image UMMA operand image of p1 (hi | lo)
   size_t cur = 0;
   for (int i = 0; i < TPSPP_WS_COUNT; ++i) {
     off[i] = cur;
@@ -822,10 +840,11 @@ static int run_conv(int KS, ConvSrc s0, ConvSrc s1, ConvSrc s2, const float* w, 
                     const float* wprep = nullptr) {
   ConvArgs a;
   a.out_nhwc = out_nhwc;
+  a.act = CONV_ACT_RELU; a.act_scale = 1.f; a.Cout = 64; a.wimg_stride = 0;
   a.src[0] = s0; a.src[1] = s1; a.src[2] = s2;
   a.weight = w; a.bias = bias; a.skip = skip; a.out = out;
   a.B = B; a.Ho = Ho; a.Wo = Wo; a.Ctot = s0.C + s1.C + s2.C; a.sh = sh; a.sw = sw; a.pad = (KS == 3) ? 1 : 0;
-  if (wprep != nullptr && conv_tc_eligible(a, KS)) return run_conv_tc(KS, a, wprep, st);
+  if (wprep != nullptr && conv_tc_eligible(a, KS)) return run_conv_tc(KS, a, wprep, 64, st);
   const long long M = (long long)B * Ho * Wo;
   const unsigned grid = (unsigned)((M + CV_TM - 1) / CV_TM);
   if (KS == 1) conv_ffma_kernel<1><<<grid, 256, CV_SMEM, st>>>(a);
@@ -893,19 +912,20 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   constexpr int NCHW = 0, NHWC = 1;   // internal activations are channels-last; boundary tensors stay NCHW
   const int B = d.B, h = d.h, w = d.w, H2 = d.H2, W2 = d.W2;
 
-  // tensor-core mode: one tiny launch re-lays every conv weight as its UMMA operand image (hi/lo split)
-  const float* wp[14];
-  for (int i = 0; i < 14; ++i) wp[i] = nullptr;
-  if (cfg->precision == TPSPP_HEAD_TC) {
-    WPrepLayer L[14];
+  // tensor-core mode: one tiny launch re-lays every weight matrix as its UMMA operand image (hi/lo split)
+  const float* wp[kNumTcLayers];
+  for (int i = 0; i < kNumTcLayers; ++i) wp[i] = nullptr;
+  const bool tc = cfg->precision == TPSPP_HEAD_TC;
+  if (tc) {
+    WPrepLayer L[kNumTcLayers];
     float* cur = W(TPSPP_WS_WPREP);
-    for (int i = 0; i < 14; ++i) {
+    for (int i = 0; i < kNumTcLayers; ++i) {
       L[i].w = P[kConvLayers[i].w_idx]; L[i].out = cur; L[i].Ctot = kConvLayers[i].Ctot;
-      L[i].taps = kConvLayers[i].KS * kConvLayers[i].KS;
+      L[i].taps = kConvLayers[i].KS * kConvLayers[i].KS; L[i].N = kConvLayers[i].N; L[i].NT = kConvLayers[i].NT;
       wp[i] = cur;
-      cur += conv_tc_wprep_floats(kConvLayers[i].Ctot, kConvLayers[i].KS);
+      cur += conv_tc_wprep_floats(kConvLayers[i].Ctot, kConvLayers[i].KS, kConvLayers[i].N);
     }
-    rc = conv_tc_prepare_weights(L, 14, st);
+    rc = conv_tc_prepare_weights(L, kNumTcLayers, st);
     if (rc != TPSPP_OK) return rc;
   }
 #define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != TPSPP_OK) return rc; } while (0)
@@ -944,6 +964,7 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     a.wc = P[TPSPP_P_LOC2_W]; a.bc = P[TPSPP_P_LOC2_B];
     a.wp0 = P[TPSPP_P_PLIN0_W]; a.bp0 = P[TPSPP_P_PLIN0_B]; a.wp1 = P[TPSPP_P_PLIN1_W]; a.bp1 = P[TPSPP_P_PLIN1_B];
     a.c_prime = c_prime; a.p1 = W(TPSPP_WS_P1); a.F = d.F;
+    a.p1img = (tc && d.F == 32) ? W(TPSPP_WS_P1IMG) : nullptr;
     const size_t smem = (size_t)(d.F * 65 + d.F * 256 + 2 * d.F + d.F * 33) * sizeof(float);
     loc_p1_kernel<<<B, 256, smem, st>>>(a);
     count_launch();
@@ -970,15 +991,54 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     }
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
-    MlpArgs m;
-    m.v = W(TPSPP_WS_V); m.x1 = W(TPSPP_WS_X1); m.w1 = P[TPSPP_P_FC1_W]; m.b1 = P[TPSPP_P_FC1_B];
-    m.w2 = P[TPSPP_P_FC2_W]; m.b2 = P[TPSPP_P_FC2_B]; m.out = W(TPSPP_WS_DE2); m.R = (long long)B * 64 * h;
-    dgab_mlp_kernel<<<(unsigned)((m.R + 127) / 128), 256, ML_SMEM, st>>>(m);
-    count_launch();
-    TPSPP_CHECK_CUDA(cudaGetLastError());
+    const long long R = (long long)B * 64 * h;
+    if (tc) {
+      // Mlp over the width axis as two row GEMMs on the tensor cores: rows = (b, c, h), K = w
+      ConvArgs g;
+      memset(&g, 0, sizeof(g));
+      g.src[0] = mk_src(W(TPSPP_WS_V), 64, 1, (int)R, NHWC); g.src[1] = none; g.src[2] = none;
+      g.B = 1; g.Ho = 1; g.Wo = (int)R; g.Ctot = 64; g.sh = 1; g.sw = 1; g.pad = 0; g.out_nhwc = 1;
+      g.bias = P[TPSPP_P_FC1_B]; g.skip = nullptr; g.out = W(TPSPP_WS_HID); g.act = CONV_ACT_GELU; g.act_scale = 1.f;
+      g.Cout = 256; g.wimg_stride = 0; g.weight = nullptr;
+      rc = run_conv_tc(1, g, wp[TCL_FC1], 64, st);
+      if (rc != TPSPP_OK) return rc;
+      g.src[0] = mk_src(W(TPSPP_WS_HID), 256, 1, (int)R, NHWC); g.Ctot = 256;
+      g.bias = P[TPSPP_P_FC2_B]; g.skip = W(TPSPP_WS_X1); g.out = W(TPSPP_WS_DE2); g.act = CONV_ACT_NONE; g.Cout = 64;
+      rc = run_conv_tc(1, g, wp[TCL_FC2], 64, st);
+      if (rc != TPSPP_OK) return rc;
+    } else {
+      MlpArgs m;
+      m.v = W(TPSPP_WS_V); m.x1 = W(TPSPP_WS_X1); m.w1 = P[TPSPP_P_FC1_W]; m.b1 = P[TPSPP_P_FC1_B];
+      m.w2 = P[TPSPP_P_FC2_W]; m.b2 = P[TPSPP_P_FC2_B]; m.out = W(TPSPP_WS_DE2); m.R = R;
+      dgab_mlp_kernel<<<(unsigned)((m.R + 127) / 128), 256, ML_SMEM, st>>>(m);
+      count_launch();
+      TPSPP_CHECK_CUDA(cudaGetLastError());
+    }
   }
   // attention score (tps_pp.py:303-312)
-  {
+  if (tc && d.F == 32) {
+    // three chained 1x1 contractions on the tensor cores: feat_linear.0, feat_linear.1, then the
+    // "QK^T" with per-image weights p1[b] and the tanh(64^-0.5 * .) epilogue
+    const int n = h * w;
+    ConvArgs g;
+    memset(&g, 0, sizeof(g));
+    g.src[1] = none; g.src[2] = none;
+    g.sh = 1; g.sw = 1; g.pad = 0; g.out_nhwc = 1; g.skip = nullptr; g.act_scale = 1.f; g.wimg_stride = 0;
+    g.src[0] = mk_src(W(TPSPP_WS_DE2), 64, h, w, NCHW); g.B = B; g.Ho = h; g.Wo = w; g.Ctot = 64;
+    g.bias = P[TPSPP_P_FLIN0_B]; g.out = W(TPSPP_WS_T1); g.act = CONV_ACT_NONE; g.Cout = 32;
+    rc = run_conv_tc(1, g, wp[TCL_FLIN0], 32, st);
+    if (rc != TPSPP_OK) return rc;
+    g.src[0] = mk_src(W(TPSPP_WS_T1), 32, h, w, NHWC); g.Ctot = 32;
+    g.bias = P[TPSPP_P_FLIN1_B]; g.out = W(TPSPP_WS_FS); g.Cout = 128;
+    rc = run_conv_tc(1, g, wp[TCL_FLIN1], 64, st);
+    if (rc != TPSPP_OK) return rc;
+    g.src[0] = mk_src(W(TPSPP_WS_FS), 128, h, w, NHWC); g.Ctot = 128;
+    g.bias = nullptr; g.out = pc_score; g.Cout = 32; g.act = CONV_ACT_TANH; g.act_scale = 0.125f;   // 64^-0.5 (tps_pp.py:247)
+    g.wimg_stride = 8192;
+    (void)n;
+    rc = run_conv_tc(1, g, W(TPSPP_WS_P1IMG), 32, st);
+    if (rc != TPSPP_OK) return rc;
+  } else {
     ScoreArgs a;
     a.de2 = W(TPSPP_WS_DE2); a.p1 = W(TPSPP_WS_P1);
     a.wf0 = P[TPSPP_P_FLIN0_W]; a.bf0 = P[TPSPP_P_FLIN0_B]; a.wf1 = P[TPSPP_P_FLIN1_W]; a.bf1 = P[TPSPP_P_FLIN1_B];

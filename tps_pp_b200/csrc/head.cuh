@@ -17,21 +17,27 @@ struct ConvArgs {
   float* out;            // [B,64,Ho,Wo]
   int B, Ho, Wo, Ctot, sh, sw, pad;
   int out_nhwc;          // layout of out (and skip)
+  // used by the tensor-core engine only (the FFMA kernel is 64-channel conv + bias + ReLU):
+  int act;               // CONV_ACT_*
+  float act_scale;       // tanh(scale * x)
+  int Cout;              // channels of the output tensor (column blocks of NT go to grid.y)
+  long long wimg_stride; // floats between per-image weight images (0: weights shared by all images)
 };
+enum { CONV_ACT_RELU = 0, CONV_ACT_NONE = 1, CONV_ACT_GELU = 2, CONV_ACT_TANH = 3 };
 
 
 // tcgen05 implicit-GEMM convolution (head_tc.cu).  `wprep` is the layer's weight image produced by
 // conv_tc_prepare_weights (3xTF32 hi/lo split, UMMA core-matrix order).
 bool conv_tc_eligible(const ConvArgs& a, int KS);
-int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, cudaStream_t st);
-size_t conv_tc_wprep_floats(int Ctot, int KS);           // floats needed for one layer's image
+int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st);
+size_t conv_tc_wprep_floats(int Ctot, int KS, int N);    // floats needed for one layer's image (N output rows)
 
 struct WPrepLayer {
-  const float* w;   // [64][Ctot][KS*KS]
+  const float* w;   // [N][Ctot][KS*KS]
   float* out;
-  int Ctot, taps;
+  int Ctot, taps, N, NT;
 };
-constexpr int WPREP_MAX_LAYERS = 16;
+constexpr int WPREP_MAX_LAYERS = 20;
 int conv_tc_prepare_weights(const WPrepLayer* layers, int nlayers, cudaStream_t st);
 
 }  // namespace tpspp

@@ -80,8 +80,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 // bounded mbarrier wait: a descriptor/pipeline bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 28); ++it)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
