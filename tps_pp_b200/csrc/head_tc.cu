@@ -164,10 +164,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(ConvTcArgs t) {
     for (int i = 0; i < (NHWC_SRC ? 4 : 1); ++i) gq4[i] = geo[lp + 4 * i];
 
     int tap = 0, cin0 = 0;       // running (tap, first input channel) of the chunk: no divisions in the loop
-    float4 v[4];
-    // gather(): issue the global loads of the next chunk into v (software pipeline: called right after the
-    // previous chunk's registers were stored, so the loads fly while the other stage is being consumed)
-    auto gather = [&]() {
+    float4 va[4], vb[4];
+    // gather(v): issue the global loads of the next chunk into v.  Two register sets are kept in flight
+    // (chunks c+1 and c+2), so a load has two full iterations to land before its data is split and stored.
+    auto gather = [&](float4 (&v)[4]) {
       const int dy = tap / KS, dx = tap - dy * KS;
       int s = 0, c0 = cin0;
       if (c0 >= a.src[0].C) {
@@ -208,8 +208,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(ConvTcArgs t) {
       }
     };
 
-    gather();
-    for (int ch = 0; ch < nchunks; ++ch) {
+    auto produce = [&](int ch, float4 (&v)[4]) {
       const int buf = ch & 1;
       // the MMAs that read this stage two chunks ago must have completed
       if (ch >= 2) mbar_wait_bounded(&bars[buf], (uint32_t)(((ch >> 1) - 1) & 1));
@@ -226,10 +225,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(ConvTcArgs t) {
         *reinterpret_cast<float4*>(st + off) = hi;
         *reinterpret_cast<float4*>(st + TC_A_BYTES + off) = lo;
       }
-      if (ch + 1 < nchunks) gather();
+      if (ch + 2 < nchunks) gather(v);   // refill this register set with chunk ch+2
       fence_proxy_async();     // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&fbars[buf]);
+    };
+    gather(va);
+    if (nchunks > 1) gather(vb);
+    for (int ch = 0; ch < nchunks; ch += 2) {
+      produce(ch, va);
+      if (ch + 1 < nchunks) produce(ch + 1, vb);
     }
     const int last = nchunks - 1;
     mbar_wait_bounded(&bars[last & 1], (uint32_t)((last >> 1) & 1));   // the last commit covers every MMA
