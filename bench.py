@@ -33,6 +33,17 @@ WARP_BYTES_PER_IMG = 1048576 + 262144 + 131072 + 256 + 262144 + 262144
 WARP_CONST_BYTES = 131072 + 4900 + 8192
 
 
+def _warp_traffic():
+    """dram__bytes_read+write of one warp launch from the committed ncu capture (bench never runs under ncu)."""
+    path = os.path.join(ROOT, "profiles", "warp_traffic.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return int(d["dram_bytes_per_launch"]) if int(d.get("batch", 0)) == BATCH_PER_GPU else None
+    except Exception:
+        return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -277,7 +288,7 @@ def run_ours(args):
                        "l2": "inputs 302 MB/step > 126 MB L2 (no flush needed)",
                        "native_stages": native_stages, "weights": "trained-like synthetic (seed 3)", "head": args.head},
             "roofline": {"kernel": "warp_fwd_staged_kernel<dual>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": _warp_traffic(), "peak_source": peak_src,
                          "bytes_per_launch": warp_bytes, "avg_launch_ms": warp_mean_ms,
                          "warp_only_img_per_s": B / (warp_mean_ms * 1e-3)},
             "cpu_baseline": cpu,
