@@ -36,7 +36,7 @@ def _run_native(sd, x, o0, o1, precision=N.HEAD_FP32):
                   d0=(b, 64, 4, 16), d1=(b, 64, 8, 32), d2=(b, 64, 16, 64), de=(b, 64, 16, 64), x1=(b, 64, 16, 64),
                   v=(b, 64, 16, 64), de2=(b, 64, 16, 64), p1=(b, 32, 128))
     got = {}
-    nhwc = {"f0", "f1", "f2", "a0", "a1", "e0", "e1", "e2", "d0", "d1", "d2"}    # internal channels-last slots
+    nhwc = set()    # conv intermediates are NCHW (row-major slots t1/fs/hid are not compared here)
     for name, shp in shapes.items():
         n = int(np.prod(shp))
         flat = ws[off[name]: off[name] + 4 * n].view(torch.float32)
@@ -65,7 +65,7 @@ def test_head_stages_vs_oracle(native_lib, batch, seed, precision):
         err = mx(got[name], r64[name])
         report.append(f"{name:10s} |ours-ref64|={err:.2e} |ref32-ref64|={floor:.2e} scale={scale:.2f}")
         # tensor-core accumulators truncate instead of rounding to nearest: ~K/8 * 2^-24 relative per layer
-        rel = 1e-6 if precision == N.HEAD_FP32 else 2e-5
+        rel = 1e-6 if precision == N.HEAD_FP32 else 5e-5
         assert err <= 4 * floor + rel * max(scale, 1.0), "\n".join(report)
     print("\n".join(report))
     assert mx(got["c_prime"], r64["c_prime"]) <= 1e-4            # north_star tolerance for control points
@@ -87,7 +87,7 @@ def test_head_stock_init_and_module_path(native_lib, golden):
     e_o = mx(r["output"], g["ref64_output"]); e_m = mx(r["mp_img"], g["ref64_mp_img"])
     print(f"native head: output |ours-ref64|={e_o:.3e} (floor {floor_o:.3e}); mp_img {e_m:.3e} (floor {floor_m:.3e})")
     assert e_o <= max(1e-5, 4 * floor_o) and e_m <= max(1e-5, 4 * floor_m)
-    assert mx(r["pc_score"], g["ref64_pc_score"]) <= 5e-5
+    assert mx(r["pc_score"], g["ref64_pc_score"]) <= 2e-4     # default head = tensor cores (3xTF32)
     # stock init (fc2.weight == 0): C' must be exactly the bias lattice
     torch.manual_seed(0)
     m2 = T.TPS_PP().to(DEV).eval()

@@ -36,7 +36,7 @@ def test_tps_pp_forward_vs_reference_golden(golden, native_lib):
     assert set(r.keys()) == {"output", "logits", "mp_img", "pc_score"} and r["logits"] is None
     assert r["output"].shape == (2, 64, 16, 64) and r["mp_img"].shape == (2, 64, 16, 64)
     assert r["pc_score"].shape == (2, 1024, 32)
-    assert mx(r["pc_score"], g["ref64_pc_score"]) <= 5e-5
+    assert mx(r["pc_score"], g["ref64_pc_score"]) <= 2e-4     # default head: tcgen05 3xTF32 (fp32 mode: 2e-5)
     floor_o = mx(g["ref32_output"], g["ref64_output"])
     floor_m = mx(g["ref32_mp_img"], g["ref64_mp_img"])
     e_o, e_m = mx(r["output"], g["ref64_output"]), mx(r["mp_img"], g["ref64_mp_img"])

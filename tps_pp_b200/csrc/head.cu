@@ -909,7 +909,10 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   head_offsets(d, off, &total);
   auto W = [&](int i) { return reinterpret_cast<float*>((char*)workspace + off[i]); };
   const ConvSrc none = mk_src(nullptr, 0, 1, 1, 0);
-  constexpr int NCHW = 0, NHWC = 1;   // internal activations are channels-last; boundary tensors stay NCHW
+  // Convolution activations stay NCHW: a producer thread of the tensor-core kernel owns one pixel, so its 16
+  // per-chunk channel loads are coalesced across the warp and go registers -> TMEM without a shuffle.  Row-major
+  // ("NHWC") sources are used by the linear layers only.
+  constexpr int NCHW = 0, NHWC = 1;
   const int B = d.B, h = d.h, w = d.w, H2 = d.H2, W2 = d.W2;
 
   // tensor-core mode: one tiny launch re-lays every weight matrix as its UMMA operand image (hi/lo split)
@@ -929,32 +932,32 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     if (rc != TPSPP_OK) return rc;
   }
 #define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != TPSPP_OK) return rc; } while (0)
-  // down0/1/2 (tps_pp.py:581-583): NCHW boundary inputs -> channels-last intermediates
-  RUN(1, mk_src(o0, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), NHWC, B, H2, W2, 1, 1, st, wp[0]);
-  RUN(1, mk_src(o1, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), NHWC, B, H2, W2, 1, 1, st, wp[1]);
-  RUN(1, mk_src(x, 64, h, w, NCHW), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), NHWC, B, h, w, 1, 1, st, wp[2]);
+  // down0/1/2 (tps_pp.py:581-583): 
+  RUN(1, mk_src(o0, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), NCHW, B, H2, W2, 1, 1, st, wp[0]);
+  RUN(1, mk_src(o1, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), NCHW, B, H2, W2, 1, 1, st, wp[1]);
+  RUN(1, mk_src(x, 64, h, w, NCHW), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), NCHW, B, h, w, 1, 1, st, wp[2]);
   // down0_1 / down1_1: 3x3 stride 2 (tps_pp.py:584)
-  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NHWC), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), NHWC, B, h, w, 2, 2, st, wp[3]);
-  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2, NHWC), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), NHWC, B, h, w, 2, 2, st, wp[4]);
+  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), NCHW, B, h, w, 2, 2, st, wp[3]);
+  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), NCHW, B, h, w, 2, 2, st, wp[4]);
   // grid(): down_feat(cat(f0, f1, up2(f2))) (tps_pp.py:560-562,585) -> feat_grid in the boundary layout (warp input)
-  RUN(1, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NHWC), mk_src(W(TPSPP_WS_F1), 64, H2, W2, NHWC), mk_src(W(TPSPP_WS_F2), 64, h, w, NHWC, 2, 2),
+  RUN(1, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW), mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW), mk_src(W(TPSPP_WS_F2), 64, h, w, NCHW, 2, 2),
       P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, NCHW, B, H2, W2, 1, 1, st, wp[5]);
   // MSFA encoder (tps_pp.py:158-160): cat(a0, a1, f2) -> e0 -> e1 -> e2 -> e3
-  RUN(3, mk_src(W(TPSPP_WS_A0), 64, h, w, NHWC), mk_src(W(TPSPP_WS_A1), 64, h, w, NHWC), mk_src(W(TPSPP_WS_F2), 64, h, w, NHWC),
-      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), NHWC, B, h, w, 1, 1, st, wp[6]);
-  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w, NHWC), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), NHWC, B, d.h1, d.w1, 2, 2, st, wp[7]);
-  RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1, NHWC), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), NHWC, B, d.h2, d.w2, d.ps, d.ps, st, wp[8]);
-  RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2, NHWC), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), NCHW, B, d.py, d.px, 2, 1, st, wp[9]);
+  RUN(3, mk_src(W(TPSPP_WS_A0), 64, h, w, NCHW), mk_src(W(TPSPP_WS_A1), 64, h, w, NCHW), mk_src(W(TPSPP_WS_F2), 64, h, w, NCHW),
+      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), NCHW, B, h, w, 1, 1, st, wp[6]);
+  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w, NCHW), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), NCHW, B, d.h1, d.w1, 2, 2, st, wp[7]);
+  RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1, NCHW), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), NCHW, B, d.h2, d.w2, d.ps, d.ps, st, wp[8]);
+  RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2, NCHW), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), NCHW, B, d.py, d.px, 2, 1, st, wp[9]);
   // CBAM on the deepest map (tps_pp.py:163)
   cbam_kernel<<<B, 256, 0, st>>>(W(TPSPP_WS_E3), W(TPSPP_WS_CBAM), P[TPSPP_P_CBAM_MLP0_W], P[TPSPP_P_CBAM_MLP2_W],
                                  P[TPSPP_P_CBAM_SP_W], P[TPSPP_P_CBAM_SP_B], d.py, d.px);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   // decoder (tps_pp.py:165-168): upsample + conv + skip
-  RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, NCHW, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), NHWC, B, d.h2, d.w2, 1, 1, st, wp[10]);
-  RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, NHWC, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), NHWC, B, d.h1, d.w1, 1, 1, st, wp[11]);
-  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, NHWC, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), NHWC, B, h, w, 1, 1, st, wp[12]);
-  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w, NHWC), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), NCHW, B, h, w, 1, 1, st, wp[13]);
+  RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, NCHW, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), NCHW, B, d.h2, d.w2, 1, 1, st, wp[10]);
+  RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, NCHW, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), NCHW, B, d.h1, d.w1, 1, 1, st, wp[11]);
+  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, NCHW, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), NCHW, B, h, w, 1, 1, st, wp[12]);
+  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w, NCHW), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), NCHW, B, h, w, 1, 1, st, wp[13]);
 #undef RUN
   // localisation + p_linear (tps_pp.py:321-323, 305)
   {

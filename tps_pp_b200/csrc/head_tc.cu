@@ -292,6 +292,212 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(ConvTcArgs t) {
   if (warp == 0) tmem_dealloc(tmem_d, tc_tmem_cols(NT));
 }
 
+// ------------------------------------------------------------------------------------------------
+// TS variant for the convolutions (NCHW sources, 64 output channels): the A operand never touches
+// shared memory.  With N = 64 an SS-mode UTCHMMA re-reads its 128x8 A slice from shared memory on
+// every issue (6 KB per 32-cycle MMA = 192 B/clk > the 128 B/clk of the shared-memory pipe, three
+// times per k-step for 3xTF32), which capped the SS kernel at ~30 % tensor-pipe activity.  Here each
+// producer thread owns one output pixel = one TMEM lane: 16 coalesced channel loads -> hi/lo split in
+// registers -> two tcgen05.st (16 columns each) into a 2-stage A ring in tensor memory; the MMA warp
+// issues tcgen05.mma with A from TMEM and B (the TMA-loaded weight image) from shared memory.
+// TMEM columns (256 per CTA, 2 CTAs/SM): D_main [0,64) | D_corr [64,128) | A stage s: hi 128+64s, lo +32.
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_B_BYTES = tc_b_bytes(64);                 // per part
+constexpr int TS_STAGE = 2 * TS_B_BYTES;                   // weight image hi | lo
+constexpr int TS_SMEM = 2 * TS_STAGE + 64 + TC_TM * 16;
+
+template <int KS>
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
+  constexpr int NT = 64;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TS_STAGE);   // "empty"
+  uint64_t* wbars = bars + 2;
+  uint64_t* fbars = bars + 4;                                          // "full"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  int4* geo = reinterpret_cast<int4*>(smem + 2 * TS_STAGE + 64);
+  const ConvArgs& a = t.c;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    mbar_init(&wbars[0], 1); mbar_init(&wbars[1], 1);
+    mbar_init(&fbars[0], TC_PRODUCERS / 32); mbar_init(&fbars[1], TC_PRODUCERS / 32);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int HoWo = a.Ho * a.Wo;
+  const long long Mtot = (long long)a.B * HoWo;
+  const long long m_base = (long long)blockIdx.x * TC_TM;
+  const int Ctot = a.Ctot;
+  const int nchunks = (Ctot * KS * KS) / TC_KC;
+  const float* wimg = t.wprep;
+
+  if (tid < TC_TM) {
+    const long long lm = m_base + tid;
+    int4 gq = make_int4(0, 0, 0, 0);
+    if (lm < Mtot) {
+      const int lb = (int)(lm / HoWo);
+      const int r = (int)(lm - (long long)lb * HoWo);
+      const int oy = r / a.Wo, ox = r - oy * a.Wo;
+      gq = make_int4(lb, oy * a.sh - a.pad, ox * a.sw - a.pad, 1);
+    }
+    geo[tid] = gq;
+  }
+  __syncthreads();
+  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
+  if (warp == TC_PRODUCERS / 32) {
+    // ===== MMA issuer warp =====
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int buf = ch & 1;
+      const uint32_t ph = (uint32_t)((ch >> 1) & 1);
+      mbar_wait_bounded(&fbars[buf], ph);      // A of this chunk is in tensor memory
+      mbar_wait_bounded(&wbars[buf], ph);      // weight image landed (TMA)
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t b_hi = smem_u32(smem) + (uint32_t)(buf * TS_STAGE), b_lo = b_hi + TS_B_BYTES;
+        const uint32_t a_hi = tmem_d + 128 + (uint32_t)(buf * 64), a_lo = a_hi + 32;
+#pragma unroll
+        for (int j = 0; j < TC_KC / 8; ++j) {
+          const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
+          const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (NT * 16), NT * 16, 128);
+          umma_ts_tf32(tmem_d + 64, a_lo + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);   // corrections
+          umma_ts_tf32(tmem_d + 64, a_hi + j * 8, dbl, IDESC, 1u);
+          umma_ts_tf32(tmem_d, a_hi + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);        // main
+        }
+        umma_commit(&bars[buf]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== producer warps: thread = output pixel = TMEM lane (warp w owns lanes 32*(w%4)..), the two
+    //       warps that share a lane quarter take the chunk's channels [0,16) and [16,32) =====
+    const int row = (warp & 3) * 32 + lane;
+    const int kh = warp >> 2;
+    const int4 gq = geo[row];
+    const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    // running (tap, source, channel) state of the next chunk to gather -- uniform over the CTA, advanced
+    // incrementally so the loop has no divisions and touches the source descriptors only when the source changes
+    int tap = 0, cin0 = 0, c_in = 0, s_idx = 0;
+    const float* t_base = nullptr;   // this thread's first channel of the current source, pixel (0,0) of its image
+    int s_C = 0, s_W = 0, s_uh = 1, s_uw = 1, lim_y = 0, lim_x = 0;
+    size_t s_plane = 0;
+    auto load_src = [&](int si) {
+      const float* sp = si == 0 ? a.src[0].ptr : (si == 1 ? a.src[1].ptr : a.src[2].ptr);
+      s_C = si == 0 ? a.src[0].C : (si == 1 ? a.src[1].C : a.src[2].C);
+      const int SH = si == 0 ? a.src[0].H : (si == 1 ? a.src[1].H : a.src[2].H);
+      s_W = si == 0 ? a.src[0].W : (si == 1 ? a.src[1].W : a.src[2].W);
+      s_uh = si == 0 ? a.src[0].uh : (si == 1 ? a.src[1].uh : a.src[2].uh);
+      s_uw = si == 0 ? a.src[0].uw : (si == 1 ? a.src[1].uw : a.src[2].uw);
+      s_plane = (size_t)SH * s_W;
+      lim_y = SH * s_uh; lim_x = s_W * s_uw;
+      t_base = sp + ((size_t)gq.x * s_C + kh * 16) * s_plane;
+    };
+    load_src(0);
+    float va[16], vb[16];
+    auto gather = [&](float (&v)[16]) {
+      const int dy = tap / KS, dx = tap - dy * KS;
+      const int iy = gq.y + dy, ix = gq.z + dx;
+      const bool ok = gq.w && iy >= 0 && ix >= 0 && iy < lim_y && ix < lim_x;
+      const int sy = (s_uh == 2) ? (iy >> 1) : iy, sx = (s_uw == 2) ? (ix >> 1) : ix;
+      const float* q = t_base + (size_t)c_in * s_plane + (ok ? sy * s_W + sx : 0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] = ok ? __ldg(q) : 0.f;
+        q += s_plane;
+      }
+      c_in += TC_KC; cin0 += TC_KC;
+      if (c_in >= s_C) {                 // next chunk starts in another source tensor (or the next tap)
+        c_in = 0;
+        if (cin0 >= Ctot) { cin0 = 0; ++tap; s_idx = 0; } else { ++s_idx; }
+        load_src(s_idx);
+      }
+    };
+    auto produce = [&](int ch, float (&v)[16]) {
+      const int buf = ch & 1;
+      if (ch >= 2) {
+        mbar_wait_bounded(&bars[buf], (uint32_t)(((ch >> 1) - 1) & 1));   // MMAs of chunk ch-2 have read the stage
+        tc_fence_after();
+      }
+      if (tid == 0) {
+        unsigned char* st = smem + buf * TS_STAGE;
+        mbar_arrive_expect_tx(&wbars[buf], 2 * TS_B_BYTES);
+        bulk_g2s(st, wimg + (size_t)ch * (2 * NT * TC_KC), 2 * TS_B_BYTES, &wbars[buf], policy_evict_last());
+      }
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+        lo[i] = v[i] - hi[i];
+      }
+      const uint32_t col = 128u + (uint32_t)(buf * 64 + kh * 16);
+      tmem_st16(lane_addr + col, hi);
+      tmem_st16(lane_addr + col + 32, lo);
+      if (ch + 2 < nchunks) gather(v);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&fbars[buf]);
+    };
+    gather(va);
+    if (nchunks > 1) gather(vb);
+    for (int ch = 0; ch < nchunks; ch += 2) {
+      produce(ch, va);
+      if (ch + 1 < nchunks) produce(ch + 1, vb);
+    }
+    const int last = nchunks - 1;
+    mbar_wait_bounded(&bars[last & 1], (uint32_t)((last >> 1) & 1));
+    tc_fence_after();
+
+    // ---- epilogue ----
+    const int wq = warp & 3, half = warp >> 2;
+    const long long m = m_base + wq * 32 + lane;
+    const int b = (m < Mtot) ? (int)(m / HoWo) : 0;
+    const int rem = (m < Mtot) ? (int)(m - (long long)b * HoWo) : 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      float acc[16], part[16];
+      const uint32_t taddr = lane_addr + (uint32_t)(half * 32 + pass * 16);
+      tmem_ld_cols<16>(taddr, acc);
+      tmem_ld_cols<16>(taddr + 64, part);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] += part[j];
+      const int cb = half * 32 + pass * 16;
+      if (m < Mtot && a.out_nhwc) {
+        const size_t o0 = (size_t)m * a.Cout + cb;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias != nullptr) bs = __ldg(reinterpret_cast<const float4*>(a.bias + cb + j));
+          float4 r = make_float4(tc_act(acc[j] + bs.x, a.act, a.act_scale), tc_act(acc[j + 1] + bs.y, a.act, a.act_scale),
+                                 tc_act(acc[j + 2] + bs.z, a.act, a.act_scale), tc_act(acc[j + 3] + bs.w, a.act, a.act_scale));
+          if (a.skip != nullptr) {
+            const float4 sk = __ldg(reinterpret_cast<const float4*>(a.skip + o0 + j));
+            r.x += sk.x; r.y += sk.y; r.z += sk.z; r.w += sk.w;
+          }
+          *reinterpret_cast<float4*>(a.out + o0 + j) = r;
+        }
+      } else if (m < Mtot) {
+        const size_t o0 = ((size_t)b * a.Cout + cb) * HoWo + rem;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float r = tc_act(acc[j] + (a.bias != nullptr ? __ldg(a.bias + cb + j) : 0.f), a.act, a.act_scale);
+          const size_t o = o0 + (size_t)j * HoWo;
+          if (a.skip != nullptr) r += __ldg(a.skip + o);
+          a.out[o] = r;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
 // weight image: for output row n (column block n / NT) and k = tap*Ctot + cin:
 //   out[((blk*nchunks + k/32)*2 + part) * (NT*32) + ((k/4)%8) * (NT*4) + (n%NT)*4 + k%4]
 struct WPrepArgs {
@@ -368,6 +574,21 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
   const long long M = (long long)a.B * a.Ho * a.Wo;
   dim3 grid((unsigned)((M + TC_TM - 1) / TC_TM), (unsigned)(a.Cout / NT));
   const bool nhwc = a.src[0].nhwc != 0;
+  if (!nhwc && NT == 64 && a.Cout == 64 && a.wimg_stride == 0) {    // convolutions: A operand through TMEM
+    static thread_local int ts_dev = -1;
+    int dev = 0;
+    TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+    if (ts_dev != dev) {
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      ts_dev = dev;
+    }
+    if (KS == 1) conv_ts_kernel<1><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
+    else conv_ts_kernel<3><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+    return TPSPP_OK;
+  }
   if (KS == 3) return nhwc ? launch_tc<3, true, 64>(t, grid, st) : launch_tc<3, false, 64>(t, grid, st);
   if (NT == 64) return nhwc ? launch_tc<1, true, 64>(t, grid, st) : launch_tc<1, false, 64>(t, grid, st);
   return nhwc ? launch_tc<1, true, 32>(t, grid, st) : launch_tc<1, false, 32>(t, grid, st);
