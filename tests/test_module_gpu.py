@@ -145,3 +145,25 @@ def test_tps_preprocessor_vs_oracle(native_lib):
     cc = O.classical_constants(20, (32, 100))
     o64, _ = O.classical_warp(img, cp.cpu().numpy(), cc, (32, 100), dtype=np.float64)
     assert mx(out, o64) <= 1e-5
+
+
+def test_large_shard_is_batch_independent(native_lib):
+    """BASELINE config 5 (global batch 8192 = 1024 images per GPU on 8 GPUs): one shard-sized call must equal
+    the same images pushed through in chunks -- images are independent, nothing may leak across the batch."""
+    sd = O.trained_like_state(3)
+    m = T.TPS_PP().to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    B = 1024
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn((B, 64, 16, 64), device=DEV, generator=g)
+    o0 = torch.randn((B, 32, 32, 128), device=DEV, generator=g)
+    o1 = torch.randn((B, 32, 32, 128), device=DEV, generator=g)
+    with torch.no_grad():
+        full = m(x, [o0, o1])
+        out_full = full["output"].clone(); sc_full = full["pc_score"].clone()
+        for lo in (0, 300, 1000):
+            hi = min(B, lo + 24)
+            part = m(x[lo:hi], [o0[lo:hi], o1[lo:hi]])
+            assert torch.equal(part["output"], out_full[lo:hi])
+            assert torch.equal(part["pc_score"], sc_full[lo:hi])
+    assert torch.isfinite(out_full).all()
