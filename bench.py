@@ -183,7 +183,7 @@ def run_ours(args):
     if args.head == "library":
         m.head_impl = "library"
     else:
-        m.head_precision = N.HEAD_TC if args.head == "tc" else N.HEAD_FP32
+        m.head_precision = {"tc": N.HEAD_TC, "fp32": N.HEAD_FP32, "bf16": N.HEAD_BF16}[args.head]
 
     def barrier():
         if world > 1:
@@ -283,7 +283,8 @@ def run_ours(args):
         line = {
             "metric": "tps_pp_rectified_img_per_s", "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 conv operands / f32 elsewhere" if args.head == "bf16" else "f32",
+            "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"batch-shard x{world}, no collective",
                        "l2": "inputs 302 MB/step > 126 MB L2 (no flush needed)",
                        "native_stages": native_stages, "weights": "trained-like synthetic (seed 3)", "head": args.head},
@@ -338,8 +339,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--head", default="tc", choices=["tc", "fp32", "library"],
-                    help="head arithmetic: tcgen05 3xTF32 (default), CUDA-core fp32, or cuDNN/cuBLAS library ops")
+    ap.add_argument("--head", default="tc", choices=["tc", "fp32", "bf16", "library"],
+                    help="head arithmetic: tcgen05 3xTF32 (default, fp32-level accuracy), CUDA-core fp32, "
+                         "tcgen05 with bf16 conv operands (reduced precision, reported separately), or "
+                         "cuDNN/cuBLAS library ops")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

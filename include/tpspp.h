@@ -151,7 +151,8 @@ TPSPP_API int tpspp_warp_bwd(const tpspp_warp_cfg* cfg, const void* src0, const 
  * ------------------------------------------------------------------------------------------ */
 enum {
   TPSPP_HEAD_FP32 = 0,  /* CUDA-core fp32 FMAs everywhere (parity mode)                          */
-  TPSPP_HEAD_TC = 1     /* tcgen05 tensor cores for the dense contractions       */
+  TPSPP_HEAD_TC = 1,    /* tcgen05 tensor cores, 3xTF32 error compensation: fp32-level accuracy          */
+  TPSPP_HEAD_BF16 = 2   /* as TC, but the 14 convolutions use single-pass bf16 operands (fp32 accumulate) */
 };
 
 typedef struct tpspp_head_cfg {

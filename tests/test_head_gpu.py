@@ -142,3 +142,30 @@ def test_head_rejects_bad_geometry(native_lib):
             m(torch.zeros(1, 64, 16, 50, device=DEV), [torch.zeros(1, 32, 32, 100, device=DEV)] * 2)
     with pytest.raises(RuntimeError, match="no backward"):
         m(torch.zeros(1, 64, 16, 64, device=DEV, requires_grad=True), [torch.zeros(1, 32, 32, 128, device=DEV)] * 2)
+
+
+def test_bf16_conv_mode_stated_tolerance(native_lib, golden):
+    """TPSPP_HEAD_BF16: the 14 convolutions round their operands to bf16 (fp32 accumulate); control points, the
+    score epilogue, the TPS solve and the sampler stay fp32.  Stated tolerances: feature stages
+    3e-2 of their scale, C' 1e-4, pc_score 0.15 (tanh of a 128-term dot product of bf16-perturbed features),
+    sampling grid 0.5 source pixels."""
+    g = golden("tpspp_forward.npz")
+    sd = O.trained_like_state(int(g["state_seed"]))
+    x, o0, o1 = O.synthetic_tpspp_inputs(int(g["batch"]), int(g["input_seed"]))
+    got, m = _run_native(sd, x, o0, o1, N.HEAD_BF16)
+    r64 = O.head_intermediates(sd, x, [o0, o1], dtype=torch.float64)
+    rep = []
+    for name in ["f0", "a0", "feat_grid", "e0", "e3", "d2", "de", "de2"]:
+        scale = float(r64[name].abs().max())
+        err = mx(got[name], r64[name])
+        rep.append(f"{name}: {err:.2e} / scale {scale:.2f}")
+        assert err <= 3e-2 * scale, rep
+    print("bf16 conv mode:", "; ".join(rep))
+    assert mx(got["c_prime"], r64["c_prime"]) <= 1e-4
+    c = O.tpspp_constants()
+    grid = O.tpspp_grid(got["c_prime"].numpy(), got["pc_score"].numpy(), c["hat_C"], c["P"], c["P_hat"])
+    dpx = np.abs(grid - g["ref64_grid"]) * np.array([127 / 2, 31 / 2])
+    print(f"bf16 conv mode: C' {mx(got['c_prime'], r64['c_prime']):.2e}, pc_score {mx(got['pc_score'], r64['pc_score']):.2e}, "
+          f"grid error {dpx.max():.3f} source px")
+    assert mx(got["pc_score"], r64["pc_score"]) <= 0.15
+    assert dpx.max() <= 0.5

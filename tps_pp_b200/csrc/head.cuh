@@ -29,13 +29,14 @@ enum { CONV_ACT_RELU = 0, CONV_ACT_NONE = 1, CONV_ACT_GELU = 2, CONV_ACT_TANH = 
 // tcgen05 implicit-GEMM convolution (head_tc.cu).  `wprep` is the layer's weight image produced by
 // conv_tc_prepare_weights (3xTF32 hi/lo split, UMMA core-matrix order).
 bool conv_tc_eligible(const ConvArgs& a, int KS);
-int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st);
+int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st, bool bf16 = false);
 size_t conv_tc_wprep_floats(int Ctot, int KS, int N);    // floats needed for one layer's image (N output rows)
 
 struct WPrepLayer {
   const float* w;   // [N][Ctot][KS*KS]
   float* out;
   int Ctot, taps, N, NT;
+  int bf16;         // 1: single bf16 image [chunk][4 k-groups][64][8] instead of the fp32 hi|lo pair
 };
 constexpr int WPREP_MAX_LAYERS = 20;
 int conv_tc_prepare_weights(const WPrepLayer* layers, int nlayers, cudaStream_t st);

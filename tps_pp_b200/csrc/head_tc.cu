@@ -302,13 +302,25 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(ConvTcArgs t) {
 // issues tcgen05.mma with A from TMEM and B (the TMA-loaded weight image) from shared memory.
 // TMEM columns (256 per CTA, 2 CTAs/SM): D_main [0,64) | D_corr [64,128) | A stage s: hi 128+64s, lo +32.
 // ------------------------------------------------------------------------------------------------
+template <int PLANE>
+__device__ __forceinline__ void ts_load16(const float* q, float (&v)[16], bool ok) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = ok ? __ldg(q + i * PLANE) : 0.f;
+}
+
 constexpr int TS_B_BYTES = tc_b_bytes(64);                 // per part
 constexpr int TS_STAGE = 2 * TS_B_BYTES;                   // weight image hi | lo
 constexpr int TS_SMEM = 2 * TS_STAGE + 64 + TC_TM * 16;
 
-template <int KS>
+// BF16 = true: single-pass bf16 operands (kind::f16, fp32 accumulate) instead of 3xTF32 -- the opt-in reduced
+// precision mode (TPSPP_HEAD_BF16): A packs two channels per TMEM column, the weight image is bf16.
+template <int KS, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
   constexpr int NT = 64;
+  constexpr int W_BYTES = BF16 ? NT * TC_KC * 2 : 2 * TS_B_BYTES;      // weight image bytes per chunk
+  constexpr int A_COL0 = BF16 ? 64 : 128;                              // first TMEM column of the A ring
+  constexpr int A_STAGE = BF16 ? 16 : 64;                              // TMEM columns per A stage
+  constexpr int TMEM_COLS = BF16 ? 128 : 256;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TS_STAGE);   // "empty"
   uint64_t* wbars = bars + 2;
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
     mbar_init(&fbars[0], TC_PRODUCERS / 32); mbar_init(&fbars[1], TC_PRODUCERS / 32);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -335,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
   const long long m_base = (long long)blockIdx.x * TC_TM;
   const int Ctot = a.Ctot;
   const int nchunks = (Ctot * KS * KS) / TC_KC;
-  const float* wimg = t.wprep;
+  const unsigned char* wimg = reinterpret_cast<const unsigned char*>(t.wprep);
 
   if (tid < TC_TM) {
     const long long lm = m_base + tid;
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
     geo[tid] = gq;
   }
   __syncthreads();
-  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
+  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, BF16 ? 1 : 2);
   if (warp == TC_PRODUCERS / 32) {
     // ===== MMA issuer warp =====
     for (int ch = 0; ch < nchunks; ++ch) {
@@ -360,14 +372,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t b_hi = smem_u32(smem) + (uint32_t)(buf * TS_STAGE), b_lo = b_hi + TS_B_BYTES;
-        const uint32_t a_hi = tmem_d + 128 + (uint32_t)(buf * 64), a_lo = a_hi + 32;
+        const uint32_t a_hi = tmem_d + A_COL0 + (uint32_t)(buf * A_STAGE), a_lo = a_hi + 32;
+        if (BF16) {
 #pragma unroll
-        for (int j = 0; j < TC_KC / 8; ++j) {
-          const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
-          const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (NT * 16), NT * 16, 128);
-          umma_ts_tf32(tmem_d + 64, a_lo + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);   // corrections
-          umma_ts_tf32(tmem_d + 64, a_hi + j * 8, dbl, IDESC, 1u);
-          umma_ts_tf32(tmem_d, a_hi + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);        // main
+          for (int j = 0; j < TC_KC / 16; ++j) {     // one MMA = K 16 = two 16-byte k-groups of 8 bf16
+            const uint64_t db = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
+            umma_ts_f16(tmem_d, a_hi + j * 8, db, IDESC, (ch | j) != 0 ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < TC_KC / 8; ++j) {
+            const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
+            const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (NT * 16), NT * 16, 128);
+            umma_ts_tf32(tmem_d + 64, a_lo + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);   // corrections
+            umma_ts_tf32(tmem_d + 64, a_hi + j * 8, dbl, IDESC, 1u);
+            umma_ts_tf32(tmem_d, a_hi + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);        // main
+          }
         }
         umma_commit(&bars[buf]);
       }
@@ -405,10 +425,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
       const bool ok = gq.w && iy >= 0 && ix >= 0 && iy < lim_y && ix < lim_x;
       const int sy = (s_uh == 2) ? (iy >> 1) : iy, sx = (s_uw == 2) ? (ix >> 1) : ix;
       const float* q = t_base + (size_t)c_in * s_plane + (ok ? sy * s_W + sx : 0);
+      // the 16 channel planes are a compile-time stride apart for the plane sizes of this network: one LDG with an
+      // immediate offset per channel instead of 64-bit pointer arithmetic per load
+      switch (s_plane) {
+        case 4096: ts_load16<4096>(q, v, ok); break;
+        case 1024: ts_load16<1024>(q, v, ok); break;
+        case 256: ts_load16<256>(q, v, ok); break;
+        case 64: ts_load16<64>(q, v, ok); break;
+        case 32: ts_load16<32>(q, v, ok); break;
+        default:
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        v[i] = ok ? __ldg(q) : 0.f;
-        q += s_plane;
+          for (int i = 0; i < 16; ++i) {
+            v[i] = ok ? __ldg(q) : 0.f;
+            q += s_plane;
+          }
       }
       c_in += TC_KC; cin0 += TC_KC;
       if (c_in >= s_C) {                 // next chunk starts in another source tensor (or the next tap)
@@ -425,18 +455,28 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
       }
       if (tid == 0) {
         unsigned char* st = smem + buf * TS_STAGE;
-        mbar_arrive_expect_tx(&wbars[buf], 2 * TS_B_BYTES);
-        bulk_g2s(st, wimg + (size_t)ch * (2 * NT * TC_KC), 2 * TS_B_BYTES, &wbars[buf], policy_evict_last());
+        mbar_arrive_expect_tx(&wbars[buf], W_BYTES);
+        bulk_g2s(st, wimg + (size_t)ch * W_BYTES, W_BYTES, &wbars[buf], policy_evict_last());
       }
-      float hi[16], lo[16];
+      if (BF16) {
+        uint32_t pk[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
-        lo[i] = v[i] - hi[i];
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);   // .x (low half) = even channel
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        tmem_st8(lane_addr + (uint32_t)(A_COL0 + buf * A_STAGE + kh * 8), pk);
+      } else {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+          lo[i] = v[i] - hi[i];
+        }
+        const uint32_t col = (uint32_t)(A_COL0 + buf * A_STAGE + kh * 16);
+        tmem_st16(lane_addr + col, hi);
+        tmem_st16(lane_addr + col + 32, lo);
       }
-      const uint32_t col = 128u + (uint32_t)(buf * 64 + kh * 16);
-      tmem_st16(lane_addr + col, hi);
-      tmem_st16(lane_addr + col + 32, lo);
       if (ch + 2 < nchunks) gather(v);
       tmem_st_wait();
       tc_fence_before();
@@ -463,9 +503,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
       float acc[16], part[16];
       const uint32_t taddr = lane_addr + (uint32_t)(half * 32 + pass * 16);
       tmem_ld_cols<16>(taddr, acc);
-      tmem_ld_cols<16>(taddr + 64, part);
+      if (!BF16) {
+        tmem_ld_cols<16>(taddr + 64, part);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] += part[j];
+        for (int j = 0; j < 16; ++j) acc[j] += part[j];
+      }
       const int cb = half * 32 + pass * 16;
       if (m < Mtot && a.out_nhwc) {
         const size_t o0 = (size_t)m * a.Cout + cb;
@@ -495,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, 256);
+  if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
 // weight image: for output row n (column block n / NT) and k = tap*Ctot + cin:
@@ -514,6 +556,11 @@ __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
     const int tap = k / L.Ctot, cin = k - tap * L.Ctot;
     const float w = __ldg(L.w + (size_t)n * Ktot + cin * L.taps + tap);
     const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    if (L.bf16) {   // [chunk][4 k-groups][64 n][8 bf16]
+      __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(L.out);
+      ob[(size_t)(k >> 5) * (64 * 32) + ((k >> 3) & 3) * (64 * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(w);
+      continue;
+    }
     const int blk = n / L.NT, nn = n - blk * L.NT;
     const int ch = k >> 5, kg = (k >> 2) & 7, j = k & 3;
     float* o = L.out + ((size_t)(blk * nchunks + ch) * 2) * (L.NT * 32) + kg * (L.NT * 4) + nn * 4 + j;
@@ -564,7 +611,7 @@ static int launch_tc(const ConvTcArgs& t, dim3 grid, cudaStream_t st) {
 }
 
 // NT: column tile (64, or 32 for narrow outputs); Cout / NT column blocks go to grid.y
-int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st) {
+int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st, bool bf16) {
   TPSPP_REQUIRE(NT == 64 || NT == 32, "conv_tc: column tile must be 32 or 64");
   TPSPP_REQUIRE(a.Cout % NT == 0, "conv_tc: Cout %d is not a multiple of the column tile %d", a.Cout, NT);
   TPSPP_REQUIRE(KS == 1 || NT == 64, "conv_tc: 3x3 kernels are instantiated for 64-column tiles only");
@@ -579,16 +626,21 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
     int dev = 0;
     TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
     if (ts_dev != dev) {
-      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
       ts_dev = dev;
     }
-    if (KS == 1) conv_ts_kernel<1><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
-    else conv_ts_kernel<3><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
+    if (KS == 1 && !bf16) conv_ts_kernel<1, false><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
+    else if (KS == 1) conv_ts_kernel<1, true><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
+    else if (!bf16) conv_ts_kernel<3, false><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
+    else conv_ts_kernel<3, true><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
     return TPSPP_OK;
   }
+  TPSPP_REQUIRE(!bf16, "conv_tc: the bf16 operand mode exists for the NCHW-source convolutions only");
   if (KS == 3) return nhwc ? launch_tc<3, true, 64>(t, grid, st) : launch_tc<3, false, 64>(t, grid, st);
   if (NT == 64) return nhwc ? launch_tc<1, true, 64>(t, grid, st) : launch_tc<1, false, 64>(t, grid, st);
   return nhwc ? launch_tc<1, true, 32>(t, grid, st) : launch_tc<1, false, 32>(t, grid, st);
