@@ -15,6 +15,6 @@ echo "== ncu full: warp kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:warp_fwd_staged -s 3 -c 1 -f -o gpurun_out/prof_warp \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_warp.log 2>&1
 echo "== ncu full: tensor-core conv (enc0)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 60 -c 1 -f -o gpurun_out/prof_conv_enc0 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_ts_kernel -s 48 -c 1 -f -o gpurun_out/prof_conv_enc0 \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_conv.log 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv | tee gpurun_out/smi_end.txt
