@@ -353,8 +353,17 @@ constexpr int DG_MAXH = 32;
 // dot product of a shared-memory weight row with a shared-memory vector, split over G consecutive lanes
 template <int G>
 __device__ __forceinline__ float group_dot(const float* row, const float* vec, int len, int part) {
-  float t = 0.f;
-  for (int i = part; i < len; i += G) t = __fmaf_rn(row[i], vec[i], t);
+  // four independent partial sums: the dependent LDS->FFMA chain is what bounds this kernel
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  int i = part;
+  for (; i + 3 * G < len; i += 4 * G) {
+    t0 = __fmaf_rn(row[i], vec[i], t0);
+    t1 = __fmaf_rn(row[i + G], vec[i + G], t1);
+    t2 = __fmaf_rn(row[i + 2 * G], vec[i + 2 * G], t2);
+    t3 = __fmaf_rn(row[i + 3 * G], vec[i + 3 * G], t3);
+  }
+  for (; i < len; i += G) t0 = __fmaf_rn(row[i], vec[i], t0);
+  float t = (t0 + t1) + (t2 + t3);
 #pragma unroll
   for (int m = 1; m < G; m <<= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
   return t;
@@ -428,14 +437,19 @@ __global__ void __launch_bounds__(256, 2) dgab_plane_kernel(DgabArgs a, int npla
       }
     __syncthreads();
     if (tid < 64) {
-      float t = 0.f;
-      for (int h = 0; h < H; ++h) t += us[h * 64 + tid];
-      vecw[tid] = t / (float)H;
-    } else if (tid < 64 + H) {
-      const int h = tid - 64;
-      float t = 0.f;
-      for (int w = 0; w < 64; ++w) t += us[h * 64 + w];
-      vech[h] = t / 64.f;
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+      for (int h = 0; h < H; h += 4) {       // H is a multiple of 8
+        t0 += us[h * 64 + tid]; t1 += us[(h + 1) * 64 + tid]; t2 += us[(h + 2) * 64 + tid]; t3 += us[(h + 3) * 64 + tid];
+      }
+      vecw[tid] = ((t0 + t1) + (t2 + t3)) / (float)H;
+    } else if (tid < 64 + 4 * H) {           // 4 lanes per row
+      const int h = (tid - 64) >> 2, q = (tid - 64) & 3;
+      float t0 = 0.f, t1 = 0.f;
+      for (int w = q * 16; w < q * 16 + 16; w += 2) { t0 += us[h * 64 + w]; t1 += us[h * 64 + w + 1]; }
+      float t = t0 + t1;
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      if (q == 0) vech[h] = t / 64.f;
     }
     __syncthreads();
     {  // width logits 0..63: 4 lanes each;   then logit 64 and the H+1 height logits: 8 lanes each
