@@ -60,7 +60,8 @@ enum {
 enum {
   TPSPP_VARIANT_AUTO = 0,
   TPSPP_VARIANT_GENERIC = 1, /* one thread per output pixel, direct global gathers            */
-  TPSPP_VARIANT_STAGED = 2   /* persistent CTAs, TMA bulk-copied source planes in shared mem  */
+  TPSPP_VARIANT_STAGED = 2,  /* persistent CTAs, TMA bulk-copied source planes in shared mem  */
+  TPSPP_VARIANT_TILED = 3    /* classical mode: P_hat tile resident in shared mem, batch-sliced */
 };
 
 /* Geometry of one fused warp call.  src1/out1 are the optional second sampled tensor
@@ -85,8 +86,15 @@ TPSPP_API const char* tpspp_last_error(void);
 /* Number of SMs of the current device and the cubin architecture that was loaded (e.g. 100). */
 TPSPP_API int tpspp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* Bytes of scratch the forward / backward calls need for this cfg (may be 0). */
+/* Bytes of scratch tpspp_warp_bwd needs for this cfg. */
 TPSPP_API size_t tpspp_warp_workspace_bytes(const tpspp_warp_cfg* cfg);
+
+/* Bytes of OPTIONAL scratch for tpspp_warp_fwd (0 in attention mode).  In classical mode with a large
+ * rectified grid (>= 1024 pixels, batch x pixels >= 4 Mi, F <= 64) a 256-byte-aligned workspace of this size lets the
+ * forward compute T = inv_delta_C[:, :F] . C' once per batch (tps_preprocessor.py:276-277) and run the
+ * P_hat-stationary kernel (~2x faster at 64x256); with workspace == NULL the per-pixel kernel is used.
+ * Results are the same either way. */
+TPSPP_API size_t tpspp_warp_fwd_workspace_bytes(const tpspp_warp_cfg* cfg);
 
 /*
  * Fused TPS grid generator + bilinear grid_sample (border padding, align_corners=True).
@@ -109,6 +117,7 @@ TPSPP_API size_t tpspp_warp_workspace_bytes(const tpspp_warp_cfg* cfg);
  *   out1        [B, C1, Hr, Wr] or NULL
  *   grid_out    [B, n, 2] fp32 or NULL -- optional copy of the sampling grid (tests only;
  *               the generic variant writes it, the staged variant rejects a non-NULL value)
+ *   workspace   NULL, or >= tpspp_warp_fwd_workspace_bytes(cfg) bytes, 256-byte aligned (see there)
  *
  * Arithmetic: T and Phi.T are evaluated in fp64 from the fp32 inputs and the source
  * coordinates / bilinear weights are derived in fp64; the four taps are blended in fp32 in

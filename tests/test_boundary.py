@@ -43,6 +43,9 @@ def test_workspace_query_is_host_only(native_lib):
     assert nbytes >= 256 * 1024 * 2 * 4
     bad = _native.WarpCfg(1, 0, 32, 128, 0, 0, 0, 16, 64, 32, 0, 0.5, 0, 0)
     assert native_lib.tpspp_warp_workspace_bytes(ctypes.byref(bad)) == 0
+    assert native_lib.tpspp_warp_fwd_workspace_bytes(ctypes.byref(cfg)) == 0          # attention mode: none
+    cls = _native.WarpCfg(1024, 3, 64, 256, 0, 0, 0, 64, 256, 40, 1, 0.0, 0, 0)
+    assert native_lib.tpspp_warp_fwd_workspace_bytes(ctypes.byref(cls)) == 1024 * 43 * 2 * 8
     assert b"src0 geometry" in native_lib.tpspp_last_error()
 
 

@@ -209,6 +209,46 @@ def test_classical_highres_properties(native_lib, F_):
     const = torch.full_like(timg, 3.25)
     outc, _ = TF.tps_warp(const, None, *args, mode=N.MODE_CLASSICAL, theta=0.0)
     assert mx(outc, 3.25) <= 1e-5        # bilinear weights sum to one
+    # the P_hat-stationary kernel against the plain per-pixel kernel, including control points that push the
+    # grid far outside the image and non-finite ones (clipped to the border like ATen)
+    cp_bad = cp.copy()
+    cp_bad[1] *= 7.0
+    cp_bad[2, :, 0] += 3.0
+    cp_bad[3, 1, 0] = np.nan
+    cp_bad[4, 2, 1] = np.inf
+    bad = (cu(cp_bad),) + args[1:]
+    a, _ = TF.tps_warp(timg, None, *bad, mode=N.MODE_CLASSICAL, theta=0.0, variant=N.VARIANT_TILED)
+    assert N.last_launch_count() == 2            # T kernel + P_hat-stationary kernel
+    b, _ = TF.tps_warp(timg, None, *bad, mode=N.MODE_CLASSICAL, theta=0.0, variant=N.VARIANT_GENERIC)
+    assert N.last_launch_count() == 1
+    assert torch.isfinite(a).all() and mx(a, b) <= 2e-6
+    t, _ = TF.tps_warp(timg, None, *args, mode=N.MODE_CLASSICAL, theta=0.0, variant=N.VARIANT_TILED)
+    assert mx(t[:2], o64) <= PIX_TOL
+
+
+def test_classical_tiled_auto_dispatch_and_ragged(native_lib):
+    """AUTO picks the P_hat-stationary kernel from batch x pixels >= 4 Mi; ragged tile (n % 256 != 0), a
+    ragged batch slice and bf16 pixels go through it too."""
+    F_, rs_ = 20, (36, 100)                      # 3600 pixels: 14 full tiles + 16 pixels
+    cc = O.classical_constants(F_, rs_)
+    B = 1201
+    cp = O.smooth_c_prime(O.classical_init_bias(F_), B, seed=5, amp=0.08, centre=0.0)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    timg = torch.randn((B, 1, 40, 120), device=DEV, generator=g)
+    args = (cu(cp), None, cu(cc["P_hat"]), None, cu(cc["inv_delta_C"]), rs_)
+    a, _ = TF.tps_warp(timg, None, *args, mode=N.MODE_CLASSICAL, theta=0.0)
+    assert N.last_launch_count() == 2
+    b, _ = TF.tps_warp(timg, None, *args, mode=N.MODE_CLASSICAL, theta=0.0, variant=N.VARIANT_GENERIC)
+    assert mx(a, b) <= 2e-6
+    idx = [0, 600, B - 1]
+    o64, _ = O.classical_warp(timg[idx].cpu().numpy(), cp[idx], cc, rs_, dtype=np.float64)
+    assert mx(a[idx], o64) <= PIX_TOL
+    ah, _ = TF.tps_warp(timg.bfloat16(), None, *args, mode=N.MODE_CLASSICAL, theta=0.0)
+    bh, _ = TF.tps_warp(timg.bfloat16(), None, *args, mode=N.MODE_CLASSICAL, theta=0.0, variant=N.VARIANT_GENERIC)
+    assert ah.dtype == torch.bfloat16 and mx(ah.float(), bh.float()) <= 1e-2
+    small, _ = TF.tps_warp(timg[:8], None, cu(cp[:8]), *args[1:], mode=N.MODE_CLASSICAL, theta=0.0)
+    assert N.last_launch_count() == 1            # small batch: per-pixel kernel
+    assert torch.equal(small, b[:8])
 
 
 # ------------------------------------------------------------------ backward

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("TPSPP_LIB", os.path.join(_HERE, "libtpspp.so"))
 OK = 0
 F32, BF16 = 0, 1
 MODE_ATTENTION, MODE_CLASSICAL = 0, 1
-VARIANT_AUTO, VARIANT_GENERIC, VARIANT_STAGED = 0, 1, 2
+VARIANT_AUTO, VARIANT_GENERIC, VARIANT_STAGED, VARIANT_TILED = 0, 1, 2, 3
 
 
 class WarpCfg(Structure):
@@ -46,6 +46,7 @@ _SIGNATURES = {
     "tpspp_last_launch_count": (c_int, []),
     "tpspp_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tpspp_warp_workspace_bytes": (c_size_t, [POINTER(WarpCfg)]),
+    "tpspp_warp_fwd_workspace_bytes": (c_size_t, [POINTER(WarpCfg)]),
     "tpspp_warp_fwd": (c_int, [POINTER(WarpCfg)] + [c_void_p] * 12),
     "tpspp_sample_fwd": (c_int, [POINTER(WarpCfg)] + [c_void_p] * 6),
     "tpspp_warp_bwd": (c_int, [POINTER(WarpCfg)] + [c_void_p] * 15),

@@ -59,6 +59,7 @@ struct WarpParams {
   const void* gout1;
   void* gsrc0;
   void* gsrc1;
+  double* T_ws;           // [B,K,2] fp64 T = inv_delta_C[:, :F] . C' (classical tiled forward workspace)
   float* g_grid;          // [B,n,2] workspace (accumulated with atomics)
   float* g_c_prime;
   float* g_score;
@@ -108,6 +109,41 @@ __device__ __forceinline__ Taps make_taps(CT gx, CT gy, int W, int H) {
   t.w[2] = t.dy ? (float)(ux * ty) : 0.f;
   t.w[3] = (t.dx && t.dy) ? (float)(tx * ty) : 0.f;
   return t;
+}
+
+// fp64-in taps with the FP64 pipe used as little as possible (make_taps<double> spends ~28 fp64
+// instructions, as much as 6 control points of grid arithmetic).  Per coordinate: one
+// DFMA for the pixel coordinate, the 2^52 "magic add" to round it to an integer whose low word is the
+// int, two DADDs for the signed remainder, one conversion; floor/clip/weights then run in fp32 and
+// integers.  Same taps as make_taps<double> up to one fp32 rounding of the fractional part (<= 6e-8).
+__device__ __forceinline__ void lean_coord(double g, int size, int& i0, float& frac) {
+  const double half = 0.5 * (double)(size - 1);
+  const double x = fma(g, half, half);                        // ((g + 1) / 2) * (size - 1)
+  const int hi = __double2hiint(x);
+  const unsigned ex = ((unsigned)hi >> 20) & 0x7ffu;
+  const double t = x + 4503599627370496.0;                    // 2^52: integer part lands in the low word
+  const double d = x - (t - 4503599627370496.0);              // in [-0.5, 0.5]
+  float df = (float)d;
+  int r = __double2loint(t);
+  if (df < 0.f) { r -= 1; df += 1.f; }
+  const bool nan = ex == 0x7ffu && ((hi & 0xfffff) != 0 || __double2loint(x) != 0);
+  if (hi < 0 || nan || r < 0) { r = 0; df = 0.f; }            // clip to 0 (ATen maps NaN there too)
+  else if (ex >= 1023u + 30u || r >= size - 1) { r = size - 1; df = 0.f; }
+  i0 = r; frac = df;
+}
+
+// Always-interior form: the NW tap is clamped to (size - 2) with fraction 1 at the far border, so the four
+// taps sit at off, off+1, off+W, off+W+1 (no per-tap selects); needs W, H >= 2.  Same blend as make_taps for
+// finite pixels: the far-border case only moves the unit weight from the NW to the NE/SW tap.
+__device__ __forceinline__ int make_taps_lean(double gx, double gy, int W, int H, float* w) {
+  int x0, y0; float tx, ty;
+  lean_coord(gx, W, x0, tx);
+  lean_coord(gy, H, y0, ty);
+  if (x0 >= W - 1) { x0 = W - 2; tx = 1.f; }
+  if (y0 >= H - 1) { y0 = H - 2; ty = 1.f; }
+  const float ux = 1.f - tx, uy = 1.f - ty;
+  w[0] = ux * uy; w[1] = tx * uy; w[2] = ux * ty; w[3] = tx * ty;
+  return y0 * W + x0;
 }
 
 // Same, plus what the backward pass needs: the fractional parts and d(ix)/d(gx) including the

@@ -331,7 +331,164 @@ static int launch_generic_t(const WarpParams& p, int mode, cudaStream_t stream) 
   return TPSPP_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// classical TPS (RARE) with a large rectified grid: P_hat is [n, F+3] and *constant over the batch*
+// (tps_preprocessor.py:255-282), so at 64x256 / F=40 it is 2.8 MB -- far bigger than an image.  The
+// generic kernel re-reads a pixel's P_hat row for every image (TBs of L2 traffic per launch), and its
+// fp64 grid arithmetic is one dependent chain per pixel.  Here a CTA keeps the rows of its 256-pixel tile
+// in shared memory and walks a slice of the batch ("P_hat-stationary"), four images per pass: 8 independent
+// fp64 chains per thread, then 16 independent gathers per channel.  ncu (profiles/r01_classical_tiled.md):
+// the fp64 pipe is < 20 % busy; the kernel is bound by gather latency, so the grid is sized to exactly one
+// resident wave and the gathers are batched.  (mma.sync.m8n8k4.f64 for the grid GEMM was tried: no gain.)
+// ------------------------------------------------------------------------------------------
+constexpr int CT_PIX = 256, CT_TB = 16, CT_IB = 4;
+
+// T[b] = inv_delta_C[:, :F] . C'[b] in fp64, once per batch (tps_preprocessor.py:276-277), one thread per
+// output; the tiled kernel then streams it with bulk copies instead of recomputing it in every pixel tile.
+__global__ void __launch_bounds__(256) classical_T_kernel(WarpParams p) {
+  const int o = blockIdx.x * 256 + threadIdx.x;
+  if (o >= p.B * 2 * p.K) return;
+  const int b = o / (2 * p.K), r = o - b * 2 * p.K, k = r >> 1, c = r & 1;
+  const float* row = p.hatC + (size_t)k * p.K;
+  const float* cp = p.c_prime + (size_t)b * p.F * 2 + c;
+  double a0 = 0.0, a1 = 0.0;
+  int f = 0;
+  for (; f + 1 < p.F; f += 2) {
+    a0 = fma((double)__ldg(row + f), (double)__ldg(cp + 2 * f), a0);
+    a1 = fma((double)__ldg(row + f + 1), (double)__ldg(cp + 2 * f + 2), a1);
+  }
+  if (f < p.F) a0 = fma((double)__ldg(row + f), (double)__ldg(cp + 2 * f), a0);
+  p.T_ws[o] = a0 + a1;
+}
+
+template <typename FT>
+__global__ void __launch_bounds__(CT_PIX, 3) warp_fwd_classical_tiled_kernel(WarpParams p, int imgs_per_cta) {
+  extern __shared__ __align__(16) unsigned char csm[];
+  __shared__ __align__(8) uint64_t tbar[2];
+  const int tid = threadIdx.x, K = p.K;
+  const int TG = CT_TB * K * 2;                                         // doubles per T buffer
+  double* Tbuf = reinterpret_cast<double*>(csm);                        // [2][CT_TB images][K][2]
+  float* Ph = reinterpret_cast<float*>(Tbuf + 2 * (size_t)TG);          // [CT_PIX][PITCH] rows, odd pitch
+  const int PITCH = K | 1;
+  const int pix0 = blockIdx.x * CT_PIX;
+  const int npix = min(CT_PIX, p.n - pix0);
+  const int b_lo = blockIdx.y * imgs_per_cta, b_hi = min(p.B, b_lo + imgs_per_cta);
+  for (int i = tid; i < 2 * TG; i += CT_PIX) Tbuf[i] = 0.0;             // rows past a short group stay finite
+  if (tid == 0) { mbar_init(&tbar[0], 1); mbar_init(&tbar[1], 1); fence_barrier_init(); }
+  __syncthreads();
+  // producer side (thread 0): group g of the slice -> buffer g & 1, one bulk copy of nb * 2K doubles
+  auto prefetch = [&](int g) {
+    const int gb0 = b_lo + g * CT_TB;
+    if (gb0 >= b_hi) return;
+    const uint32_t bytes = (uint32_t)(min(CT_TB, b_hi - gb0) * 2 * K * sizeof(double));
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&tbar[g & 1], bytes);
+    bulk_g2s(Tbuf + (size_t)(g & 1) * TG, p.T_ws + (size_t)gb0 * 2 * K, bytes, &tbar[g & 1], policy_evict_last());
+  };
+  if (tid == 0) prefetch(0);
+  for (int i = tid; i < npix * K; i += CT_PIX) {
+    const int r = i / K, k = i - r * K;
+    Ph[(size_t)r * PITCH + k] = __ldg(p.P_hat + (size_t)pix0 * K + i);
+  }
+  const int pix = pix0 + tid;
+  const bool active = tid < npix;
+  const float* ph = Ph + (size_t)tid * PITCH;
+  for (int b0 = b_lo, g = 0; b0 < b_hi; b0 += CT_TB, ++g) {
+    const int nb = min(CT_TB, b_hi - b0);
+    __syncthreads();                            // everyone is done with group g-1's buffer (and Ph is visible)
+    if (tid == 0) prefetch(g + 1);
+    mbar_wait(&tbar[g & 1], (g >> 1) & 1);
+    const double* Tsm = Tbuf + (size_t)(g & 1) * TG;
+    if (!active) continue;
+    // CT_IB images per pass: one P_hat load + conversion feeds 2*CT_IB independent fp64 FMA chains, and the
+    // (Tx, Ty) pair of an image is one 16-byte broadcast load
+    for (int bq = 0; bq < nb; bq += CT_IB) {
+      double gx[CT_IB], gy[CT_IB];
+#pragma unroll
+      for (int i = 0; i < CT_IB; ++i) gx[i] = gy[i] = 0.0;
+      const double2* T0 = reinterpret_cast<const double2*>(Tsm + (size_t)bq * 2 * K);
+      for (int k = 0; k < K; ++k) {
+        const double h = (double)ph[k];
+#pragma unroll
+        for (int i = 0; i < CT_IB; ++i) {
+          const double2 tk = T0[(size_t)i * K + k];      // images past nb read stale-but-finite T rows; results unused
+          gx[i] = fma(h, tk.x, gx[i]);
+          gy[i] = fma(h, tk.y, gy[i]);
+        }
+      }
+      // taps of all CT_IB images first, then channel by channel 4*CT_IB independent gathers in flight per
+      // thread (the kernel is bound by gather latency, not by the fp64 pipe); images past nb alias the last
+      // valid one and only their stores are predicated off
+      float w[CT_IB][4];
+      const FT* q[CT_IB];
+      FT* op[CT_IB];
+      const size_t plane = (size_t)p.H0 * p.W0;
+      const int W = p.W0;
+#pragma unroll
+      for (int i = 0; i < CT_IB; ++i) {
+        const int b = min(b0 + bq + i, b_hi - 1);
+        if (p.grid_out != nullptr && bq + i < nb) {
+          p.grid_out[((size_t)b * p.n + pix) * 2] = (float)gx[i];
+          p.grid_out[((size_t)b * p.n + pix) * 2 + 1] = (float)gy[i];
+        }
+        const int off = make_taps_lean(gx[i], gy[i], W, p.H0, w[i]);
+        q[i] = (const FT*)p.src0 + (size_t)b * p.C0 * plane + off;
+        op[i] = (FT*)p.out0 + (size_t)b * p.C0 * p.n + pix;
+      }
+      for (int c = 0; c < p.C0; ++c) {
+        float v[CT_IB][4];
+#pragma unroll
+        for (int i = 0; i < CT_IB; ++i) {
+          v[i][0] = ldf(q[i]); v[i][1] = ldf(q[i] + 1); v[i][2] = ldf(q[i] + W); v[i][3] = ldf(q[i] + W + 1);
+          q[i] += plane;
+        }
+#pragma unroll
+        for (int i = 0; i < CT_IB; ++i) {
+          if (bq + i < nb) stf(op[i], blend4(v[i][0], v[i][1], v[i][2], v[i][3], w[i]));
+          op[i] += p.n;
+        }
+      }
+    }
+  }
+}
+
+// structural requirements of the P_hat-stationary kernel ...
+static bool classical_tiled_supported(const tpspp_warp_cfg* cfg, const WarpParams& p) {
+  return cfg->mode == TPSPP_MODE_CLASSICAL && p.C1 == 0 && p.K <= 67 && p.W0 >= 2 && p.H0 >= 2 && p.T_ws != nullptr;
+}
+// ... and when AUTO picks it: every CTA first loads its tile's P_hat rows, which only pays off with enough
+// images per CTA (64x256 from B = 256; 32x100 from B ~ 1300 -- below that the per-pixel kernel is faster)
+static bool classical_tiled_eligible(const tpspp_warp_cfg* cfg, const WarpParams& p) {
+  return classical_tiled_supported(cfg, p) && p.n >= 4 * CT_PIX && (size_t)p.B * p.n >= ((size_t)1 << 22);
+}
+
+template <typename FT>
+static int launch_classical_tiled_t(const WarpParams& p, cudaStream_t stream) {
+  const int tiles = (p.n + CT_PIX - 1) / CT_PIX;
+  const size_t smem = 2 * (size_t)CT_TB * p.K * 2 * sizeof(double) + (size_t)CT_PIX * (p.K | 1) * sizeof(float);
+  TPSPP_CHECK_CUDA(cudaFuncSetAttribute(warp_fwd_classical_tiled_kernel<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // exactly one resident wave: batch slices sized so that tiles x chunks fits the CTAs the chip can hold
+  int resident = 0;
+  TPSPP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, warp_fwd_classical_tiled_kernel<FT>, CT_PIX, smem));
+  int chunks = max(1, resident * sm_count() / tiles);
+  int per = (p.B + chunks - 1) / chunks;
+  per = (per + CT_IB - 1) / CT_IB * CT_IB;
+  chunks = (p.B + per - 1) / per;
+  classical_T_kernel<<<(p.B * 2 * p.K + 255) / 256, 256, 0, stream>>>(p);
+  count_launch();
+  dim3 grid(tiles, chunks);
+  warp_fwd_classical_tiled_kernel<FT><<<grid, CT_PIX, smem, stream>>>(p, per);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
 static int launch_generic(const tpspp_warp_cfg* cfg, const WarpParams& p, int mode, cudaStream_t stream) {
+  // an explicit TPSPP_VARIANT_GENERIC request keeps the plain kernel (tests compare the two)
+  if (mode == 1 && cfg->variant == TPSPP_VARIANT_AUTO && classical_tiled_eligible(cfg, p)) {
+    if (cfg->feat_dtype == TPSPP_BF16) return launch_classical_tiled_t<__nv_bfloat16>(p, stream);
+    return launch_classical_tiled_t<float>(p, stream);
+  }
   TPSPP_REQUIRE(p.B <= 65535, "batch %d exceeds the generic kernel's grid.y limit (65535)", p.B);
   if (cfg->feat_dtype == TPSPP_BF16) return launch_generic_t<__nv_bfloat16>(p, mode, stream);
   return launch_generic_t<float>(p, mode, stream);
@@ -349,11 +506,15 @@ void fill_params(const tpspp_warp_cfg* cfg, WarpParams* p) {
 
 using namespace tpspp;
 
+extern "C" size_t tpspp_warp_fwd_workspace_bytes(const tpspp_warp_cfg* cfg) {
+  if (validate_cfg(cfg) != TPSPP_OK || cfg->mode != TPSPP_MODE_CLASSICAL) return 0;
+  return ((size_t)cfg->batch * (cfg->num_fiducial + 3) * 2 * sizeof(double) + 255) & ~(size_t)255;
+}
+
 extern "C" int tpspp_warp_fwd(const tpspp_warp_cfg* cfg, const void* src0, const void* src1,
                               const float* c_prime, const float* pc_score, const float* P_hat,
                               const float* P, const float* inv_delta_C, void* out0, void* out1,
                               float* grid_out, void* workspace, tpspp_stream_t stream) {
-  (void)workspace;
   reset_launch_count();
   int rc = validate_cfg(cfg);
   if (rc != TPSPP_OK) return rc;
@@ -368,6 +529,8 @@ extern "C" int tpspp_warp_fwd(const tpspp_warp_cfg* cfg, const void* src0, const
   fill_params(cfg, &p);
   p.src0 = src0; p.src1 = src1; p.c_prime = c_prime; p.score = pc_score; p.P_hat = P_hat; p.P = P;
   p.hatC = inv_delta_C; p.out0 = out0; p.out1 = out1; p.grid_out = grid_out;
+  TPSPP_REQUIRE(((uintptr_t)workspace & 255) == 0, "tpspp_warp_fwd: workspace must be 256-byte aligned");
+  p.T_ws = reinterpret_cast<double*>(workspace);
   cudaStream_t st = (cudaStream_t)stream;
   int variant = cfg->variant;
   if (variant == TPSPP_VARIANT_AUTO) {
@@ -378,6 +541,13 @@ extern "C" int tpspp_warp_fwd(const tpspp_warp_cfg* cfg, const void* src0, const
   }
   if (variant == TPSPP_VARIANT_STAGED) return launch_staged(cfg, p, st);
   if (variant == TPSPP_VARIANT_GENERIC) return launch_generic(cfg, p, cfg->mode, st);
+  if (variant == TPSPP_VARIANT_TILED) {
+    TPSPP_REQUIRE(classical_tiled_supported(cfg, p),
+                  "tpspp_warp_fwd: TPSPP_VARIANT_TILED needs classical mode, one source, F <= 64, a source of at "
+                  "least 2x2 and a workspace of tpspp_warp_fwd_workspace_bytes()");
+    if (cfg->feat_dtype == TPSPP_BF16) return launch_classical_tiled_t<__nv_bfloat16>(p, st);
+    return launch_classical_tiled_t<float>(p, st);
+  }
   set_error("tpspp_warp_fwd: unknown variant %d", cfg->variant);
   return TPSPP_E_INVALID;
 }

@@ -80,9 +80,11 @@ class _TpsWarp(torch.autograd.Function):
         out1 = (torch.empty((b, src1.shape[1], out_size[0], out_size[1]), dtype=src1.dtype, device=src1.device)
                 if src1 is not None else None)
         with torch.cuda.device(src0.device):
+            nbytes = int(N.lib().tpspp_warp_fwd_workspace_bytes(ctypes.byref(cfg)))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=src0.device) if nbytes else None
             N.check(N.lib().tpspp_warp_fwd(ctypes.byref(cfg), _ptr(src0), _ptr(src1), _ptr(c_prime), _ptr(pc_score),
                                            _ptr(P_hat), _ptr(P), _ptr(inv_delta_C), _ptr(out0), _ptr(out1),
-                                           None, None, _stream(src0)), "tpspp_warp_fwd")
+                                           None, _ptr(ws), _stream(src0)), "tpspp_warp_fwd")
         ctx.save_for_backward(src0, src1, c_prime, pc_score, P_hat, P, inv_delta_C)
         ctx.cfg_args = (out_size, mode, theta)
         return out0, out1
