@@ -30,6 +30,7 @@ BATCH_PER_GPU = 256
 WORKLOAD = "TPS_PP rectifier alone fp32 forward, batch 256/GPU, F=32 (2x16) control points, x[64,16,64]+outs 2x[32,32,128]"
 # algorithmic bytes of the fused warp per image (TPS++ fp32, output + mp_img)
 WARP_BYTES_PER_IMG = 1048576 + 262144 + 131072 + 256 + 262144 + 262144
+HEAD_GFLOP_PER_IMG = 0.82          # convs 720.6 M + DGAB/MLP 76.4 M + score 21.4 M + localization 1.1 M
 WARP_CONST_BYTES = 131072 + 4900 + 8192
 
 
@@ -42,6 +43,16 @@ def _warp_traffic():
         return int(d["dram_bytes_per_launch"]) if int(d.get("batch", 0)) == BATCH_PER_GPU else None
     except Exception:
         return None
+
+
+def _tensor_peak():
+    """Dense bf16 TFLOP/s measured on this pool (sustained figure: the head runs inside a long step)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            d = json.load(fh)
+        return float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), "measured bf16 sustained (MEASURED_PEAKS.json)"
+    except Exception:
+        return 2250.0, "nominal dense bf16 (B200_PROFILING.md fallback)"
 
 
 def _peaks():
@@ -272,6 +283,8 @@ def run_ours(args):
     peak, peak_src = _peaks()
     warp_bytes = B * WARP_BYTES_PER_IMG + WARP_CONST_BYTES
     achieved = warp_bytes / (warp_mean_ms * 1e-3) / 1e9
+    tpeak, tpeak_src = _tensor_peak()
+    head_ms = total_ms / args.steps - warp_mean_ms            # GFLOP / ms == TFLOP/s
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -292,6 +305,16 @@ def run_ours(args):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": _warp_traffic(), "peak_source": peak_src,
                          "bytes_per_launch": warp_bytes, "avg_launch_ms": warp_mean_ms,
                          "warp_only_img_per_s": B / (warp_mean_ms * 1e-3)},
+            # everything before the warp (convs, DGAB, localization, score): SURVEY 8(d) counts 0.82 GFLOP/img of
+            # dense contractions.  The fp32-parity mode spends three TF32 MMAs per product (3xTF32) at half the
+            # bf16 rate, so its own ceiling is peak/6; both fractions are reported.
+            "roofline_head": {"kernels": "conv_ts_kernel / conv_tc_kernel / dgab_plane_kernel / loc_p1_kernel",
+                              "bound": "tensor", "achieved": HEAD_GFLOP_PER_IMG * B / head_ms, "peak": tpeak,
+                              "unit": "TFLOP/s", "frac": HEAD_GFLOP_PER_IMG * B / head_ms / tpeak,
+                              "frac_of_3xtf32_ceiling": (HEAD_GFLOP_PER_IMG * B / head_ms / (tpeak / 6.0)
+                                                         if args.head == "tc" else None),
+                              "peak_source": tpeak_src, "gflop_per_img": HEAD_GFLOP_PER_IMG,
+                              "avg_head_ms": head_ms, "share_of_step": head_ms / (total_ms / args.steps)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hout.numel() * 4,
                     "steps": e2e_steps},
