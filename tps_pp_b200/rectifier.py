@@ -139,6 +139,7 @@ class TPS_PP(_BaseModule):
         # "auto": native kernels whenever autograd is not recording (inference); the library-op head is kept
         # for training, where its backward comes from torch autograd (the warp's backward is native either way)
         self.head_impl = "auto"
+        self._last_head_native = None
         # tcgen05 3xTF32 convolutions (fp32-level accuracy); N.HEAD_FP32 = CUDA-core only
         self.head_precision = N.HEAD_TC
         self._head_ws = None
@@ -230,7 +231,8 @@ class TPS_PP(_BaseModule):
     # ------------------------------------------------------------------ forward
     @property
     def native_stages(self):
-        nat = self._use_native_head(None)
+        # what the last forward actually ran; before any forward, what the current grad mode would select
+        nat = self._last_head_native if self._last_head_native is not None else self._use_native_head(None)
         return {"warp": True, "down": nat, "msfa": nat, "cbam": nat, "dgab": nat, "localization": nat, "score": nat}
 
     def _use_native_head(self, batch_img) -> bool:
@@ -242,7 +244,8 @@ class TPS_PP(_BaseModule):
 
     def head(self, batch_img: torch.Tensor, outs: Sequence[torch.Tensor]):
         """Everything before the warp: -> (feat_grid, C' [B,F,2], pc_score [B,n,F])."""
-        if self._use_native_head(batch_img):
+        self._last_head_native = self._use_native_head(batch_img)
+        if self._last_head_native:
             if torch.is_grad_enabled() and (batch_img.requires_grad or any(p.requires_grad for p in self.parameters())):
                 raise RuntimeError("tps_pp_b200: head_impl='native' has no backward yet; use torch.no_grad() or "
                                    "head_impl='auto'/'library' for training")
