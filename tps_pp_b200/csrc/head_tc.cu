@@ -25,6 +25,7 @@
 #include "head.cuh"
 #include "tc.cuh"
 
+#include <cuda.h>
 #include <string.h>
 
 namespace tpspp {
@@ -310,7 +311,7 @@ __device__ __forceinline__ void ts_load16(const float* q, float (&v)[16], bool o
 
 constexpr int TS_B_BYTES = tc_b_bytes(64);                 // per part
 constexpr int TS_STAGE = 2 * TS_B_BYTES;                   // weight image hi | lo
-constexpr int TS_SMEM = 2 * TS_STAGE + 64 + TC_TM * 16;
+constexpr int TS_SMEM = 2 * TS_STAGE + 64 + TC_TM * 16 + 256;
 
 // BF16 = true: single-pass bf16 operands (kind::f16, fp32 accumulate) instead of 3xTF32 -- the opt-in reduced
 // precision mode (TPSPP_HEAD_BF16): A packs two channels per TMEM column, the weight image is bf16.
@@ -327,8 +328,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
   uint64_t* fbars = bars + 4;                                          // "full"
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   int4* geo = reinterpret_cast<int4*>(smem + 2 * TS_STAGE + 64);
+  float* bias_s = reinterpret_cast<float*>(smem + 2 * TS_STAGE + 64 + TC_TM * 16);   // [64]
   const ConvArgs& a = t.c;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches stay on the uniform datapath
 
   if (tid == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
     mbar_init(&fbars[0], TC_PRODUCERS / 32); mbar_init(&fbars[1], TC_PRODUCERS / 32);
     fence_barrier_init();
   }
+  if (tid < NT) bias_s[tid] = a.bias != nullptr ? __ldg(a.bias + tid) : 0.f;
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -523,21 +527,321 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
           }
           *reinterpret_cast<float4*>(a.out + o0 + j) = r;
         }
-      } else if (m < Mtot) {
-        const size_t o0 = ((size_t)b * a.Cout + cb) * HoWo + rem;
+      } else if (m < Mtot) {             // [B, 64, Ho, Wo]: lane = pixel, coalesced per channel
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + cb);       // warp-uniform: broadcast loads
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float r = tc_act(acc[j] + (a.bias != nullptr ? __ldg(a.bias + cb + j) : 0.f), a.act, a.act_scale);
-          const size_t o = o0 + (size_t)j * HoWo;
-          if (a.skip != nullptr) r += __ldg(a.skip + o);
-          a.out[o] = r;
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bs = b4[j >> 2];
+          acc[j] += bs.x; acc[j + 1] += bs.y; acc[j + 2] += bs.z; acc[j + 3] += bs.w;
         }
+        if (a.act == CONV_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = tc_act(acc[j], a.act, a.act_scale);
+        }
+        const size_t o0 = ((size_t)b * a.Cout + cb) * HoWo + rem;
+        if (a.skip != nullptr) {
+          const float* sk = a.skip + o0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += __ldg(sk + (size_t)j * HoWo);
+        }
+        float* po = a.out + o0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) po[(size_t)j * HoWo] = acc[j];
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged form of the TS convolution (stride-1 convolutions whose 128-pixel tile is a TH x TW rectangle of one
+// image).  The per-thread global gathers of conv_ts_kernel cost ~2000 warp instructions per 32-channel chunk (address
+// arithmetic, padding predicates, the chunk state machine) against ~400 that do useful work, so the tensor pipe idled.
+// Here the activations arrive by one cp.async.bulk.tensor (4-D tensor map over [B,C,H,W], box = 32 channels x the
+// tile's halo rectangle, out-of-bounds = the convolution's zero padding) per 32-channel group, and the K loop runs
+// (channel group, tap): the nine taps of a 3x3 filter read the same shared-memory halo tile at shifted offsets, so
+// global/L2 traffic per tile drops 9x and a producer thread's chunk is 16 LDS + the hi/lo split + two tcgen05.st.
+// Nearest-upsampled sources use a box in the low-resolution tensor and index it with (y >> 1, x >> 1).
+// ------------------------------------------------------------------------------------------------
+struct ConvTmaArgs {
+  ConvTcArgs t;
+  CUtensorMap tmap[3];
+  int TW, TH, BW, BH;      // tile and box (halo) extent in pixels; CHS = BW * BH floats per channel
+};
+constexpr int TM_XH = 4;   // x halo of a 3x3 box: the innermost TMA coordinate must be 16-byte aligned (probed: x = -1 traps)
+constexpr int TM_TILE_MAX = 32 * (4 * 72) * 4;                            // 3x3 at TW = 64: 4 rows x 72 columns
+__host__ __device__ constexpr int tm_tile_bytes(int KS) { return KS == 3 ? ((TM_TILE_MAX + 1023) / 1024) * 1024 : 16384; }
+__host__ __device__ constexpr int tm_smem_bytes(int KS) { return 2 * tm_tile_bytes(KS) + 2 * TS_STAGE + 512 + 1024; }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
+
+template <int KS>
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_constant__ ConvTmaArgs g) {
+  constexpr int NT = 64, T = KS * KS;
+  constexpr int XH = KS == 3 ? TM_XH : 0;
+  constexpr int W_BYTES = 2 * TS_B_BYTES;
+  constexpr int TILE_BYTES = tm_tile_bytes(KS);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = smem;                                   // 2 activation tiles [32 ch][BH][BW]
+  unsigned char* wst = smem + 2 * TILE_BYTES;                    // 2 weight stages (hi | lo image of a chunk)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + 2 * TS_STAGE);
+  uint64_t* a_empty = bars;          // [2] MMAs that read A stage / weight stage completed
+  uint64_t* a_full = bars + 2;       // [2] all 8 producer warps stored their part of the chunk
+  uint64_t* w_full = bars + 4;       // [2] weight image landed
+  uint64_t* t_full = bars + 6;       // [2] activation tile landed
+  uint64_t* t_empty = bars + 8;      // [2] all 8 producer warps are done reading the tile
+  uint64_t* d_empty = bars + 10;     // [1] the epilogue has drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* bias_s = reinterpret_cast<float*>(bars + 12);          // [64]
+  const ConvArgs& a = g.t.c;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_empty[i], 1); mbar_init(&a_full[i], TC_PRODUCERS / 32); mbar_init(&w_full[i], 1);
+      mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TC_PRODUCERS / 32);
+    }
+    mbar_init(d_empty, TC_PRODUCERS / 32);
+    fence_barrier_init();
+  }
+  if (tid < NT) bias_s[tid] = a.bias != nullptr ? __ldg(a.bias + tid) : 0.f;
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int HoWo = a.Ho * a.Wo;
+  const int ntiles = (int)(((long long)a.B * HoWo) / TC_TM);
+  const int ncc = a.Ctot / TC_KC;
+  const int nchunks = ncc * T;
+  const int CHS = g.BW * g.BH;
+  const uint32_t tile_tx = (uint32_t)(CHS * TC_KC * 4);
+  const unsigned char* wimg = reinterpret_cast<const unsigned char*>(g.t.wprep);
+  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
+
+  // persistent over tiles blockIdx.x, blockIdx.x + gridDim.x, ...: TMEM, barriers and the TMA pipeline are set up once,
+  // and the first activation tile of the next output tile is already in flight while this one runs its epilogue
+  // (channel-group counter gcc and chunk counter gch run across tiles and drive the mbarrier phases)
+  auto issue_tile = [&](int tile, int cc, int gcc) {
+    const long long m_base = (long long)tile * TC_TM;
+    const int img = (int)(m_base / HoWo);
+    const int rem0 = (int)(m_base - (long long)img * HoWo);
+    const int oy0 = rem0 / a.Wo, ox0 = rem0 - oy0 * a.Wo;
+    int s = 0, c0 = cc * TC_KC;
+    if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { c0 -= a.src[1].C; s = 2; } }
+    const int up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
+    const int y0 = oy0 - a.pad;
+    mbar_arrive_expect_tx(&t_full[gcc & 1], tile_tx);
+    tma_load_4d(tiles + (gcc & 1) * TILE_BYTES, &g.tmap[s], up ? ((ox0 - 2 * XH) >> 1) : (ox0 - XH), up ? (y0 >> 1) : y0, c0, img,
+                &t_full[gcc & 1], policy_evict_first());
+  };
+
+  if (warp == TC_PRODUCERS / 32) {
+    // ===== MMA issuer warp (chunk order: channel group major, tap minor) =====
+    int gch = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      if (it >= 1) {
+        mbar_wait_bounded(d_empty, (uint32_t)((it - 1) & 1));
+        tc_fence_after();
+      }
+      for (int ch = 0; ch < nchunks; ++ch, ++gch) {
+        const int buf = gch & 1;
+        const uint32_t ph = (uint32_t)((gch >> 1) & 1);
+        mbar_wait_bounded(&a_full[buf], ph);
+        mbar_wait_bounded(&w_full[buf], ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE), b_lo = b_hi + TS_B_BYTES;
+          const uint32_t a_hi = tmem_d + 128 + (uint32_t)(buf * 64), a_lo = a_hi + 32;
+#pragma unroll
+          for (int j = 0; j < TC_KC / 8; ++j) {
+            const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
+            const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (NT * 16), NT * 16, 128);
+            umma_ts_tf32(tmem_d + 64, a_lo + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
+            umma_ts_tf32(tmem_d + 64, a_hi + j * 8, dbl, IDESC, 1u);
+            umma_ts_tf32(tmem_d, a_hi + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
+          }
+          umma_commit(&a_empty[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== producer warps: thread = output pixel = TMEM lane; warps w and w+4 split a chunk's 32 channels =====
+    const int row = (warp & 3) * 32 + lane;
+    const int kh = warp >> 2;
+    const int pr = row / g.TW, pc = row - pr * g.TW;            // position inside the tile rectangle
+    const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    int gch = 0, gcc = 0;
+    if (tid == 0 && (int)blockIdx.x < ntiles) issue_tile(blockIdx.x, 0, 0);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long m_base = (long long)tile * TC_TM;
+      const int img = (int)(m_base / HoWo);
+      const int rem0 = (int)(m_base - (long long)img * HoWo);
+      const int oy0 = rem0 / a.Wo, ox0 = rem0 - oy0 * a.Wo;
+      for (int cc = 0; cc < ncc; ++cc, ++gcc) {
+        const int tb = gcc & 1;
+        if (tid == 0) {                          // next channel group: of this tile, or the first one of the next tile
+          const int ntile = cc + 1 < ncc ? tile : tile + (int)gridDim.x;
+          if (ntile < ntiles) {
+            if (gcc + 1 >= 2) mbar_wait_bounded(&t_empty[(gcc + 1) & 1], (uint32_t)((((gcc + 1) >> 1) - 1) & 1));
+            issue_tile(ntile, cc + 1 < ncc ? cc + 1 : 0, gcc + 1);
+          }
+        }
+        __syncwarp();
+        int s = 0, c0 = cc * TC_KC;
+        if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { s = 2; } }
+        const bool up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
+        const int by = up ? ((oy0 - a.pad) >> 1) : (oy0 - a.pad), bx = up ? ((ox0 - 2 * XH) >> 1) : (ox0 - XH);
+        const float* tile_s = reinterpret_cast<const float*>(tiles + tb * TILE_BYTES) + (size_t)(kh * 16) * CHS;
+        mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc >> 1) & 1));
+#pragma unroll 1
+        for (int tap = 0; tap < T; ++tap, ++gch) {
+          const int buf = gch & 1;
+          const int dy = tap / KS, dx = tap - dy * KS;
+          int iy = oy0 + pr + dy - a.pad, ix = ox0 + pc + dx - a.pad;
+          if (up) { iy >>= 1; ix >>= 1; }
+          const float* q = tile_s + (iy - by) * g.BW + (ix - bx);
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = q[(size_t)i * CHS];
+          if (gch >= 2) {
+            mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch >> 1) - 1) & 1));   // MMAs of chunk gch-2 have read the stage
+            tc_fence_after();
+          }
+          if (tid == 0) {
+            mbar_arrive_expect_tx(&w_full[buf], W_BYTES);
+            bulk_g2s(wst + buf * TS_STAGE, wimg + (size_t)(tap * ncc + cc) * W_BYTES, W_BYTES, &w_full[buf], policy_evict_last());
+          }
+          float hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+            lo[i] = v[i] - hi[i];
+          }
+          const uint32_t col = (uint32_t)(128 + buf * 64 + kh * 16);
+          tmem_st16(lane_addr + col, hi);
+          tmem_st16(lane_addr + col + 32, lo);
+          if (tap == T - 1) {                      // the tile's last reads are in registers: hand the buffer back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[tb]);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[buf]);
+        }
+      }
+      const int last = gch - 1;
+      mbar_wait_bounded(&a_empty[last & 1], (uint32_t)((last >> 1) & 1));
+      tc_fence_after();
+
+      // ---- epilogue (NCHW): lane = pixel, coalesced per channel ----
+      const int wq = warp & 3, half = warp >> 2;
+      const int oy = oy0 + pr, ox = ox0 + pc;
+      const bool relu = a.act == CONV_ACT_RELU;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        float acc[16], part[16];
+        const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * 32 + pass * 16);
+        tmem_ld_cols<16>(taddr, acc);
+        tmem_ld_cols<16>(taddr + 64, part);
+        const int cb = half * 32 + pass * 16;
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + cb);       // warp-uniform: broadcast loads
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bs = b4[j >> 2];
+          acc[j] += part[j] + bs.x; acc[j + 1] += part[j + 1] + bs.y; acc[j + 2] += part[j + 2] + bs.z; acc[j + 3] += part[j + 3] + bs.w;
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = tc_act(acc[j], a.act, a.act_scale);
+        }
+        const size_t o0 = ((size_t)img * a.Cout + cb) * HoWo + (size_t)oy * a.Wo + ox;
+        if (a.skip != nullptr) {
+          const float* sk = a.skip + o0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += __ldg(sk + (size_t)j * HoWo);
+        }
+        float* po = a.out + o0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) po[(size_t)j * HoWo] = acc[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty);       // the MMA warp may overwrite the accumulator with the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
+// ---- host side of the TMA path ----
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tmap_encode_fn>(p);
+  }
+  return fn;
+}
+
+// stride-1 NCHW convolution whose tile is a rectangle of one image, every source either full or half resolution
+static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g) {
+  if (a.sh != 1 || a.sw != 1 || a.out_nhwc || a.wimg_stride != 0 || a.Cout != 64) return false;
+  if (a.pad != (KS == 3 ? 1 : 0)) return false;
+  const int TW = a.Wo < 128 ? a.Wo : 128;
+  if (TW < 16 || 128 % TW || a.Wo % TW) return false;
+  const int TH = 128 / TW;
+  if (a.Ho % TH) return false;
+  const int BW = KS == 3 ? TW + 2 * TM_XH : TW, BH = KS == 3 ? TH + 2 : TH;
+  if (BW > 256 || BH > 256 || (size_t)BW * BH * TC_KC * 4 > (size_t)tm_tile_bytes(KS)) return false;
+  tmap_encode_fn enc = tmap_encoder();
+  if (enc == nullptr) return false;
+  for (int s = 0; s < 3; ++s) {
+    const ConvSrc& sc = a.src[s];
+    if (sc.C == 0) continue;
+    if (sc.nhwc || sc.C % TC_KC || sc.uh != sc.uw || (sc.uh != 1 && sc.uh != 2)) return false;
+    if (sc.H * sc.uh != a.Ho || sc.W * sc.uw != a.Wo) return false;
+    if ((sc.W * 4) % 16 || ((uintptr_t)sc.ptr & 15)) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)sc.W, (cuuint64_t)sc.H, (cuuint64_t)sc.C, (cuuint64_t)a.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)sc.W * 4, (cuuint64_t)sc.W * sc.H * 4, (cuuint64_t)sc.W * sc.H * sc.C * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)TC_KC, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&g->tmap[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sc.ptr), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  g->TW = TW; g->TH = TH; g->BW = BW; g->BH = BH;
+  return true;
 }
 
 // weight image: for output row n (column block n / NT) and k = tap*Ctot + cin:
@@ -622,9 +926,25 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
   dim3 grid((unsigned)((M + TC_TM - 1) / TC_TM), (unsigned)(a.Cout / NT));
   const bool nhwc = a.src[0].nhwc != 0;
   if (!nhwc && NT == 64 && a.Cout == 64 && a.wimg_stride == 0) {    // convolutions: A operand through TMEM
-    static thread_local int ts_dev = -1;
     int dev = 0;
     TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+    ConvTmaArgs g;
+    if (!bf16 && conv_tma_plan(KS, a, &g)) {      // stride-1, rectangular tiles: activations staged by TMA
+      g.t = t;
+      static thread_local int tma_dev = -1;
+      if (tma_dev != dev) {
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
+        tma_dev = dev;
+      }
+      dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()));
+      if (KS == 1) conv_tma_kernel<1><<<pgrid, TC_THREADS, tm_smem_bytes(1), st>>>(g);
+      else conv_tma_kernel<3><<<pgrid, TC_THREADS, tm_smem_bytes(3), st>>>(g);
+      count_launch();
+      TPSPP_CHECK_CUDA(cudaGetLastError());
+      return TPSPP_OK;
+    }
+    static thread_local int ts_dev = -1;
     if (ts_dev != dev) {
       TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
       TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
