@@ -844,6 +844,222 @@ static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g) {
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-major linear layers (feat_linear.1, the QK^T score with per-image weights, DGAB's Mlp fc1/fc2):
+// out[R, Cout] = act(A[R, K] . W^T + b) (+ skip), R a multiple of 128.  Same TS scheme as the convolutions --
+// thread = row = TMEM lane -- with the [128 rows x 32 k] operand tile brought in by one 2-D TMA box per chunk
+// (128-byte rows, SWIZZLE_128B so that the per-row 16-byte reads of a warp hit distinct banks), persistent
+// over row tiles.  When K <= 64 the split A operand of a tile stays in tensor memory while the kernel walks the
+// Cout / NT column blocks, so fc1 (K = 64, Cout = 256) reads and splits its input once instead of four times;
+// the weight images stream through a 4-stage shared-memory ring filled by the MMA warp three items ahead.
+// ------------------------------------------------------------------------------------------------
+struct LinTmaArgs {
+  ConvTcArgs t;
+  CUtensorMap tmap;
+  int rows_per_img;        // rows that share one weight image (per-image weights), else 0
+};
+constexpr int LN_WSTAGES = 4;
+__host__ __device__ constexpr int ln_smem_bytes() { return 2 * 16384 + LN_WSTAGES * TS_STAGE + 512 + 1024; }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_constant__ LinTmaArgs g) {
+  constexpr int W_BYTES = 2 * NT * TC_KC * 4;                      // hi | lo image of one (block, chunk)
+  constexpr int HC = NT / 2;                                       // output columns per producer-warp half
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = smem;                                     // 2 x [128 rows][32 floats], 128B-swizzled
+  unsigned char* wst = smem + 2 * 16384;                           // LN_WSTAGES weight stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + LN_WSTAGES * TS_STAGE);
+  uint64_t* a_empty = bars;                  // [2]
+  uint64_t* a_full = bars + 2;               // [2]
+  uint64_t* t_full = bars + 4;               // [2]
+  uint64_t* t_empty = bars + 6;              // [2]
+  uint64_t* w_full = bars + 8;               // [4]
+  uint64_t* w_empty = bars + 12;             // [4]
+  uint64_t* d_full = bars + 16;
+  uint64_t* d_empty = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* bias_s = reinterpret_cast<float*>(bars + 20);             // [<= 256]... kept in global when larger
+  const ConvArgs& a = g.t.c;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_empty[i], 1); mbar_init(&a_full[i], TC_PRODUCERS / 32);
+      mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TC_PRODUCERS / 32);
+    }
+    for (int i = 0; i < LN_WSTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    mbar_init(d_full, 1); mbar_init(d_empty, TC_PRODUCERS / 32);
+    fence_barrier_init();
+  }
+  (void)bias_s;
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const long long R = (long long)a.B * a.Ho * a.Wo;
+  const int ntiles = (int)(R / TC_TM);
+  const int nchunks = a.Ctot / TC_KC;
+  const int nblocks = a.Cout / NT;
+  const float* wbase = g.t.wprep;
+  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
+
+  if (warp == TC_PRODUCERS / 32) {
+    // ===== MMA issuer warp: items (tile, block, chunk); also streams the weight images =====
+    // prefetch cursor: three items ahead of the issue cursor
+    int p_tile = blockIdx.x, p_nb = 0, p_ch = 0;
+    int wi_load = 0;
+    auto load_next_weights = [&]() {                       // whole warp: the cursor stays warp-uniform
+      if (p_tile >= ntiles) return;
+      const int st = wi_load & (LN_WSTAGES - 1);
+      if (wi_load >= LN_WSTAGES) mbar_wait_bounded(&w_empty[st], (uint32_t)(((wi_load / LN_WSTAGES) - 1) & 1));
+      const float* wsrc = wbase + (size_t)(g.rows_per_img > 0 ? ((long long)p_tile * TC_TM) / g.rows_per_img : 0) * (size_t)a.wimg_stride +
+                          (size_t)(p_nb * nchunks + p_ch) * (2 * NT * TC_KC);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&w_full[st], W_BYTES);
+        bulk_g2s(wst + st * TS_STAGE, wsrc, W_BYTES, &w_full[st], policy_evict_last());
+      }
+      __syncwarp();
+      ++wi_load;
+      if (++p_ch == nchunks) { p_ch = 0; if (++p_nb == nblocks) { p_nb = 0; p_tile += gridDim.x; } }
+    };
+    load_next_weights(); load_next_weights(); load_next_weights();
+    int wi = 0, di = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int nb = 0; nb < nblocks; ++nb, ++di) {
+        if (di >= 1) {
+          mbar_wait_bounded(d_empty, (uint32_t)((di - 1) & 1));
+          tc_fence_after();
+        }
+        for (int ch = 0; ch < nchunks; ++ch, ++wi) {
+          const int st = wi & (LN_WSTAGES - 1);
+          const int ga = it * nchunks + ch;                 // A-stage use counter of this chunk
+          mbar_wait_bounded(&w_full[st], (uint32_t)((wi / LN_WSTAGES) & 1));
+          if (nb == 0) mbar_wait_bounded(&a_full[ga & 1], (uint32_t)((ga >> 1) & 1));
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t b_hi = smem_u32(wst) + (uint32_t)(st * TS_STAGE), b_lo = b_hi + NT * TC_KC * 4;
+            const uint32_t a_hi = tmem_d + 128 + (uint32_t)((ga & 1) * 64), a_lo = a_hi + 32;
+#pragma unroll
+            for (int j = 0; j < TC_KC / 8; ++j) {
+              const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
+              const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (NT * 16), NT * 16, 128);
+              umma_ts_tf32(tmem_d + 64, a_lo + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
+              umma_ts_tf32(tmem_d + 64, a_hi + j * 8, dbl, IDESC, 1u);
+              umma_ts_tf32(tmem_d, a_hi + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
+            }
+            umma_commit(&w_empty[st]);
+            if (nb == nblocks - 1) umma_commit(&a_empty[ga & 1]);
+            if (ch == nchunks - 1) umma_commit(d_full);
+          }
+          __syncwarp();
+          load_next_weights();
+        }
+      }
+    }
+  } else {
+    // ===== producer / epilogue warps =====
+    const int row = (warp & 3) * 32 + lane;
+    const int kh = warp >> 2;
+    const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    int gcc = 0, ga = 0, di = 0;
+    auto issue_tile = [&](int tile, int ch, int gcc_) {
+      mbar_arrive_expect_tx(&t_full[gcc_ & 1], 16384);
+      tma_load_2d(tiles + (gcc_ & 1) * 16384, &g.tmap, ch * TC_KC, tile * TC_TM, &t_full[gcc_ & 1], policy_evict_first());
+    };
+    if (tid == 0 && (int)blockIdx.x < ntiles) issue_tile(blockIdx.x, 0, 0);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int ch = 0; ch < nchunks; ++ch, ++gcc, ++ga) {
+        const int tb = gcc & 1;
+        if (tid == 0) {
+          const int ntile = ch + 1 < nchunks ? tile : tile + (int)gridDim.x;
+          if (ntile < ntiles) {
+            if (gcc + 1 >= 2) mbar_wait_bounded(&t_empty[(gcc + 1) & 1], (uint32_t)((((gcc + 1) >> 1) - 1) & 1));
+            issue_tile(ntile, ch + 1 < nchunks ? ch + 1 : 0, gcc + 1);
+          }
+        }
+        __syncwarp();
+        mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc >> 1) & 1));
+        // this row's 16 floats of the chunk half: 16-byte pieces 4kh .. 4kh+3, stored at piece ^ (row & 7)
+        const unsigned char* rp = tiles + tb * 16384 + row * 128;
+        float4 v4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v4[i] = *reinterpret_cast<const float4*>(rp + (((kh * 4 + i) ^ (row & 7)) << 4));
+        const float* v = reinterpret_cast<const float*>(v4);
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+          lo[i] = v[i] - hi[i];
+        }
+        const int buf = ga & 1;
+        if (ga >= 2) {
+          mbar_wait_bounded(&a_empty[buf], (uint32_t)(((ga >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t col = (uint32_t)(128 + buf * 64 + kh * 16);
+        tmem_st16(lane_addr + col, hi);
+        tmem_st16(lane_addr + col + 32, lo);
+        // only now is the tile buffer released: the tcgen05.st above consume every value read from it, so no shared-memory
+        // load of this warp can still be in flight when the TMA producer is allowed to overwrite the buffer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[tb]);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[buf]);
+      }
+      const long long m = (long long)tile * TC_TM + row;
+      for (int nb = 0; nb < nblocks; ++nb, ++di) {
+        mbar_wait_bounded(d_full, (uint32_t)(di & 1));
+        tc_fence_after();
+        const int cb0 = nb * NT + kh * HC;                        // first output column of this thread's part
+        const size_t o0 = (size_t)m * a.Cout + cb0;
+#pragma unroll 1
+        for (int pass = 0; pass < HC / 16; ++pass) {
+          float acc[16], part[16];
+          const uint32_t taddr = lane_addr + (uint32_t)(kh * HC + pass * 16);
+          tmem_ld_cols<16>(taddr, acc);
+          tmem_ld_cols<16>(taddr + 64, part);
+          const int cb = cb0 + pass * 16;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.bias != nullptr) bs = __ldg(reinterpret_cast<const float4*>(a.bias + cb + j));
+            float4 r = make_float4(acc[j] + (part[j] + bs.x), acc[j + 1] + (part[j + 1] + bs.y), acc[j + 2] + (part[j + 2] + bs.z),
+                                   acc[j + 3] + (part[j + 3] + bs.w));
+            if (a.act == CONV_ACT_GELU) { r.x = tc_gelu(r.x); r.y = tc_gelu(r.y); r.z = tc_gelu(r.z); r.w = tc_gelu(r.w); }
+            else if (a.act == CONV_ACT_TANH) { r.x = tanhf(r.x * a.act_scale); r.y = tanhf(r.y * a.act_scale); r.z = tanhf(r.z * a.act_scale); r.w = tanhf(r.w * a.act_scale); }
+            else if (a.act == CONV_ACT_RELU) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+            if (a.skip != nullptr) {
+              const float4 sk = __ldg(reinterpret_cast<const float4*>(a.skip + o0 + pass * 16 + j));
+              r.x += sk.x; r.y += sk.y; r.z += sk.z; r.w += sk.w;
+            }
+            *reinterpret_cast<float4*>(a.out + o0 + pass * 16 + j) = r;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
 // weight image: for output row n (column block n / NT) and k = tap*Ctot + cin:
 //   out[((blk*nchunks + k/32)*2 + part) * (NT*32) + ((k/4)%8) * (NT*4) + (n%NT)*4 + k%4]
 struct WPrepArgs {
@@ -914,6 +1130,34 @@ static int launch_tc(const ConvTcArgs& t, dim3 grid, cudaStream_t st) {
   return TPSPP_OK;
 }
 
+// row-major [R, K] source, row-major output, R % 128 == 0, and either K <= 64 (A stays in TMEM across the column
+// blocks) or a single column block
+static bool lin_tma_plan(const ConvArgs& a, int NT, LinTmaArgs* g) {
+  const ConvSrc& sc = a.src[0];
+  if (!sc.nhwc || a.src[1].C != 0 || a.src[2].C != 0 || !a.out_nhwc || sc.uh != 1 || sc.uw != 1) return false;
+  if (a.sh != 1 || a.sw != 1 || a.pad != 0 || a.Ctot != sc.C || a.Ctot % TC_KC || a.Cout % NT) return false;
+  const long long R = (long long)a.B * a.Ho * a.Wo;
+  if (R % TC_TM || R > 0x7fffffffLL || sc.H * sc.W * (long long)a.B != R) return false;
+  const int nchunks = a.Ctot / TC_KC, nblocks = a.Cout / NT;
+  if (nchunks > 2 && nblocks != 1) return false;
+  g->rows_per_img = 0;
+  if (a.wimg_stride != 0) {
+    const long long per = (long long)a.Ho * a.Wo;
+    if (per % TC_TM) return false;
+    g->rows_per_img = (int)per;
+  }
+  if (((uintptr_t)sc.ptr & 15) || ((uintptr_t)a.out & 15) || (a.skip && ((uintptr_t)a.skip & 15))) return false;
+  tmap_encode_fn enc = tmap_encoder();
+  if (enc == nullptr) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)a.Ctot, (cuuint64_t)R};
+  const cuuint64_t strides[1] = {(cuuint64_t)a.Ctot * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_TM};
+  const cuuint32_t es[2] = {1, 1};
+  return enc(&g->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sc.ptr), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // NT: column tile (64, or 32 for narrow outputs); Cout / NT column blocks go to grid.y
 int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st, bool bf16) {
   TPSPP_REQUIRE(NT == 64 || NT == 32, "conv_tc: column tile must be 32 or 64");
@@ -961,6 +1205,24 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
     return TPSPP_OK;
   }
   TPSPP_REQUIRE(!bf16, "conv_tc: the bf16 operand mode exists for the NCHW-source convolutions only");
+  LinTmaArgs lg;
+  if (KS == 1 && nhwc && lin_tma_plan(a, NT, &lg)) {
+    lg.t = t;
+    int dev = 0;
+    TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+    static thread_local int lin_dev = -1;
+    if (lin_dev != dev) {
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(lin_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes()));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(lin_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes()));
+      lin_dev = dev;
+    }
+    dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()));
+    if (NT == 64) lin_tma_kernel<64><<<pgrid, TC_THREADS, ln_smem_bytes(), st>>>(lg);
+    else lin_tma_kernel<32><<<pgrid, TC_THREADS, ln_smem_bytes(), st>>>(lg);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+    return TPSPP_OK;
+  }
   if (KS == 3) return nhwc ? launch_tc<3, true, 64>(t, grid, st) : launch_tc<3, false, 64>(t, grid, st);
   if (NT == 64) return nhwc ? launch_tc<1, true, 64>(t, grid, st) : launch_tc<1, false, 64>(t, grid, st);
   return nhwc ? launch_tc<1, true, 32>(t, grid, st) : launch_tc<1, false, 32>(t, grid, st);
