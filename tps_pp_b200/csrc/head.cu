@@ -539,6 +539,178 @@ __global__ void __launch_bounds__(256, 2) dgab_plane_kernel(DgabArgs a, int npla
   }
 }
 
+// Warp-per-plane form of the same block: a [H,64] plane is 2H elements per lane, so LayerNorm statistics, the two
+// gate soft-maxes and the row/column means are warp shuffles and the whole plane needs no block barrier (the
+// block-per-plane kernel above spends most of its 5.7 us per plane waiting in ~13 __syncthreads).  16 warps per CTA,
+// one CTA per SM, weights shared in shared memory, per-warp scratch for the gated plane.
+constexpr int DW_WARPS = 16;
+template <int H>
+__global__ void __launch_bounds__(DW_WARPS * 32, 1) dgab_warp_kernel(DgabArgs a, int nplanes) {
+  extern __shared__ __align__(16) float dsm[];
+  constexpr int n = H * 64, E = 2 * H;             // E elements per lane: idx = lane + 32 i  ->  h = i >> 1, w = lane + 32 (i & 1)
+  const int F = a.F, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int LW = 64 + F + 1, LH = H + F + 1;
+  float* n1w = dsm;                      // [n] x4
+  float* n1b = n1w + n;
+  float* n2w = n1b + n;
+  float* n2b = n2w + n;
+  float* wpT = n2b + n;                  // [64][65]  wpT[w][j] = proj.weight[j][w]
+  float* wws = wpT + 64 * 65;            // [65][LW]
+  float* whs = wws + 65 * LW;            // [H+1][LH]
+  float* scratch = dsm + ((4 * n + 64 * 65 + 65 * LW + (H + 1) * LH + 3) & ~3);   // 16-byte aligned (float4 reads of `as`)
+  const int per_warp = (n + (64 + F) + (H + F) + 3) & ~3;
+  float* as = scratch + (size_t)warp * per_warp;   // [H][64] gated plane (the normalised plane stays in registers)
+  float* vecw = as + n;                            // [64+F] = colmean | y
+  float* vech = vecw + 64 + F;                     // [H+F]  = rowmean | y
+
+  for (int i = tid; i < 4096; i += DW_WARPS * 32) wpT[(i & 63) * 65 + (i >> 6)] = __ldg(a.wp + i);
+  for (int i = tid; i < 65 * (64 + F); i += DW_WARPS * 32) { const int r = i / (64 + F); wws[r * LW + (i - r * (64 + F))] = __ldg(a.ww + i); }
+  for (int i = tid; i < (H + 1) * (H + F); i += DW_WARPS * 32) { const int r = i / (H + F); whs[r * LH + (i - r * (H + F))] = __ldg(a.wh + i); }
+  for (int i = tid; i < n; i += DW_WARPS * 32) {
+    n1w[i] = __ldg(a.n1w + i); n1b[i] = __ldg(a.n1b + i); n2w[i] = __ldg(a.n2w + i); n2b[i] = __ldg(a.n2b + i);
+  }
+  const float bp0 = __ldg(a.bp + lane), bp1 = __ldg(a.bp + lane + 32);
+  __syncthreads();
+
+  const int stride = gridDim.x * DW_WARPS;
+  for (int pl = blockIdx.x * DW_WARPS + warp; pl < nplanes; pl += stride) {
+    const size_t plane = (size_t)pl * n;
+    float xv[E];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) { xv[i] = __ldg(a.x + plane + lane + 32 * i); s += xv[i]; }
+    for (int f = lane; f < F; f += 32) { const float y = __ldg(a.e3 + (size_t)pl * F + f); vecw[64 + f] = y; vech[H + f] = y; }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    const float mean = s / (float)n;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) { const float d = xv[i] - mean; q = __fmaf_rn(d, d, q); }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) q += __shfl_xor_sync(0xffffffffu, q, k);
+    const float rstd = rsqrtf(q / (float)n + 1e-5f);
+    float u[E];
+    float c0 = 0.f, c1 = 0.f;                      // column sums of w = lane and w = lane + 32
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const int idx = lane + 32 * i;
+      u[i] = (xv[i] - mean) * rstd * n1w[idx] + n1b[idx];
+      if (i & 1) c1 += u[i]; else c0 += u[i];
+    }
+    vecw[lane] = c0 / (float)H;
+    vecw[lane + 32] = c1 / (float)H;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {                  // row means
+      float t = u[2 * h] + u[2 * h + 1];
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
+      if (lane == (h & 31)) vech[h] = t / 64.f;
+    }
+    __syncwarp();
+    // gate logits: width logits lane and lane + 32, the 65th by a warp reduction; height logits on lanes 0..H
+    float l0 = 0.f, l1 = 0.f, l64 = 0.f, lhv = 0.f;
+    {
+      const float* r0 = wws + lane * LW;
+      const float* r1 = wws + (lane + 32) * LW;
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+      for (int k = 0; k + 1 < 64 + F; k += 2) {
+        const float v0 = vecw[k], v1 = vecw[k + 1];
+        t0 = __fmaf_rn(r0[k], v0, t0); t1 = __fmaf_rn(r0[k + 1], v1, t1);
+        t2 = __fmaf_rn(r1[k], v0, t2); t3 = __fmaf_rn(r1[k + 1], v1, t3);
+      }
+      if ((64 + F) & 1) { const float v0 = vecw[64 + F - 1]; t0 = __fmaf_rn(r0[64 + F - 1], v0, t0); t2 = __fmaf_rn(r1[64 + F - 1], v0, t2); }
+      l0 = t0 + t1; l1 = t2 + t3;
+      const float* r64 = wws + 64 * LW;
+      float t = 0.f;
+      for (int k = lane; k < 64 + F; k += 32) t = __fmaf_rn(r64[k], vecw[k], t);
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
+      l64 = t;
+      if (lane <= H) {
+        const float* rh = whs + lane * LH;
+        float h0 = 0.f, h1 = 0.f;
+        for (int k = 0; k + 1 < H + F; k += 2) { h0 = __fmaf_rn(rh[k], vech[k], h0); h1 = __fmaf_rn(rh[k + 1], vech[k + 1], h1); }
+        if ((H + F) & 1) h0 = __fmaf_rn(rh[H + F - 1], vech[H + F - 1], h0);
+        lhv = h0 + h1;
+      }
+    }
+    // soft-max over the 64 width logits (two per lane) and over the H height logits (lanes 0..H-1)
+    float vw0, vw1, vhv;
+    {
+      float m = fmaxf(l0, l1);
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+      const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+      float t = e0 + e1;
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
+      vw0 = e0 / t; vw1 = e1 / t;
+      float mh = lane < H ? lhv : -INFINITY;
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, k));
+      const float eh = lane < H ? expf(lhv - mh) : 0.f;
+      float th = eh;
+#pragma unroll
+      for (int k = 16; k >= 1; k >>= 1) th += __shfl_xor_sync(0xffffffffu, th, k);
+      vhv = eh / th;
+    }
+    const float hl = __shfl_sync(0xffffffffu, lhv, H), wl = l64;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float vh = __shfl_sync(0xffffffffu, vhv, i >> 1);
+      const float vw = (i & 1) ? vw1 : vw0;
+      as[lane + 32 * i] = (vh * u[i]) * hl + (vw * u[i]) * wl;     // same association as DGAB.py:50
+    }
+    __syncwarp();
+    // proj over the width axis + residual: lane -> output columns j = lane, lane + 32, all H rows
+    float o[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) o[i] = 0.f;
+#pragma unroll 1
+    for (int w = 0; w < 64; w += 4) {
+      float wa[4], wb[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { wa[t] = wpT[(w + t) * 65 + lane]; wb[t] = wpT[(w + t) * 65 + lane + 32]; }
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float4 av = *reinterpret_cast<const float4*>(as + h * 64 + w);   // warp-wide broadcast
+        o[2 * h] = __fmaf_rn(av.x, wa[0], o[2 * h]); o[2 * h] = __fmaf_rn(av.y, wa[1], o[2 * h]);
+        o[2 * h] = __fmaf_rn(av.z, wa[2], o[2 * h]); o[2 * h] = __fmaf_rn(av.w, wa[3], o[2 * h]);
+        o[2 * h + 1] = __fmaf_rn(av.x, wb[0], o[2 * h + 1]); o[2 * h + 1] = __fmaf_rn(av.y, wb[1], o[2 * h + 1]);
+        o[2 * h + 1] = __fmaf_rn(av.z, wb[2], o[2 * h + 1]); o[2 * h + 1] = __fmaf_rn(av.w, wb[3], o[2 * h + 1]);
+      }
+    }
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      o[i] = xv[i] + (o[i] + ((i & 1) ? bp1 : bp0));
+      a.x1[plane + lane + 32 * i] = o[i];
+      s2 += o[i];
+    }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, k);
+    const float mean2 = s2 / (float)n;
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) { const float d = o[i] - mean2; q2 = __fmaf_rn(d, d, q2); }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, k);
+    const float rstd2 = rsqrtf(q2 / (float)n + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const int idx = lane + 32 * i;
+      a.v[plane + idx] = (o[i] - mean2) * rstd2 * n2w[idx] + n2b[idx];
+    }
+    __syncwarp();          // this warp's scratch is rewritten by its next plane
+  }
+}
+
+static size_t dgab_warp_smem(int H, int F) {
+  const int n = H * 64;
+  return sizeof(float) * (size_t)(4 * n + 64 * 65 + 65 * (64 + F + 1) + (H + 1) * (H + F + 1) +
+                                  DW_WARPS * (n + (64 + F) + (H + F) + 4) + 8);
+}
+
 static size_t dgab_plane_smem(int H, int F) {
   const int n = H * 64;
   return sizeof(float) * (size_t)(64 * 65 + 65 * (64 + F + 1) + (H + 1) * (H + F + 1) + 6 * n + (64 + F) + (H + F) + 65 +
@@ -997,7 +1169,14 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     a.n1w = P[TPSPP_P_NORM1_W]; a.n1b = P[TPSPP_P_NORM1_B]; a.n2w = P[TPSPP_P_NORM2_W]; a.n2b = P[TPSPP_P_NORM2_B];
     a.wh = P[TPSPP_P_MLP_H_W]; a.ww = P[TPSPP_P_MLP_W_W]; a.wp = P[TPSPP_P_PROJ_W]; a.bp = P[TPSPP_P_PROJ_B];
     a.x1 = W(TPSPP_WS_X1); a.v = W(TPSPP_WS_V); a.H = h; a.F = d.F;
-    {
+    if ((h == 8 || h == 16) && d.F <= 32 && dgab_warp_smem(h, d.F) <= 220 * 1024) {      // warp-per-plane kernel
+      const size_t smem = dgab_warp_smem(h, d.F);
+      auto kern = h == 8 ? dgab_warp_kernel<8> : dgab_warp_kernel<16>;
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int grid = sm_count();
+      if (grid > (B * 64 + DW_WARPS - 1) / DW_WARPS) grid = (B * 64 + DW_WARPS - 1) / DW_WARPS;
+      kern<<<grid, DW_WARPS * 32, smem, st>>>(a, B * 64);
+    } else {
       const size_t smem = dgab_plane_smem(h, d.F);
       auto kern = h == 8 ? dgab_plane_kernel<2> : h == 16 ? dgab_plane_kernel<4> : h == 24 ? dgab_plane_kernel<6>
                                                                                             : dgab_plane_kernel<8>;
