@@ -267,54 +267,98 @@ __global__ void __launch_bounds__(256) loc_p1_kernel(LocArgs a) {
     en[k * 65 + c] = __ldg(a.e3 + (size_t)b * 64 * F + i);
   }
   __syncthreads();
+  // The CTA is one image and the whole launch is a single wave, so its time is the length of the dependent FMA chains
+  // below: every loop carries four independent outputs (each still summed in index order, so results are unchanged).
   {  // z1[k][m] = relu(Wa[m,:] . en[k,:] + ba[m]), m = tid
     float w[64];
 #pragma unroll
     for (int c = 0; c < 64; ++c) w[c] = __ldg(a.wa + tid * 64 + c);
     const float bs = __ldg(a.ba + tid);
-    for (int k = 0; k < F; ++k) {
+    int k = 0;
+    for (; k + 3 < F; k += 4) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        s0 = __fmaf_rn(w[c], en[k * 65 + c], s0); s1 = __fmaf_rn(w[c], en[(k + 1) * 65 + c], s1);
+        s2 = __fmaf_rn(w[c], en[(k + 2) * 65 + c], s2); s3 = __fmaf_rn(w[c], en[(k + 3) * 65 + c], s3);
+      }
+      z1[k * 256 + tid] = fmaxf(s0 + bs, 0.f); z1[(k + 1) * 256 + tid] = fmaxf(s1 + bs, 0.f);
+      z1[(k + 2) * 256 + tid] = fmaxf(s2 + bs, 0.f); z1[(k + 3) * 256 + tid] = fmaxf(s3 + bs, 0.f);
+    }
+    for (; k < F; ++k) {
       float s = 0.f;
 #pragma unroll
       for (int c = 0; c < 64; ++c) s = __fmaf_rn(w[c], en[k * 65 + c], s);
       z1[k * 256 + tid] = fmaxf(s + bs, 0.f);
     }
   }
-  // t1[k][q] = Wp0[q,:] . en[k,:] + bp0[q]
-  for (int o = tid; o < F * 32; o += 256) {
-    const int k = o >> 5, q = o & 31;
-    float s = 0.f;
-    for (int c = 0; c < 64; ++c) s = __fmaf_rn(__ldg(a.wp0 + q * 64 + c), en[k * 65 + c], s);
-    t1[k * 33 + q] = s + __ldg(a.bp0 + q);
+  // t1[k][q] = Wp0[q,:] . en[k,:] + bp0[q]: thread -> q = tid & 31, control points (tid >> 5) + 8 i, four at a time
+  {
+    const int q = tid & 31;
+    const float bq = __ldg(a.bp0 + q);
+    for (int k0 = tid >> 5; k0 < F; k0 += 32) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const int k1 = min(k0 + 8, F - 1), k2 = min(k0 + 16, F - 1), k3 = min(k0 + 24, F - 1);
+#pragma unroll 8
+      for (int c = 0; c < 64; ++c) {
+        const float wv = __ldg(a.wp0 + q * 64 + c);
+        s0 = __fmaf_rn(wv, en[k0 * 65 + c], s0); s1 = __fmaf_rn(wv, en[k1 * 65 + c], s1);
+        s2 = __fmaf_rn(wv, en[k2 * 65 + c], s2); s3 = __fmaf_rn(wv, en[k3 * 65 + c], s3);
+      }
+      t1[k0 * 33 + q] = s0 + bq;
+      if (k0 + 8 < F) t1[(k0 + 8) * 33 + q] = s1 + bq;
+      if (k0 + 16 < F) t1[(k0 + 16) * 33 + q] = s2 + bq;
+      if (k0 + 24 < F) t1[(k0 + 24) * 33 + q] = s3 + bq;
+    }
   }
   __syncthreads();
   // z2[k*2+j] = relu(Wb[j,:] . z1[k,:] + bb[j]) : 8 lanes per output
   for (int o0 = (tid >> 3); o0 < 2 * F; o0 += 32) {
     const int k = o0 >> 1, j = o0 & 1, l = tid & 7;
     float s = 0.f;
+#pragma unroll 8
     for (int m = l; m < 256; m += 8) s = __fmaf_rn(__ldg(a.wb + j * 256 + m), z1[k * 256 + m], s);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     if (l == 0) z2[o0] = fmaxf(s + __ldg(a.bb + j), 0.f);
   }
-  // p1[k][r] = Wp1[r,:] . t1[k,:] + bp1[r]
-  for (int o = tid; o < F * 128; o += 256) {
-    const int k = o >> 7, r = o & 127;
-    float s = 0.f;
+  // p1[k][r] = Wp1[r,:] . t1[k,:] + bp1[r]: thread -> r = tid & 127, control points (tid >> 7) + 2 i, four at a time
+  {
+    const int r = tid & 127;
+    float wr[32];
 #pragma unroll
-    for (int q = 0; q < 32; ++q) s = __fmaf_rn(__ldg(a.wp1 + r * 32 + q), t1[k * 33 + q], s);
-    const float pv = s + __ldg(a.bp1 + r);
-    a.p1[((size_t)b * F + k) * 128 + r] = pv;
-    if (a.p1img != nullptr) {      // B operand of the score GEMM: row n = control point k, K index = r
-      const float hi = __uint_as_float(__float_as_uint(pv) & 0xFFFFE000u);
-      float* o = a.p1img + (size_t)b * 8192 + (size_t)(r >> 5) * 2048 + ((r >> 2) & 7) * 128 + k * 4 + (r & 3);
-      o[0] = hi;
-      o[1024] = pv - hi;
+    for (int q = 0; q < 32; ++q) wr[q] = __ldg(a.wp1 + r * 32 + q);
+    const float br = __ldg(a.bp1 + r);
+    for (int k0 = tid >> 7; k0 < F; k0 += 8) {
+      float sv[4] = {0.f, 0.f, 0.f, 0.f};
+      int kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) kk[u] = min(k0 + 2 * u, F - 1);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sv[u] = __fmaf_rn(wr[q], t1[kk[u] * 33 + q], sv[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 2 * u;
+        if (k >= F) break;
+        const float pv = sv[u] + br;
+        a.p1[((size_t)b * F + k) * 128 + r] = pv;
+        if (a.p1img != nullptr) {      // B operand of the score GEMM: row n = control point k, K index = r
+          const float hi = __uint_as_float(__float_as_uint(pv) & 0xFFFFE000u);
+          float* o = a.p1img + (size_t)b * 8192 + (size_t)(r >> 5) * 2048 + ((r >> 2) & 7) * 128 + k * 4 + (r & 3);
+          o[0] = hi;
+          o[1024] = pv - hi;
+        }
+      }
     }
   }
   __syncthreads();
   if (tid < 2 * F) {
     float s = 0.f;
+#pragma unroll 8
     for (int i = 0; i < 2 * F; ++i) s = __fmaf_rn(__ldg(a.wc + tid * 2 * F + i), z2[i], s);
     a.c_prime[(size_t)b * 2 * F + tid] = s + __ldg(a.bc + tid);
   }

@@ -572,6 +572,7 @@ struct ConvTmaArgs {
   ConvTcArgs t;
   CUtensorMap tmap[3];
   int TW, TH, BW, BH;      // tile and box (halo) extent in pixels; CHS = BW * BH floats per channel
+  int S;                   // convolution stride (1, or 2 for 3x3: one box per filter row, rows strided by the tensor map)
 };
 constexpr int TM_XH = 4;   // x halo of a 3x3 box: the innermost TMA coordinate must be 16-byte aligned (probed: x = -1 traps)
 constexpr int TM_TILE_MAX = 32 * (4 * 72) * 4;                            // 3x3 at TW = 64: 4 rows x 72 columns
@@ -637,7 +638,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_co
   // persistent over tiles blockIdx.x, blockIdx.x + gridDim.x, ...: TMEM, barriers and the TMA pipeline are set up once,
   // and the first activation tile of the next output tile is already in flight while this one runs its epilogue
   // (channel-group counter gcc and chunk counter gch run across tiles and drive the mbarrier phases)
-  auto issue_tile = [&](int tile, int cc, int gcc) {
+  const int S = g.S, NG = (KS == 3 && S == 2) ? 3 : 1, TG = T / NG;   // tile loads per channel group, taps per load
+  auto issue_tile = [&](int tile, int cc, int grp, int gcc) {
     const long long m_base = (long long)tile * TC_TM;
     const int img = (int)(m_base / HoWo);
     const int rem0 = (int)(m_base - (long long)img * HoWo);
@@ -645,9 +647,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_co
     int s = 0, c0 = cc * TC_KC;
     if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { c0 -= a.src[1].C; s = 2; } }
     const int up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
-    const int y0 = oy0 - a.pad;
+    const int y0 = S * oy0 - a.pad + grp;
     mbar_arrive_expect_tx(&t_full[gcc & 1], tile_tx);
-    tma_load_4d(tiles + (gcc & 1) * TILE_BYTES, &g.tmap[s], up ? ((ox0 - 2 * XH) >> 1) : (ox0 - XH), up ? (y0 >> 1) : y0, c0, img,
+    tma_load_4d(tiles + (gcc & 1) * TILE_BYTES, &g.tmap[s], up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH), up ? (y0 >> 1) : y0, c0, img,
                 &t_full[gcc & 1], policy_evict_first());
   };
 
@@ -688,35 +690,39 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_co
     const int pr = row / g.TW, pc = row - pr * g.TW;            // position inside the tile rectangle
     const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     int gch = 0, gcc = 0;
-    if (tid == 0 && (int)blockIdx.x < ntiles) issue_tile(blockIdx.x, 0, 0);
+    if (tid == 0 && (int)blockIdx.x < ntiles) issue_tile(blockIdx.x, 0, 0, 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long m_base = (long long)tile * TC_TM;
       const int img = (int)(m_base / HoWo);
       const int rem0 = (int)(m_base - (long long)img * HoWo);
       const int oy0 = rem0 / a.Wo, ox0 = rem0 - oy0 * a.Wo;
-      for (int cc = 0; cc < ncc; ++cc, ++gcc) {
+      for (int cc = 0; cc < ncc; ++cc)
+      for (int grp = 0; grp < NG; ++grp, ++gcc) {
         const int tb = gcc & 1;
-        if (tid == 0) {                          // next channel group: of this tile, or the first one of the next tile
-          const int ntile = cc + 1 < ncc ? tile : tile + (int)gridDim.x;
+        if (tid == 0) {                          // next tile load: next filter row, next channel group, or the next output tile
+          int ntile = tile, ncc_ = cc, ngrp = grp + 1;
+          if (ngrp == NG) { ngrp = 0; if (++ncc_ == ncc) { ncc_ = 0; ntile = tile + (int)gridDim.x; } }
           if (ntile < ntiles) {
             if (gcc + 1 >= 2) mbar_wait_bounded(&t_empty[(gcc + 1) & 1], (uint32_t)((((gcc + 1) >> 1) - 1) & 1));
-            issue_tile(ntile, cc + 1 < ncc ? cc + 1 : 0, gcc + 1);
+            issue_tile(ntile, ncc_, ngrp, gcc + 1);
           }
         }
         __syncwarp();
         int s = 0, c0 = cc * TC_KC;
         if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { s = 2; } }
         const bool up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
-        const int by = up ? ((oy0 - a.pad) >> 1) : (oy0 - a.pad), bx = up ? ((ox0 - 2 * XH) >> 1) : (ox0 - XH);
+        const int by = up ? ((oy0 - a.pad) >> 1) : (oy0 - a.pad), bx = up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH);
         const float* tile_s = reinterpret_cast<const float*>(tiles + tb * TILE_BYTES) + (size_t)(kh * 16) * CHS;
         mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc >> 1) & 1));
 #pragma unroll 1
-        for (int tap = 0; tap < T; ++tap, ++gch) {
+        for (int tg = 0; tg < TG; ++tg, ++gch) {
           const int buf = gch & 1;
+          const int tap = grp * TG + tg;
           const int dy = tap / KS, dx = tap - dy * KS;
-          int iy = oy0 + pr + dy - a.pad, ix = ox0 + pc + dx - a.pad;
+          int iy = oy0 + pr + dy - a.pad, ix = S * (ox0 + pc) + dx - a.pad;
           if (up) { iy >>= 1; ix >>= 1; }
-          const float* q = tile_s + (iy - by) * g.BW + (ix - bx);
+          // stride 2: the box of this filter row already holds input rows 2 oy + dy - pad, one per tile row
+          const float* q = tile_s + (S == 2 ? pr : iy - by) * g.BW + (ix - bx);
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = q[(size_t)i * CHS];
@@ -737,7 +743,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_co
           const uint32_t col = (uint32_t)(128 + buf * 64 + kh * 16);
           tmem_st16(lane_addr + col, hi);
           tmem_st16(lane_addr + col + 32, lo);
-          if (tap == T - 1) {                      // the tile's last reads are in registers: hand the buffer back
+          if (tg == TG - 1) {                      // the tile's last reads are in registers: hand the buffer back
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[tb]);
           }
@@ -813,34 +819,38 @@ static tmap_encode_fn tmap_encoder() {
   return fn;
 }
 
-// stride-1 NCHW convolution whose tile is a rectangle of one image, every source either full or half resolution
+// NCHW convolution whose tile is a rectangle of one image, every source either full or half resolution
 static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g) {
-  if (a.sh != 1 || a.sw != 1 || a.out_nhwc || a.wimg_stride != 0 || a.Cout != 64) return false;
+  if (a.sh != a.sw || (a.sh != 1 && !(a.sh == 2 && KS == 3)) || a.out_nhwc || a.wimg_stride != 0 || a.Cout != 64) return false;
   if (a.pad != (KS == 3 ? 1 : 0)) return false;
+  const int S = a.sh;
   const int TW = a.Wo < 128 ? a.Wo : 128;
   if (TW < 16 || 128 % TW || a.Wo % TW) return false;
   const int TH = 128 / TW;
   if (a.Ho % TH) return false;
-  const int BW = KS == 3 ? TW + 2 * TM_XH : TW, BH = KS == 3 ? TH + 2 : TH;
+  // stride 1: one halo box serves all taps.  stride 2: one box per filter row -- full-width input rows 2 oy + dy - 1
+  // (the tensor map walks rows with element stride 2; TMA cannot stride the innermost dimension, so the threads read
+  // columns 2 ox + dx - 1 themselves)
+  const int BW = KS == 3 ? S * TW + 2 * TM_XH : TW, BH = (KS == 3 && S == 1) ? TH + 2 : TH;
   if (BW > 256 || BH > 256 || (size_t)BW * BH * TC_KC * 4 > (size_t)tm_tile_bytes(KS)) return false;
   tmap_encode_fn enc = tmap_encoder();
   if (enc == nullptr) return false;
   for (int s = 0; s < 3; ++s) {
     const ConvSrc& sc = a.src[s];
     if (sc.C == 0) continue;
-    if (sc.nhwc || sc.C % TC_KC || sc.uh != sc.uw || (sc.uh != 1 && sc.uh != 2)) return false;
-    if (sc.H * sc.uh != a.Ho || sc.W * sc.uw != a.Wo) return false;
+    if (sc.nhwc || sc.C % TC_KC || sc.uh != sc.uw || (sc.uh != 1 && sc.uh != 2) || (S == 2 && sc.uh != 1)) return false;
+    if (sc.H * sc.uh != a.Ho * S || sc.W * sc.uw != a.Wo * S) return false;
     if ((sc.W * 4) % 16 || ((uintptr_t)sc.ptr & 15)) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)sc.W, (cuuint64_t)sc.H, (cuuint64_t)sc.C, (cuuint64_t)a.B};
     const cuuint64_t strides[3] = {(cuuint64_t)sc.W * 4, (cuuint64_t)sc.W * sc.H * 4, (cuuint64_t)sc.W * sc.H * sc.C * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)TC_KC, 1};
-    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)BW, (cuuint32_t)(BH * S), (cuuint32_t)TC_KC, 1};
+    const cuuint32_t es[4] = {1, (cuuint32_t)S, 1, 1};
     if (enc(&g->tmap[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sc.ptr), dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return false;
   }
-  g->TW = TW; g->TH = TH; g->BW = BW; g->BH = BH;
+  g->TW = TW; g->TH = TH; g->BW = BW; g->BH = BH; g->S = S;
   return true;
 }
 
