@@ -577,7 +577,9 @@ struct ConvTmaArgs {
 constexpr int TM_XH = 4;   // x halo of a 3x3 box: the innermost TMA coordinate must be 16-byte aligned (probed: x = -1 traps)
 constexpr int TM_TILE_MAX = 32 * (4 * 72) * 4;                            // 3x3 at TW = 64: 4 rows x 72 columns
 __host__ __device__ constexpr int tm_tile_bytes(int KS) { return KS == 3 ? ((TM_TILE_MAX + 1023) / 1024) * 1024 : 16384; }
-__host__ __device__ constexpr int tm_smem_bytes(int KS) { return 2 * tm_tile_bytes(KS) + 2 * TS_STAGE + 512 + 1024; }
+__host__ __device__ constexpr int tm_tile_bufs(int KS) { return KS == 3 ? 2 : 4; }
+__host__ __device__ constexpr int tm_smem_bytes(int KS) { return tm_tile_bufs(KS) * tm_tile_bytes(KS) + 2 * TS_STAGE + 512 + 1024; }
+constexpr int TM_THREADS = TC_THREADS + 32;                                // 8 producer warps, MMA warp, TMA warp
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar,
                                             uint64_t policy) {
@@ -589,33 +591,32 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, in
 }
 
 template <int KS>
-__global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_constant__ ConvTmaArgs g) {
+__global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_constant__ ConvTmaArgs g) {
   constexpr int NT = 64, T = KS * KS;
   constexpr int XH = KS == 3 ? TM_XH : 0;
   constexpr int W_BYTES = 2 * TS_B_BYTES;
   constexpr int TILE_BYTES = tm_tile_bytes(KS);
+  constexpr int NTB = tm_tile_bufs(KS);                          // activation tile buffers in flight
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* tiles = smem;                                   // 2 activation tiles [32 ch][BH][BW]
-  unsigned char* wst = smem + 2 * TILE_BYTES;                    // 2 weight stages (hi | lo image of a chunk)
+  unsigned char* tiles = smem;                                   // NTB activation tiles [32 ch][BH][BW]
+  unsigned char* wst = smem + NTB * TILE_BYTES;                  // 2 weight stages (hi | lo image of a chunk)
   uint64_t* bars = reinterpret_cast<uint64_t*>(wst + 2 * TS_STAGE);
   uint64_t* a_empty = bars;          // [2] MMAs that read A stage / weight stage completed
   uint64_t* a_full = bars + 2;       // [2] all 8 producer warps stored their part of the chunk
   uint64_t* w_full = bars + 4;       // [2] weight image landed
-  uint64_t* t_full = bars + 6;       // [2] activation tile landed
-  uint64_t* t_empty = bars + 8;      // [2] all 8 producer warps are done reading the tile
-  uint64_t* d_empty = bars + 10;     // [1] the epilogue has drained the accumulator
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-  float* bias_s = reinterpret_cast<float*>(bars + 12);          // [64]
+  uint64_t* t_full = bars + 6;       // [4] activation tile landed
+  uint64_t* t_empty = bars + 10;     // [4] all 8 producer warps are done reading the tile
+  uint64_t* d_empty = bars + 14;     // [1] the epilogue has drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  float* bias_s = reinterpret_cast<float*>(bars + 16);          // [64]
   const ConvArgs& a = g.t.c;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_empty[i], 1); mbar_init(&a_full[i], TC_PRODUCERS / 32); mbar_init(&w_full[i], 1);
-      mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TC_PRODUCERS / 32);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_empty[i], 1); mbar_init(&a_full[i], TC_PRODUCERS / 32); mbar_init(&w_full[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TC_PRODUCERS / 32); }
     mbar_init(d_empty, TC_PRODUCERS / 32);
     fence_barrier_init();
   }
@@ -648,9 +649,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_co
     if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { c0 -= a.src[1].C; s = 2; } }
     const int up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
     const int y0 = S * oy0 - a.pad + grp;
-    mbar_arrive_expect_tx(&t_full[gcc & 1], tile_tx);
-    tma_load_4d(tiles + (gcc & 1) * TILE_BYTES, &g.tmap[s], up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH), up ? (y0 >> 1) : y0, c0, img,
-                &t_full[gcc & 1], policy_evict_first());
+    const int tb = gcc % NTB;
+    mbar_arrive_expect_tx(&t_full[tb], tile_tx);
+    tma_load_4d(tiles + tb * TILE_BYTES, &g.tmap[s], up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH), up ? (y0 >> 1) : y0, c0, img,
+                &t_full[tb], policy_evict_first());
   };
 
   if (warp == TC_PRODUCERS / 32) {
@@ -683,6 +685,39 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_co
         __syncwarp();
       }
     }
+  } else if (warp == TC_PRODUCERS / 32 + 1) {
+    // ===== TMA warp: activation tiles NTB - 1 loads ahead of the producers, the weight image of chunk g as soon as the
+    //       MMAs of chunk g - 2 have released its stage.  (Issued from a producer thread, each tile load stalled all
+    //       eight producer warps for ~1300 cycles -- 40 % of a stride-2 convolution's time.) =====
+    const int ngroups = ncc * NG;                       // tile loads per output tile
+    long long nloads = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) nloads += ngroups;
+    int l_tile = blockIdx.x, l_cc = 0, l_grp = 0, l_idx = 0;      // cursor of the next tile load to issue
+    auto issue_next_tile = [&]() {
+      if (l_idx >= nloads) return;
+      if (l_idx >= NTB) mbar_wait_bounded(&t_empty[l_idx % NTB], (uint32_t)(((l_idx / NTB) - 1) & 1));
+      if (elect_one_sync()) issue_tile(l_tile, l_cc, l_grp, l_idx);
+      __syncwarp();
+      ++l_idx;
+      if (++l_grp == NG) { l_grp = 0; if (++l_cc == ncc) { l_cc = 0; l_tile += gridDim.x; } }
+    };
+    for (int i = 0; i < NTB - 1; ++i) issue_next_tile();
+    int gch = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int cc = 0; cc < ncc; ++cc)
+        for (int grp = 0; grp < NG; ++grp) {
+          issue_next_tile();
+          for (int tg = 0; tg < TG; ++tg, ++gch) {
+            const int buf = gch & 1;
+            if (gch >= 2) mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch >> 1) - 1) & 1));
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&w_full[buf], W_BYTES);
+              bulk_g2s(wst + buf * TS_STAGE, wimg + (size_t)((grp * TG + tg) * ncc + cc) * W_BYTES, W_BYTES, &w_full[buf],
+                       policy_evict_last());
+            }
+            __syncwarp();
+          }
+        }
   } else {
     // ===== producer warps: thread = output pixel = TMEM lane; warps w and w+4 split a chunk's 32 channels =====
     const int row = (warp & 3) * 32 + lane;
@@ -690,7 +725,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_co
     const int pr = row / g.TW, pc = row - pr * g.TW;            // position inside the tile rectangle
     const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     int gch = 0, gcc = 0;
-    if (tid == 0 && (int)blockIdx.x < ntiles) issue_tile(blockIdx.x, 0, 0, 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long m_base = (long long)tile * TC_TM;
       const int img = (int)(m_base / HoWo);
@@ -698,22 +732,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_co
       const int oy0 = rem0 / a.Wo, ox0 = rem0 - oy0 * a.Wo;
       for (int cc = 0; cc < ncc; ++cc)
       for (int grp = 0; grp < NG; ++grp, ++gcc) {
-        const int tb = gcc & 1;
-        if (tid == 0) {                          // next tile load: next filter row, next channel group, or the next output tile
-          int ntile = tile, ncc_ = cc, ngrp = grp + 1;
-          if (ngrp == NG) { ngrp = 0; if (++ncc_ == ncc) { ncc_ = 0; ntile = tile + (int)gridDim.x; } }
-          if (ntile < ntiles) {
-            if (gcc + 1 >= 2) mbar_wait_bounded(&t_empty[(gcc + 1) & 1], (uint32_t)((((gcc + 1) >> 1) - 1) & 1));
-            issue_tile(ntile, ncc_, ngrp, gcc + 1);
-          }
-        }
-        __syncwarp();
+        const int tb = gcc % NTB;
         int s = 0, c0 = cc * TC_KC;
         if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { s = 2; } }
         const bool up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
         const int by = up ? ((oy0 - a.pad) >> 1) : (oy0 - a.pad), bx = up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH);
         const float* tile_s = reinterpret_cast<const float*>(tiles + tb * TILE_BYTES) + (size_t)(kh * 16) * CHS;
-        mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc >> 1) & 1));
+        mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc / NTB) & 1));
 #pragma unroll 1
         for (int tg = 0; tg < TG; ++tg, ++gch) {
           const int buf = gch & 1;
@@ -729,10 +754,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tma_kernel(const __grid_co
           if (gch >= 2) {
             mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch >> 1) - 1) & 1));   // MMAs of chunk gch-2 have read the stage
             tc_fence_after();
-          }
-          if (tid == 0) {
-            mbar_arrive_expect_tx(&w_full[buf], W_BYTES);
-            bulk_g2s(wst + buf * TS_STAGE, wimg + (size_t)(tap * ncc + cc) * W_BYTES, W_BYTES, &w_full[buf], policy_evict_last());
           }
           float hi[16], lo[16];
 #pragma unroll
@@ -945,6 +966,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
       if (++p_ch == nchunks) { p_ch = 0; if (++p_nb == nblocks) { p_nb = 0; p_tile += gridDim.x; } }
     };
     load_next_weights(); load_next_weights(); load_next_weights();
+    // operand tiles are issued from here as well, two chunks ahead: when this warp has seen a_full of chunk c, the
+    // producers have already released that chunk's tile buffer (they arrive on t_empty before a_full), so the load of
+    // chunk c + 2 never waits -- and the eight producer warps no longer stall behind one thread's TMA bookkeeping
+    int t_tile = blockIdx.x, t_ch = 0, t_idx = 0;
+    auto load_next_tile = [&]() {
+      if (t_tile >= ntiles) return;
+      const int tb = t_idx & 1;
+      if (t_idx >= 2) mbar_wait_bounded(&t_empty[tb], (uint32_t)(((t_idx >> 1) - 1) & 1));
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&t_full[tb], 16384);
+        tma_load_2d(tiles + tb * 16384, &g.tmap, t_ch * TC_KC, t_tile * TC_TM, &t_full[tb], policy_evict_first());
+      }
+      __syncwarp();
+      ++t_idx;
+      if (++t_ch == nchunks) { t_ch = 0; t_tile += gridDim.x; }
+    };
+    load_next_tile(); load_next_tile();
     int wi = 0, di = 0, it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       for (int nb = 0; nb < nblocks; ++nb, ++di) {
@@ -956,7 +994,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
           const int st = wi & (LN_WSTAGES - 1);
           const int ga = it * nchunks + ch;                 // A-stage use counter of this chunk
           mbar_wait_bounded(&w_full[st], (uint32_t)((wi / LN_WSTAGES) & 1));
-          if (nb == 0) mbar_wait_bounded(&a_full[ga & 1], (uint32_t)((ga >> 1) & 1));
+          if (nb == 0) { mbar_wait_bounded(&a_full[ga & 1], (uint32_t)((ga >> 1) & 1)); load_next_tile(); }
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t b_hi = smem_u32(wst) + (uint32_t)(st * TS_STAGE), b_lo = b_hi + NT * TC_KC * 4;
@@ -984,22 +1022,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
     const int kh = warp >> 2;
     const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     int gcc = 0, ga = 0, di = 0;
-    auto issue_tile = [&](int tile, int ch, int gcc_) {
-      mbar_arrive_expect_tx(&t_full[gcc_ & 1], 16384);
-      tma_load_2d(tiles + (gcc_ & 1) * 16384, &g.tmap, ch * TC_KC, tile * TC_TM, &t_full[gcc_ & 1], policy_evict_first());
-    };
-    if (tid == 0 && (int)blockIdx.x < ntiles) issue_tile(blockIdx.x, 0, 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int ch = 0; ch < nchunks; ++ch, ++gcc, ++ga) {
         const int tb = gcc & 1;
-        if (tid == 0) {
-          const int ntile = ch + 1 < nchunks ? tile : tile + (int)gridDim.x;
-          if (ntile < ntiles) {
-            if (gcc + 1 >= 2) mbar_wait_bounded(&t_empty[(gcc + 1) & 1], (uint32_t)((((gcc + 1) >> 1) - 1) & 1));
-            issue_tile(ntile, ch + 1 < nchunks ? ch + 1 : 0, gcc + 1);
-          }
-        }
-        __syncwarp();
         mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc >> 1) & 1));
         // this row's 16 floats of the chunk half: 16-byte pieces 4kh .. 4kh+3, stored at piece ^ (row & 7)
         const unsigned char* rp = tiles + tb * 16384 + row * 128;
@@ -1192,8 +1217,8 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
         tma_dev = dev;
       }
       dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()));
-      if (KS == 1) conv_tma_kernel<1><<<pgrid, TC_THREADS, tm_smem_bytes(1), st>>>(g);
-      else conv_tma_kernel<3><<<pgrid, TC_THREADS, tm_smem_bytes(3), st>>>(g);
+      if (KS == 1) conv_tma_kernel<1><<<pgrid, TM_THREADS, tm_smem_bytes(1), st>>>(g);
+      else conv_tma_kernel<3><<<pgrid, TM_THREADS, tm_smem_bytes(3), st>>>(g);
       count_launch();
       TPSPP_CHECK_CUDA(cudaGetLastError());
       return TPSPP_OK;
