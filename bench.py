@@ -308,7 +308,7 @@ def run_ours(args):
             # everything before the warp (convs, DGAB, localization, score): SURVEY 8(d) counts 0.82 GFLOP/img of
             # dense contractions.  The fp32-parity mode spends three TF32 MMAs per product (3xTF32) at half the
             # bf16 rate, so its own ceiling is peak/6; both fractions are reported.
-            "roofline_head": {"kernels": "conv_ts_kernel / conv_tc_kernel / dgab_plane_kernel / loc_p1_kernel",
+            "roofline_head": {"kernels": "conv_tma_kernel / conv_ts_kernel / lin_tma_kernel / conv_tc_kernel / dgab_warp_kernel / loc_p1_kernel / cbam_kernel",
                               "bound": "tensor", "achieved": HEAD_GFLOP_PER_IMG * B / head_ms, "peak": tpeak,
                               "unit": "TFLOP/s", "frac": HEAD_GFLOP_PER_IMG * B / head_ms / tpeak,
                               "frac_of_3xtf32_ceiling": (HEAD_GFLOP_PER_IMG * B / head_ms / (tpeak / 6.0)
