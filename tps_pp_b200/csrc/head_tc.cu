@@ -590,11 +590,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, in
       : "memory");
 }
 
-template <int KS>
+// BF16 = true: single-pass bf16 operands (kind::f16, fp32 accumulate) -- the opt-in TPSPP_HEAD_BF16 mode: A packs two
+// channels per TMEM column, the weight image is bf16, no correction accumulator.
+template <int KS, bool BF16>
 __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_constant__ ConvTmaArgs g) {
   constexpr int NT = 64, T = KS * KS;
   constexpr int XH = KS == 3 ? TM_XH : 0;
-  constexpr int W_BYTES = 2 * TS_B_BYTES;
+  constexpr int W_BYTES = BF16 ? NT * TC_KC * 2 : 2 * TS_B_BYTES;
   constexpr int TILE_BYTES = tm_tile_bytes(KS);
   constexpr int NTB = tm_tile_bufs(KS);                          // activation tile buffers in flight
   extern __shared__ unsigned char smem_raw[];
@@ -634,7 +636,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
   const int CHS = g.BW * g.BH;
   const uint32_t tile_tx = (uint32_t)(CHS * TC_KC * 4);
   const unsigned char* wimg = reinterpret_cast<const unsigned char*>(g.t.wprep);
-  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
+  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, BF16 ? 1 : 2);
 
   // persistent over tiles blockIdx.x, blockIdx.x + gridDim.x, ...: TMEM, barriers and the TMA pipeline are set up once,
   // and the first activation tile of the next output tile is already in flight while this one runs its epilogue
@@ -672,13 +674,21 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         if (elect_one_sync()) {
           const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE), b_lo = b_hi + TS_B_BYTES;
           const uint32_t a_hi = tmem_d + 128 + (uint32_t)(buf * 64), a_lo = a_hi + 32;
+          if (BF16) {
 #pragma unroll
-          for (int j = 0; j < TC_KC / 8; ++j) {
-            const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
-            const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (NT * 16), NT * 16, 128);
-            umma_ts_tf32(tmem_d + 64, a_lo + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
-            umma_ts_tf32(tmem_d + 64, a_hi + j * 8, dbl, IDESC, 1u);
-            umma_ts_tf32(tmem_d, a_hi + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
+            for (int j = 0; j < TC_KC / 16; ++j) {     // one MMA = K 16 = two 16-byte k-groups of 8 bf16
+              const uint64_t db = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
+              umma_ts_f16(tmem_d, a_hi + j * 8, db, IDESC, (ch | j) != 0 ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_KC / 8; ++j) {
+              const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
+              const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (NT * 16), NT * 16, 128);
+              umma_ts_tf32(tmem_d + 64, a_lo + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
+              umma_ts_tf32(tmem_d + 64, a_hi + j * 8, dbl, IDESC, 1u);
+              umma_ts_tf32(tmem_d, a_hi + j * 8, dbh, IDESC, (ch | j) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&a_empty[buf]);
         }
@@ -755,15 +765,25 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
             mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch >> 1) - 1) & 1));   // MMAs of chunk gch-2 have read the stage
             tc_fence_after();
           }
-          float hi[16], lo[16];
+          if (BF16) {
+            uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
-            lo[i] = v[i] - hi[i];
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);   // .x (low half) = even channel
+              pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            tmem_st8(lane_addr + (uint32_t)(128 + buf * 64 + kh * 8), pk);
+          } else {
+            float hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+              lo[i] = v[i] - hi[i];
+            }
+            const uint32_t col = (uint32_t)(128 + buf * 64 + kh * 16);
+            tmem_st16(lane_addr + col, hi);
+            tmem_st16(lane_addr + col + 32, lo);
           }
-          const uint32_t col = (uint32_t)(128 + buf * 64 + kh * 16);
-          tmem_st16(lane_addr + col, hi);
-          tmem_st16(lane_addr + col + 32, lo);
           if (tg == TG - 1) {                      // the tile's last reads are in registers: hand the buffer back
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[tb]);
@@ -787,7 +807,12 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         float acc[16], part[16];
         const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * 32 + pass * 16);
         tmem_ld_cols<16>(taddr, acc);
-        tmem_ld_cols<16>(taddr + 64, part);
+        if (BF16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) part[j] = 0.f;
+        } else {
+          tmem_ld_cols<16>(taddr + 64, part);
+        }
         const int cb = half * 32 + pass * 16;
         const float4* b4 = reinterpret_cast<const float4*>(bias_s + cb);       // warp-uniform: broadcast loads
 #pragma unroll
@@ -1208,17 +1233,21 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
     int dev = 0;
     TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
     ConvTmaArgs g;
-    if (!bf16 && conv_tma_plan(KS, a, &g)) {      // stride-1, rectangular tiles: activations staged by TMA
+    if (conv_tma_plan(KS, a, &g)) {               // rectangular tiles: activations staged by TMA
       g.t = t;
       static thread_local int tma_dev = -1;
       if (tma_dev != dev) {
-        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
-        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
         tma_dev = dev;
       }
       dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()));
-      if (KS == 1) conv_tma_kernel<1><<<pgrid, TM_THREADS, tm_smem_bytes(1), st>>>(g);
-      else conv_tma_kernel<3><<<pgrid, TM_THREADS, tm_smem_bytes(3), st>>>(g);
+      if (KS == 1 && !bf16) conv_tma_kernel<1, false><<<pgrid, TM_THREADS, tm_smem_bytes(1), st>>>(g);
+      else if (KS == 1) conv_tma_kernel<1, true><<<pgrid, TM_THREADS, tm_smem_bytes(1), st>>>(g);
+      else if (!bf16) conv_tma_kernel<3, false><<<pgrid, TM_THREADS, tm_smem_bytes(3), st>>>(g);
+      else conv_tma_kernel<3, true><<<pgrid, TM_THREADS, tm_smem_bytes(3), st>>>(g);
       count_launch();
       TPSPP_CHECK_CUDA(cudaGetLastError());
       return TPSPP_OK;
