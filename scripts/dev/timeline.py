@@ -2,7 +2,6 @@ import sys, ctypes, torch, numpy as np
 sys.path.insert(0, '/root/repo')
 from oracle import tpspp_oracle as O
 import tps_pp_b200 as T
-from tps_pp_b200 import _native as N
 DEV='cuda:0'
 m = T.TPS_PP().to(DEV).eval(); m.load_state_dict(O.trained_like_state(3), strict=True)
 B=256
@@ -14,15 +13,10 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 4096)()
 lib = ctypes.CDLL('/root/repo/tps_pp_b200/libtpspp.so')
 print('rc', lib.tpspp_dbg_read(buf))
-a = np.array(buf[:]).reshape(512, 8)
-t0 = a[20, 0]
-print('chunk  M:a_full  M:w_full  M:issued | P:start  P:a_empty_ok  P:st_done  P:arrived   (cycles rel.)')
-for ch in range(20, 60):
-    r = a[ch] - t0
-    print(ch, r[0], r[1], r[2], '|', r[3], r[4], r[5], r[6])
-
-b = np.array(buf[:])[2048:2048+512].reshape(128, 4)
-print('gcc: before_issue  before_t_full_wait  after_t_full_wait (rel)')
-for gc in range(2, 8):
-    r = b[gc] - t0
-    print(gc, r[0], r[1], r[2])
+a = np.array(buf[:])
+t0 = a[8 * 16 + 0]
+print('gj | MMA: loop_top fc1_next_issued a2_full_seen fc2_c0_issued fc2_c1_issued | EPI: wait_d1 d1_seen gelu_done a2_empty_ok a2_full_arrived')
+for gj in range(8, 20):
+    r = a[gj * 16: gj * 16 + 13] - t0
+    print(gj, r[0], r[1], r[2], r[3], r[4], '|', r[8], r[9], r[10], r[11], r[12])
+print('a1_full seen per tile', (a[2048:2056] - t0).tolist())

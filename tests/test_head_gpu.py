@@ -157,7 +157,7 @@ def test_head_is_deterministic_over_many_tiles(native_lib, precision):
         for i, nm in enumerate(names):
             lo = off[nm]
             hi = off[names[i + 1]] if i + 1 < len(names) else runs[0][3].numel()
-            if hi > lo:
+            if hi > lo and nm != "hid":      # "hid" is only written by the two-launch Mlp fallback (fused kernel: stays in TMEM)
                 assert torch.equal(runs[0][3][lo:hi], r[3][lo:hi]), f"workspace slot {nm}"
     assert torch.isfinite(runs[0][2]).all()
 

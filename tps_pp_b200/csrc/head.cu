@@ -1236,7 +1236,12 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     TPSPP_CHECK_CUDA(cudaGetLastError());
     const long long R = (long long)B * 64 * h;
     if (tc) {
-      // Mlp over the width axis as two row GEMMs on the tensor cores: rows = (b, c, h), K = w
+      // Mlp over the width axis on the tensor cores: rows = (b, c, h), K = w.  Fused kernel first (hidden tensor stays
+      // in tensor memory); the two-launch form is the fallback
+      rc = run_mlp_fused(W(TPSPP_WS_V), W(TPSPP_WS_X1), wp[TCL_FC1], P[TPSPP_P_FC1_B], wp[TCL_FC2], P[TPSPP_P_FC2_B],
+                         W(TPSPP_WS_DE2), R, st);
+      if (rc < 0) return rc;
+      if (rc == 1) {
       ConvArgs g;
       memset(&g, 0, sizeof(g));
       g.src[0] = mk_src(W(TPSPP_WS_V), 64, 1, (int)R, NHWC); g.src[1] = none; g.src[2] = none;
@@ -1249,6 +1254,7 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
       g.bias = P[TPSPP_P_FC2_B]; g.skip = W(TPSPP_WS_X1); g.out = W(TPSPP_WS_DE2); g.act = CONV_ACT_NONE; g.Cout = 64;
       rc = run_conv_tc(1, g, wp[TCL_FC2], 64, st);
       if (rc != TPSPP_OK) return rc;
+      }
     } else {
       MlpArgs m;
       m.v = W(TPSPP_WS_V); m.x1 = W(TPSPP_WS_X1); m.w1 = P[TPSPP_P_FC1_W]; m.b1 = P[TPSPP_P_FC1_B];

@@ -30,6 +30,9 @@ enum { CONV_ACT_RELU = 0, CONV_ACT_NONE = 1, CONV_ACT_GELU = 2, CONV_ACT_TANH = 
 // conv_tc_prepare_weights (3xTF32 hi/lo split, UMMA core-matrix order).
 bool conv_tc_eligible(const ConvArgs& a, int KS);
 int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st, bool bf16 = false);
+// DGAB Mlp fused (fc1 + GELU + fc2 + residual) on the weight images of fc1/fc2; returns 1 if not applicable
+int run_mlp_fused(const float* v, const float* x1, const float* w1img, const float* b1, const float* w2img, const float* b2,
+                  float* out, long long R, cudaStream_t st);
 size_t conv_tc_wprep_floats(int Ctot, int KS, int N);    // floats needed for one layer's image (N output rows)
 
 struct WPrepLayer {

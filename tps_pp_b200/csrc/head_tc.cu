@@ -45,6 +45,19 @@ struct ConvTcArgs {
 };
 
 __device__ __forceinline__ float tc_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// Branch-free GELU for the tensor-core Mlp epilogues: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. one
+// fp32 ulp of the result and well below the 3xTF32 GEMM error), ~15 instructions.  libdevice's erff costs ~53 per
+// element here because its two magnitude ranges diverge inside a warp; it was 60 % of the fused Mlp kernel.
+__device__ __forceinline__ float tc_gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.f - p * t * __expf(-z * z);          // erf(|x| / sqrt 2)
+  return 0.5f * x * (1.f + copysignf(e, x));
+}
 __device__ __forceinline__ float tc_act(float x, int act, float scale) {
   switch (act) {
     case CONV_ACT_RELU: return fmaxf(x, 0.f);
@@ -1099,7 +1112,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
             if (a.bias != nullptr) bs = __ldg(reinterpret_cast<const float4*>(a.bias + cb + j));
             float4 r = make_float4(acc[j] + (part[j] + bs.x), acc[j + 1] + (part[j + 1] + bs.y), acc[j + 2] + (part[j + 2] + bs.z),
                                    acc[j + 3] + (part[j + 3] + bs.w));
-            if (a.act == CONV_ACT_GELU) { r.x = tc_gelu(r.x); r.y = tc_gelu(r.y); r.z = tc_gelu(r.z); r.w = tc_gelu(r.w); }
+            if (a.act == CONV_ACT_GELU) { r.x = tc_gelu_fast(r.x); r.y = tc_gelu_fast(r.y); r.z = tc_gelu_fast(r.z); r.w = tc_gelu_fast(r.w); }
             else if (a.act == CONV_ACT_TANH) { r.x = tanhf(r.x * a.act_scale); r.y = tanhf(r.y * a.act_scale); r.z = tanhf(r.z * a.act_scale); r.w = tanhf(r.w * a.act_scale); }
             else if (a.act == CONV_ACT_RELU) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
             if (a.skip != nullptr) {
@@ -1118,6 +1131,271 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DGAB's Mlp fused: out = x1 + fc2(GELU(fc1(v) + b1)) + b2 over rows of 64 (DGAB.py:17-23,76) without the
+// [R,256] hidden tensor ever leaving the SM (it was 268 MB written + 268 MB read per step).  One 512-column CTA
+// per SM, persistent over 128-row tiles:
+//   TMEM   A1 [0,128)  : the split input tile (K = 64: two chunks of hi 32 | lo 32), kept for all four hidden blocks
+//          D1 [128,256): two fc1 accumulators (64-wide hidden blocks alternate; correction terms merged in)
+//          A2 [256,384): GELU(D1 + b1) split again -- the A operand of fc2 for that block (K = 64)
+//          D2 [384,512): fc2 accumulator, summed over the four hidden blocks
+//   smem   fc1 weight images resident (128 KB), fc2 weight chunks through a 4-stage ring, the input tile's two chunks
+//   warps  0-15 produce A1, run the per-block GELU epilogue (D1 -> A2) and the final epilogue; warp 16 issues MMAs
+//          (fc1 of block j+1 is issued before fc2 of block j, so it overlaps block j's GELU); warp 17 feeds TMA.
+// ------------------------------------------------------------------------------------------------
+struct MlpFusedArgs {
+  CUtensorMap tmap;                  // v [R, 64] row-major, box 32 x 128, SWIZZLE_128B
+  const float *w1img, *w2img;        // wprep images of fc1 (4 blocks x 2 chunks) and fc2 (8 chunks), NT = 64
+  const float *b1, *b2, *skip;
+  float* out;
+  long long R;
+};
+constexpr int MF_WARPS_E = 16;
+constexpr int MF_THREADS = (MF_WARPS_E + 2) * 32;
+constexpr int MF_W1_BYTES = 8 * TS_STAGE, MF_W2_STAGES = 4;
+constexpr int MF_SMEM = MF_W1_BYTES + MF_W2_STAGES * TS_STAGE + 2 * 16384 + 512 + 1024;
+
+__global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const __grid_constant__ MlpFusedArgs g) {
+  constexpr int NT = 64;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* w1s = smem;                                        // [4 blocks][2 chunks] x 16 KB
+  unsigned char* w2s = smem + MF_W1_BYTES;                          // ring of fc2 chunks
+  unsigned char* vts = w2s + MF_W2_STAGES * TS_STAGE;               // input tile: chunk 0 | chunk 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vts + 2 * 16384);
+  uint64_t* w1_full = bars;            // 1
+  uint64_t* v_full = bars + 1;         // [2]
+  uint64_t* v_empty = bars + 3;        // [2]
+  uint64_t* a1_full = bars + 5;
+  uint64_t* a1_empty = bars + 6;
+  uint64_t* d1_full = bars + 7;        // [2]
+  uint64_t* d1_empty = bars + 9;       // [2]
+  uint64_t* a2_full = bars + 11;
+  uint64_t* a2_empty = bars + 12;
+  uint64_t* d2_full = bars + 13;
+  uint64_t* d2_empty = bars + 14;
+  uint64_t* w2_full = bars + 15;       // [4]
+  uint64_t* w2_empty = bars + 19;      // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+  if (tid == 0) {
+    mbar_init(w1_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], MF_WARPS_E); }
+    mbar_init(a1_full, MF_WARPS_E); mbar_init(a1_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], MF_WARPS_E); }
+    mbar_init(a2_full, MF_WARPS_E); mbar_init(a2_empty, 1);
+    mbar_init(d2_full, 1); mbar_init(d2_empty, MF_WARPS_E);
+    for (int i = 0; i < MF_W2_STAGES; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  const int ntiles = (int)(g.R / TC_TM);
+  const int n_my = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
+  constexpr uint32_t PART = NT * TC_KC * 4;                          // bytes of the hi (or lo) image of a chunk
+
+  if (warp == MF_WARPS_E) {
+    // ===== MMA issuer warp =====
+    if (n_my > 0) mbar_wait_bounded(w1_full, 0);
+    // d_corr == d_main merges the 3xTF32 correction terms into the one accumulator (fc1: K = 64, 24 accumulation steps)
+    auto mma_chunk = [&](uint32_t d_main, uint32_t d_corr, uint32_t a_base, uint32_t b_base, bool first) {   // one elected lane
+#pragma unroll
+      for (int kk = 0; kk < TC_KC / 8; ++kk) {
+        const uint64_t dbh = umma_smem_desc(b_base + kk * 2 * (NT * 16), NT * 16, 128);
+        const uint64_t dbl = umma_smem_desc(b_base + PART + kk * 2 * (NT * 16), NT * 16, 128);
+        const uint32_t a_hi = a_base + kk * 8, a_lo = a_hi + 32;
+        umma_ts_tf32(d_main, a_hi, dbh, IDESC, (first && kk == 0) ? 0u : 1u);
+        umma_ts_tf32(d_corr, a_lo, dbh, IDESC, (first && kk == 0 && d_corr != d_main) ? 0u : 1u);
+        umma_ts_tf32(d_corr, a_hi, dbl, IDESC, 1u);
+      }
+    };
+    auto issue_fc1 = [&](int gj) {           // hidden block gj & 3 of tile gj >> 2: D1[gj & 1] = A1 . W1_j^T
+      const int db = gj & 1;
+      if (gj >= 2) { mbar_wait_bounded(&d1_empty[db], (uint32_t)(((gj >> 1) - 1) & 1)); }
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const int j = gj & 3;
+        const uint32_t d1 = tmem_d + 128 + (uint32_t)(db * 64);
+        for (int c = 0; c < 2; ++c)
+          mma_chunk(d1, d1, tmem_d + (uint32_t)(c * 64), smem_u32(w1s) + (uint32_t)((j * 2 + c) * TS_STAGE), c == 0);
+        umma_commit(&d1_full[db]);
+        if (j == 3) umma_commit(a1_empty);
+      }
+      __syncwarp();
+    };
+    for (int it = 0; it < n_my; ++it) {
+      mbar_wait_bounded(a1_full, (uint32_t)(it & 1));
+      issue_fc1(it * 4);
+      for (int j = 0; j < 4; ++j) {
+        const int gj = it * 4 + j;
+        if (j < 3) issue_fc1(gj + 1);        // overlaps the GELU epilogue of block j
+        mbar_wait_bounded(a2_full, (uint32_t)(gj & 1));
+        if (j == 0 && it >= 1) mbar_wait_bounded(d2_empty, (uint32_t)((it - 1) & 1));
+        for (int c = 0; c < 2; ++c) {
+          const int wi = gj * 2 + c, st = wi & (MF_W2_STAGES - 1);
+          mbar_wait_bounded(&w2_full[st], (uint32_t)((wi / MF_W2_STAGES) & 1));
+          tc_fence_after();
+          if (elect_one_sync()) {
+            mma_chunk(tmem_d + 384, tmem_d + 448, tmem_d + 256 + (uint32_t)(c * 64), smem_u32(w2s) + (uint32_t)(st * TS_STAGE), j == 0 && c == 0);
+            umma_commit(&w2_empty[st]);
+            if (c == 1) { umma_commit(a2_empty); if (j == 3) umma_commit(d2_full); }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == MF_WARPS_E + 1) {
+    // ===== TMA warp: resident fc1 images once, then input-tile chunks and fc2 chunks, polled round-robin =====
+    if (n_my > 0 && elect_one_sync()) {
+      mbar_arrive_expect_tx(w1_full, MF_W1_BYTES);
+      for (int i = 0; i < 8; ++i)
+        bulk_g2s(w1s + i * TS_STAGE, reinterpret_cast<const unsigned char*>(g.w1img) + (size_t)i * TS_STAGE, TS_STAGE, w1_full,
+                 policy_evict_last());
+    }
+    __syncwarp();
+    const int total_v = n_my * 2, total_w = n_my * 8;
+    int vi = 0, wi = 0;
+    while (vi < total_v || wi < total_w) {
+      if (vi < total_v) {
+        const int it = vi >> 1, c = vi & 1;
+        int ok = 1;
+        if (it >= 1) ok = mbar_test_wait(&v_empty[c], (uint32_t)((it - 1) & 1)) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&v_full[c], 16384);
+            tma_load_2d(vts + c * 16384, &g.tmap, c * TC_KC, (int)((blockIdx.x + (long long)it * gridDim.x) * TC_TM), &v_full[c],
+                        policy_evict_first());
+          }
+          __syncwarp();
+          ++vi;
+        }
+      }
+      if (wi < total_w) {
+        const int st = wi & (MF_W2_STAGES - 1);
+        int ok = 1;
+        if (wi >= MF_W2_STAGES) ok = mbar_test_wait(&w2_empty[st], (uint32_t)(((wi / MF_W2_STAGES) - 1) & 1)) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&w2_full[st], TS_STAGE);
+            bulk_g2s(w2s + st * TS_STAGE, reinterpret_cast<const unsigned char*>(g.w2img) + (size_t)(wi & 7) * TS_STAGE, TS_STAGE,
+                     &w2_full[st], policy_evict_last());
+          }
+          __syncwarp();
+          ++wi;
+        }
+      }
+    }
+  } else {
+    // ===== producer / epilogue warps: lane quarter q = warp & 3 (TMEM lanes), column part p = warp >> 2 =====
+    const int q = warp & 3, p = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
+    float b1r[4][16];                   // this thread's fc1 biases: hidden column j*64 + p*16 + i
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) b1r[j][i] = __ldg(g.b1 + j * 64 + p * 16 + i);
+    // A1 of tile `it`: this thread's 8 floats of each chunk (pieces 2p, 2p+1 of its 128-byte row)
+    auto produce_a1 = [&](int it) {
+      if (it >= 1) { mbar_wait_bounded(a1_empty, (uint32_t)((it - 1) & 1)); tc_fence_after(); }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        mbar_wait_bounded(&v_full[c], (uint32_t)(it & 1));
+        const unsigned char* rp = vts + c * 16384 + row * 128;
+        const float4 x0 = *reinterpret_cast<const float4*>(rp + (((2 * p) ^ (row & 7)) << 4));
+        const float4 x1 = *reinterpret_cast<const float4*>(rp + (((2 * p + 1) ^ (row & 7)) << 4));
+        const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          hi[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+          lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+        }
+        tmem_st8(lane_addr + (uint32_t)(c * 64 + p * 8), hi);
+        tmem_st8(lane_addr + (uint32_t)(c * 64 + 32 + p * 8), lo);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&v_empty[c]);       // after the tcgen05.st that consumed the loads
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a1_full);
+    };
+    if (n_my > 0) produce_a1(0);
+    for (int it = 0; it < n_my; ++it) {
+      const long long m = ((long long)blockIdx.x + (long long)it * gridDim.x) * TC_TM + row;
+      // ---- per hidden block: D1 -> + b1 -> GELU -> split -> A2 ----
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int gj = it * 4 + j;
+        const int db = gj & 1;
+        mbar_wait_bounded(&d1_full[db], (uint32_t)((gj >> 1) & 1));
+        tc_fence_after();
+        float acc[16];
+        tmem_ld_cols<16>(lane_addr + (uint32_t)(128 + db * 64 + p * 16), acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d1_empty[db]);       // D1 is in registers: fc1 of block gj + 2 may overwrite it
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float bj = b1r[0][i];
+          if (j == 1) bj = b1r[1][i]; else if (j == 2) bj = b1r[2][i]; else if (j == 3) bj = b1r[3][i];
+          const float h = tc_gelu_fast(acc[i] + bj);
+          hi[i] = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
+          lo[i] = h - hi[i];
+        }
+        if (gj >= 1) { mbar_wait_bounded(a2_empty, (uint32_t)((gj - 1) & 1)); tc_fence_after(); }
+        const uint32_t col = (uint32_t)(256 + (p >> 1) * 64 + (p & 1) * 16);
+        tmem_st16(lane_addr + col, hi);
+        tmem_st16(lane_addr + col + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a2_full);
+      }
+      // the next tile's A1 goes in before this tile's final epilogue (A1 was released by fc1 of block 3), so the MMA
+      // warp starts the next tile while fc2 of block 3 drains; the residual is fetched before waiting for D2
+      if (it + 1 < n_my) produce_a1(it + 1);
+      const size_t o0 = (size_t)m * 64 + p * 16;
+      float4 skv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) skv[i] = __ldg(reinterpret_cast<const float4*>(g.skip + o0 + 4 * i));
+      // ---- final epilogue: D2 + b2 + skip -> out[m, p*16 .. p*16+15] ----
+      mbar_wait_bounded(d2_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      {
+        float acc[16], part[16];
+        tmem_ld_cols<16>(lane_addr + (uint32_t)(384 + p * 16), acc);
+        tmem_ld_cols<16>(lane_addr + (uint32_t)(448 + p * 16), part);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d2_empty);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 bs = __ldg(reinterpret_cast<const float4*>(g.b2 + p * 16 + i));
+          const float4 sk = skv[i >> 2];
+          float4 r;
+          r.x = (acc[i] + (part[i] + bs.x)) + sk.x; r.y = (acc[i + 1] + (part[i + 1] + bs.y)) + sk.y;
+          r.z = (acc[i + 2] + (part[i + 2] + bs.z)) + sk.z; r.w = (acc[i + 3] + (part[i + 3] + bs.w)) + sk.w;
+          *reinterpret_cast<float4*>(g.out + o0 + i) = r;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 512);
 }
 
 // weight image: for output row n (column block n / NT) and k = tap*Ctot + cin:
@@ -1216,6 +1494,36 @@ static bool lin_tma_plan(const ConvArgs& a, int NT, LinTmaArgs* g) {
   return enc(&g->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sc.ptr), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// fused Mlp launcher; returns 1 when the fused kernel does not apply (caller falls back to fc1 / fc2 launches)
+int run_mlp_fused(const float* v, const float* x1, const float* w1img, const float* b1, const float* w2img, const float* b2,
+                  float* out, long long R, cudaStream_t st) {
+  if (R % TC_TM || R > 0x7fffffffLL || (((uintptr_t)v | (uintptr_t)x1 | (uintptr_t)out | (uintptr_t)b2) & 15)) return 1;
+  tmap_encode_fn enc = tmap_encoder();
+  if (enc == nullptr) return 1;
+  MlpFusedArgs g;
+  const cuuint64_t dims[2] = {64, (cuuint64_t)R};
+  const cuuint64_t strides[1] = {64 * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_TM};
+  const cuuint32_t es[2] = {1, 1};
+  if (enc(&g.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(v), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 1;
+  g.w1img = w1img; g.w2img = w2img; g.b1 = b1; g.b2 = b2; g.skip = x1; g.out = out; g.R = R;
+  static thread_local int mf_dev = -1;
+  int dev = 0;
+  TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (mf_dev != dev) {
+    TPSPP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM));
+    mf_dev = dev;
+  }
+  const long long ntiles = R / TC_TM;
+  dim3 grid((unsigned)min(ntiles, (long long)sm_count()));
+  mlp_fused_kernel<<<grid, MF_THREADS, MF_SMEM, st>>>(g);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
 }
 
 // NT: column tile (64, or 32 for narrow outputs); Cout / NT column blocks go to grid.y
