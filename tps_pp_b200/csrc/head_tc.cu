@@ -1155,7 +1155,7 @@ struct MlpFusedArgs {
 constexpr int MF_WARPS_E = 16;
 constexpr int MF_THREADS = (MF_WARPS_E + 2) * 32;
 constexpr int MF_W1_BYTES = 8 * TS_STAGE, MF_W2_STAGES = 4;
-constexpr int MF_SMEM = MF_W1_BYTES + MF_W2_STAGES * TS_STAGE + 2 * 16384 + 512 + 1024;
+constexpr int MF_SMEM = MF_W1_BYTES + MF_W2_STAGES * TS_STAGE + 2 * 16384 + 1536 + 1024;
 
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const __grid_constant__ MlpFusedArgs g) {
   constexpr int NT = 64;
@@ -1179,6 +1179,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const __grid_c
   uint64_t* w2_full = bars + 15;       // [4]
   uint64_t* w2_empty = bars + 19;      // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  float* b1s = reinterpret_cast<float*>(bars + 24);               // [256] fc1 bias (warp-uniform float4 reads)
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
@@ -1192,6 +1193,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const __grid_c
     for (int i = 0; i < MF_W2_STAGES; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
     fence_barrier_init();
   }
+  if (tid < 256) b1s[tid] = __ldg(g.b1 + tid);
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -1300,11 +1302,6 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const __grid_c
     const int q = warp & 3, p = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
-    float b1r[4][16];                   // this thread's fc1 biases: hidden column j*64 + p*16 + i
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int i = 0; i < 16; ++i) b1r[j][i] = __ldg(g.b1 + j * 64 + p * 16 + i);
     // A1 of tile `it`: this thread's 8 floats of each chunk (pieces 2p, 2p+1 of its 128-byte row)
     auto produce_a1 = [&](int it) {
       if (it >= 1) { mbar_wait_bounded(a1_empty, (uint32_t)((it - 1) & 1)); tc_fence_after(); }
@@ -1347,10 +1344,11 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&d1_empty[db]);       // D1 is in registers: fc1 of block gj + 2 may overwrite it
         float hi[16], lo[16];
+        const float4* bq = reinterpret_cast<const float4*>(b1s + j * 64 + p * 16);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float bj = b1r[0][i];
-          if (j == 1) bj = b1r[1][i]; else if (j == 2) bj = b1r[2][i]; else if (j == 3) bj = b1r[3][i];
+          const float4 b4 = bq[i >> 2];
+          const float bj = (i & 3) == 0 ? b4.x : (i & 3) == 1 ? b4.y : (i & 3) == 2 ? b4.z : b4.w;
           const float h = tc_gelu_fast(acc[i] + bj);
           hi[i] = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
           lo[i] = h - hi[i];
