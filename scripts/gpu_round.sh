@@ -18,6 +18,6 @@ echo "== bench bf16 conv operands"; timeout 900 python bench.py --steps 10 --war
 echo "== ncu full: the 11 TMA-staged convolutions of one step (enc0 = 7th) and the 4 linear-layer launches"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tma_kernel -s 33 -c 11 -f -o gpurun_out/prof_conv_tma \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_conv.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lin_tma_kernel|dgab_warp_kernel|loc_p1_kernel" -s 18 -c 6 -f -o gpurun_out/prof_lin \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lin_tma_kernel|mlp_fused_kernel|dgab_warp_kernel|loc_p1_kernel" -s 15 -c 5 -f -o gpurun_out/prof_lin \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_lin.log 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv | tee gpurun_out/smi_end.txt
