@@ -1,3 +1,6 @@
+"""Dev tool: prints the clock64 timeline written by an INSTRUMENTED build of libtpspp.so (a temporary `g_dbg` device
+array + `tpspp_dbg_read` export added by hand to the kernel under study; see profiles/r01_conv_timeline.md).  It does
+not work against the shipped library."""
 import sys, ctypes, torch, numpy as np
 sys.path.insert(0, '/root/repo')
 from oracle import tpspp_oracle as O
