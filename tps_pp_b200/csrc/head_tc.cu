@@ -1,27 +1,29 @@
 // tcgen05 (5th-gen tensor core) implicit-GEMM engine of the TPS_PP head.
 //
-// One kernel template serves every dense contraction of the head:
-//   * the 14 convolutions (reference tps_pp.py:126-131,149-169,538-548,560-562,581-585): up to three
-//     concatenated inputs, nearest up-sampling, stride, zero padding, bias + ReLU (+ decoder skip);
-//   * the linear layers that act on a contiguous feature axis, as 1x1 "convolutions" over rows:
-//     feat_linear.0/.1 (tps_pp.py:258-261,306), the attention score QK^T with per-image weights
-//     p1[b] and a tanh(scale * .) epilogue (tps_pp.py:293-299), DGAB's Mlp fc1 (+GELU) / fc2 (+residual)
-//     over the width axis (DGAB.py:17-23,76).
+// Every dense contraction of the head is D[128 rows x N] += A[128 x K] . B[N x K]^T with M = 128 UMMA tiles and fp32
+// accumulators in tensor memory:
+//   * the 14 convolutions (reference tps_pp.py:126-131,149-169,538-548,560-562,581-585): up to three concatenated
+//     inputs, nearest up-sampling, stride, zero padding, bias + ReLU (+ decoder skip);
+//   * the linear layers that act on a contiguous feature axis, as row GEMMs: feat_linear.0/.1 (tps_pp.py:258-261,306),
+//     the attention score QK^T with per-image weights p1[b] and a tanh(scale * .) epilogue (tps_pp.py:293-299),
+//     DGAB's Mlp fc1 (+GELU) / fc2 (+residual) over the width axis (DGAB.py:17-23,76).
 //
-// fp32 accuracy comes from 3xTF32 error compensation: every fp32 operand is split into hi (the 19 bits
-// the tf32 datapath reads) and lo = x - hi, and  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (fp32 accumulate
-// in TMEM) drops only the lo*lo term (2^-22 relative).
+// fp32 accuracy comes from 3xTF32 error compensation: every fp32 operand is split into hi (the 19 bits the tf32
+// datapath reads) and lo = x - hi, and  D_main += A_hi*B_hi,  D_corr += A_lo*B_hi + A_hi*B_lo  (separate TMEM
+// accumulators, summed in the epilogue) drops only the lo*lo term (2^-22 relative).
 //
-// Per CTA: a 128-row x NT-column output tile (NT = 64 or 32); blockIdx.y selects the column block.
-// K is ordered (tap, cin) and cut into chunks of 32: a chunk lies inside one filter tap and one input
-// tensor.  All 256 threads gather chunk c+1 from global memory (software pipelined), split it and store
-// it in the UMMA core-matrix layout ([k/4][row][4 floats], 16-byte k-groups) while the tensor core runs
-// chunk c (2-deep ring of full/empty mbarriers; tcgen05.commit releases a buffer).  Warp specialised:
-// warps 0-7 produce operand tiles and later run the epilogue; warp 8 only waits for "stage full" and
-// issues the 12 MMAs of a chunk from one elected lane -- in warp-uniform control flow, so descriptors stay
-// in uniform registers (a divergent `if (tid == 0)` issuer costs ~30 SASS instructions per MMA in
-// R2UR waterfall loops and was the bottleneck).  The chunk's weight image arrives by one cp.async.bulk
-// (TMA), so weights never touch registers or L1.  Accumulators: 3 x (128 TMEM lanes x NT fp32 columns).
+// Kernels in this file (DESIGN.md section 4 has the measurements behind each):
+//   conv_tma_kernel<KS,BF16>  convolutions whose 128-pixel tile is a rectangle of one image: activations arrive by TMA
+//                             tensor-map boxes (halo tile shared by the nine taps), A operand in tensor memory (thread =
+//                             pixel = TMEM lane), persistent CTAs, dedicated MMA and TMA warps.
+//   conv_ts_kernel<KS,BF16>   same TS scheme with per-thread global gathers: the three smallest layers.
+//   lin_tma_kernel<NT>        row-major linear layers (feat_linear.1, QK^T): 2-D swizzled TMA tiles, A kept in TMEM
+//                             across the column blocks.
+//   mlp_fused_kernel          DGAB's Mlp in one kernel: fc1 -> GELU -> fc2 -> + residual, hidden tensor stays in TMEM.
+//   conv_tc_kernel<KS,..,NT>  the first-generation SS kernel (A operand staged in shared memory): feat_linear.0 only.
+//   wprep_kernel              per-forward weight images (hi/lo split, UMMA core-matrix order).
+// Warp roles are selected on a warp index obtained with __shfl_sync so the compiler can prove the branches uniform
+// (a plain tid >> 5 costs two R2UR per global load inside a role); MMAs are issued by one elected lane.
 #include "head.cuh"
 #include "tc.cuh"
 
