@@ -190,7 +190,7 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
-    B = BATCH_PER_GPU
+    B = args.batch
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.randn((B, 64, 16, 64), device=dev, generator=gen)
     o0 = torch.randn((B, 32, 32, 128), device=dev, generator=gen)
@@ -306,11 +306,12 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 conv operands / f32 elsewhere" if args.head == "bf16" else "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"batch-shard x{world}, no collective",
+            "config": {"workload": WORKLOAD if B == BATCH_PER_GPU else WORKLOAD.replace("batch 256/GPU", f"batch {B}/GPU (non-default shard size)"),
+                       "global_batch": world * B, "parallelism": f"batch-shard x{world}, no collective",
                        "l2": "inputs 302 MB/step > 126 MB L2 (no flush needed)",
                        "native_stages": native_stages, "weights": "trained-like synthetic (seed 3)", "head": args.head},
             "roofline": {"kernel": "warp_fwd_staged_kernel<dual>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": _warp_traffic(), "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": _warp_traffic() if B == BATCH_PER_GPU else None, "peak_source": peak_src,
                          "bytes_per_launch": warp_bytes, "avg_launch_ms": warp_mean_ms,
                          "warp_only_img_per_s": B / (warp_mean_ms * 1e-3)},
             # everything before the warp (convs, DGAB, localization, score): SURVEY 8(d) counts 0.82 GFLOP/img of
@@ -370,6 +371,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU,
+                    help="images per GPU (default = BASELINE configs[1]; 1024 = the per-GPU shard of config 5 at 8 GPUs)")
     ap.add_argument("--head", default="tc", choices=["tc", "fp32", "bf16", "library"],
                     help="head arithmetic: tcgen05 3xTF32 (default, fp32-level accuracy), CUDA-core fp32, "
                          "tcgen05 with bf16 conv operands (reduced precision, reported separately), or "
