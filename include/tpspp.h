@@ -204,7 +204,8 @@ TPSPP_API size_t tpspp_head_workspace_bytes(const tpspp_head_cfg* cfg);
 TPSPP_API int tpspp_head_workspace_offsets(const tpspp_head_cfg* cfg, size_t* offsets);
 
 /*
- * x [B,64,h,w], o0/o1 [B,32,2h,2w] fp32 NCHW; params: HOST array of TPSPP_P_COUNT DEVICE pointers.
+ * x [B,64,h,w], o0/o1 [B,32,2h,2w] fp32 NCHW; params: HOST array of TPSPP_P_COUNT DEVICE pointers
+ * (each contiguous and 16-byte aligned, as torch allocates them).
  * Outputs: feat_grid [B,64,2h,2w] (tps_pp.py:585), c_prime [B,F,2] (tps_pp.py:321-323),
  *          pc_score [B,h*w,F] (tps_pp.py:324).  workspace: 256-byte aligned,
  *          >= tpspp_head_workspace_bytes(cfg).

@@ -270,9 +270,12 @@ __global__ void __launch_bounds__(256) loc_p1_kernel(LocArgs a) {
   // The CTA is one image and the whole launch is a single wave, so its time is the length of the dependent FMA chains
   // below: every loop carries four independent outputs (each still summed in index order, so results are unchanged).
   {  // z1[k][m] = relu(Wa[m,:] . en[k,:] + ba[m]), m = tid
-    float w[64];
-#pragma unroll
-    for (int c = 0; c < 64; ++c) w[c] = __ldg(a.wa + tid * 64 + c);
+    float w[64];                     // this thread's row of loc1.0: 16 x 16-byte loads (rows are 256 B apart across
+#pragma unroll                      // lanes, so scalar loads were 64 fully uncoalesced requests per warp: LG-throttle bound)
+    for (int c = 0; c < 64; c += 4) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.wa + tid * 64 + c));
+      w[c] = t4.x; w[c + 1] = t4.y; w[c + 2] = t4.z; w[c + 3] = t4.w;
+    }
     const float bs = __ldg(a.ba + tid);
     int k = 0;
     for (; k + 3 < F; k += 4) {
@@ -299,11 +302,16 @@ __global__ void __launch_bounds__(256) loc_p1_kernel(LocArgs a) {
     for (int k0 = tid >> 5; k0 < F; k0 += 32) {
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       const int k1 = min(k0 + 8, F - 1), k2 = min(k0 + 16, F - 1), k3 = min(k0 + 24, F - 1);
-#pragma unroll 8
-      for (int c = 0; c < 64; ++c) {
-        const float wv = __ldg(a.wp0 + q * 64 + c);
-        s0 = __fmaf_rn(wv, en[k0 * 65 + c], s0); s1 = __fmaf_rn(wv, en[k1 * 65 + c], s1);
-        s2 = __fmaf_rn(wv, en[k2 * 65 + c], s2); s3 = __fmaf_rn(wv, en[k3 * 65 + c], s3);
+#pragma unroll 4
+      for (int c4 = 0; c4 < 64; c4 += 4) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wp0 + q * 64 + c4));
+        const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c4 + u;
+          s0 = __fmaf_rn(wq[u], en[k0 * 65 + c], s0); s1 = __fmaf_rn(wq[u], en[k1 * 65 + c], s1);
+          s2 = __fmaf_rn(wq[u], en[k2 * 65 + c], s2); s3 = __fmaf_rn(wq[u], en[k3 * 65 + c], s3);
+        }
       }
       t1[k0 * 33 + q] = s0 + bq;
       if (k0 + 8 < F) t1[(k0 + 8) * 33 + q] = s1 + bq;
@@ -328,7 +336,10 @@ __global__ void __launch_bounds__(256) loc_p1_kernel(LocArgs a) {
     const int r = tid & 127;
     float wr[32];
 #pragma unroll
-    for (int q = 0; q < 32; ++q) wr[q] = __ldg(a.wp1 + r * 32 + q);
+    for (int q = 0; q < 32; q += 4) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.wp1 + r * 32 + q));
+      wr[q] = t4.x; wr[q + 1] = t4.y; wr[q + 2] = t4.z; wr[q + 3] = t4.w;
+    }
     const float br = __ldg(a.bp1 + r);
     for (int k0 = tid >> 7; k0 < F; k0 += 8) {
       float sv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -358,8 +369,16 @@ __global__ void __launch_bounds__(256) loc_p1_kernel(LocArgs a) {
   __syncthreads();
   if (tid < 2 * F) {
     float s = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < 2 * F; ++i) s = __fmaf_rn(__ldg(a.wc + tid * 2 * F + i), z2[i], s);
+    int i = 0;
+    if ((F & 1) == 0) {                // rows of loc2 are 8F bytes: 16-byte loads when that is a multiple of 16
+#pragma unroll 4
+      for (; i + 3 < 2 * F; i += 4) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wc + tid * 2 * F + i));
+        s = __fmaf_rn(w4.x, z2[i], s); s = __fmaf_rn(w4.y, z2[i + 1], s);
+        s = __fmaf_rn(w4.z, z2[i + 2], s); s = __fmaf_rn(w4.w, z2[i + 3], s);
+      }
+    }
+    for (; i < 2 * F; ++i) s = __fmaf_rn(__ldg(a.wc + tid * 2 * F + i), z2[i], s);
     a.c_prime[(size_t)b * 2 * F + tid] = s + __ldg(a.bc + tid);
   }
 }
@@ -1131,7 +1150,10 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   if (d.B == 0) return TPSPP_OK;
   TPSPP_REQUIRE(x && o0 && o1 && P && feat_grid && c_prime && pc_score && workspace, "tpspp_head_fwd: null pointer");
   TPSPP_REQUIRE(((uintptr_t)workspace & 255) == 0, "tpspp_head_fwd: workspace must be 256-byte aligned");
-  for (int i = 0; i < TPSPP_P_COUNT; ++i) TPSPP_REQUIRE(P[i] != nullptr, "tpspp_head_fwd: params[%d] is NULL", i);
+  for (int i = 0; i < TPSPP_P_COUNT; ++i) {
+    TPSPP_REQUIRE(P[i] != nullptr, "tpspp_head_fwd: params[%d] is NULL", i);
+    TPSPP_REQUIRE(((uintptr_t)P[i] & 15) == 0, "tpspp_head_fwd: params[%d] must be 16-byte aligned (vector loads)", i);
+  }
   if (d.B == 0) return TPSPP_OK;
   rc = head_attrs_once();
   if (rc != TPSPP_OK) return rc;
