@@ -762,7 +762,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { s = 2; } }
         const bool up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
         const int by = up ? ((oy0 - a.pad) >> 1) : (oy0 - a.pad), bx = up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH);
-        const float* tile_s = reinterpret_cast<const float*>(tiles + tb * TILE_BYTES) + (size_t)(kh * 16) * CHS;
+        const uint32_t cstride = 4u * (uint32_t)CHS;
+        const uint32_t tile_a = smem_u32(tiles + tb * TILE_BYTES) + (uint32_t)(kh * 16) * cstride;
         mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc / NTB) & 1));
 #pragma unroll 1
         for (int tg = 0; tg < TG; ++tg, ++gch) {
@@ -772,10 +773,12 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           int iy = oy0 + pr + dy - a.pad, ix = S * (ox0 + pc) + dx - a.pad;
           if (up) { iy >>= 1; ix >>= 1; }
           // stride 2: the box of this filter row already holds input rows 2 oy + dy - pad, one per tile row
-          const float* q = tile_s + (S == 2 ? pr : iy - by) * g.BW + (ix - bx);
+          // 32-bit shared-memory addresses: with generic pointers the 16 channel loads cost ~6 instructions each
+          // (64-bit index arithmetic on the run-time channel stride) -- a fifth of the 3x3 kernels' instruction stream
+          const uint32_t qa = tile_a + 4u * (uint32_t)((S == 2 ? pr : iy - by) * g.BW + (ix - bx));
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = q[(size_t)i * CHS];
+          for (int i = 0; i < 16; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(qa + (uint32_t)i * cstride));
           if (gch >= 2) {
             mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch >> 1) - 1) & 1));   // MMAs of chunk gch-2 have read the stage
             tc_fence_after();
