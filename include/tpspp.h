@@ -86,6 +86,15 @@ TPSPP_API const char* tpspp_last_error(void);
 /* Number of SMs of the current device and the cubin architecture that was loaded (e.g. 100). */
 TPSPP_API int tpspp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Measurement aid (bench.py): after tpspp_launch_profile(1) on the calling thread, tpspp_head_fwd records one CUDA
+ * event on its stream before its first and after each of its kernel launches (the library creates up to 65 events
+ * once and keeps them); tpspp_launch_profile_read synchronises on the last one and returns the milliseconds of the
+ * launches of the most recent call in launch order (wprep, the 14 convolutions with cbam after the 10th, localisation,
+ * DGAB gate, Mlp, feat_linear.0, feat_linear.1, score) followed by the launches of later calls on the same thread
+ * (the module's tpspp_warp_fwd) until the next tpspp_head_fwd.  tpspp_launch_profile(0) turns it off. */
+TPSPP_API int tpspp_launch_profile(int enable);
+TPSPP_API int tpspp_launch_profile_read(float* ms, int capacity, int* count);
+
 /* Bytes of scratch tpspp_warp_bwd needs for this cfg. */
 TPSPP_API size_t tpspp_warp_workspace_bytes(const tpspp_warp_cfg* cfg);
 

@@ -44,6 +44,8 @@ _SIGNATURES = {
     "tpspp_version": (c_int, []),
     "tpspp_last_error": (c_char_p, []),
     "tpspp_last_launch_count": (c_int, []),
+    "tpspp_launch_profile": (c_int, [c_int]),
+    "tpspp_launch_profile_read": (c_int, [POINTER(ctypes.c_float), c_int, POINTER(c_int)]),
     "tpspp_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tpspp_warp_workspace_bytes": (c_size_t, [POINTER(WarpCfg)]),
     "tpspp_warp_fwd_workspace_bytes": (c_size_t, [POINTER(WarpCfg)]),

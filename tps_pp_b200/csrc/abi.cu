@@ -14,7 +14,33 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch(int n) { g_launches += n; }
+// ---- optional per-launch profiling (tpspp_launch_profile): one CUDA event after every kernel launch ----
+constexpr int PROF_MAX = 64;
+static thread_local bool g_prof_on = false;
+static thread_local cudaEvent_t g_prof_ev[PROF_MAX + 1];
+static thread_local int g_prof_have = 0;      // events created so far
+static thread_local int g_prof_n = 0;         // launches recorded in the current call
+static thread_local cudaStream_t g_prof_stream = nullptr;
+
+static void prof_record() {
+  if (g_prof_n > PROF_MAX) return;
+  while (g_prof_have <= g_prof_n) {
+    if (cudaEventCreate(&g_prof_ev[g_prof_have]) != cudaSuccess) { g_prof_on = false; return; }
+    ++g_prof_have;
+  }
+  cudaEventRecord(g_prof_ev[g_prof_n], g_prof_stream);
+  ++g_prof_n;
+}
+void prof_begin(cudaStream_t st) {            // called at the top of an entry point that wants its launches timed
+  if (!g_prof_on) return;
+  g_prof_stream = st;
+  g_prof_n = 0;
+  prof_record();
+}
+void count_launch(int n) {
+  g_launches += n;
+  if (g_prof_on && g_prof_n > 0) prof_record();
+}
 void reset_launch_count() { g_launches = 0; }
 
 int sm_count() {
@@ -56,6 +82,23 @@ int validate_cfg(const tpspp_warp_cfg* cfg) {
 extern "C" int tpspp_version(void) { return TPSPP_ABI_VERSION; }
 extern "C" const char* tpspp_last_error(void) { return tpspp::g_err; }
 extern "C" int tpspp_last_launch_count(void) { return tpspp::g_launches; }
+
+extern "C" int tpspp_launch_profile(int enable) {
+  tpspp::g_prof_on = enable != 0;
+  tpspp::g_prof_n = 0;
+  return TPSPP_OK;
+}
+extern "C" int tpspp_launch_profile_read(float* ms, int capacity, int* count) {
+  using namespace tpspp;
+  TPSPP_REQUIRE(ms != nullptr && count != nullptr && capacity >= 0, "tpspp_launch_profile_read: bad arguments");
+  *count = 0;
+  if (g_prof_n < 2) return TPSPP_OK;
+  TPSPP_CHECK_CUDA(cudaEventSynchronize(g_prof_ev[g_prof_n - 1]));
+  const int n = g_prof_n - 1 < capacity ? g_prof_n - 1 : capacity;
+  for (int i = 0; i < n; ++i) TPSPP_CHECK_CUDA(cudaEventElapsedTime(&ms[i], g_prof_ev[i], g_prof_ev[i + 1]));
+  *count = n;
+  return TPSPP_OK;
+}
 
 extern "C" int tpspp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

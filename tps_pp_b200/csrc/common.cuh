@@ -17,6 +17,7 @@ namespace tpspp {
 // ---------------------------------------------------------------- host side
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void prof_begin(cudaStream_t st);      // no-op unless tpspp_launch_profile(1) was called on this thread
 void reset_launch_count();
 int sm_count();
 

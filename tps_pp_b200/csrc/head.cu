@@ -1144,6 +1144,7 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
                               const float* const* P, float* feat_grid, float* c_prime, float* pc_score,
                               void* workspace, tpspp_stream_t stream) {
   reset_launch_count();
+  prof_begin((cudaStream_t)stream);
   HeadDims d;
   int rc = head_dims(cfg, &d);
   if (rc != TPSPP_OK) return rc;
