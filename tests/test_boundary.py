@@ -124,3 +124,16 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in text.replace("# oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_launch_profile_is_a_no_op_without_work(native_lib):
+    """Host-only part of the measurement aid: enabling it and reading before any head call yields zero launches."""
+    import ctypes
+    buf = (ctypes.c_float * 8)()
+    cnt = ctypes.c_int(-1)
+    assert native_lib.tpspp_launch_profile(1) == 0
+    assert native_lib.tpspp_launch_profile_read(buf, 8, ctypes.byref(cnt)) == 0 and cnt.value == 0
+    assert native_lib.tpspp_launch_profile(0) == 0
+    assert native_lib.tpspp_launch_profile_read(None, 8, ctypes.byref(cnt)) != 0       # bad arguments are reported
+    assert b"tpspp_launch_profile_read" in native_lib.tpspp_last_error()
+
