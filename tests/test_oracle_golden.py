@@ -91,3 +91,27 @@ def test_backward_restatement_matches_autograd():
     assert mx(gsrc, srct.grad) < 1e-10
     assert mx(dC, cpt.grad) / float(cpt.grad.abs().max()) < 1e-10
     assert mx(ds, st.grad) / float(st.grad.abs().max()) < 1e-10
+
+
+def test_sampler_restatement_vs_aten_on_random_and_edge_grids():
+    """The numpy sampler against torch's own grid_sample (the third-party code the reference calls at tps_pp.py:606-615),
+    including coordinates far outside the image, exactly on the border, and the (0,1)-coordinates-into-a-[-1,1]-sampler
+    quirk of TPS_PP.  Runs anywhere torch does -- no reference tree needed."""
+    rs = np.random.RandomState(0)
+    for (b, c, h, w, hr, wr) in ((2, 3, 5, 7, 4, 6), (1, 2, 16, 64, 16, 64), (3, 1, 1, 9, 2, 3)):
+        src = rs.standard_normal((b, c, h, w))
+        grid = rs.uniform(-1.6, 1.6, size=(b, hr, wr, 2))
+        grid[0, 0, 0] = (-1.0, -1.0); grid[0, 0, 1] = (1.0, 1.0); grid[0, 1, 0] = (7.5, -9.0); grid[0, 1, 1] = (0.0, 0.0)
+        for dt, tol in ((np.float64, 1e-13), (np.float32, 2e-6)):
+            ours = O.grid_sample(src, grid, dtype=dt)
+            ref = torch.nn.functional.grid_sample(torch.from_numpy(src.astype(dt)), torch.from_numpy(grid.astype(dt)),
+                                                  mode="bilinear", padding_mode="border", align_corners=True).numpy()
+            assert mx(ours, ref) <= tol, (b, c, h, w, dt)
+        # backward restatement against autograd in fp64
+        ts = torch.from_numpy(src).requires_grad_()
+        tg = torch.from_numpy(grid).requires_grad_()
+        out = torch.nn.functional.grid_sample(ts, tg, mode="bilinear", padding_mode="border", align_corners=True)
+        go = rs.standard_normal(out.shape)
+        out.backward(torch.from_numpy(go))
+        gs, gg = O.grid_sample_backward(src, grid, go, dtype=np.float64)
+        assert mx(gs, ts.grad.numpy()) <= 1e-12 and mx(gg, tg.grad.numpy()) <= 1e-12
