@@ -15,7 +15,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -200,7 +199,6 @@ def run_ours(args):
     import torch.distributed as dist
     import tps_pp_b200 as T
     from tps_pp_b200 import _native as N
-    from tps_pp_b200 import functional as TF
 
     rank, world, local = _dist_env()
     if not torch.cuda.is_available():

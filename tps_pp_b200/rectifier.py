@@ -18,9 +18,8 @@ ABI, :mod:`tps_pp_b200.functional`) or -- until its kernel lands -- a cuDNN/cuBL
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence
 
-import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
