@@ -178,15 +178,18 @@ def run_reference(args):
     rank, world, _ = _dist_env()
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
-    batch = 128
+    # same config as our arm: batch 256 per step, exactly --steps timed steps after --warmup untimed ones
+    # (~0.65 s per step on the 16 host cores of the GPU box: the default 20 + 5 run takes ~20 s)
+    steps = max(1, args.steps)
+    warm = max(0, args.warmup)
+    batch = args.batch
     ips, ms, cores = _cpu_reference(steps, warm, batch)
     line = {
         "impl": "reference", "metric": "tps_pp_rectified_img_per_s", "value": ips, "unit": "img/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"batch {batch} per step on host CPU"},
+        "config": {"workload": WORKLOAD if batch == BATCH_PER_GPU else WORKLOAD.replace("batch 256/GPU", f"batch {batch}/GPU (non-default shard size)"),
+                   "global_batch": batch, "sample": f"batch {batch} per step on host CPU, {cores} threads"},
         "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} steps of batch {batch} (median), torch CPU fp32, {cores} threads"},
         "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -336,9 +339,9 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = _cpu_reference(steps=5, warmup=1, batch=128)
+        ips, ms, cores = _cpu_reference(steps=8, warmup=1, batch=B)
         cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
-               "sample": f"5 steps of batch 128 (median {ms:.0f} ms), oracle torch-CPU fp32, {cores} threads"}
+               "sample": f"8 steps of batch {B} (median {ms:.0f} ms), oracle torch-CPU fp32, {cores} threads"}
     if rank == 0:
         h2d = sum(t_.numel() * 4 for t_ in (x, o0, o1))
         line = {

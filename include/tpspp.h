@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TPSPP_ABI_VERSION 1
+#define TPSPP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TPSPP_API __attribute__((visibility("default")))
@@ -179,7 +179,14 @@ typedef struct tpspp_head_cfg {
   int32_t point_h, point_w; /* control-point lattice (2, 16)                                     */
   int32_t p_stride;         /* stride of the third MSFA encoder conv (2)                         */
   int32_t precision;        /* TPSPP_HEAD_*                                                      */
+  int32_t flags;            /* TPSPP_HEAD_FLAG_* (0 = none)                                      */
 } tpspp_head_cfg;
+
+/* flags.  WEIGHTS_CACHED: the caller guarantees that `workspace` was last written by a tpspp_head_fwd call with the
+ * same cfg and the same parameter VALUES (pointers and contents unchanged since), so the tensor-core weight images in
+ * TPSPP_WS_WPREP are still valid and their re-layout launch is skipped.  The caller owns that invariant -- the
+ * library cannot see weight updates (tps_pp_b200/rectifier.py keys it on torch's per-tensor version counters). */
+enum { TPSPP_HEAD_FLAG_WEIGHTS_CACHED = 1 };
 
 /* Index of each learnable tensor in the `params` pointer table = state_dict order of the
  * reference module (tps_pp.py:94-119,253-285,538-548).                      */

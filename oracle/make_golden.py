@@ -76,6 +76,8 @@ def main():
     gold_const['init_keys'] = np.array(list(init_sd.keys()))
     gold_const['init_sums'] = np.array([float(v.double().sum()) for v in init_sd.values()])
     gold_const['init_abs_sums'] = np.array([float(v.double().abs().sum()) for v in init_sd.values()])
+    m.init_weights()     # mmcv BaseModule.init_weights(): re-draws the six direct ConvModule children
+    gold_const['init2_sums'] = np.array([float(v.double().sum()) for v in m.state_dict().values()])
 
     # ---- grid generator + sampler (warp only) ------------------------------
     print('warp (TPS++)')
@@ -254,7 +256,78 @@ def main():
     sdc = tp.state_dict()
     oc = O.classical_localization(sdc, torch.from_numpy(img))
     check("classical C'", _mx(oc, rc), 1e-6)
+    nrtr_fixture(write=not args.check)
     print('all oracle checks passed' + ('' if args.check else f'; fixtures written to {GOLD}'))
+
+
+def nrtr_fixture(write: bool, batch: int = 2):
+    """BASELINE config 1 / north_star "identical NRTR argmax decodes": run the unmodified reference recogniser
+    (ResNetABI_v2_large(strides=[1,2,2,1,2]) -> TPS_PP -> NRTR encoder -> greedy 40-step decoder,
+    encode_decode_recognizer.py:107-122,184-225) on a seeded synthetic batch, capture what the backbone hands to
+    ``tpsnet(x, outs)`` (resnet_v2_large.py:189-191) and the rectifier's ``output``, and measure how much
+    perturbation of that ``output`` the argmax decode tolerates: ``safe_delta`` is the largest tested uniform noise
+    amplitude with zero changed argmax positions over several draws.  The ``-m gpu`` test asserts
+    ``|ours - ref32| <= safe_delta`` -- the on-GPU proxy for "identical decodes" (the recogniser itself cannot travel
+    to the GPU box); the direct replay through the reference network is ``scripts/nrtr_argmax_check.py``."""
+    import contextlib
+    import io
+    from . import nrtr_loader as L
+    print('NRTR argmax fixture (config 1)')
+    ns = L.load_nrtr()
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tps = ns.TPS_PP()
+        bb = ns.ResNetABI_v2_large(arch_settings=[3, 4, 6, 6, 3], strides=[1, 2, 2, 1, 2])
+        enc = ns.NRTREncoder()
+        dec = ns.NRTRDecoder(num_classes=93, start_idx=91, padding_idx=92, max_seq_len=40)
+    conv = ns.AttnConvertor('DICT90', with_unknown=True, max_seq_len=40)
+    for mod in (tps, bb, enc, dec):
+        mod.eval()
+    img = torch.randn(batch, 3, 32, 128, generator=torch.Generator().manual_seed(1234))
+    metas = [{'valid_ratio': 1.0}] * batch
+
+    def decode(tpsnet):
+        with torch.no_grad():
+            f = bb(img, tpsnet, True)['output']
+            probs = dec(f, enc(f, metas), None, metas, train_mode=False)
+        idx, _ = conv.tensor2idx(probs, metas)
+        return conv.idx2str(idx), probs
+
+    stock = {k: v.detach().clone() for k, v in tps.state_dict().items()}
+    out = {'img': img.numpy(), 'deltas': np.array([1e-4, 3e-4, 1e-3])}
+    for name, sd in (('stock', stock), ('trained', O.trained_like_state(3))):
+        tps.load_state_dict(sd, strict=True)
+        cap = {}
+
+        def tapped(x, outs, **kw):
+            r = tps(x, outs, **kw)
+            cap.update(x=x.detach().clone(), o0=outs[0].detach().clone(), o1=outs[1].detach().clone(),
+                       output=r['output'].detach().clone())
+            return r
+        strings, probs = decode(tapped)
+        ref_arg = probs.argmax(-1)
+        top2 = probs.topk(2, -1).values
+        flips = []
+        for delta in out['deltas']:
+            worst = 0
+            for trial in range(3):
+                gen = torch.Generator().manual_seed(100 + trial)
+                noisy = cap['output'] + (torch.rand(cap['output'].shape, generator=gen) * 2 - 1) * float(delta)
+                _, pr = decode(lambda x, outs, **kw: {'output': noisy})
+                worst = max(worst, int((pr.argmax(-1) != ref_arg).sum()))
+            flips.append(worst)
+        safe = max([float(d) for d, f in zip(out['deltas'], flips) if f == 0], default=0.0)
+        print(f'    {name}: decode {strings[0]!r}; min top-1 margin {float((top2[..., 0] - top2[..., 1]).min()):.2e}; '
+              f'argmax flips under uniform noise {dict(zip([float(d) for d in out["deltas"]], flips))} -> safe_delta {safe:.0e}')
+        check(f'{name}: 1e-4 noise leaves every argmax in place (SURVEY C-10)', float(flips[0]), 0.0)
+        out.update({'x': cap['x'].numpy(), 'o0': cap['o0'].numpy(), 'o1': cap['o1'].numpy(),
+                    f'{name}_ref_output': cap['output'].numpy(), f'{name}_ref_argmax': ref_arg.numpy().astype(np.int16),
+                    f'{name}_safe_delta': np.array(safe), f'{name}_flips': np.array(flips),
+                    f'{name}_strings': np.array(strings),
+                    f'{name}_state_digest': np.array([float(v.double().abs().sum()) for v in sd.values()])})
+    # the drop-in module under the same seed must hold the stock weights bit-for-bit (so the fixture need not carry them)
+    if write:
+        np.savez_compressed(os.path.join(GOLD, 'nrtr_argmax.npz'), **out)
 
 
 if __name__ == '__main__':

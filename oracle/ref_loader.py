@@ -12,7 +12,8 @@ modules, mmcv/mmdet/timm absent), so the handful of third-party symbols its
 hot-path files use are stubbed here with their documented behaviour
 (SURVEY.md App. B):
 
-* ``mmcv.cnn.ConvModule``  -> ``self.conv = Conv2d(bias=True)``, ``self.activate = ReLU(inplace=True)``
+* ``mmcv.cnn.ConvModule``  -> ``self.conv = Conv2d(bias=True)``, ``self.activate = ReLU(inplace=True)``,
+  followed by mmcv's ctor-time ``init_weights()`` = ``kaiming_normal_(fan_out, relu)`` + zero bias
   (mmcv-full 1.3.8-1.5.0 with ``norm_cfg=None``; used at ``tps_pp.py:126-131,149-154,538-548``)
 * ``mmcv.runner.BaseModule`` -> ``nn.Module`` + ``init_weights()``
 * ``timm.models.layers.DropPath`` -> identity (``DGAB.py:67``, drop_path=0)
@@ -64,6 +65,13 @@ class _ConvModule(nn.Module):
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size,
                               stride=stride, padding=padding, bias=True)
         self.activate = nn.ReLU(inplace=True)
+        self.init_weights()
+
+    def init_weights(self):
+        # mmcv ConvModule.init_weights (called at the end of its ctor and again by BaseModule.init_weights):
+        # kaiming_init(conv, a=0, mode='fan_out', nonlinearity='relu', distribution='normal'), bias = 0
+        nn.init.kaiming_normal_(self.conv.weight, a=0, mode='fan_out', nonlinearity='relu')
+        nn.init.constant_(self.conv.bias, 0)
 
     def forward(self, x):
         return self.activate(self.conv(x))
@@ -75,7 +83,13 @@ class _BaseModule(nn.Module):
         self.init_cfg = init_cfg
 
     def init_weights(self):
-        pass
+        # mmcv BaseModule.init_weights with init_cfg=None: direct children that define init_weights, once
+        if getattr(self, "_is_init", False):
+            return
+        for m in self.children():
+            if hasattr(m, "init_weights"):
+                m.init_weights()
+        self._is_init = True
 
 
 def _mod(name, **attrs):

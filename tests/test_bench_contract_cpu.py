@@ -26,18 +26,20 @@ def _check(line, n_gpus):
 
 
 def test_reference_arm_single_process():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--batch", "32"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = _json_lines(r.stdout)
     assert len(lines) == 1
     _check(lines[0], 1)
+    # --steps / --warmup / --batch are honoured exactly (the driver compares them with our arm: same_config)
+    assert lines[0]["steps"] == 2 and lines[0]["warmup"] == 1 and lines[0]["config"]["global_batch"] == 32
 
 
 def test_reference_arm_under_torchrun_prints_once():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29571", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-           "--warmup", "1"]
+           "--warmup", "1", "--batch", "32"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = _json_lines(r.stdout)

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     for name in declared:
         assert hasattr(native_lib, name), f"libtpspp.so does not export {name}"
     assert set(declared) == set(_native.exported_symbols())
-    assert native_lib.tpspp_version() == 1
+    assert native_lib.tpspp_version() == 2
 
 
 def test_cfg_struct_matches_header():
@@ -34,6 +34,14 @@ def test_cfg_struct_matches_header():
             continue
         names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
     assert names == [f[0] for f in _native.WarpCfg._fields_]
+    body = re.search(r"typedef struct tpspp_head_cfg \{(.*?)\} tpspp_head_cfg;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+    assert names == [f[0] for f in _native.HeadCfg._fields_]
 
 
 def test_workspace_query_is_host_only(native_lib):
@@ -83,7 +91,6 @@ def test_state_dict_layout_and_init_match_reference(golden):
     g = golden("constants.npz")
     torch.manual_seed(0)
     m = T.TPS_PP()
-    m.init_weights()
     sd = m.state_dict()
     assert list(sd.keys()) == [str(k) for k in g["init_keys"]]
     assert len(sd) == 60 and sum(p.numel() for p in m.parameters()) == 546597
@@ -91,6 +98,26 @@ def test_state_dict_layout_and_init_match_reference(golden):
     abss = np.array([float(v.double().abs().sum()) for v in sd.values()])
     assert np.array_equal(sums, g["init_sums"]) and np.array_equal(abss, g["init_abs_sums"])
     assert float(sd["TPE.localization_fc2.weight"].abs().max()) == 0.0
+    # the 14 ConvModule convs carry mmcv's ctor-time kaiming-normal(fan_out, relu) init with zero bias
+    w = sd["down0_1.conv.weight"]
+    assert abs(float(w.std()) - (2.0 / (64 * 9)) ** 0.5) < 0.05 * (2.0 / (64 * 9)) ** 0.5
+    assert float(sd["down0_1.conv.bias"].abs().max()) == 0.0 and float(sd["MSFA.conv.k_encoder.0.conv.bias"].abs().max()) == 0.0
+    # BaseModule.init_weights(): the six direct ConvModule children are drawn again, once
+    m.init_weights()
+    sd2 = m.state_dict()
+    sums2 = np.array([float(v.double().sum()) for v in sd2.values()])
+    assert np.array_equal(sums2, g["init2_sums"])
+    m.init_weights()
+    assert np.array_equal(np.array([float(v.double().sum()) for v in m.state_dict().values()]), g["init2_sums"])
+
+
+def test_head_param_shapes_table_matches_module():
+    """functional.head_param_shapes is what head_forward validates the 58 tensors against before handing raw
+    pointers to the kernels (a module built for another geometry must raise, not read out of bounds)."""
+    from tps_pp_b200 import functional as TF
+    m = T.TPS_PP()
+    assert [tuple(p.shape) for p in m.parameters()] == TF.head_param_shapes(16, 64, 32)
+    assert TF.head_param_shapes(8, 64, 16) != TF.head_param_shapes(16, 64, 32)     # LayerNorm / gate weights follow (h, F)
 
 
 def test_constants_match_reference_buffers(golden):

@@ -8,6 +8,8 @@ from oracle import tpspp_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+# whole-module pixels: |ours - ref64| must not exceed the reference's own fp32 error |ref32 - ref64|
+FLOOR_K = 1.0
 
 
 def mx(a, b):
@@ -41,8 +43,41 @@ def test_tps_pp_forward_vs_reference_golden(golden, native_lib):
     floor_m = mx(g["ref32_mp_img"], g["ref64_mp_img"])
     e_o, e_m = mx(r["output"], g["ref64_output"]), mx(r["mp_img"], g["ref64_mp_img"])
     print(f"output |ours-ref64|={e_o:.3e} (ref32-ref64 floor {floor_o:.3e}); mp_img {e_m:.3e} (floor {floor_m:.3e})")
-    assert e_o <= max(1e-5, 4 * floor_o)
-    assert e_m <= max(1e-5, 4 * floor_m)
+    assert e_o <= max(1e-5, FLOOR_K * floor_o)
+    assert e_m <= max(1e-5, FLOOR_K * floor_m)
+
+
+@pytest.mark.parametrize("weights", ["stock", "trained"])
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+def test_nrtr_argmax_proxy(golden, native_lib, weights, precision):
+    """north_star "identical NRTR argmax decodes" / BASELINE config 1, on the GPU.  The fixture
+    (oracle/make_golden.py::nrtr_fixture) holds what the reference backbone hands to ``tpsnet(x, outs)`` for a
+    seeded 32x128 batch, the reference rectifier's fp32 ``output`` and ``safe_delta``: the largest perturbation of
+    that output (uniform noise, several draws) under which the reference layer3-5 + NRTR greedy decode keeps every
+    argmax.  The recogniser cannot travel to the GPU box, so the test asserts the sufficient condition
+    ``|ours - ref32| <= safe_delta / 2`` and, for the stock (random-init, config 1) weights, the tighter 1e-4 of SURVEY C-10."""
+    from tps_pp_b200 import _native as N
+    g = golden("nrtr_argmax.npz")
+    if weights == "stock":
+        torch.manual_seed(0)
+        m = T.TPS_PP().to(DEV).eval()
+    else:
+        m = T.TPS_PP().to(DEV).eval()
+        m.load_state_dict(O.trained_like_state(3), strict=True)
+    digest = np.array([float(v.double().abs().sum()) for v in m.state_dict().values()])
+    assert np.allclose(digest, g[f"{weights}_state_digest"], rtol=1e-12, atol=0), "fixture weights differ"
+    m.head_precision = N.HEAD_TC if precision == "tc" else N.HEAD_FP32
+    x, o0, o1 = (torch.from_numpy(g[k]).to(DEV) for k in ("x", "o0", "o1"))
+    with torch.no_grad():
+        r = m(x, [o0, o1])
+    assert all(m.native_stages.values())
+    err = mx(r["output"], g[f"{weights}_ref_output"])
+    safe = float(g[f"{weights}_safe_delta"])
+    print(f"nrtr proxy [{weights}/{precision}]: |output - ref32| = {err:.3e}; decode-safe perturbation {safe:.0e}")
+    assert safe >= 1e-4
+    assert err <= 0.5 * safe
+    if weights == "stock":
+        assert err <= 1e-4
 
 
 def test_tps_pp_head_control_points(golden, native_lib):
@@ -69,8 +104,8 @@ def test_tps_pp_random_init_matches_oracle(native_lib):
     r64 = O.tps_pp_forward(sd, x, [o0, o1], dtype=torch.float64, sampler="numpy")
     r32 = O.tps_pp_forward(sd, x, [o0, o1], dtype=torch.float32)
     floor = mx(r32["output"], r64["output"])
-    assert mx(r["output"], r64["output"]) <= max(1e-5, 4 * floor)
-    assert mx(r["mp_img"], r64["mp_img"]) <= max(1e-5, 4 * mx(r32["mp_img"], r64["mp_img"]))
+    assert mx(r["output"], r64["output"]) <= max(1e-5, FLOOR_K * floor)
+    assert mx(r["mp_img"], r64["mp_img"]) <= max(1e-5, FLOOR_K * mx(r32["mp_img"], r64["mp_img"]))
 
 
 def test_tps_pp_autograd_reaches_every_parameter(native_lib):

@@ -115,3 +115,19 @@ def test_sampler_restatement_vs_aten_on_random_and_edge_grids():
         out.backward(torch.from_numpy(go))
         gs, gg = O.grid_sample_backward(src, grid, go, dtype=np.float64)
         assert mx(gs, ts.grad.numpy()) <= 1e-12 and mx(gg, tg.grad.numpy()) <= 1e-12
+
+
+def test_nrtr_fixture_weights_are_reproducible(golden):
+    """tests/golden/nrtr_argmax.npz carries no rectifier weights: "stock" = the drop-in module under seed 0
+    (bit-equal to the reference ctor, mmcv ConvModule kaiming init included), "trained" = trained_like_state(3)."""
+    import torch
+    import tps_pp_b200 as T
+    g = golden("nrtr_argmax.npz")
+    torch.manual_seed(0)
+    m = T.TPS_PP()
+    digest = np.array([float(v.double().abs().sum()) for v in m.state_dict().values()])
+    assert np.array_equal(digest, g["stock_state_digest"])
+    digest = np.array([float(v.double().abs().sum()) for v in O.trained_like_state(3).values()])
+    assert np.array_equal(digest, g["trained_state_digest"])
+    assert g["x"].shape == (2, 64, 16, 64) and g["o0"].shape == (2, 32, 32, 128)
+    assert float(g["stock_safe_delta"]) >= 1e-4 and int(g["stock_flips"][0]) == 0 and int(g["trained_flips"][0]) == 0

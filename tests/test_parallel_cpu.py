@@ -54,6 +54,21 @@ def _worker(rank, world, port, q):
         err = max(float((p.grad - r.grad).abs().max()) for p, r in zip(model.parameters(), ref.parameters()))
         views_ok = all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in model.parameters())
         mean_loss, = PAR.all_reduce_scalars([float(loss) / world], "cpu")
+        # second step after optimizer.zero_grad() (set_to_none=True drops the views): the bucket must pull the fresh
+        # gradients in and re-attach, so the all-reduce still averages THIS step's gradients
+        opt = torch.optim.SGD(model.parameters(), lr=0.0)
+        opt.zero_grad()
+        assert all(p.grad is None for p in model.parameters())
+        loss = ((model(xs) - ts) ** 2).sum() / data.shape[0] * world
+        loss.backward()
+        bucket.all_reduce_mean()
+        err2 = max(float((p.grad - r.grad).abs().max()) for p, r in zip(model.parameters(), ref.parameters()))
+        base = bucket.flat.data_ptr()
+        views2 = all(p.grad.data_ptr() == base + 4 * off for p, off in zip(bucket.params, bucket.offsets))
+        model.zero_grad(set_to_none=False)          # in-place zeroing keeps the views
+        views2 = views2 and all(p.grad.data_ptr() == base + 4 * off for p, off in zip(bucket.params, bucket.offsets))
+        err = max(err, err2)
+        views_ok = views_ok and views2 and bucket.reattached == len(bucket.params)
         q.put((rank, err, views_ok, xs.shape[0], mean_loss))
     finally:
         dist.destroy_process_group()

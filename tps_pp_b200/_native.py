@@ -32,11 +32,13 @@ class HeadCfg(Structure):
     """Mirror of ``tpspp_head_cfg`` (include/tpspp.h)."""
     _fields_ = [
         ("batch", c_int32), ("height", c_int32), ("width", c_int32), ("point_h", c_int32), ("point_w", c_int32),
-        ("p_stride", c_int32), ("precision", c_int32),
+        ("p_stride", c_int32), ("precision", c_int32), ("flags", c_int32),
     ]
 
 
 HEAD_FP32, HEAD_TC, HEAD_BF16 = 0, 1, 2
+HEAD_FLAG_WEIGHTS_CACHED = 1
+ABI_VERSION = 2
 P_COUNT = 58
 WS_NAMES = ("f0", "f1", "f2", "a0", "a1", "e0", "e1", "e2", "e3", "cbam", "d0", "d1", "d2", "de", "x1", "v", "de2", "p1", "wprep", "t1", "fs", "hid", "p1img")
 
@@ -84,7 +86,7 @@ def lib() -> ctypes.CDLL:
                 raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild it")
             fn.restype = res
             fn.argtypes = args
-        if handle.tpspp_version() != 1:
+        if handle.tpspp_version() != ABI_VERSION:
             raise RuntimeError("libtpspp ABI version mismatch; rebuild it")
         _lib = handle
     return _lib

@@ -1174,6 +1174,7 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   for (int i = 0; i < kNumTcLayers; ++i) wp[i] = nullptr;
   const bool bf16 = cfg->precision == TPSPP_HEAD_BF16;   // convolutions with bf16 operands; linear layers stay 3xTF32
   const bool tc = cfg->precision == TPSPP_HEAD_TC || bf16;
+  const bool weights_cached = (cfg->flags & TPSPP_HEAD_FLAG_WEIGHTS_CACHED) != 0;
   if (tc) {
     WPrepLayer L[kNumTcLayers];
     float* cur = W(TPSPP_WS_WPREP);
@@ -1184,8 +1185,10 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
       wp[i] = cur;
       cur += conv_tc_wprep_floats(kConvLayers[i].Ctot, kConvLayers[i].KS, kConvLayers[i].N);
     }
-    rc = conv_tc_prepare_weights(L, kNumTcLayers, st);
-    if (rc != TPSPP_OK) return rc;
+    if (!weights_cached) {     // else: the images of the previous call with these weights are still in the workspace
+      rc = conv_tc_prepare_weights(L, kNumTcLayers, st);
+      if (rc != TPSPP_OK) return rc;
+    }
   }
 #define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != TPSPP_OK) return rc; } while (0)
   // down0/1/2 (tps_pp.py:581-583): 

@@ -870,17 +870,50 @@ typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static tmap_encode_fn tmap_encoder() {
-  static tmap_encode_fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // function-local static: initialised exactly once, thread-safe (C++11)
+  static const tmap_encode_fn fn = []() -> tmap_encode_fn {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<tmap_encode_fn>(p);
-  }
+      return reinterpret_cast<tmap_encode_fn>(p);
+    return nullptr;
+  }();
   return fn;
+}
+
+// cuTensorMapEncodeTiled costs a driver call per map and a forward needs ~25 of them; the head's buffers keep their
+// addresses from call to call (caller-owned workspace), so encoded maps are kept in a small per-thread cache keyed on
+// every argument of the encode.
+struct TmapKey {
+  const void* ptr;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], es[4];
+  int rank, swizzle;
+};
+static bool tmap_cached(CUtensorMap* out, int rank, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,
+                        const cuuint32_t* box, const cuuint32_t* es, CUtensorMapSwizzle swz) {
+  constexpr int CAP = 96;
+  struct Entry { TmapKey k; CUtensorMap m; };
+  static thread_local Entry cache[CAP];
+  static thread_local int used = 0, next = 0;
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = ptr; k.rank = rank; k.swizzle = (int)swz;
+  for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.es[i] = es[i]; }
+  for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
+  for (int i = 0; i < used; ++i)
+    if (memcmp(&cache[i].k, &k, sizeof(k)) == 0) { *out = cache[i].m; return true; }
+  tmap_encode_fn enc = tmap_encoder();
+  if (enc == nullptr) return false;
+  CUtensorMap m;
+  if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  const int slot = used < CAP ? used++ : (next++ % CAP);
+  cache[slot].k = k; cache[slot].m = m;
+  *out = m;
+  return true;
 }
 
 // NCHW convolution whose tile is a rectangle of one image, every source either full or half resolution
@@ -897,8 +930,6 @@ static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g) {
   // columns 2 ox + dx - 1 themselves)
   const int BW = KS == 3 ? S * TW + 2 * TM_XH : TW, BH = (KS == 3 && S == 1) ? TH + 2 : TH;
   if (BW > 256 || BH > 256 || (size_t)BW * BH * TC_KC * 4 > (size_t)tm_tile_bytes(KS)) return false;
-  tmap_encode_fn enc = tmap_encoder();
-  if (enc == nullptr) return false;
   for (int s = 0; s < 3; ++s) {
     const ConvSrc& sc = a.src[s];
     if (sc.C == 0) continue;
@@ -909,10 +940,7 @@ static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g) {
     const cuuint64_t strides[3] = {(cuuint64_t)sc.W * 4, (cuuint64_t)sc.W * sc.H * 4, (cuuint64_t)sc.W * sc.H * sc.C * 4};
     const cuuint32_t box[4] = {(cuuint32_t)BW, (cuuint32_t)(BH * S), (cuuint32_t)TC_KC, 1};
     const cuuint32_t es[4] = {1, (cuuint32_t)S, 1, 1};
-    if (enc(&g->tmap[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sc.ptr), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return false;
+    if (!tmap_cached(&g->tmap[s], 4, sc.ptr, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
   }
   g->TW = TW; g->TH = TH; g->BW = BW; g->BH = BH; g->S = S;
   return true;
@@ -1487,31 +1515,23 @@ static bool lin_tma_plan(const ConvArgs& a, int NT, LinTmaArgs* g) {
     g->rows_per_img = (int)per;
   }
   if (((uintptr_t)sc.ptr & 15) || ((uintptr_t)a.out & 15) || (a.skip && ((uintptr_t)a.skip & 15))) return false;
-  tmap_encode_fn enc = tmap_encoder();
-  if (enc == nullptr) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)a.Ctot, (cuuint64_t)R};
   const cuuint64_t strides[1] = {(cuuint64_t)a.Ctot * 4};
   const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_TM};
   const cuuint32_t es[2] = {1, 1};
-  return enc(&g->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sc.ptr), dims, strides, box, es,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return tmap_cached(&g->tmap, 2, sc.ptr, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // fused Mlp launcher; returns 1 when the fused kernel does not apply (caller falls back to fc1 / fc2 launches)
 int run_mlp_fused(const float* v, const float* x1, const float* w1img, const float* b1, const float* w2img, const float* b2,
                   float* out, long long R, cudaStream_t st) {
   if (R % TC_TM || R > 0x7fffffffLL || (((uintptr_t)v | (uintptr_t)x1 | (uintptr_t)out | (uintptr_t)b2) & 15)) return 1;
-  tmap_encode_fn enc = tmap_encoder();
-  if (enc == nullptr) return 1;
   MlpFusedArgs g;
   const cuuint64_t dims[2] = {64, (cuuint64_t)R};
   const cuuint64_t strides[1] = {64 * 4};
   const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_TM};
   const cuuint32_t es[2] = {1, 1};
-  if (enc(&g.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(v), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return 1;
+  if (!tmap_cached(&g.tmap, 2, v, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   g.w1img = w1img; g.w2img = w2img; g.b1 = b1; g.b2 = b2; g.skip = x1; g.out = out; g.R = R;
   static thread_local int mf_dev = -1;
   int dev = 0;
@@ -1533,6 +1553,9 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
   TPSPP_REQUIRE(NT == 64 || NT == 32, "conv_tc: column tile must be 32 or 64");
   TPSPP_REQUIRE(a.Cout % NT == 0, "conv_tc: Cout %d is not a multiple of the column tile %d", a.Cout, NT);
   TPSPP_REQUIRE(KS == 1 || NT == 64, "conv_tc: 3x3 kernels are instantiated for 64-column tiles only");
+  // the TMA-staged kernels are the product path: without the driver's tensor-map encoder fail loudly instead of
+  // silently dropping to the (2x slower) gather-fed kernels
+  TPSPP_REQUIRE(tmap_encoder() != nullptr, "conv_tc: cuTensorMapEncodeTiled is not available from this CUDA driver");
   ConvTcArgs t;
   t.c = a;
   t.wprep = wprep;

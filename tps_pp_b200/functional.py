@@ -160,9 +160,25 @@ def grid_sample_border(src0: torch.Tensor, grid: torch.Tensor, src1: Optional[to
 
 
 # ----------------------------------------------------------------------------- head
-def head_cfg(batch, height, width, point_size, p_stride, precision=N.HEAD_FP32) -> N.HeadCfg:
+def head_cfg(batch, height, width, point_size, p_stride, precision=N.HEAD_FP32, flags=0) -> N.HeadCfg:
     return N.HeadCfg(int(batch), int(height), int(width), int(point_size[0]), int(point_size[1]), int(p_stride),
-                     int(precision))
+                     int(precision), int(flags))
+
+
+def head_param_shapes(h: int, w: int, f: int, c: int = 64):
+    """Shapes of the 58 parameter tensors in state_dict order for an ``h x w`` feature map with
+    ``f`` control points -- what the native kernels size their reads from."""
+    conv3 = lambda ci, co: [(co, ci, 3, 3), (co,)]
+    lin = lambda ci, co: [(co, ci), (co,)]
+    shapes = conv3(3 * c, 64) + conv3(64, 64) * 3                                   # MSFA encoder
+    shapes += [(64 // 16, 64, 1, 1), (64, 64 // 16, 1, 1), (1, 2, 3, 3), (1,)]      # CBAM
+    shapes += conv3(64, 64) * 3 + conv3(64, c)                                      # MSFA decoder
+    shapes += lin(c, 32) + lin(32, 128) + lin(c, 32) + lin(32, 128)                 # p_linear, feat_linear
+    shapes += [(h, w), (h, w), (h + 1, h + f), (w + 1, w + f)] + lin(c, c) + [(h, w), (h, w)]   # DGAB gate
+    shapes += lin(c, 4 * c) + lin(4 * c, c)                                         # Mlp
+    shapes += lin(c, 256) + lin(256, 2) + lin(2 * f, 2 * f)                         # localisation
+    shapes += [(c, 32, 1, 1), (c,)] * 2 + [(c, 64, 1, 1), (c,)] + conv3(c, c) * 2 + [(c, 3 * c, 1, 1), (c,)]   # down*
+    return shapes
 
 
 def head_workspace_offsets(cfg: N.HeadCfg):
@@ -173,10 +189,12 @@ def head_workspace_offsets(cfg: N.HeadCfg):
 
 
 def head_forward(x: torch.Tensor, o0: torch.Tensor, o1: torch.Tensor, params, point_size, p_stride,
-                 precision=N.HEAD_FP32, workspace: Optional[torch.Tensor] = None):
+                 precision=N.HEAD_FP32, workspace: Optional[torch.Tensor] = None, weights_cached: bool = False):
     """Native control-point attention head (reference tps_pp.py:581-594), inference only (no autograd).
 
     ``params``: the module's parameters in state_dict order (58 fp32 CUDA tensors).
+    ``weights_cached``: ``workspace`` was last used by a call with the same parameter values (the tensor-core
+    weight images inside it are reused; see ``TPSPP_HEAD_FLAG_WEIGHTS_CACHED`` in include/tpspp.h).
     Returns ``(feat_grid, c_prime, pc_score, workspace)``."""
     for nm, t in (("batch_img", x), ("outs[0]", o0), ("outs[1]", o1)):
         _require_cuda(nm, t, torch.float32)
@@ -188,20 +206,28 @@ def head_forward(x: torch.Tensor, o0: torch.Tensor, o1: torch.Tensor, params, po
     params = list(params)
     if len(params) != N.P_COUNT:
         raise RuntimeError(f"tps_pp_b200: expected {N.P_COUNT} parameter tensors, got {len(params)}")
+    f = point_size[0] * point_size[1]
     table = (ctypes.c_void_p * N.P_COUNT)()
-    for i, p in enumerate(params):
+    # the kernels size every weight read from (h, w, F): a module built for another geometry must fail here, like
+    # the reference's layer_norm / linear calls do, instead of reading out of bounds
+    for i, (p, shp) in enumerate(zip(params, head_param_shapes(h, w, f))):
         _require_cuda(f"param[{i}]", p, torch.float32)
         if not p.is_contiguous():
             raise RuntimeError(f"tps_pp_b200: param[{i}] must be contiguous")
+        if tuple(p.shape) != shp:
+            raise RuntimeError(f"tps_pp_b200: param[{i}] has shape {tuple(p.shape)} but a [{b},{c},{h},{w}] input with "
+                               f"{f} control points needs {shp} (module built for another img_size / point_size?)")
         table[i] = p.data_ptr()
     cfg = head_cfg(b, h, w, point_size, p_stride, precision)
-    f = point_size[0] * point_size[1]
     with torch.cuda.device(x.device):
         nbytes = int(N.lib().tpspp_head_workspace_bytes(ctypes.byref(cfg)))
         if nbytes == 0 and b > 0:
             raise RuntimeError("tpspp_head_workspace_bytes failed: " + N.last_error())
         if workspace is None or workspace.numel() < nbytes or workspace.device != x.device:
             workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+            weights_cached = False
+        if weights_cached:
+            cfg.flags |= N.HEAD_FLAG_WEIGHTS_CACHED
         feat_grid = torch.empty((b, 64, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
         c_prime = torch.empty((b, f, 2), dtype=torch.float32, device=x.device)
         score = torch.empty((b, h * w, f), dtype=torch.float32, device=x.device)

@@ -33,7 +33,13 @@ def shard_batch(tensors: Sequence[torch.Tensor], rank: int, world: int) -> List[
 class GradBucket:
     """All gradients of a module in ONE flat fp32 buffer (TPS_PP: 0.547 M params = 2.19 MB), so the training
     step issues a single all-reduce that NCCL runs over NVLink/NVSwitch; parameters' ``.grad`` are views
-    into the buffer, so backward writes straight into it (no pack/unpack copies)."""
+    into the buffer, so backward writes straight into it (no pack/unpack copies).
+
+    ``optimizer.zero_grad()`` (torch >= 2.0 default ``set_to_none=True``, which mmcv's OptimizerHook and
+    ``module.zero_grad()`` use as well) drops those views: backward then allocates fresh ``.grad`` tensors and
+    the flat buffer would go stale.  :meth:`zero` and :meth:`all_reduce_mean` therefore re-attach every parameter
+    whose ``.grad`` no longer aliases its slot (copying a fresh gradient into the slot first), so either
+    ``bucket.zero()`` or any flavour of ``zero_grad`` can be used between steps."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params = [p for p in params if p.requires_grad]
@@ -42,16 +48,42 @@ class GradBucket:
         dev, dt = self.params[0].device, self.params[0].dtype
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=dt, device=dev)
+        self.offsets = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            self.offsets.append(off)
             off += p.numel()
+        self.reattached = 0          # parameters whose view had been dropped and was restored (diagnostic)
+        self._attach(copy=False)
+
+    def _slot(self, i: int) -> torch.Tensor:
+        p = self.params[i]
+        return self.flat[self.offsets[i]: self.offsets[i] + p.numel()].view_as(p)
+
+    def _attach(self, copy: bool) -> None:
+        """Make every ``p.grad`` a view of its slot again.  ``copy``: a detached gradient written by backward since
+        the views were dropped is moved into the slot; a missing gradient (``None``) zeroes the slot."""
+        base, esz = self.flat.data_ptr(), self.flat.element_size()
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is not None and g.data_ptr() == base + self.offsets[i] * esz and g.is_contiguous():
+                continue
+            slot = self._slot(i)
+            if copy:
+                if g is None:
+                    slot.zero_()
+                else:
+                    slot.copy_(g)
+                self.reattached += 1
+            p.grad = slot
 
     def zero(self):
         self.flat.zero_()
+        self._attach(copy=False)
 
     def all_reduce_mean(self, group=None, async_op: bool = False):
         """Average over ranks (DDP semantics).  Returns the work handle when ``async_op``."""
+        self._attach(copy=True)      # gradients that landed outside the bucket (after a zero_grad) are pulled in
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
         world = dist.get_world_size(group)

@@ -64,9 +64,22 @@ class _BaseModule(nn.Module):
         self.init_cfg = init_cfg
 
     def init_weights(self):
-        # the reference's TPS_PP has no init_cfg: mmcv's BaseModule.init_weights() leaves the
-        # constructor initialisation untouched
+        # mmcv BaseModule.init_weights() with init_cfg=None: calls init_weights() of the direct children that
+        # have one, once -- for TPS_PP these are the six down* ConvModules (MSFA/TPE are plain nn.Modules in
+        # the reference, tps_pp.py:172,231), whose kaiming-normal initialisation is drawn again
+        if getattr(self, "_is_init", False):
+            return None
+        for name in getattr(self, "_convmodule_children", ()):
+            _convmodule_init(self.get_submodule(name + ".conv"))
+        self._is_init = True
         return None
+
+
+def _convmodule_init(conv: nn.Conv2d) -> None:
+    """mmcv ``ConvModule.init_weights`` (runs at the end of the ConvModule ctor): ``kaiming_init(conv, a=0,
+    mode='fan_out', nonlinearity='relu', distribution='normal')`` and a zero bias."""
+    nn.init.kaiming_normal_(conv.weight, a=0, mode="fan_out", nonlinearity="relu")
+    nn.init.constant_(conv.bias, 0)
 
 
 @BACKBONES.register_module()
@@ -90,7 +103,10 @@ class TPS_PP(_BaseModule):
         hh, ww = img_size
 
         def conv(path, cin, cout, k, bias=True):
-            return _attach(self, path, nn.Conv2d(cin, cout, k, bias=bias))
+            m = _attach(self, path, nn.Conv2d(cin, cout, k, bias=bias))
+            if path.endswith(".conv"):      # an mmcv ConvModule in the reference: its ctor re-initialises the conv
+                _convmodule_init(m)
+            return m
 
         def lin(path, cin, cout, bias=True):
             return _attach(self, path, nn.Linear(cin, cout, bias=bias))
@@ -124,6 +140,7 @@ class TPS_PP(_BaseModule):
         conv("down0.conv", 32, c, 1); conv("down1.conv", 32, c, 1); conv("down2.conv", 64, c, 1)
         conv("down0_1.conv", c, c, 3); conv("down1_1.conv", c, c, 3)
         conv("down_feat.conv", 3 * c, c, 1)
+        self._convmodule_children = ("down0", "down1", "down2", "down0_1", "down1_1", "down_feat")
         # constants (tps_pp.py:353-366); P is a plain attribute in the reference (re-uploaded
         # every forward at :472) -- here a non-persistent buffer so state_dict keys stay identical
         hat_c, p_hat, p, _ = K.attention_tps_buffers(point_size, rectified_img_size)
@@ -141,7 +158,9 @@ class TPS_PP(_BaseModule):
         self._last_head_native = None
         # tcgen05 3xTF32 convolutions (fp32-level accuracy); N.HEAD_FP32 = CUDA-core only
         self.head_precision = N.HEAD_TC
-        self._head_ws = None
+        # native-head workspaces, one per (device, stream): concurrent forwards on different streams must not share
+        # intermediates.  Each entry remembers which parameter values its tensor-core weight images were built from.
+        self._head_ws = {}
         self._last_head_launches = 0
 
     # ------------------------------------------------------------------ stages
@@ -248,9 +267,19 @@ class TPS_PP(_BaseModule):
             if torch.is_grad_enabled() and (batch_img.requires_grad or any(p.requires_grad for p in self.parameters())):
                 raise RuntimeError("tps_pp_b200: head_impl='native' has no backward yet; use torch.no_grad() or "
                                    "head_impl='auto'/'library' for training")
-            fg, cp, sc, self._head_ws = TF.head_forward(batch_img, outs[0], outs[1], list(self.parameters()),
-                                                        self.point_size, self.p_stride, self.head_precision,
-                                                        self._head_ws)
+            b, c, h, w = batch_img.shape
+            if (h, w) != tuple(self.img_size) or c != self.num_img_channel:
+                raise RuntimeError(f"tps_pp_b200: TPS_PP(img_size={tuple(self.img_size)}, num_img_channel="
+                                   f"{self.num_img_channel}) got batch_img {tuple(batch_img.shape)}")
+            params = list(self.parameters())
+            key = (batch_img.device.index, torch.cuda.current_stream(batch_img.device).cuda_stream)
+            stamp = (b, self.head_precision, tuple((p.data_ptr(), p._version) for p in params))
+            ws, ws_stamp = self._head_ws.get(key, (None, None))
+            fg, cp, sc, ws = TF.head_forward(batch_img, outs[0], outs[1], params, self.point_size, self.p_stride,
+                                             self.head_precision, ws, weights_cached=(ws_stamp == stamp))
+            if len(self._head_ws) >= 8 and key not in self._head_ws:
+                self._head_ws.clear()            # streams come and go: bound what the module pins
+            self._head_ws[key] = (ws, stamp)
             self._last_head_launches = N.last_launch_count()
             return fg, cp, sc
         self._last_head_launches = 0
