@@ -294,7 +294,7 @@ def nrtr_fixture(write: bool, batch: int = 2):
         return conv.idx2str(idx), probs
 
     stock = {k: v.detach().clone() for k, v in tps.state_dict().items()}
-    out = {'img': img.numpy(), 'deltas': np.array([1e-4, 3e-4, 1e-3])}
+    out = {'img': img.numpy(), 'deltas': np.array([1e-4, 1e-3, 2e-3, 4e-3])}
     for name, sd in (('stock', stock), ('trained', O.trained_like_state(3))):
         tps.load_state_dict(sd, strict=True)
         cap = {}
@@ -320,6 +320,13 @@ def nrtr_fixture(write: bool, batch: int = 2):
         print(f'    {name}: decode {strings[0]!r}; min top-1 margin {float((top2[..., 0] - top2[..., 1]).min()):.2e}; '
               f'argmax flips under uniform noise {dict(zip([float(d) for d in out["deltas"]], flips))} -> safe_delta {safe:.0e}')
         check(f'{name}: 1e-4 noise leaves every argmax in place (SURVEY C-10)', float(flips[0]), 0.0)
+        # fp64 twin of the rectifier on the same captured tensors (oracle fp64 == reference fp64 twin to 3e-12, above):
+        # the reference's own fp32 error |ref32 - ref64| is the floor no independent fp32 implementation can beat (F6)
+        r64 = O.tps_pp_forward({k: v for k, v in sd.items()}, cap['x'].numpy(), [cap['o0'].numpy(), cap['o1'].numpy()],
+                               dtype=torch.float64, sampler='numpy')
+        floor = _mx(cap['output'], r64['output'])
+        print(f'    {name}: reference fp32 vs fp64 twin on this batch: {floor:.3e}')
+        out[f'{name}_ref64_output'] = np.asarray(r64['output'], dtype=np.float64).astype(np.float32)
         out.update({'x': cap['x'].numpy(), 'o0': cap['o0'].numpy(), 'o1': cap['o1'].numpy(),
                     f'{name}_ref_output': cap['output'].numpy(), f'{name}_ref_argmax': ref_arg.numpy().astype(np.int16),
                     f'{name}_safe_delta': np.array(safe), f'{name}_flips': np.array(flips),

@@ -126,8 +126,8 @@ def test_nrtr_fixture_weights_are_reproducible(golden):
     torch.manual_seed(0)
     m = T.TPS_PP()
     digest = np.array([float(v.double().abs().sum()) for v in m.state_dict().values()])
-    assert np.array_equal(digest, g["stock_state_digest"])
+    assert np.allclose(digest, g["stock_state_digest"], rtol=1e-6, atol=0)
     digest = np.array([float(v.double().abs().sum()) for v in O.trained_like_state(3).values()])
-    assert np.array_equal(digest, g["trained_state_digest"])
+    assert np.allclose(digest, g["trained_state_digest"], rtol=1e-6, atol=0)
     assert g["x"].shape == (2, 64, 16, 64) and g["o0"].shape == (2, 32, 32, 128)
-    assert float(g["stock_safe_delta"]) >= 1e-4 and int(g["stock_flips"][0]) == 0 and int(g["trained_flips"][0]) == 0
+    assert float(g["stock_safe_delta"]) >= 1e-3 and float(g["trained_safe_delta"]) >= 1e-3 and int(g["stock_flips"][0]) == 0 and int(g["trained_flips"][0]) == 0
