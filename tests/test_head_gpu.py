@@ -248,3 +248,35 @@ def test_geometry_mismatch_raises_instead_of_reading_out_of_bounds(native_lib):
         m(x, [o, o])
     with pytest.raises(RuntimeError, match="needs"):
         TF.head_forward(x, o, o, list(m.parameters()), (1, 16), 2, N.HEAD_TC)
+
+
+def test_fused_down_kernel_equals_separate_launches(native_lib):
+    """down0 + down1 + down2 + down_feat as one TMEM-chained kernel (default) against the four separate tensor-core
+    launches (TPSPP_HEAD_FLAG_UNFUSED_DOWN): same 3xTF32 arithmetic up to the accumulator split, so f0/f1/f2 and
+    feat_grid agree to ~1e-6 of their scale; 5 images = 160 tiles > one per SM, so the persistent loop wraps."""
+    sd = O.trained_like_state(3)
+    x, o0, o1 = O.synthetic_tpspp_inputs(5, 21)
+    res = {}
+    for flags in (0, N.HEAD_FLAG_UNFUSED_DOWN):
+        m = T.TPS_PP().to(DEV).eval()
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            fg, cp, sc, ws = TF.head_forward(torch.from_numpy(x).to(DEV), torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV),
+                                             list(m.parameters()), (2, 16), 2, N.HEAD_TC, flags=flags)
+        launches = N.last_launch_count()
+        off = TF.head_workspace_offsets(TF.head_cfg(5, 16, 64, (2, 16), 2, N.HEAD_TC))
+        def slot(name, shp):
+            n = int(np.prod(shp))
+            return ws[off[name]: off[name] + 4 * n].view(torch.float32).view(shp).clone()
+        res[flags] = dict(fg=fg, f0=slot("f0", (5, 64, 32, 128)), f1=slot("f1", (5, 64, 32, 128)), f2=slot("f2", (5, 64, 16, 64)),
+                          cp=cp, sc=sc, launches=launches)
+    assert res[0]["launches"] == res[N.HEAD_FLAG_UNFUSED_DOWN]["launches"] - 3
+    r64 = O.head_intermediates(sd, x, [o0, o1], dtype=torch.float64)
+    for k, name in (("f0", "f0"), ("f1", "f1"), ("f2", "f2"), ("fg", "feat_grid")):
+        a, b = res[0][k], res[N.HEAD_FLAG_UNFUSED_DOWN][k]
+        scale = float(b.abs().max())
+        e_f, e_u = mx(a, r64[name]), mx(b, r64[name])
+        print(f"{name}: fused-vs-separate {mx(a, b):.2e}; |fused-ref64| {e_f:.2e}, |separate-ref64| {e_u:.2e}, scale {scale:.2f}")
+        assert mx(a, b) <= 2e-6 * max(scale, 1.0)
+        assert e_f <= 1.5 * e_u + 1e-6 * max(scale, 1.0)
+    assert mx(res[0]["cp"], res[N.HEAD_FLAG_UNFUSED_DOWN]["cp"]) <= 1e-6

@@ -1191,14 +1191,25 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     }
   }
 #define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != TPSPP_OK) return rc; } while (0)
-  // down0/1/2 (tps_pp.py:581-583): 
+  // down0/1/2 + grid()/down_feat (tps_pp.py:581-583,585,560-562): one fused tensor-core kernel in the 3xTF32 mode; f0/f1/f2
+  // are still written (once) for the stride-2 convolutions and the MSFA encoder
+  bool fused_down = false;
+  if (tc && !bf16 && !(cfg->flags & TPSPP_HEAD_FLAG_UNFUSED_DOWN)) {
+    rc = run_down_fused(x, o0, o1, wp[0], wp[1], wp[2], wp[5], P[TPSPP_P_DOWN0_B], P[TPSPP_P_DOWN1_B], P[TPSPP_P_DOWN2_B],
+                        P[TPSPP_P_DOWNFEAT_B], W(TPSPP_WS_F0), W(TPSPP_WS_F1), W(TPSPP_WS_F2), feat_grid, B, h, w, st);
+    if (rc < 0) return rc;
+    fused_down = rc == TPSPP_OK;
+  }
+  if (!fused_down) {
   RUN(1, mk_src(o0, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), NCHW, B, H2, W2, 1, 1, st, wp[0], bf16);
   RUN(1, mk_src(o1, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), NCHW, B, H2, W2, 1, 1, st, wp[1], bf16);
   RUN(1, mk_src(x, 64, h, w, NCHW), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), NCHW, B, h, w, 1, 1, st, wp[2], bf16);
+  }
   // down0_1 / down1_1: 3x3 stride 2 (tps_pp.py:584)
   RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), NCHW, B, h, w, 2, 2, st, wp[3], bf16);
   RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), NCHW, B, h, w, 2, 2, st, wp[4], bf16);
   // grid(): down_feat(cat(f0, f1, up2(f2))) (tps_pp.py:560-562,585) -> feat_grid in the boundary layout (warp input)
+  if (!fused_down)
   RUN(1, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW), mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW), mk_src(W(TPSPP_WS_F2), 64, h, w, NCHW, 2, 2),
       P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, NCHW, B, H2, W2, 1, 1, st, wp[5], bf16);
   // MSFA encoder (tps_pp.py:158-160): cat(a0, a1, f2) -> e0 -> e1 -> e2 -> e3

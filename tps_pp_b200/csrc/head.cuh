@@ -33,6 +33,10 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
 // DGAB Mlp fused (fc1 + GELU + fc2 + residual) on the weight images of fc1/fc2; returns 1 if not applicable
 int run_mlp_fused(const float* v, const float* x1, const float* w1img, const float* b1, const float* w2img, const float* b2,
                   float* out, long long R, cudaStream_t st);
+// down0 + down1 + down2 + down_feat in one kernel (tps_pp.py:538-540,548,560-562,581-585); returns 1 if not applicable
+int run_down_fused(const float* x, const float* o0, const float* o1, const float* w0img, const float* w1img, const float* w2img,
+                   const float* wfimg, const float* b0, const float* b1, const float* b2, const float* bf, float* f0, float* f1,
+                   float* f2, float* fg, int B, int h, int w, cudaStream_t st);
 size_t conv_tc_wprep_floats(int Ctot, int KS, int N);    // floats needed for one layer's image (N output rows)
 
 struct WPrepLayer {

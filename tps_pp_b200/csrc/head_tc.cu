@@ -1428,6 +1428,331 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const __grid_c
   if (warp == 0) tmem_dealloc(tmem_d, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// down0 + down1 + down2 + grid()/down_feat in ONE kernel (reference tps_pp.py:538-540,548,560-562,581-585):
+//     f0 = relu(W0 o0 + b0)   f1 = relu(W1 o1 + b1)   f2 = relu(W2 x + b2)
+//     feat_grid = relu(Wf cat(f0, f1, up2(f2)) + bf)
+// As four launches these wrote f0/f1 (268 MB each at B = 256) and read them back for down_feat, re-read f2 four
+// times for the nearest up-sampling: 1.5 GB of DRAM traffic for 0.67 GB of compulsory I/O.  Here a 128-pixel tile
+// (2 rows x 64 columns of the 2h x 128 map = 1 row x 32 columns of the h x 64 map) goes through the MLP-style
+// TMEM chain: the three 1x1 GEMMs land in tensor memory, their bias+ReLU epilogue stores f_j once (the stride-2
+// 3x3 convolutions need f0/f1, the MSFA encoder needs f2) and re-feeds the split values as the A operand of down_feat;
+// up2(f2) is the same TMEM lane mapping evaluated at (y >> 1, x >> 1), i.e. down2 is computed on the replicated
+// rows (4x redundant, 8 MFLOP/img) and only the even/even lanes store f2.
+//   TMEM   A1 ring [0,128)   : two slots of a split 32-channel input chunk (hi 32 | lo 32); 4 chunks per tile (o0, o1, x, x)
+//          D1      [128,256) : two accumulators of the f_j GEMMs (blocks alternate; 3xTF32 corrections merged, K <= 64)
+//          A2      [256,384) : split relu(D1 + b_j): two 32-channel chunks, the A operand of down_feat for block j
+//          D2      [384,512) : down_feat accumulator main | corrections, summed over the three blocks (K = 192)
+//   smem   W0, W1, W2 images resident (64 KB), Wf chunks through a 4-stage ring, two sets of input boxes (o0 | o1 | x)
+//   warps  0-15 workers (lane quarter q = TMEM lanes = pixels, part p = 8 / 16 of the channels), 16 MMA issuer, 17 TMA
+// ------------------------------------------------------------------------------------------------
+struct DownFusedArgs {
+  CUtensorMap tm_o0, tm_o1, tm_x;      // o0/o1 [B,32,2h,128] box 64 x 2 x 32; x [B,64,h,64] box 32 x 1 x 64
+  const float *w0img, *w1img, *w2img, *wfimg;
+  const float *b0, *b1, *b2, *bf;
+  float *f0, *f1, *f2, *fg;
+  int B, h;                            // h = rows of x (the outs have 2h rows, 128 columns)
+};
+constexpr int DF_WARPS = 16;
+constexpr int DF_THREADS = (DF_WARPS + 2) * 32;
+constexpr int DF_WF_STAGES = 4;
+constexpr int DF_IN_SET = 16384 + 16384 + 8192;                   // o0 box | o1 box | x box
+constexpr int DF_SMEM = 4 * TS_STAGE + DF_WF_STAGES * TS_STAGE + 2 * DF_IN_SET + 2048 + 1024;
+
+__global__ void __launch_bounds__(DF_THREADS, 1) down_fused_kernel(const __grid_constant__ DownFusedArgs g) {
+  constexpr int NT = 64;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* wres = smem;                                       // W0 | W1 | W2 chunk 0 | W2 chunk 1, 16 KB each
+  unsigned char* wfs = smem + 4 * TS_STAGE;                         // ring of down_feat weight chunks
+  unsigned char* ins = wfs + DF_WF_STAGES * TS_STAGE;               // 2 sets x (o0 16 KB | o1 16 KB | x 8 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ins + 2 * DF_IN_SET);
+  uint64_t* wres_full = bars;          // 1
+  uint64_t* in_full = bars + 1;        // [2 sets][3 inputs]
+  uint64_t* in_empty = bars + 7;       // [2][3]
+  uint64_t* a1_full = bars + 13;       // [2]
+  uint64_t* a1_empty = bars + 15;      // [2]
+  uint64_t* d1_full = bars + 17;       // [2]
+  uint64_t* d1_empty = bars + 19;      // [2]
+  uint64_t* a2_full = bars + 21;
+  uint64_t* a2_empty = bars + 22;
+  uint64_t* d2_full = bars + 23;
+  uint64_t* d2_empty = bars + 24;
+  uint64_t* wf_full = bars + 25;       // [4]
+  uint64_t* wf_empty = bars + 29;      // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
+  float* bias_s = reinterpret_cast<float*>(bars + 34);             // [4][64]: b0 | b1 | b2 | bf
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+  if (tid == 0) {
+    mbar_init(wres_full, 1);
+    for (int i = 0; i < 6; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], DF_WARPS); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a1_full[i], DF_WARPS); mbar_init(&a1_empty[i], 1);
+      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], DF_WARPS);
+    }
+    mbar_init(a2_full, DF_WARPS); mbar_init(a2_empty, 1);
+    mbar_init(d2_full, 1); mbar_init(d2_empty, DF_WARPS);
+    for (int i = 0; i < DF_WF_STAGES; ++i) { mbar_init(&wf_full[i], 1); mbar_init(&wf_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (tid < 256) {
+    const float* bsrc = (tid >> 6) == 0 ? g.b0 : (tid >> 6) == 1 ? g.b1 : (tid >> 6) == 2 ? g.b2 : g.bf;
+    bias_s[tid] = __ldg(bsrc + (tid & 63));
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  const int tiles_per_img = g.h * 2;
+  const int ntiles = g.B * tiles_per_img;
+  const int n_my = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
+  constexpr uint32_t PART = NT * TC_KC * 4;                          // bytes of the hi (or lo) image of a chunk
+
+  if (warp == DF_WARPS) {
+    // ===== MMA issuer warp =====
+    if (n_my > 0) mbar_wait_bounded(wres_full, 0);
+    auto mma_chunk = [&](uint32_t d_main, uint32_t d_corr, uint32_t a_base, uint32_t b_base, bool first) {   // one elected lane
+#pragma unroll
+      for (int kk = 0; kk < TC_KC / 8; ++kk) {
+        const uint64_t dbh = umma_smem_desc(b_base + kk * 2 * (NT * 16), NT * 16, 128);
+        const uint64_t dbl = umma_smem_desc(b_base + PART + kk * 2 * (NT * 16), NT * 16, 128);
+        const uint32_t a_hi = a_base + kk * 8, a_lo = a_hi + 32;
+        umma_ts_tf32(d_main, a_hi, dbh, IDESC, (first && kk == 0) ? 0u : 1u);
+        umma_ts_tf32(d_corr, a_lo, dbh, IDESC, (first && kk == 0 && d_corr != d_main) ? 0u : 1u);
+        umma_ts_tf32(d_corr, a_hi, dbl, IDESC, 1u);
+      }
+    };
+    // stage 1 of block j (0: o0, 1: o1, 2: x) of tile `it`: D1[gj & 1] = A1 chunk(s) . W_j^T
+    auto issue_s1 = [&](int it, int j) {
+      const int gj = it * 3 + j, db = gj & 1;
+      if (gj >= 2) mbar_wait_bounded(&d1_empty[db], (uint32_t)(((gj >> 1) - 1) & 1));
+      const int c0 = j, nc = j == 2 ? 2 : 1;                       // A1 chunks of the block: tile-local index c0 .. c0 + nc - 1
+      for (int c = 0; c < nc; ++c) {
+        const int gc = it * 4 + c0 + c, slot = gc & 1;
+        mbar_wait_bounded(&a1_full[slot], (uint32_t)((gc >> 1) & 1));
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t d1 = tmem_d + 128 + (uint32_t)(db * 64);
+          mma_chunk(d1, d1, tmem_d + (uint32_t)(slot * 64), smem_u32(wres) + (uint32_t)((c0 + c) * TS_STAGE), c == 0);
+          umma_commit(&a1_empty[slot]);
+          if (c == nc - 1) umma_commit(&d1_full[db]);
+        }
+        __syncwarp();
+      }
+    };
+    if (n_my > 0) issue_s1(0, 0);
+    for (int it = 0; it < n_my; ++it) {
+      for (int j = 0; j < 3; ++j) {
+        const int gj = it * 3 + j;
+        if (j < 2) issue_s1(it, j + 1);                  // overlaps the epilogue of block j
+        else if (it + 1 < n_my) issue_s1(it + 1, 0);     // next tile's first block overlaps this tile's last epilogues
+        mbar_wait_bounded(a2_full, (uint32_t)(gj & 1));
+        if (j == 0 && it >= 1) mbar_wait_bounded(d2_empty, (uint32_t)((it - 1) & 1));
+        for (int c = 0; c < 2; ++c) {
+          const int wi = gj * 2 + c, st = wi & (DF_WF_STAGES - 1);
+          mbar_wait_bounded(&wf_full[st], (uint32_t)((wi / DF_WF_STAGES) & 1));
+          tc_fence_after();
+          if (elect_one_sync()) {
+            mma_chunk(tmem_d + 384, tmem_d + 448, tmem_d + 256 + (uint32_t)(c * 64), smem_u32(wfs) + (uint32_t)(st * TS_STAGE),
+                      j == 0 && c == 0);
+            umma_commit(&wf_empty[st]);
+            if (c == 1) { umma_commit(a2_empty); if (j == 2) umma_commit(d2_full); }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == DF_WARPS + 1) {
+    // ===== TMA warp: resident weight images once; then input boxes (two sets ahead) and down_feat weight chunks =====
+    if (n_my > 0 && elect_one_sync()) {
+      mbar_arrive_expect_tx(wres_full, 4 * TS_STAGE);
+      bulk_g2s(wres, g.w0img, TS_STAGE, wres_full, policy_evict_last());
+      bulk_g2s(wres + TS_STAGE, g.w1img, TS_STAGE, wres_full, policy_evict_last());
+      bulk_g2s(wres + 2 * TS_STAGE, g.w2img, 2 * TS_STAGE, wres_full, policy_evict_last());
+    }
+    __syncwarp();
+    const int total_in = n_my * 3, total_w = n_my * 6;
+    int ii = 0, wi = 0;
+    while (ii < total_in || wi < total_w) {
+      if (ii < total_in) {
+        const int it = ii / 3, k = ii - it * 3, set = it & 1;
+        int ok = 1;
+        if (it >= 2) ok = mbar_test_wait(&in_empty[set * 3 + k], (uint32_t)(((it >> 1) - 1) & 1)) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {
+          if (elect_one_sync()) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+            const int r = rem >> 1, c0 = rem & 1;
+            unsigned char* dst = ins + set * DF_IN_SET + (k == 0 ? 0 : k == 1 ? 16384 : 32768);
+            uint64_t* bar = &in_full[set * 3 + k];
+            if (k < 2) {
+              mbar_arrive_expect_tx(bar, 16384);
+              tma_load_4d(dst, k == 0 ? &g.tm_o0 : &g.tm_o1, 64 * c0, 2 * r, 0, img, bar, policy_evict_first());
+            } else {
+              mbar_arrive_expect_tx(bar, 8192);
+              tma_load_4d(dst, &g.tm_x, 32 * c0, r, 0, img, bar, policy_evict_first());
+            }
+          }
+          __syncwarp();
+          ++ii;
+        }
+      }
+      if (wi < total_w) {
+        const int st = wi & (DF_WF_STAGES - 1);
+        int ok = 1;
+        if (wi >= DF_WF_STAGES) ok = mbar_test_wait(&wf_empty[st], (uint32_t)(((wi / DF_WF_STAGES) - 1) & 1)) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&wf_full[st], TS_STAGE);
+            bulk_g2s(wfs + st * TS_STAGE, reinterpret_cast<const unsigned char*>(g.wfimg) + (size_t)(wi % 6) * TS_STAGE, TS_STAGE,
+                     &wf_full[st], policy_evict_last());
+          }
+          __syncwarp();
+          ++wi;
+        }
+      }
+    }
+  } else {
+    // ===== worker warps: lane quarter q = warp & 3 (TMEM lanes 32q.. = tile pixels), channel part p = warp >> 2 =====
+    const int q = warp & 3, p = warp >> 2;
+    const int m = q * 32 + lane;                       // pixel of the tile: row m >> 6, column m & 63
+    const int ty = m >> 6, tx = m & 63;
+    const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
+    const int H2 = 2 * g.h;
+    constexpr int W2 = 128;
+    // A1 chunk c (0: o0, 1: o1, 2/3: x channels 0-31 / 32-63) of tile `it`: this thread's 8 channels p*8 .. p*8+7
+    auto produce_a1 = [&](int it, int c) {
+      const int set = it & 1, k = c < 2 ? c : 2;
+      const int gc = it * 4 + c, slot = gc & 1;
+      mbar_wait_bounded(&in_full[set * 3 + k], (uint32_t)((it >> 1) & 1));
+      const unsigned char* base = ins + set * DF_IN_SET + (k == 0 ? 0 : k == 1 ? 16384 : 32768);
+      float v[8];
+      if (c < 2) {
+        const float* sp = reinterpret_cast<const float*>(base) + (p * 8) * 128 + m;            // [32 ch][2 rows][64]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = sp[i * 128];
+      } else {
+        const float* sp = reinterpret_cast<const float*>(base) + ((c - 2) * 32 + p * 8) * 32 + (tx >> 1);   // [64 ch][32]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = sp[i * 32];
+      }
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        hi[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+        lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+      }
+      if (gc >= 2) { mbar_wait_bounded(&a1_empty[slot], (uint32_t)(((gc >> 1) - 1) & 1)); tc_fence_after(); }
+      tmem_st8(lane_addr + (uint32_t)(slot * 64 + p * 8), hi);
+      tmem_st8(lane_addr + (uint32_t)(slot * 64 + 32 + p * 8), lo);
+      if (c != 2) {                                     // the x box serves two chunks: released after the second
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&in_empty[set * 3 + k]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a1_full[slot]);
+    };
+    // block epilogue, critical part: D1 -> + b_j -> ReLU -> split -> A2 of down_feat.  The values stay in `acc`; their
+    // global stores are issued afterwards (block_store), off the MMA -> epilogue -> MMA dependency chain.
+    auto block_epilogue = [&](int it, int j, float (&acc)[16]) {
+      const int gj = it * 3 + j, db = gj & 1;
+      mbar_wait_bounded(&d1_full[db], (uint32_t)((gj >> 1) & 1));
+      tc_fence_after();
+      tmem_ld_cols<16>(lane_addr + (uint32_t)(128 + db * 64 + p * 16), acc);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d1_empty[db]);          // D1 is in registers: the block after next may overwrite it
+      const float4* bq = reinterpret_cast<const float4*>(bias_s + j * 64 + p * 16);
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 b4 = bq[i >> 2];
+        acc[i] = fmaxf(acc[i] + b4.x, 0.f); acc[i + 1] = fmaxf(acc[i + 1] + b4.y, 0.f);
+        acc[i + 2] = fmaxf(acc[i + 2] + b4.z, 0.f); acc[i + 3] = fmaxf(acc[i + 3] + b4.w, 0.f);
+      }
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        hi[i] = __uint_as_float(__float_as_uint(acc[i]) & 0xFFFFE000u);
+        lo[i] = acc[i] - hi[i];
+      }
+      if (gj >= 1) { mbar_wait_bounded(a2_empty, (uint32_t)((gj - 1) & 1)); tc_fence_after(); }
+      const uint32_t col = (uint32_t)(256 + (p >> 1) * 64 + (p & 1) * 16);
+      tmem_st16(lane_addr + col, hi);
+      tmem_st16(lane_addr + col + 32, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a2_full);
+    };
+    auto block_store = [&](int it, int j, const float (&acc)[16]) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+      const int r = rem >> 1, c0 = rem & 1;
+      if (j < 2) {
+        float* po = (j == 0 ? g.f0 : g.f1) + (((size_t)img * 64 + p * 16) * H2 + (2 * r + ty)) * W2 + 64 * c0 + tx;
+        const size_t plane = (size_t)H2 * W2;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = acc[i];
+      } else if (ty == 0 && (tx & 1) == 0) {              // f2 lives at half resolution: one writer per 2x2 block
+        float* po = g.f2 + (((size_t)img * 64 + p * 16) * g.h + r) * 64 + 32 * c0 + (tx >> 1);
+        const size_t plane = (size_t)g.h * 64;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = acc[i];
+      }
+    };
+    if (n_my > 0) { produce_a1(0, 0); produce_a1(0, 1); }
+    float e0[16];
+    if (n_my > 0) block_epilogue(0, 0, e0);
+    for (int it = 0; it < n_my; ++it) {
+      // (block 0's critical part already ran: before the loop / before the previous tile's final stores)
+      produce_a1(it, 2); produce_a1(it, 3);
+      block_store(it, 0, e0);
+      float e1[16];
+      block_epilogue(it, 1, e1);
+      if (it + 1 < n_my) { produce_a1(it + 1, 0); produce_a1(it + 1, 1); }
+      block_store(it, 1, e1);
+      block_epilogue(it, 2, e1);
+      block_store(it, 2, e1);
+      // ---- final epilogue: feat_grid = relu(D2 + bf).  D2 is pulled into registers and released, then the next tile's
+      //      first block goes through its critical part before this tile's feat_grid stores are issued ----
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+      const int r = rem >> 1, c0 = rem & 1;
+      mbar_wait_bounded(d2_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      float acc[16], part[16];
+      tmem_ld_cols<16>(lane_addr + (uint32_t)(384 + p * 16), acc);
+      tmem_ld_cols<16>(lane_addr + (uint32_t)(448 + p * 16), part);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty);
+      if (it + 1 < n_my) block_epilogue(it + 1, 0, e0);
+      const float4* bq = reinterpret_cast<const float4*>(bias_s + 3 * 64 + p * 16);
+      float* po = g.fg + (((size_t)img * 64 + p * 16) * H2 + (2 * r + ty)) * W2 + 64 * c0 + tx;
+      const size_t plane = (size_t)H2 * W2;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 b4 = bq[i >> 2];
+        po[(size_t)i * plane] = fmaxf(acc[i] + (part[i] + b4.x), 0.f);
+        po[(size_t)(i + 1) * plane] = fmaxf(acc[i + 1] + (part[i + 1] + b4.y), 0.f);
+        po[(size_t)(i + 2) * plane] = fmaxf(acc[i + 2] + (part[i + 2] + b4.z), 0.f);
+        po[(size_t)(i + 3) * plane] = fmaxf(acc[i + 3] + (part[i + 3] + b4.w), 0.f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 512);
+}
+
 // weight image: for output row n (column block n / NT) and k = tap*Ctot + cin:
 //   out[((blk*nchunks + k/32)*2 + part) * (NT*32) + ((k/4)%8) * (NT*4) + (n%NT)*4 + k%4]
 struct WPrepArgs {
@@ -1543,6 +1868,49 @@ int run_mlp_fused(const float* v, const float* x1, const float* w1img, const flo
   const long long ntiles = R / TC_TM;
   dim3 grid((unsigned)min(ntiles, (long long)sm_count()));
   mlp_fused_kernel<<<grid, MF_THREADS, MF_SMEM, st>>>(g);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
+// fused down0 + down1 + down2 + down_feat launcher; returns 1 when the fused kernel does not apply (caller runs the four
+// separate convolutions instead: other widths, misaligned pointers)
+int run_down_fused(const float* x, const float* o0, const float* o1, const float* w0img, const float* w1img, const float* w2img,
+                   const float* wfimg, const float* b0, const float* b1, const float* b2, const float* bf, float* f0, float* f1,
+                   float* f2, float* fg, int B, int h, int w, cudaStream_t st) {
+  if (w != 64 || h < 1 || B < 1) return 1;
+  if ((((uintptr_t)x | (uintptr_t)o0 | (uintptr_t)o1 | (uintptr_t)w0img | (uintptr_t)w1img | (uintptr_t)w2img | (uintptr_t)wfimg) & 15) != 0)
+    return 1;
+  TPSPP_REQUIRE(tmap_encoder() != nullptr, "down_fused: cuTensorMapEncodeTiled is not available from this CUDA driver");
+  DownFusedArgs g;
+  {
+    const cuuint64_t dims[4] = {128, (cuuint64_t)(2 * h), 32, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {128 * 4, (cuuint64_t)128 * 2 * h * 4, (cuuint64_t)128 * 2 * h * 32 * 4};
+    const cuuint32_t box[4] = {64, 2, 32, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (!tmap_cached(&g.tm_o0, 4, o0, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (!tmap_cached(&g.tm_o1, 4, o1, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  }
+  {
+    const cuuint64_t dims[4] = {64, (cuuint64_t)h, 64, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {64 * 4, (cuuint64_t)64 * h * 4, (cuuint64_t)64 * h * 64 * 4};
+    const cuuint32_t box[4] = {32, 1, 64, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (!tmap_cached(&g.tm_x, 4, x, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  }
+  g.w0img = w0img; g.w1img = w1img; g.w2img = w2img; g.wfimg = wfimg;
+  g.b0 = b0; g.b1 = b1; g.b2 = b2; g.bf = bf;
+  g.f0 = f0; g.f1 = f1; g.f2 = f2; g.fg = fg; g.B = B; g.h = h;
+  static thread_local int df_dev = -1;
+  int dev = 0;
+  TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (df_dev != dev) {
+    TPSPP_CHECK_CUDA(cudaFuncSetAttribute(down_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM));
+    df_dev = dev;
+  }
+  const long long ntiles = (long long)B * h * 2;
+  dim3 grid((unsigned)min(ntiles, (long long)sm_count()));
+  down_fused_kernel<<<grid, DF_THREADS, DF_SMEM, st>>>(g);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;

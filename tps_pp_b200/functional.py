@@ -189,7 +189,8 @@ def head_workspace_offsets(cfg: N.HeadCfg):
 
 
 def head_forward(x: torch.Tensor, o0: torch.Tensor, o1: torch.Tensor, params, point_size, p_stride,
-                 precision=N.HEAD_FP32, workspace: Optional[torch.Tensor] = None, weights_cached: bool = False):
+                 precision=N.HEAD_FP32, workspace: Optional[torch.Tensor] = None, weights_cached: bool = False,
+                 flags: int = 0):
     """Native control-point attention head (reference tps_pp.py:581-594), inference only (no autograd).
 
     ``params``: the module's parameters in state_dict order (58 fp32 CUDA tensors).
@@ -218,7 +219,7 @@ def head_forward(x: torch.Tensor, o0: torch.Tensor, o1: torch.Tensor, params, po
             raise RuntimeError(f"tps_pp_b200: param[{i}] has shape {tuple(p.shape)} but a [{b},{c},{h},{w}] input with "
                                f"{f} control points needs {shp} (module built for another img_size / point_size?)")
         table[i] = p.data_ptr()
-    cfg = head_cfg(b, h, w, point_size, p_stride, precision)
+    cfg = head_cfg(b, h, w, point_size, p_stride, precision, flags)
     with torch.cuda.device(x.device):
         nbytes = int(N.lib().tpspp_head_workspace_bytes(ctypes.byref(cfg)))
         if nbytes == 0 and b > 0:

@@ -161,6 +161,7 @@ class TPS_PP(_BaseModule):
         # native-head workspaces, one per (device, stream): concurrent forwards on different streams must not share
         # intermediates.  Each entry remembers which parameter values its tensor-core weight images were built from.
         self._head_ws = {}
+        self.head_flags = 0          # extra TPSPP_HEAD_FLAG_* bits (A/B measurements, tests)
         self._last_head_launches = 0
 
     # ------------------------------------------------------------------ stages
@@ -273,10 +274,11 @@ class TPS_PP(_BaseModule):
                                    f"{self.num_img_channel}) got batch_img {tuple(batch_img.shape)}")
             params = list(self.parameters())
             key = (batch_img.device.index, torch.cuda.current_stream(batch_img.device).cuda_stream)
-            stamp = (b, self.head_precision, tuple((p.data_ptr(), p._version) for p in params))
+            stamp = (b, self.head_precision, self.head_flags, tuple((p.data_ptr(), p._version) for p in params))
             ws, ws_stamp = self._head_ws.get(key, (None, None))
             fg, cp, sc, ws = TF.head_forward(batch_img, outs[0], outs[1], params, self.point_size, self.p_stride,
-                                             self.head_precision, ws, weights_cached=(ws_stamp == stamp))
+                                             self.head_precision, ws, weights_cached=(ws_stamp == stamp),
+                                             flags=self.head_flags)
             if len(self._head_ws) >= 8 and key not in self._head_ws:
                 self._head_ws.clear()            # streams come and go: bound what the module pins
             self._head_ws[key] = (ws, stamp)
