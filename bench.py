@@ -55,20 +55,22 @@ def _tensor_peak():
         return 2250.0, "nominal dense bf16 (B200_PROFILING.md fallback)"
 
 
-_TAIL = ["enc0", "enc1", "enc2", "enc3", "cbam", "dec0", "dec1", "dec2", "dec3", "localization+p_linear", "dgab_gate",
-         "mlp_fused", "feat_linear.0", "feat_linear.1", "score_qkt", "fused_warp"]
-HEAD_LAUNCHES_FUSED = ["down_fused(down0+down1+down2+down_feat)", "down0_1", "down1_1"] + _TAIL
-HEAD_LAUNCHES_UNFUSED = ["down0", "down1", "down2", "down0_1", "down1_1", "down_feat"] + _TAIL
+_MID = ["enc0", "enc1", "enc2", "enc3", "cbam", "dec0", "dec1", "dec2", "dec3", "localization+p_linear", "dgab_gate", "mlp_fused"]
+_DOWN = (["down_fused(down0+down1+down2+down_feat)", "down0_1", "down1_1"],
+         ["down0", "down1", "down2", "down0_1", "down1_1", "down_feat"])
+_SCORE = (["score_fused(feat_linear.0+.1+qkt)"], ["feat_linear.0", "feat_linear.1", "score_qkt"])
 
 
 def _launch_names(n):
     """Names of the library's launches of one forward, in order (the weight re-layout launch is skipped when the
-    cached images are valid; the bf16 / fp32 modes run the four down* convolutions separately)."""
-    for names in (HEAD_LAUNCHES_FUSED, HEAD_LAUNCHES_UNFUSED):
-        if n == len(names):
-            return names
-        if n == len(names) + 1:
-            return ["wprep"] + names
+    cached images are valid; the bf16 / fp32 modes and the A/B flags run the fused stages as separate launches)."""
+    for down in _DOWN:
+        for score in _SCORE:
+            names = down + _MID + score + ["fused_warp"]
+            if n == len(names):
+                return names
+            if n == len(names) + 1:
+                return ["wprep"] + names
     return None
 
 

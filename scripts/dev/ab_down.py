@@ -15,7 +15,7 @@ o1 = torch.randn((B, 32, 32, 128), device=dev, generator=gen)
 m = T.TPS_PP().to(dev).eval()
 bench._trained_like_(m)
 lib = N.lib()
-for flags in (0, N.HEAD_FLAG_UNFUSED_DOWN, 0):
+for flags in (0, N.HEAD_FLAG_UNFUSED_DOWN | N.HEAD_FLAG_UNFUSED_SCORE, 0):
     m.head_flags = flags
     with torch.no_grad():
         for _ in range(5):

@@ -91,7 +91,7 @@ def test_head_stock_init_and_module_path(native_lib, golden):
         r = m(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
     with torch.no_grad():
         assert all(m.native_stages.values())
-    assert m._last_head_launches >= 18
+    assert m._last_head_launches >= 16          # 17 launches with the fused down / score kernels (+1 weight re-layout)
     floor_o = mx(g["ref32_output"], g["ref64_output"]); floor_m = mx(g["ref32_mp_img"], g["ref64_mp_img"])
     e_o = mx(r["output"], g["ref64_output"]); e_m = mx(r["mp_img"], g["ref64_mp_img"])
     print(f"native head: output |ours-ref64|={e_o:.3e} (floor {floor_o:.3e}); mp_img {e_m:.3e} (floor {floor_m:.3e})")
@@ -280,3 +280,25 @@ def test_fused_down_kernel_equals_separate_launches(native_lib):
         assert mx(a, b) <= 2e-6 * max(scale, 1.0)
         assert e_f <= 1.5 * e_u + 1e-6 * max(scale, 1.0)
     assert mx(res[0]["cp"], res[N.HEAD_FLAG_UNFUSED_DOWN]["cp"]) <= 1e-6
+
+
+def test_fused_score_chain_equals_separate_launches(native_lib):
+    """feat_linear.0 -> feat_linear.1 -> tanh(QK^T/8) chained through tensor memory (default) against the three
+    separate tensor-core launches (TPSPP_HEAD_FLAG_UNFUSED_SCORE), and both against the fp64 oracle."""
+    sd = O.trained_like_state(3)
+    x, o0, o1 = O.synthetic_tpspp_inputs(21, 33)        # 168 tiles > one per SM
+    res = {}
+    for flags in (0, N.HEAD_FLAG_UNFUSED_SCORE):
+        m = T.TPS_PP().to(DEV).eval()
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            fg, cp, sc, ws = TF.head_forward(torch.from_numpy(x).to(DEV), torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV),
+                                             list(m.parameters()), (2, 16), 2, N.HEAD_TC, flags=flags)
+        res[flags] = (sc.clone(), N.last_launch_count())
+    assert res[0][1] == res[N.HEAD_FLAG_UNFUSED_SCORE][1] - 2
+    r64 = O.head_intermediates(sd, x, [o0, o1], dtype=torch.float64)
+    e_f, e_u = mx(res[0][0], r64["pc_score"]), mx(res[N.HEAD_FLAG_UNFUSED_SCORE][0], r64["pc_score"])
+    print(f"pc_score: fused-vs-separate {mx(res[0][0], res[N.HEAD_FLAG_UNFUSED_SCORE][0]):.2e}; |fused-ref64| {e_f:.2e}, "
+          f"|separate-ref64| {e_u:.2e}")
+    assert mx(res[0][0], res[N.HEAD_FLAG_UNFUSED_SCORE][0]) <= 5e-6
+    assert e_f <= 2e-4 and e_f <= 1.25 * e_u + 2e-6

@@ -68,7 +68,8 @@ def test_nrtr_argmax_proxy(golden, native_lib, weights, precision):
     else:
         m = T.TPS_PP().to(DEV).eval()
         m.load_state_dict(O.trained_like_state(3), strict=True)
-    digest = np.array([float(v.double().abs().sum()) for v in m.state_dict().values()])
+    keys = list(O.trained_like_state(3).keys()) if weights == "trained" else list(m.state_dict().keys())   # fixture order
+    digest = np.array([float(m.state_dict()[k].double().abs().sum()) for k in keys])
     assert np.allclose(digest, g[f"{weights}_state_digest"], rtol=1e-6, atol=0), "fixture weights differ"   # (LAPACK inverse in the buffers)
     m.head_precision = N.HEAD_TC if precision == "tc" else N.HEAD_FP32
     x, o0, o1 = (torch.from_numpy(g[k]).to(DEV) for k in ("x", "o0", "o1"))

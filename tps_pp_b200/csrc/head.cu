@@ -1302,7 +1302,16 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     }
   }
   // attention score (tps_pp.py:303-312)
-  if (tc && d.F == 32) {
+  bool fused_score = false;
+  if (tc && d.F == 32 && !(cfg->flags & TPSPP_HEAD_FLAG_UNFUSED_SCORE)) {
+    // feat_linear.0 -> feat_linear.1 -> tanh(QK^T / 8) chained through tensor memory in one kernel
+    rc = run_score_fused(W(TPSPP_WS_DE2), wp[TCL_FLIN0], wp[TCL_FLIN1], W(TPSPP_WS_P1IMG), P[TPSPP_P_FLIN0_B], P[TPSPP_P_FLIN1_B],
+                         pc_score, B, h, w, d.F, 0.125f, st);     // 64^-0.5 (tps_pp.py:247)
+    if (rc < 0) return rc;
+    fused_score = rc == TPSPP_OK;
+  }
+  if (fused_score) {
+  } else if (tc && d.F == 32) {
     // three chained 1x1 contractions on the tensor cores: feat_linear.0, feat_linear.1, then the
     // "QK^T" with per-image weights p1[b] and the tanh(64^-0.5 * .) epilogue
     const int n = h * w;

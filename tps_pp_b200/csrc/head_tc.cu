@@ -1753,6 +1753,291 @@ __global__ void __launch_bounds__(DF_THREADS, 1) down_fused_kernel(const __grid_
   if (warp == 0) tmem_dealloc(tmem_d, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Attention score chain in ONE kernel (reference tps_pp.py:258-261,293-312):
+//     t = feat_linear.0(de')  (64 -> 32)    f = feat_linear.1(t)  (32 -> 128)    s = tanh(64^-1/2 . f . p1[b]^T)  (128 -> F = 32)
+// As three launches the [rows, 32] and [rows, 128] intermediates went through HBM (0.17 GB written, 0.17 GB read back).
+// Here a 128-pixel tile (2 rows x 64 columns of one image) walks the three GEMMs through tensor memory:
+//   TMEM   A1 [0,128)   : split de' tile, K = 64 (two chunks of hi 32 | lo 32), thread = pixel = TMEM lane
+//          D1 [128,160) : feat_linear.0 accumulator (N = 32, 3xTF32 corrections merged, K = 64)
+//          A2 [192,256) : split (D1 + b0): one chunk, the A operand of feat_linear.1
+//          D2 [256,320) : feat_linear.1 accumulator of one 64-column block (two blocks per tile; corrections merged, K = 32)
+//          A3 [320,448) : split (D2 + b1): two chunks, the A operand of the score GEMM for that block
+//          D3 [448,512) : score accumulator main 32 | corrections 32, summed over the two blocks (K = 128)
+//   smem   feat_linear.0/.1 weight images resident (48 KB), the per-image score operand p1[b] (32 KB) and the de' tile
+//          (32 KB) double-buffered
+// ------------------------------------------------------------------------------------------------
+struct ScoreFusedArgs {
+  CUtensorMap tm_de;                   // de' [B,64,h,64] box 64 x 2 x 32
+  const float *w0img, *w1img, *p1img;  // images: fl0 (2 chunks x 8 KB), fl1 (2 blocks x 16 KB), p1 per image (32 KB)
+  const float *b0, *b1;
+  float* score;                        // [B, h*64, 32]
+  int B, h;
+  float scale;
+};
+constexpr int SF_WARPS = 16;
+constexpr int SF_THREADS = (SF_WARPS + 2) * 32;
+constexpr int SF_SMEM = 16384 + 32768 + 2 * 32768 + 2 * 32768 + 1024 + 1024;
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(SF_THREADS, 1) score_fused_kernel(const __grid_constant__ ScoreFusedArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* w0s = smem;                      // fl0: chunk c at c * 8 KB (hi 4 KB | lo 4 KB)
+  unsigned char* w1s = smem + 16384;              // fl1: block b at b * 16 KB (hi 8 KB | lo 8 KB)
+  unsigned char* p1s = w1s + 32768;               // 2 sets x 32 KB: chunk c at c * 8 KB (hi 4 KB | lo 4 KB)
+  unsigned char* ins = p1s + 2 * 32768;           // 2 sets x (chunk 0 16 KB | chunk 1 16 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ins + 2 * 32768);
+  uint64_t* wres_full = bars;
+  uint64_t* in_full = bars + 1;      // [2]
+  uint64_t* in_empty = bars + 3;     // [2]
+  uint64_t* p1_full = bars + 5;      // [2]
+  uint64_t* p1_empty = bars + 7;     // [2]
+  uint64_t* a1_full = bars + 9;
+  uint64_t* a1_empty = bars + 10;
+  uint64_t* d1_full = bars + 11;
+  uint64_t* d1_empty = bars + 12;
+  uint64_t* a2_full = bars + 13;
+  uint64_t* a2_empty = bars + 14;
+  uint64_t* d2_full = bars + 15;
+  uint64_t* d2_empty = bars + 16;
+  uint64_t* a3_full = bars + 17;
+  uint64_t* a3_empty = bars + 18;
+  uint64_t* d3_full = bars + 19;
+  uint64_t* d3_empty = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  float* bias_s = reinterpret_cast<float*>(bars + 22);             // b0 [32] | b1 [128]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+  if (tid == 0) {
+    mbar_init(wres_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], SF_WARPS);
+      mbar_init(&p1_full[i], 1); mbar_init(&p1_empty[i], 1);
+    }
+    mbar_init(a1_full, SF_WARPS); mbar_init(a1_empty, 1);
+    mbar_init(d1_full, 1); mbar_init(d1_empty, SF_WARPS);
+    mbar_init(a2_full, SF_WARPS); mbar_init(a2_empty, 1);
+    mbar_init(d2_full, 1); mbar_init(d2_empty, SF_WARPS);
+    mbar_init(a3_full, SF_WARPS); mbar_init(a3_empty, 1);
+    mbar_init(d3_full, 1); mbar_init(d3_empty, SF_WARPS);
+    fence_barrier_init();
+  }
+  if (tid < 160) bias_s[tid] = tid < 32 ? __ldg(g.b0 + tid) : __ldg(g.b1 + tid - 32);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  const int tiles_per_img = g.h / 2;
+  const int ntiles = g.B * tiles_per_img;
+  const int n_my = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  constexpr uint32_t IDESC32 = umma_instr_desc(TC_TM, 32, 2), IDESC64 = umma_instr_desc(TC_TM, 64, 2);
+
+  if (warp == SF_WARPS) {
+    // ===== MMA issuer warp =====
+    if (n_my > 0) mbar_wait_bounded(wres_full, 0);
+    // one 32-wide K chunk: NTW = columns of the weight image (its hi part is NTW * 128 bytes, k-groups NTW * 16 bytes apart)
+    auto mma_chunk = [&](uint32_t idesc, int NTW, uint32_t d_main, uint32_t d_corr, uint32_t a_base, uint32_t b_base, bool first) {
+#pragma unroll
+      for (int kk = 0; kk < TC_KC / 8; ++kk) {
+        const uint64_t dbh = umma_smem_desc(b_base + kk * 2 * (NTW * 16), NTW * 16, 128);
+        const uint64_t dbl = umma_smem_desc(b_base + NTW * 128 + kk * 2 * (NTW * 16), NTW * 16, 128);
+        const uint32_t a_hi = a_base + kk * 8, a_lo = a_hi + 32;
+        umma_ts_tf32(d_main, a_hi, dbh, idesc, (first && kk == 0) ? 0u : 1u);
+        umma_ts_tf32(d_corr, a_lo, dbh, idesc, (first && kk == 0 && d_corr != d_main) ? 0u : 1u);
+        umma_ts_tf32(d_corr, a_hi, dbl, idesc, 1u);
+      }
+    };
+    for (int it = 0; it < n_my; ++it) {
+      const int set = it & 1;
+      // feat_linear.0: D1 = A1 . W0^T
+      mbar_wait_bounded(a1_full, (uint32_t)(it & 1));
+      if (it >= 1) mbar_wait_bounded(d1_empty, (uint32_t)((it - 1) & 1));
+      tc_fence_after();
+      if (elect_one_sync()) {
+        for (int c = 0; c < 2; ++c)
+          mma_chunk(IDESC32, 32, tmem_d + 128, tmem_d + 128, tmem_d + (uint32_t)(c * 64), smem_u32(w0s) + (uint32_t)(c * 8192), c == 0);
+        umma_commit(a1_empty);
+        umma_commit(d1_full);
+      }
+      __syncwarp();
+      mbar_wait_bounded(a2_full, (uint32_t)(it & 1));
+      mbar_wait_bounded(&p1_full[set], (uint32_t)((it >> 1) & 1));
+      for (int b = 0; b < 2; ++b) {
+        const int gb = it * 2 + b;
+        // feat_linear.1, column block b: D2 = A2 . W1_b^T
+        if (gb >= 1) mbar_wait_bounded(d2_empty, (uint32_t)((gb - 1) & 1));
+        tc_fence_after();
+        if (elect_one_sync()) {
+          mma_chunk(IDESC64, 64, tmem_d + 256, tmem_d + 256, tmem_d + 192, smem_u32(w1s) + (uint32_t)(b * 16384), true);
+          umma_commit(d2_full);
+          if (b == 1) umma_commit(a2_empty);
+        }
+        __syncwarp();
+        // score GEMM over the block's 64 features: D3 (+)= A3 . p1[img]^T chunks 2b, 2b+1
+        mbar_wait_bounded(a3_full, (uint32_t)(gb & 1));
+        if (b == 0 && it >= 1) mbar_wait_bounded(d3_empty, (uint32_t)((it - 1) & 1));
+        tc_fence_after();
+        if (elect_one_sync()) {
+          for (int c = 0; c < 2; ++c)
+            mma_chunk(IDESC32, 32, tmem_d + 448, tmem_d + 480, tmem_d + 320 + (uint32_t)(c * 64),
+                      smem_u32(p1s) + (uint32_t)(set * 32768 + (2 * b + c) * 8192), b == 0 && c == 0);
+          umma_commit(a3_empty);
+          if (b == 1) { umma_commit(d3_full); umma_commit(&p1_empty[set]); }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == SF_WARPS + 1) {
+    // ===== TMA warp =====
+    if (n_my > 0 && elect_one_sync()) {
+      mbar_arrive_expect_tx(wres_full, 16384 + 32768);
+      bulk_g2s(w0s, g.w0img, 16384, wres_full, policy_evict_last());
+      bulk_g2s(w1s, g.w1img, 32768, wres_full, policy_evict_last());
+    }
+    __syncwarp();
+    for (int it = 0; it < n_my; ++it) {
+      const int set = it & 1;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int img = tile / tiles_per_img, rp = tile - img * tiles_per_img;
+      if (it >= 2) {
+        mbar_wait_bounded(&in_empty[set], (uint32_t)(((it >> 1) - 1) & 1));
+        mbar_wait_bounded(&p1_empty[set], (uint32_t)(((it >> 1) - 1) & 1));
+      }
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&in_full[set], 32768);
+        tma_load_4d(ins + set * 32768, &g.tm_de, 0, 2 * rp, 0, img, &in_full[set], policy_evict_first());
+        tma_load_4d(ins + set * 32768 + 16384, &g.tm_de, 0, 2 * rp, 32, img, &in_full[set], policy_evict_first());
+        mbar_arrive_expect_tx(&p1_full[set], 32768);
+        bulk_g2s(p1s + set * 32768, g.p1img + (size_t)img * 8192, 32768, &p1_full[set], policy_evict_last());
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== worker warps: lane quarter q = warp & 3 (TMEM lanes = tile pixels), part p = warp >> 2 =====
+    const int q = warp & 3, p = warp >> 2;
+    const int m = q * 32 + lane;
+    const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
+    auto produce_a1 = [&](int it) {
+      const int set = it & 1;
+      mbar_wait_bounded(&in_full[set], (uint32_t)((it >> 1) & 1));
+      if (it >= 1) { mbar_wait_bounded(a1_empty, (uint32_t)((it - 1) & 1)); tc_fence_after(); }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float* sp = reinterpret_cast<const float*>(ins + set * 32768 + c * 16384) + (p * 8) * 128 + m;   // [32 ch][2][64]
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = sp[i * 128];
+          hi[i] = __float_as_uint(v) & 0xFFFFE000u;
+          lo[i] = __float_as_uint(v - __uint_as_float(hi[i]));
+        }
+        tmem_st8(lane_addr + (uint32_t)(c * 64 + p * 8), hi);
+        tmem_st8(lane_addr + (uint32_t)(c * 64 + 32 + p * 8), lo);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&in_empty[set]);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a1_full);
+    };
+    if (n_my > 0) produce_a1(0);
+    for (int it = 0; it < n_my; ++it) {
+      // ---- feat_linear.0 epilogue: D1 + b0 -> split -> A2 (8 of the 32 columns per thread) ----
+      {
+        mbar_wait_bounded(d1_full, (uint32_t)(it & 1));
+        tc_fence_after();
+        float acc[8];
+        tmem_ld8(lane_addr + (uint32_t)(128 + p * 8), acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d1_empty);
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = acc[i] + bias_s[p * 8 + i];
+          hi[i] = __float_as_uint(v) & 0xFFFFE000u;
+          lo[i] = __float_as_uint(v - __uint_as_float(hi[i]));
+        }
+        if (it >= 1) { mbar_wait_bounded(a2_empty, (uint32_t)((it - 1) & 1)); tc_fence_after(); }
+        tmem_st8(lane_addr + (uint32_t)(192 + p * 8), hi);
+        tmem_st8(lane_addr + (uint32_t)(192 + 32 + p * 8), lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a2_full);
+      }
+      if (it + 1 < n_my) produce_a1(it + 1);              // overlaps this tile's feat_linear.1 / score GEMMs
+      // ---- feat_linear.1 epilogues: D2 + b1 -> split -> A3, one 64-column block at a time ----
+#pragma unroll 1
+      for (int b = 0; b < 2; ++b) {
+        const int gb = it * 2 + b;
+        mbar_wait_bounded(d2_full, (uint32_t)(gb & 1));
+        tc_fence_after();
+        float acc[16];
+        tmem_ld_cols<16>(lane_addr + (uint32_t)(256 + p * 16), acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d2_empty);
+        float hi[16], lo[16];
+        const float4* bq = reinterpret_cast<const float4*>(bias_s + 32 + b * 64 + p * 16);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = bq[i >> 2];
+          const float v0 = acc[i] + b4.x, v1 = acc[i + 1] + b4.y, v2 = acc[i + 2] + b4.z, v3 = acc[i + 3] + b4.w;
+          hi[i] = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u); lo[i] = v0 - hi[i];
+          hi[i + 1] = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u); lo[i + 1] = v1 - hi[i + 1];
+          hi[i + 2] = __uint_as_float(__float_as_uint(v2) & 0xFFFFE000u); lo[i + 2] = v2 - hi[i + 2];
+          hi[i + 3] = __uint_as_float(__float_as_uint(v3) & 0xFFFFE000u); lo[i + 3] = v3 - hi[i + 3];
+        }
+        if (gb >= 1) { mbar_wait_bounded(a3_empty, (uint32_t)((gb - 1) & 1)); tc_fence_after(); }
+        const uint32_t col = (uint32_t)(320 + (p >> 1) * 64 + (p & 1) * 16);
+        tmem_st16(lane_addr + col, hi);
+        tmem_st16(lane_addr + col + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a3_full);
+      }
+      // ---- score epilogue: tanh(scale * D3) -> pc_score[row, 8p .. 8p+7] ----
+      {
+        mbar_wait_bounded(d3_full, (uint32_t)(it & 1));
+        tc_fence_after();
+        float acc[8], part[8];
+        tmem_ld8(lane_addr + (uint32_t)(448 + p * 8), acc);
+        tmem_ld8(lane_addr + (uint32_t)(480 + p * 8), part);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d3_empty);
+        const size_t row = (size_t)((int)blockIdx.x + it * (int)gridDim.x) * TC_TM + m;
+        float4 r0, r1;
+        r0.x = tanhf((acc[0] + part[0]) * g.scale); r0.y = tanhf((acc[1] + part[1]) * g.scale);
+        r0.z = tanhf((acc[2] + part[2]) * g.scale); r0.w = tanhf((acc[3] + part[3]) * g.scale);
+        r1.x = tanhf((acc[4] + part[4]) * g.scale); r1.y = tanhf((acc[5] + part[5]) * g.scale);
+        r1.z = tanhf((acc[6] + part[6]) * g.scale); r1.w = tanhf((acc[7] + part[7]) * g.scale);
+        float4* po = reinterpret_cast<float4*>(g.score + row * 32 + p * 8);
+        po[0] = r0; po[1] = r1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 512);
+}
+
 // weight image: for output row n (column block n / NT) and k = tap*Ctot + cin:
 //   out[((blk*nchunks + k/32)*2 + part) * (NT*32) + ((k/4)%8) * (NT*4) + (n%NT)*4 + k%4]
 struct WPrepArgs {
@@ -1911,6 +2196,34 @@ int run_down_fused(const float* x, const float* o0, const float* o1, const float
   const long long ntiles = (long long)B * h * 2;
   dim3 grid((unsigned)min(ntiles, (long long)sm_count()));
   down_fused_kernel<<<grid, DF_THREADS, DF_SMEM, st>>>(g);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
+// fused feat_linear.0 -> feat_linear.1 -> tanh(QK^T / 8); returns 1 when not applicable (F != 32, odd geometry)
+int run_score_fused(const float* de2, const float* w0img, const float* w1img, const float* p1img, const float* b0, const float* b1,
+                    float* score, int B, int h, int w, int F, float scale, cudaStream_t st) {
+  if (w != 64 || F != 32 || h < 2 || (h & 1) || B < 1) return 1;
+  if ((((uintptr_t)de2 | (uintptr_t)w0img | (uintptr_t)w1img | (uintptr_t)p1img | (uintptr_t)score) & 15) != 0) return 1;
+  TPSPP_REQUIRE(tmap_encoder() != nullptr, "score_fused: cuTensorMapEncodeTiled is not available from this CUDA driver");
+  ScoreFusedArgs g;
+  const cuuint64_t dims[4] = {64, (cuuint64_t)h, 64, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {64 * 4, (cuuint64_t)64 * h * 4, (cuuint64_t)64 * h * 64 * 4};
+  const cuuint32_t box[4] = {64, 2, 32, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  if (!tmap_cached(&g.tm_de, 4, de2, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  g.w0img = w0img; g.w1img = w1img; g.p1img = p1img; g.b0 = b0; g.b1 = b1; g.score = score; g.B = B; g.h = h; g.scale = scale;
+  static thread_local int sf_dev = -1;
+  int dev = 0;
+  TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (sf_dev != dev) {
+    TPSPP_CHECK_CUDA(cudaFuncSetAttribute(score_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+    sf_dev = dev;
+  }
+  const long long ntiles = (long long)B * (h / 2);
+  dim3 grid((unsigned)min(ntiles, (long long)sm_count()));
+  score_fused_kernel<<<grid, SF_THREADS, SF_SMEM, st>>>(g);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;
