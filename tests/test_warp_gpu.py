@@ -340,3 +340,35 @@ def test_bf16_features(consts):
     assert out.dtype == torch.bfloat16
     o64, m64, _ = O.tpspp_warp(fgb.float().cpu().numpy(), xb.float().cpu().numpy(), cp, s, c, dtype=np.float64)
     assert mx(out.float(), o64) <= 2 ** -8 * max(1.0, float(np.abs(o64).max()))   # one bf16 ulp of the output
+
+
+def test_staged_backward_equals_generic_full_geometry(consts):
+    """The shared-memory staged backward (default for the TPS++ geometry) against the per-pixel global-atomics kernel at
+    the module's real plane sizes (64 channels, 32x128 + 16x64 sources), B = 7: 448 planes over 148 persistent CTAs, so
+    image segments split across CTAs and the accumulation-buffer ring wraps."""
+    c, hat, ph, P = consts
+    B = 7
+    cp, s, fg, x = _inputs(B, 77, C=64)
+    rs = np.random.RandomState(2)
+    go0 = cu(rs.standard_normal((B, 64, 16, 64)).astype(np.float32))
+    go1 = cu(rs.standard_normal((B, 64, 16, 64)).astype(np.float32))
+    grads = {}
+    for variant in (N.VARIANT_AUTO, N.VARIANT_GENERIC):
+        TF.BWD_VARIANT = variant
+        try:
+            tfg, tx, tcp, ts = (cu(fg).requires_grad_(), cu(x).requires_grad_(), cu(cp).requires_grad_(), cu(s).requires_grad_())
+            out, mp = TF.tps_warp(tfg, tx, tcp, ts, ph, P, hat, (16, 64))
+            ((out * go0).sum() + (mp * go1).sum()).backward()
+            grads[variant] = [t.grad.clone() for t in (tfg, tx, tcp, ts)]
+            launches = N.last_launch_count()
+        finally:
+            TF.BWD_VARIANT = N.VARIANT_AUTO
+        if variant == N.VARIANT_AUTO:
+            pass
+    a, g = grads[N.VARIANT_AUTO], grads[N.VARIANT_GENERIC]
+    assert mx(a[0], g[0]) <= 2e-5 and mx(a[1], g[1]) <= 2e-5          # d src: same taps, different summation order
+    assert mx(a[2], g[2]) <= 2e-4 * float(g[2].abs().max())
+    assert mx(a[3], g[3]) <= 2e-4 * float(g[3].abs().max())
+    gs0, gs1, dC, ds = _oracle_bwd(fg[:2], x[:2], cp[:2], s[:2], c, go0[:2].cpu().numpy(), go1[:2].cpu().numpy())
+    assert mx(a[0][:2], gs0) <= 2e-5 and mx(a[1][:2], gs1) <= 2e-5
+    assert mx(a[2][:2], dC) <= 2e-4 * float(np.abs(dC).max())

@@ -16,6 +16,9 @@ import torch
 from . import _native as N
 
 _DT = {torch.float32: N.F32, torch.bfloat16: N.BF16}
+# kernel variant of tpspp_warp_bwd: AUTO = shared-memory staged kernel where it applies (TPS++ geometry, fp32);
+# GENERIC forces the per-pixel global-atomics kernel (tests / A-B measurements)
+BWD_VARIANT = N.VARIANT_AUTO
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -94,7 +97,7 @@ class _TpsWarp(torch.autograd.Function):
         src0, src1, c_prime, pc_score, P_hat, P, inv_delta_C = ctx.saved_tensors
         out_size, mode, theta = ctx.cfg_args
         f = c_prime.shape[1]
-        cfg = _cfg(src0, src1, out_size, f, mode, theta, N.VARIANT_AUTO)
+        cfg = _cfg(src0, src1, out_size, f, mode, theta, BWD_VARIANT)
         need = ctx.needs_input_grad
         if g0 is None:
             g0 = torch.zeros((src0.shape[0], src0.shape[1]) + tuple(out_size), dtype=src0.dtype, device=src0.device)
