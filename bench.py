@@ -197,14 +197,17 @@ def run_reference(args):
     # (~0.65 s per step on the 16 host cores of the GPU box: the default 20 + 5 run takes ~20 s)
     steps = max(1, args.steps)
     warm = max(0, args.warmup)
-    batch = args.batch
+    batch = args.batch if args.global_batch <= 0 else min(256, args.global_batch)     # bounded sample of the global batch
     ips, ms, cores = _cpu_reference(steps, warm, batch)
     line = {
         "impl": "reference", "metric": "tps_pp_rectified_img_per_s", "value": ips, "unit": "img/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if batch == BATCH_PER_GPU else WORKLOAD.replace("batch 256/GPU", f"batch {batch}/GPU (non-default shard size)"),
-                   "global_batch": batch, "sample": f"batch {batch} per step on host CPU, {cores} threads"},
+        "scaling": "strong" if args.global_batch > 0 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": (WORKLOAD if batch == BATCH_PER_GPU and args.global_batch <= 0 else
+                                WORKLOAD.replace("batch 256/GPU", f"global batch {args.global_batch} split over {args.gpus} GPU(s) (BASELINE configs[4] shard)"
+                                                 if args.global_batch > 0 else f"batch {batch}/GPU (non-default shard size)")),
+                   "global_batch": args.global_batch if args.global_batch > 0 else batch,
+                   "sample": f"batch {batch} per step on host CPU, {cores} threads"},
         "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} steps of batch {batch} (median), torch CPU fp32, {cores} threads"},
         "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -230,6 +233,11 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = False
 
     B = args.batch
+    strong = args.global_batch > 0
+    if strong:      # BASELINE configs[4]: a fixed global batch split over the ranks (images are independent: no exchange)
+        from tps_pp_b200.parallel import shard_bounds
+        lo, hi = shard_bounds(args.global_batch, rank, world)
+        B = hi - lo
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.randn((B, 64, 16, 64), device=dev, generator=gen)
     o0 = torch.randn((B, 32, 32, 128), device=dev, generator=gen)
@@ -344,8 +352,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, warp_mean_ms = (float(v) for v in t.tolist())
-    value = world * B * args.steps / (total_ms * 1e-3)
-    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+    gB = args.global_batch if strong else world * B          # images all ranks process per step
+    value = gB * args.steps / (total_ms * 1e-3)
+    e2e_value = gB * e2e_steps / (e2e_ms * 1e-3)
     peak, peak_src = _peaks()
     warp_bytes = B * WARP_BYTES_PER_IMG + WARP_CONST_BYTES
     achieved = warp_bytes / (warp_mean_ms * 1e-3) / 1e9
@@ -354,18 +363,22 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = _cpu_reference(steps=8, warmup=1, batch=B)
+        sb = min(B, 256)
+        ips, ms, cores = _cpu_reference(steps=8, warmup=1, batch=sb)
         cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
-               "sample": f"8 steps of batch {B} (median {ms:.0f} ms), oracle torch-CPU fp32, {cores} threads"}
+               "sample": f"8 steps of batch {sb} (median {ms:.0f} ms), oracle torch-CPU fp32, {cores} threads"}
     if rank == 0:
         h2d = sum(t_.numel() * 4 for t_ in (x, o0, o1))
         line = {
             "metric": "tps_pp_rectified_img_per_s", "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 conv operands / f32 elsewhere" if args.head == "bf16" else "f32",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "bf16 conv operands / f32 elsewhere" if args.head == "bf16" else "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD if B == BATCH_PER_GPU else WORKLOAD.replace("batch 256/GPU", f"batch {B}/GPU (non-default shard size)"),
-                       "global_batch": world * B, "parallelism": f"batch-shard x{world}, no collective",
+            "config": {"workload": (WORKLOAD if B == BATCH_PER_GPU and not strong else
+                                    WORKLOAD.replace("batch 256/GPU", f"global batch {gB} split over {world} GPU(s) (BASELINE configs[4] shard)"
+                                                     if strong else f"batch {B}/GPU (non-default shard size)")),
+                       "global_batch": gB, "parallelism": f"batch-shard x{world}, no collective",
                        "l2": "inputs 302 MB/step > 126 MB L2 (no flush needed)",
                        "native_stages": native_stages, "weights": "trained-like synthetic (seed 3)", "head": args.head},
             "roofline": {"kernel": "warp_fwd_staged_kernel<dual>", "bound": "hbm", "achieved": achieved, "peak": peak,
@@ -425,6 +438,177 @@ def _trained_like_(m):
     m.load_state_dict(new, strict=False)
 
 
+# ----------------------------------------------------------------------------- BASELINE configs[3]
+def _classical_inputs(F_, B, dev, seed):
+    """img [B,3,64,256] ~ N(0,1); C' = the classical init lattice + a smooth per-image field."""
+    from tps_pp_b200 import constants as K
+    inv, ph, _ = K.classical_tps_buffers(F_, (64, 256))
+    base = torch.from_numpy(K.classical_init_bias(F_)).float()
+    g = torch.Generator().manual_seed(seed)
+    a = (torch.rand(B, 1, generator=g) - 0.5) * 0.2
+    fr = 0.5 + 1.5 * torch.rand(B, 1, generator=g)
+    phs = 6.2831853 * torch.rand(B, 1, generator=g)
+    cp = base[None].repeat(B, 1, 1)
+    cp[..., 1] = cp[..., 1] + a * torch.sin(fr * 3.14159265 * cp[..., 0] + phs)
+    cp[..., 0] = cp[..., 0] * (1 + (torch.rand(B, 1, generator=g) - 0.5) * 0.1)
+    gd = torch.Generator(device=dev).manual_seed(seed) if dev != "cpu" else g
+    img = torch.randn((B, 3, 64, 256), device=dev, generator=gd)
+    return img, cp.contiguous(), torch.from_numpy(inv), torch.from_numpy(ph)
+
+
+def _classical_cpu(F_, steps, warmup, batch):
+    """The reference's classical path on host cores: GridGenerator.build_P_prime (two bmm) + F.grid_sample
+    (tps_preprocessor.py:72-83,270-282), restated in oracle/tpspp_oracle.py with the same torch CPU ops."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    img, cp, inv, ph = _classical_inputs(F_, batch, "cpu", 0)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            Bq = cp.shape[0]
+            T_ = torch.bmm(inv[None].expand(Bq, -1, -1), torch.cat([cp, torch.zeros(Bq, 3, 2)], 1))
+            grid = torch.bmm(ph[None].expand(Bq, -1, -1), T_).reshape(Bq, 64, 256, 2)
+            torch.nn.functional.grid_sample(img, grid, padding_mode="border", align_corners=True)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    med = statistics.median(times)
+    return batch / med, med * 1e3, cores
+
+
+def run_classical(args):
+    """BASELINE configs[3]: high-res classical TPS rectification, 64x256x3 input, F = 20 / 40, batch 1024 per GPU: the
+    fused grid generator + bilinear warp alone (the localisation network is not part of the north_star path)."""
+    F_ = args.F
+    B = args.batch
+    workload = f"classical TPS warp (GridGenerator + grid_sample), 64x256x3 fp32, F={F_}, batch {B}/GPU (BASELINE configs[3])"
+    rank, world, local = _dist_env()
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sb = min(B, 128)
+        ips, ms, cores = _classical_cpu(F_, max(1, args.steps), max(0, args.warmup), sb)
+        print(json.dumps({
+            "impl": "reference", "metric": "classical_tps_rectified_img_per_s", "value": ips, "unit": "img/s", "n_gpus": args.gpus,
+            "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": B, "sample": f"batch {sb} per step on host CPU, {cores} threads"},
+            "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
+                             "sample": f"{max(1, args.steps)} steps of batch {sb} (median), torch CPU fp32 bmm + grid_sample, {cores} threads"},
+            "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import torch.distributed as dist
+    from tps_pp_b200 import _native as N, functional as TF
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the TPS hot path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N.device_info()
+    img, cp, inv, ph = _classical_inputs(F_, B, dev, 1234 + rank)
+    cp, inv, ph = cp.to(dev), inv.to(dev), ph.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(src):
+        return TF.tps_warp(src, None, cp, None, ph, None, inv, (64, 256), mode=N.MODE_CLASSICAL, theta=0.0)[0]
+
+    launches = 0
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step(img)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step(img)
+            launches += N.last_launch_count()
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        total_ms = e0.elapsed_time(e1)
+        # end to end with host buffers: H2D of the images + control points, D2H of the rectified images, every step
+        himg, hcp = img.cpu().pin_memory(), cp.cpu().pin_memory()
+        hout = torch.empty_like(himg).pin_memory()
+        dimg = [torch.empty_like(img) for _ in range(2)]
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_run(nsteps):
+            for k in range(2):
+                ev_free[k].record(main)
+            for i in range(nsteps):
+                k = i & 1
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_free[k])
+                    dimg[k].copy_(himg, non_blocking=True)
+                    cp.copy_(hcp, non_blocking=True)
+                    ev_in[k].record(s_in)
+                main.wait_event(ev_in[k])
+                r = step(dimg[k])
+                ev_done[k].record(main); ev_free[k].record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[k])
+                    hout.copy_(r, non_blocking=True)
+                r.record_stream(s_out)
+            main.wait_stream(s_out)
+
+        e2e_run(2)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        e2e_steps = max(3, min(args.steps, 8))
+        e2e_run(e2e_steps)
+        f1.record()
+        barrier()
+        e2e_ms = f0.elapsed_time(f1)
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = (float(v) for v in t.tolist())
+    step_ms = total_ms / args.steps
+    peak, peak_src = _peaks()
+    # SURVEY 8(d): 2 * C*H*W*4 + 8F bytes per image; constants (P_hat [n, F+3], inv_delta_C) once per launch
+    bytes_launch = B * (2 * 3 * 64 * 256 * 4 + 8 * F_) + 16384 * (F_ + 3) * 4 + (F_ + 3) ** 2 * 4
+    achieved = bytes_launch / (step_ms * 1e-3) / 1e9
+    dfma = B * 16384 * (F_ + 3) * 2                       # fp64 FMAs of grid = P_hat . T per launch
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, ms, cores = _classical_cpu(F_, 5, 1, 128)
+        cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
+               "sample": f"5 steps of batch 128 (median {ms:.0f} ms), torch CPU fp32 bmm + grid_sample, {cores} threads"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "classical_tps_rectified_img_per_s", "value": world * B * args.steps / (total_ms * 1e-3), "unit": "img/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 pixels / f64 grid", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": world * B, "parallelism": f"batch-shard x{world}, no collective",
+                       "l2": f"images {B * 3 * 64 * 256 * 4 >> 20} MB/step > 126 MB L2 (no flush needed)"},
+            "roofline": {"kernel": "classical_T_kernel + warp_fwd_classical_tiled_kernel (timed together: the step is these two launches)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "bytes_per_launch": bytes_launch, "avg_launch_ms": step_ms,
+                         "fp64_fma_per_launch": dfma,
+                         "note": "the grid P_hat.T is evaluated in fp64 (pixel parity 1e-5 needs coordinates to ~1e-8): "
+                                 f"{dfma / 1e9:.2f} G DFMA per launch is a second floor next to the HBM one"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "img/s", "h2d_bytes_per_step": himg.numel() * 4 + hcp.numel() * 4,
+                    "d2h_bytes_per_step": hout.numel() * 4, "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,12 +618,23 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU,
                     help="images per GPU (default = BASELINE configs[1]; 1024 = the per-GPU shard of config 5 at 8 GPUs)")
+    ap.add_argument("--workload", default="tps_pp", choices=["tps_pp", "classical64x256"],
+                    help="tps_pp = BASELINE configs[1] (default, the headline line); classical64x256 = configs[3], the high-res "
+                         "classical TPS warp (64x256x3 images, batch 1024, --F 20|40 control points)")
+    ap.add_argument("--F", type=int, default=20, choices=[20, 40], help="control points of the classical64x256 workload")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="BASELINE configs[4]: split this many images over the ranks (strong scaling, e.g. 8192) instead of "
+                         "--batch per GPU (weak scaling)")
     ap.add_argument("--head", default="tc", choices=["tc", "fp32", "bf16", "library"],
                     help="head arithmetic: tcgen05 3xTF32 (default, fp32-level accuracy), CUDA-core fp32, "
                          "tcgen05 with bf16 conv operands (reduced precision, reported separately), or "
                          "cuDNN/cuBLAS library ops")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "classical64x256":
+        if args.batch == BATCH_PER_GPU:
+            args.batch = 1024
+        run_classical(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
