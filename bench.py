@@ -249,7 +249,9 @@ def run_ours(args):
     if args.head == "library":
         m.head_impl = "library"
     else:
-        m.head_precision = {"tc": N.HEAD_TC, "fp32": N.HEAD_FP32, "bf16": N.HEAD_BF16}[args.head]
+        m.head_precision = {"tc": N.HEAD_TC, "tc3x": N.HEAD_TC, "fp32": N.HEAD_FP32, "bf16": N.HEAD_BF16}[args.head]
+        if args.head == "tc3x":          # A/B: 3x3 convolutions as all-tf32 3xTF32 instead of tf32 + bf16 corrections
+            m.head_flags |= N.HEAD_FLAG_TF32X3_CONV
 
     def barrier():
         if world > 1:
@@ -625,8 +627,8 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="BASELINE configs[4]: split this many images over the ranks (strong scaling, e.g. 8192) instead of "
                          "--batch per GPU (weak scaling)")
-    ap.add_argument("--head", default="tc", choices=["tc", "fp32", "bf16", "library"],
-                    help="head arithmetic: tcgen05 3xTF32 (default, fp32-level accuracy), CUDA-core fp32, "
+    ap.add_argument("--head", default="tc", choices=["tc", "tc3x", "fp32", "bf16", "library"],
+                    help="head arithmetic: tcgen05 split-fp32 (default, fp32-level accuracy; tc3x = all-tf32 3xTF32 convs), CUDA-core fp32, "
                          "tcgen05 with bf16 conv operands (reduced precision, reported separately), or "
                          "cuDNN/cuBLAS library ops")
     args = ap.parse_args()

@@ -187,8 +187,11 @@ typedef struct tpspp_head_cfg {
  * TPSPP_WS_WPREP are still valid and their re-layout launch is skipped.  The caller owns that invariant -- the
  * library cannot see weight updates (tps_pp_b200/rectifier.py keys it on torch's per-tensor version counters). */
 /* UNFUSED_DOWN / UNFUSED_SCORE: run down0/down1/down2/down_feat (feat_linear.0/.1/QK^T) as separate launches instead of
- * the fused kernels (A/B measurements, tests). */
-enum { TPSPP_HEAD_FLAG_WEIGHTS_CACHED = 1, TPSPP_HEAD_FLAG_UNFUSED_DOWN = 2, TPSPP_HEAD_FLAG_UNFUSED_SCORE = 4 };
+ * the fused kernels (A/B measurements, tests).
+ * TF32X3_CONV: run the 3x3 convolutions as all-tf32 3xTF32 (12 MMAs per 32-channel chunk) instead of the default tf32 main
+ * term + bf16 correction terms (8 MMAs, same fp32-level accuracy) -- A/B measurements, tests. */
+enum { TPSPP_HEAD_FLAG_WEIGHTS_CACHED = 1, TPSPP_HEAD_FLAG_UNFUSED_DOWN = 2, TPSPP_HEAD_FLAG_UNFUSED_SCORE = 4,
+       TPSPP_HEAD_FLAG_TF32X3_CONV = 8 };
 
 /* Index of each learnable tensor in the `params` pointer table = state_dict order of the
  * reference module (tps_pp.py:94-119,253-285,538-548).                      */

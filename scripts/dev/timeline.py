@@ -1,25 +1,24 @@
-"""Dev tool: prints the clock64 timeline written by an INSTRUMENTED build of libtpspp.so (a temporary `g_dbg` device
-array + `tpspp_dbg_read` export added by hand to the kernel under study; see profiles/r01_conv_timeline.md).  It does
-not work against the shipped library."""
+"""Dev tool: prints the clock64 timeline written by an INSTRUMENTED build of libtpspp.so (-DTPSPP_TIMELINE: conv_pair_kernel
+records events of CTA 0 for global chunk steps 128..191 into g_tl; `tpspp_dbg_read` copies it out).  The last
+conv_pair_kernel launch of the forward (dec3) is what remains in the buffer.  Not part of the shipped library."""
 import sys, ctypes, torch, numpy as np
 sys.path.insert(0, '/root/repo')
-from oracle import tpspp_oracle as O
 import tps_pp_b200 as T
-DEV='cuda:0'
-m = T.TPS_PP().to(DEV).eval(); m.load_state_dict(O.trained_like_state(3), strict=True)
-B=256
+from tps_pp_b200 import _native as N
+DEV = 'cuda:0'
+m = T.TPS_PP().to(DEV).eval()
+B = 256
 g = torch.Generator(device=DEV).manual_seed(5)
 x = torch.randn((B, 64, 16, 64), device=DEV, generator=g); o0 = torch.randn((B, 32, 32, 128), device=DEV, generator=g); o1 = torch.randn((B, 32, 32, 128), device=DEV, generator=g)
 with torch.no_grad():
     for _ in range(3): m(x, [o0, o1])
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 4096)()
-lib = ctypes.CDLL('/root/repo/tps_pp_b200/libtpspp.so')
+buf = (ctypes.c_longlong * 2048)()
+lib = N.lib()
 print('rc', lib.tpspp_dbg_read(buf))
-a = np.array(buf[:])
-t0 = a[8 * 16 + 0]
-print('gj | MMA: loop_top fc1_next_issued a2_full_seen fc2_c0_issued fc2_c1_issued | EPI: wait_d1 d1_seen gelu_done a2_empty_ok a2_full_arrived')
-for gj in range(8, 20):
-    r = a[gj * 16: gj * 16 + 13] - t0
-    print(gj, r[0], r[1], r[2], r[3], r[4], '|', r[8], r[9], r[10], r[11], r[12])
-print('a1_full seen per tile', (a[2048:2056] - t0).tolist())
+a = np.array(buf[:]).reshape(64, 32)
+t0 = a[0, 0]
+print('step | MMA: top waited issued | P warp0: lds a_empty st_issued st_waited arrived | P warp15: same')
+for i in range(0, 40):
+    r = a[i] - t0
+    print(128 + i, r[0:3].tolist(), '|', r[8:13].tolist(), '|', r[16:21].tolist())

@@ -23,12 +23,12 @@ def mx(a, b):
     return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))))
 
 
-def _run_native(sd, x, o0, o1, precision=N.HEAD_FP32):
+def _run_native(sd, x, o0, o1, precision=N.HEAD_FP32, flags=0):
     m = T.TPS_PP().to(DEV).eval()
     m.load_state_dict(sd, strict=True)
     with torch.no_grad():
         fg, cp, sc, ws = TF.head_forward(torch.from_numpy(x).to(DEV), torch.from_numpy(o0).to(DEV),
-                                         torch.from_numpy(o1).to(DEV), list(m.parameters()), (2, 16), 2, precision)
+                                         torch.from_numpy(o1).to(DEV), list(m.parameters()), (2, 16), 2, precision, flags=flags)
     torch.cuda.synchronize()
     b = x.shape[0]
     cfg = TF.head_cfg(b, 16, 64, (2, 16), 2)
@@ -50,14 +50,16 @@ def _run_native(sd, x, o0, o1, precision=N.HEAD_FP32):
     return got, m
 
 
-@pytest.mark.parametrize("batch,seed,precision", [(2, 0, N.HEAD_FP32), (5, 11, N.HEAD_FP32),
-                                                  (2, 0, N.HEAD_TC), (7, 11, N.HEAD_TC), (1, 4, N.HEAD_TC),
-                                                  (19, 5, N.HEAD_TC)])   # 19 images: 152 tiles > one per resident CTA pair
-def test_head_stages_vs_oracle(native_lib, batch, seed, precision):
-    """precision TC = tcgen05 convolutions with 3xTF32 error compensation: same fp32-level acceptance rule."""
+@pytest.mark.parametrize("batch,seed,precision,flags", [
+    (2, 0, N.HEAD_FP32, 0), (5, 11, N.HEAD_FP32, 0), (2, 0, N.HEAD_TC, 0), (7, 11, N.HEAD_TC, 0), (1, 4, N.HEAD_TC, 0),
+    (19, 5, N.HEAD_TC, 0),                                  # 19 images: 152 tiles > one per resident CTA pair
+    (7, 11, N.HEAD_TC, N.HEAD_FLAG_TF32X3_CONV), (19, 5, N.HEAD_TC, N.HEAD_FLAG_TF32X3_CONV)])
+def test_head_stages_vs_oracle(native_lib, batch, seed, precision, flags):
+    """precision TC = tcgen05 convolutions with split-fp32 error compensation (default: tf32 main term + bf16 correction
+    terms; flag TF32X3_CONV: all-tf32 3xTF32): same fp32-level acceptance rule."""
     sd = O.trained_like_state(3)
     x, o0, o1 = O.synthetic_tpspp_inputs(batch, seed)
-    got, _ = _run_native(sd, x, o0, o1, precision)
+    got, _ = _run_native(sd, x, o0, o1, precision, flags)
     r32 = O.head_intermediates(sd, x, [o0, o1], dtype=torch.float32)
     r64 = O.head_intermediates(sd, x, [o0, o1], dtype=torch.float64)
     report = []

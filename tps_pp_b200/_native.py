@@ -40,6 +40,7 @@ HEAD_FP32, HEAD_TC, HEAD_BF16 = 0, 1, 2
 HEAD_FLAG_WEIGHTS_CACHED = 1
 HEAD_FLAG_UNFUSED_DOWN = 2
 HEAD_FLAG_UNFUSED_SCORE = 4
+HEAD_FLAG_TF32X3_CONV = 8
 ABI_VERSION = 2
 P_COUNT = 58
 WS_NAMES = ("f0", "f1", "f2", "a0", "a1", "e0", "e1", "e2", "e3", "cbam", "d0", "d1", "d2", "de", "x1", "v", "de2", "p1", "wprep", "t1", "fs", "hid", "p1img")

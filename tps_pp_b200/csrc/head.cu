@@ -1087,14 +1087,14 @@ static ConvSrc mk_src(const float* p, int C, int H, int W, int nhwc, int uh = 1,
 
 static int run_conv(int KS, ConvSrc s0, ConvSrc s1, ConvSrc s2, const float* w, const float* bias, const float* skip,
                     float* out, int out_nhwc, int B, int Ho, int Wo, int sh, int sw, cudaStream_t st,
-                    const float* wprep = nullptr, bool bf16 = false) {
+                    const float* wprep = nullptr, int mode = CM_TF32X3) {
   ConvArgs a;
   a.out_nhwc = out_nhwc;
   a.act = CONV_ACT_RELU; a.act_scale = 1.f; a.Cout = 64; a.wimg_stride = 0;
   a.src[0] = s0; a.src[1] = s1; a.src[2] = s2;
   a.weight = w; a.bias = bias; a.skip = skip; a.out = out;
   a.B = B; a.Ho = Ho; a.Wo = Wo; a.Ctot = s0.C + s1.C + s2.C; a.sh = sh; a.sw = sw; a.pad = (KS == 3) ? 1 : 0;
-  if (wprep != nullptr && conv_tc_eligible(a, KS)) return run_conv_tc(KS, a, wprep, 64, st, bf16);
+  if (wprep != nullptr && conv_tc_eligible(a, KS)) return run_conv_tc(KS, a, wprep, 64, st, mode);
   const long long M = (long long)B * Ho * Wo;
   const unsigned grid = (unsigned)((M + CV_TM - 1) / CV_TM);
   if (KS == 1) conv_ffma_kernel<1><<<grid, 256, CV_SMEM, st>>>(a);
@@ -1175,13 +1175,20 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   const bool bf16 = cfg->precision == TPSPP_HEAD_BF16;   // convolutions with bf16 operands; linear layers stay 3xTF32
   const bool tc = cfg->precision == TPSPP_HEAD_TC || bf16;
   const bool weights_cached = (cfg->flags & TPSPP_HEAD_FLAG_WEIGHTS_CACHED) != 0;
+  // operand mode per convolution: the four 1x1 layers of the fused down kernel keep the 3xTF32 images it reads (they
+  // are HBM-bound); the ten 3x3 layers run the tf32 + bf16-correction form unless the A/B flag asks for 3xTF32
+  int cmode[14];
+  for (int i = 0; i < 14; ++i) {
+    const bool one = kConvLayers[i].KS == 1;
+    cmode[i] = bf16 ? CM_BF16 : ((one || (cfg->flags & TPSPP_HEAD_FLAG_TF32X3_CONV)) ? CM_TF32X3 : CM_MIX);
+  }
   if (tc) {
     WPrepLayer L[kNumTcLayers];
     float* cur = W(TPSPP_WS_WPREP);
     for (int i = 0; i < kNumTcLayers; ++i) {
       L[i].w = P[kConvLayers[i].w_idx]; L[i].out = cur; L[i].Ctot = kConvLayers[i].Ctot;
       L[i].taps = kConvLayers[i].KS * kConvLayers[i].KS; L[i].N = kConvLayers[i].N; L[i].NT = kConvLayers[i].NT;
-      L[i].bf16 = (bf16 && i < 14) ? 1 : 0;
+      L[i].bf16 = i < 14 ? cmode[i] : CM_TF32X3;
       wp[i] = cur;
       cur += conv_tc_wprep_floats(kConvLayers[i].Ctot, kConvLayers[i].KS, kConvLayers[i].N);
     }
@@ -1201,33 +1208,33 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     fused_down = rc == TPSPP_OK;
   }
   if (!fused_down) {
-  RUN(1, mk_src(o0, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), NCHW, B, H2, W2, 1, 1, st, wp[0], bf16);
-  RUN(1, mk_src(o1, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), NCHW, B, H2, W2, 1, 1, st, wp[1], bf16);
-  RUN(1, mk_src(x, 64, h, w, NCHW), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), NCHW, B, h, w, 1, 1, st, wp[2], bf16);
+  RUN(1, mk_src(o0, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), NCHW, B, H2, W2, 1, 1, st, wp[0], cmode[0]);
+  RUN(1, mk_src(o1, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), NCHW, B, H2, W2, 1, 1, st, wp[1], cmode[1]);
+  RUN(1, mk_src(x, 64, h, w, NCHW), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), NCHW, B, h, w, 1, 1, st, wp[2], cmode[2]);
   }
   // down0_1 / down1_1: 3x3 stride 2 (tps_pp.py:584)
-  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), NCHW, B, h, w, 2, 2, st, wp[3], bf16);
-  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), NCHW, B, h, w, 2, 2, st, wp[4], bf16);
+  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), NCHW, B, h, w, 2, 2, st, wp[3], cmode[3]);
+  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), NCHW, B, h, w, 2, 2, st, wp[4], cmode[4]);
   // grid(): down_feat(cat(f0, f1, up2(f2))) (tps_pp.py:560-562,585) -> feat_grid in the boundary layout (warp input)
   if (!fused_down)
   RUN(1, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW), mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW), mk_src(W(TPSPP_WS_F2), 64, h, w, NCHW, 2, 2),
-      P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, NCHW, B, H2, W2, 1, 1, st, wp[5], bf16);
+      P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, NCHW, B, H2, W2, 1, 1, st, wp[5], cmode[5]);
   // MSFA encoder (tps_pp.py:158-160): cat(a0, a1, f2) -> e0 -> e1 -> e2 -> e3
   RUN(3, mk_src(W(TPSPP_WS_A0), 64, h, w, NCHW), mk_src(W(TPSPP_WS_A1), 64, h, w, NCHW), mk_src(W(TPSPP_WS_F2), 64, h, w, NCHW),
-      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), NCHW, B, h, w, 1, 1, st, wp[6], bf16);
-  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w, NCHW), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), NCHW, B, d.h1, d.w1, 2, 2, st, wp[7], bf16);
-  RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1, NCHW), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), NCHW, B, d.h2, d.w2, d.ps, d.ps, st, wp[8], bf16);
-  RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2, NCHW), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), NCHW, B, d.py, d.px, 2, 1, st, wp[9], bf16);
+      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), NCHW, B, h, w, 1, 1, st, wp[6], cmode[6]);
+  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w, NCHW), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), NCHW, B, d.h1, d.w1, 2, 2, st, wp[7], cmode[7]);
+  RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1, NCHW), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), NCHW, B, d.h2, d.w2, d.ps, d.ps, st, wp[8], cmode[8]);
+  RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2, NCHW), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), NCHW, B, d.py, d.px, 2, 1, st, wp[9], cmode[9]);
   // CBAM on the deepest map (tps_pp.py:163)
   cbam_kernel<<<B, 256, 0, st>>>(W(TPSPP_WS_E3), W(TPSPP_WS_CBAM), P[TPSPP_P_CBAM_MLP0_W], P[TPSPP_P_CBAM_MLP2_W],
                                  P[TPSPP_P_CBAM_SP_W], P[TPSPP_P_CBAM_SP_B], d.py, d.px);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   // decoder (tps_pp.py:165-168): upsample + conv + skip
-  RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, NCHW, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), NCHW, B, d.h2, d.w2, 1, 1, st, wp[10], bf16);
-  RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, NCHW, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), NCHW, B, d.h1, d.w1, 1, 1, st, wp[11], bf16);
-  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, NCHW, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), NCHW, B, h, w, 1, 1, st, wp[12], bf16);
-  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w, NCHW), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), NCHW, B, h, w, 1, 1, st, wp[13], bf16);
+  RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, NCHW, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), NCHW, B, d.h2, d.w2, 1, 1, st, wp[10], cmode[10]);
+  RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, NCHW, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), NCHW, B, d.h1, d.w1, 1, 1, st, wp[11], cmode[11]);
+  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, NCHW, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), NCHW, B, h, w, 1, 1, st, wp[12], cmode[12]);
+  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w, NCHW), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), NCHW, B, h, w, 1, 1, st, wp[13], cmode[13]);
 #undef RUN
   // localisation + p_linear (tps_pp.py:321-323, 305)
   {

@@ -24,12 +24,14 @@ struct ConvArgs {
   long long wimg_stride; // floats between per-image weight images (0: weights shared by all images)
 };
 enum { CONV_ACT_RELU = 0, CONV_ACT_NONE = 1, CONV_ACT_GELU = 2, CONV_ACT_TANH = 3 };
+// operand mode of a tensor-core convolution (head_tc.cu): 3xTF32 | single-pass bf16 | tf32 main term + bf16 corrections
+enum { CM_TF32X3 = 0, CM_BF16 = 1, CM_MIX = 2 };
 
 
 // tcgen05 implicit-GEMM convolution (head_tc.cu).  `wprep` is the layer's weight image produced by
 // conv_tc_prepare_weights (3xTF32 hi/lo split, UMMA core-matrix order).
 bool conv_tc_eligible(const ConvArgs& a, int KS);
-int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st, bool bf16 = false);
+int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st, int mode = CM_TF32X3);
 // DGAB Mlp fused (fc1 + GELU + fc2 + residual) on the weight images of fc1/fc2; returns 1 if not applicable
 int run_mlp_fused(const float* v, const float* x1, const float* w1img, const float* b1, const float* w2img, const float* b2,
                   float* out, long long R, cudaStream_t st);
@@ -46,7 +48,7 @@ struct WPrepLayer {
   const float* w;   // [N][Ctot][KS*KS]
   float* out;
   int Ctot, taps, N, NT;
-  int bf16;         // 1: single bf16 image [chunk][4 k-groups][64][8] instead of the fp32 hi|lo pair
+  int bf16;         // CM_*: 1 = single bf16 image [chunk][4 k-groups][64][8], 2 = tf32 hi | bf16 w | bf16 lo, 0 = fp32 hi|lo pair
 };
 constexpr int WPREP_MAX_LAYERS = 20;
 int conv_tc_prepare_weights(const WPrepLayer* layers, int nlayers, cudaStream_t st);

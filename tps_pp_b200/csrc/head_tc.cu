@@ -308,6 +308,69 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(ConvTcArgs t) {
   if (warp == 0) tmem_dealloc(tmem_d, tc_tmem_cols(NT));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Operand modes of the convolution kernels.
+//   CM_TF32X3  3xTF32: D_main += A_hi B_hi, D_corr += A_lo B_hi + A_hi B_lo, all kind::tf32 (12 MMAs of K = 8 per chunk).
+//   CM_BF16    single-pass bf16 operands (the opt-in reduced-precision mode).
+//   CM_MIX     fp32-level accuracy at 2/3 of the tensor time: the main term stays kind::tf32 (4 MMAs of K = 8), the two
+//              correction terms -- 2^-11 of the result, so 8 significant bits are enough -- run as kind::f16 with bf16
+//              operands (2 + 2 MMAs of K = 16, each half the cycles of a tf32 MMA): A_lo(bf16) B(bf16) + A(bf16) B_lo(bf16).
+//              bf16 keeps the fp32 exponent range, so unlike an fp16 split there is no overflow/underflow case.
+//              Error per product: |a_lo| <= 2^-10 |a| and bf16 round-to-nearest is 2^-9 relative => <= 2^-18 |a w| per
+//              correction term, unbiased (the all-tf32 form truncates a_lo/w_lo to 11 bits inside the tensor core: 2^-20,
+//              biased); the dropped lo*lo term is 2^-21 as before.
+//   A stage in tensor memory (64 columns): hi tf32 [0,32) | lo bf16x2 [32,48) | a bf16x2 [48,64)
+//   weight image of a chunk (16 KB):       hi tf32 8 KB    | w bf16 4 KB      | lo bf16 4 KB   (k-group-major, see wprep_kernel)
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t MIX_B_BF = 8192, MIX_B_LO = 12288;    // byte offsets of the bf16 images inside a chunk's weight image
+
+// one elected lane: the 8 MMAs of a chunk (a_base = first TMEM column of the A stage, b_base = shared address of the image)
+template <int NT>
+__device__ __forceinline__ void mix_mma_chunk(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t idesc_tf, uint32_t idesc_bf,
+                                              bool first) {
+#pragma unroll
+  for (int j = 0; j < TC_KC / 16; ++j) {        // corrections: K = 16 bf16 per MMA = two 16-byte k-groups
+    const uint64_t dbw = umma_smem_desc(b_base + MIX_B_BF + j * 2 * (NT * 16), NT * 16, 128);
+    const uint64_t dbl = umma_smem_desc(b_base + MIX_B_LO + j * 2 * (NT * 16), NT * 16, 128);
+    umma_ts_f16(tmem_d + 64, a_base + 32 + j * 8, dbw, idesc_bf, (first && j == 0) ? 0u : 1u);
+    umma_ts_f16(tmem_d + 64, a_base + 48 + j * 8, dbl, idesc_bf, 1u);
+  }
+#pragma unroll
+  for (int j = 0; j < TC_KC / 8; ++j) {         // main term: K = 8 tf32 per MMA
+    const uint64_t dbh = umma_smem_desc(b_base + j * 2 * (NT * 16), NT * 16, 128);
+    umma_ts_tf32(tmem_d, a_base + j * 8, dbh, idesc_tf, (first && j == 0) ? 0u : 1u);
+  }
+}
+// producer thread: its 16 channels (half kh of the chunk) -> the three parts of the A stage
+__device__ __forceinline__ void mix_split(const float (&v)[16], float (&hi)[16], uint32_t (&lo2)[8], uint32_t (&a2)[8]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - hi[2 * i], v[2 * i + 1] - hi[2 * i + 1]);   // .x (low half) = even channel
+    const __nv_bfloat162 x2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    lo2[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    a2[i] = *reinterpret_cast<const uint32_t*>(&x2);
+  }
+}
+__device__ __forceinline__ void mix_store_a(uint32_t stage_addr, int kh, const float (&v)[16]) {
+  float hi[16];
+  uint32_t lo2[8], a2[8];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - hi[2 * i], v[2 * i + 1] - hi[2 * i + 1]);   // .x (low half) = even channel
+    const __nv_bfloat162 x2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    lo2[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    a2[i] = *reinterpret_cast<const uint32_t*>(&x2);
+  }
+  tmem_st16(stage_addr + (uint32_t)(kh * 16), hi);
+  tmem_st8(stage_addr + (uint32_t)(32 + kh * 8), lo2);
+  tmem_st8(stage_addr + (uint32_t)(48 + kh * 8), a2);
+}
+
 // ------------------------------------------------------------------------------------------------
 // TS variant for the convolutions (NCHW sources, 64 output channels): the A operand never touches
 // shared memory.  With N = 64 an SS-mode UTCHMMA re-reads its 128x8 A slice from shared memory on
@@ -330,8 +393,9 @@ constexpr int TS_SMEM = 2 * TS_STAGE + 64 + TC_TM * 16 + 256;
 
 // BF16 = true: single-pass bf16 operands (kind::f16, fp32 accumulate) instead of 3xTF32 -- the opt-in reduced
 // precision mode (TPSPP_HEAD_BF16): A packs two channels per TMEM column, the weight image is bf16.
-template <int KS, bool BF16>
+template <int KS, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
+  constexpr bool BF16 = MODE == CM_BF16, MIX = MODE == CM_MIX;
   constexpr int NT = 64;
   constexpr int W_BYTES = BF16 ? NT * TC_KC * 2 : 2 * TS_B_BYTES;      // weight image bytes per chunk
   constexpr int A_COL0 = BF16 ? 64 : 128;                              // first TMEM column of the A ring
@@ -381,6 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
   }
   __syncthreads();
   constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, BF16 ? 1 : 2);
+  constexpr uint32_t IDESC_BF = umma_instr_desc(TC_TM, NT, 1);
   if (warp == TC_PRODUCERS / 32) {
     // ===== MMA issuer warp =====
     for (int ch = 0; ch < nchunks; ++ch) {
@@ -398,6 +463,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
             const uint64_t db = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
             umma_ts_f16(tmem_d, a_hi + j * 8, db, IDESC, (ch | j) != 0 ? 1u : 0u);
           }
+        } else if (MIX) {
+          mix_mma_chunk<NT>(tmem_d, a_hi, b_hi, IDESC, IDESC_BF, ch == 0);
         } else {
 #pragma unroll
           for (int j = 0; j < TC_KC / 8; ++j) {
@@ -485,6 +552,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
           pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
         }
         tmem_st8(lane_addr + (uint32_t)(A_COL0 + buf * A_STAGE + kh * 8), pk);
+      } else if (MIX) {
+        mix_store_a(lane_addr + (uint32_t)(A_COL0 + buf * A_STAGE), kh, v);
       } else {
         float hi[16], lo[16];
 #pragma unroll
@@ -607,8 +676,9 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, in
 
 // BF16 = true: single-pass bf16 operands (kind::f16, fp32 accumulate) -- the opt-in TPSPP_HEAD_BF16 mode: A packs two
 // channels per TMEM column, the weight image is bf16, no correction accumulator.
-template <int KS, bool BF16>
+template <int KS, int MODE>
 __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_constant__ ConvTmaArgs g) {
+  constexpr bool BF16 = MODE == CM_BF16, MIX = MODE == CM_MIX;
   constexpr int NT = 64, T = KS * KS;
   constexpr int XH = KS == 3 ? TM_XH : 0;
   constexpr int W_BYTES = BF16 ? NT * TC_KC * 2 : 2 * TS_B_BYTES;
@@ -652,6 +722,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
   const uint32_t tile_tx = (uint32_t)(CHS * TC_KC * 4);
   const unsigned char* wimg = reinterpret_cast<const unsigned char*>(g.t.wprep);
   constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, BF16 ? 1 : 2);
+  constexpr uint32_t IDESC_BF = umma_instr_desc(TC_TM, NT, 1);
 
   // persistent over tiles blockIdx.x, blockIdx.x + gridDim.x, ...: TMEM, barriers and the TMA pipeline are set up once,
   // and the first activation tile of the next output tile is already in flight while this one runs its epilogue
@@ -674,7 +745,11 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
 
   if (warp == TC_PRODUCERS / 32) {
     // ===== MMA issuer warp (chunk order: channel group major, tap minor) =====
+    // A barrier wait costs the issuing warp 130-260 cycles even when the barrier completed long ago (clock64 timeline,
+    // profiles/r02_conv_experiments.md), so the barriers of chunk g+1 are probed (non-blocking test_wait) BEFORE the MMAs of
+    // chunk g are issued -- the probe's latency hides behind the issue -- and only a failed probe is waited for afterwards.
     int gch = 0, it = 0;
+    int ok_a = 0, ok_w = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       if (it >= 1) {
         mbar_wait_bounded(d_empty, (uint32_t)((it - 1) & 1));
@@ -683,8 +758,13 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
       for (int ch = 0; ch < nchunks; ++ch, ++gch) {
         const int buf = gch & 1;
         const uint32_t ph = (uint32_t)((gch >> 1) & 1);
-        mbar_wait_bounded(&a_full[buf], ph);
-        mbar_wait_bounded(&w_full[buf], ph);
+        if (!ok_a) mbar_wait_bounded(&a_full[buf], ph);
+        if (!ok_w) mbar_wait_bounded(&w_full[buf], ph);
+        {
+          const uint32_t ph1 = (uint32_t)(((gch + 1) >> 1) & 1);
+          ok_a = __shfl_sync(0xffffffffu, mbar_test_wait(&a_full[buf ^ 1], ph1) ? 1 : 0, 0);
+          ok_w = __shfl_sync(0xffffffffu, mbar_test_wait(&w_full[buf ^ 1], ph1) ? 1 : 0, 0);
+        }
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE), b_lo = b_hi + TS_B_BYTES;
@@ -695,6 +775,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
               const uint64_t db = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
               umma_ts_f16(tmem_d, a_hi + j * 8, db, IDESC, (ch | j) != 0 ? 1u : 0u);
             }
+          } else if (MIX) {
+            mix_mma_chunk<NT>(tmem_d, a_hi, b_hi, IDESC, IDESC_BF, ch == 0);
           } else {
 #pragma unroll
             for (int j = 0; j < TC_KC / 8; ++j) {
@@ -779,6 +861,10 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(qa + (uint32_t)i * cstride));
+          // split first, wait second: only the tcgen05.st sit between "stage free" and "stage full"
+          float mhi[16];
+          uint32_t mlo2[8], ma2[8];
+          if (MIX) mix_split(v, mhi, mlo2, ma2);
           if (gch >= 2) {
             mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch >> 1) - 1) & 1));   // MMAs of chunk gch-2 have read the stage
             tc_fence_after();
@@ -791,6 +877,11 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
               pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
             }
             tmem_st8(lane_addr + (uint32_t)(128 + buf * 64 + kh * 8), pk);
+          } else if (MIX) {
+            const uint32_t sa = lane_addr + (uint32_t)(128 + buf * 64);
+            tmem_st16(sa + (uint32_t)(kh * 16), mhi);
+            tmem_st8(sa + (uint32_t)(32 + kh * 8), mlo2);
+            tmem_st8(sa + (uint32_t)(48 + kh * 8), ma2);
           } else {
             float hi[16], lo[16];
 #pragma unroll
@@ -864,6 +955,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, 256);
 }
+
 
 // ---- host side of the TMA path ----
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -2054,6 +2146,16 @@ __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
     const int tap = k / L.Ctot, cin = k - tap * L.Ctot;
     const float w = __ldg(L.w + (size_t)n * Ktot + cin * L.taps + tap);
     const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    if (L.bf16 == CM_MIX) {   // per chunk: hi tf32 [8 k-groups][64 n][4] | w bf16 [4 k-groups][64 n][8] | lo bf16 (same)
+      // weights are prepared once, so the tf32 part is rounded to nearest (|lo| <= 2^-11 |w|)
+      const float whi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
+      unsigned char* oc = reinterpret_cast<unsigned char*>(L.out) + (size_t)(k >> 5) * 16384;
+      reinterpret_cast<float*>(oc)[((k >> 2) & 7) * (64 * 4) + n * 4 + (k & 3)] = whi;
+      const int o16 = ((k >> 3) & 3) * (64 * 8) + n * 8 + (k & 7);
+      reinterpret_cast<__nv_bfloat16*>(oc + MIX_B_BF)[o16] = __float2bfloat16_rn(w);
+      reinterpret_cast<__nv_bfloat16*>(oc + MIX_B_LO)[o16] = __float2bfloat16_rn(w - whi);
+      continue;
+    }
     if (L.bf16) {   // [chunk][4 k-groups][64 n][8 bf16]
       __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(L.out);
       ob[(size_t)(k >> 5) * (64 * 32) + ((k >> 3) & 3) * (64 * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(w);
@@ -2230,7 +2332,8 @@ int run_score_fused(const float* de2, const float* w0img, const float* w1img, co
 }
 
 // NT: column tile (64, or 32 for narrow outputs); Cout / NT column blocks go to grid.y
-int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st, bool bf16) {
+int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st, int mode) {
+  const bool bf16 = mode == CM_BF16;
   TPSPP_REQUIRE(NT == 64 || NT == 32, "conv_tc: column tile must be 32 or 64");
   TPSPP_REQUIRE(a.Cout % NT == 0, "conv_tc: Cout %d is not a multiple of the column tile %d", a.Cout, NT);
   TPSPP_REQUIRE(KS == 1 || NT == 64, "conv_tc: 3x3 kernels are instantiated for 64-column tiles only");
@@ -2251,38 +2354,40 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
       g.t = t;
       static thread_local int tma_dev = -1;
       if (tma_dev != dev) {
-        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
-        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
-        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
-        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1, CM_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, CM_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1, CM_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, CM_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1, CM_MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, CM_MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
         tma_dev = dev;
       }
       dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()));
-      if (KS == 1 && !bf16) conv_tma_kernel<1, false><<<pgrid, TM_THREADS, tm_smem_bytes(1), st>>>(g);
-      else if (KS == 1) conv_tma_kernel<1, true><<<pgrid, TM_THREADS, tm_smem_bytes(1), st>>>(g);
-      else if (!bf16) conv_tma_kernel<3, false><<<pgrid, TM_THREADS, tm_smem_bytes(3), st>>>(g);
-      else conv_tma_kernel<3, true><<<pgrid, TM_THREADS, tm_smem_bytes(3), st>>>(g);
+      auto kern = KS == 1 ? (mode == CM_BF16 ? conv_tma_kernel<1, CM_BF16> : mode == CM_MIX ? conv_tma_kernel<1, CM_MIX> : conv_tma_kernel<1, CM_TF32X3>)
+                          : (mode == CM_BF16 ? conv_tma_kernel<3, CM_BF16> : mode == CM_MIX ? conv_tma_kernel<3, CM_MIX> : conv_tma_kernel<3, CM_TF32X3>);
+      kern<<<pgrid, TM_THREADS, tm_smem_bytes(KS), st>>>(g);
       count_launch();
       TPSPP_CHECK_CUDA(cudaGetLastError());
       return TPSPP_OK;
     }
     static thread_local int ts_dev = -1;
     if (ts_dev != dev) {
-      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, CM_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3, CM_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, CM_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3, CM_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, CM_MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<3, CM_MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
       ts_dev = dev;
     }
-    if (KS == 1 && !bf16) conv_ts_kernel<1, false><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
-    else if (KS == 1) conv_ts_kernel<1, true><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
-    else if (!bf16) conv_ts_kernel<3, false><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
-    else conv_ts_kernel<3, true><<<grid, TC_THREADS, TS_SMEM, st>>>(t);
+    auto kern = KS == 1 ? (mode == CM_BF16 ? conv_ts_kernel<1, CM_BF16> : mode == CM_MIX ? conv_ts_kernel<1, CM_MIX> : conv_ts_kernel<1, CM_TF32X3>)
+                        : (mode == CM_BF16 ? conv_ts_kernel<3, CM_BF16> : mode == CM_MIX ? conv_ts_kernel<3, CM_MIX> : conv_ts_kernel<3, CM_TF32X3>);
+    kern<<<grid, TC_THREADS, TS_SMEM, st>>>(t);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
     return TPSPP_OK;
   }
-  TPSPP_REQUIRE(!bf16, "conv_tc: the bf16 operand mode exists for the NCHW-source convolutions only");
+  TPSPP_REQUIRE(mode == CM_TF32X3, "conv_tc: the bf16 / mixed operand modes exist for the NCHW-source convolutions only");
   LinTmaArgs lg;
   if (KS == 1 && nhwc && lin_tma_plan(a, NT, &lg)) {
     lg.t = t;
