@@ -235,6 +235,35 @@ TPSPP_API int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const fl
                              const float* const* params, float* feat_grid, float* c_prime,
                              float* pc_score, void* workspace, tpspp_stream_t stream);
 
+/* ---- Backbone stage in front of the rectifier -------------------------------------
+ * Replaces what `ResNetABI_v2_large.forward` computes before it calls `tpsnet(x, outs)`
+ * (backbones/resnet_v2_large.py:131-135 stem, :109-129 layers, :176-191 forward; block = layers/conv_layer.py:12-33 over
+ * mmcv's BasicBlock), eval mode: stem conv+BN+ReLU, layer1 (3 blocks, 32 ch), layer2 (4 blocks, 64 ch, stride 2).
+ * The reference-side binding is `tps_pp_b200/backbone.py` (drop-in `ResNetABI_v2_large`). */
+typedef struct {
+  int32_t batch;
+  int32_t height, width;    /* image size (32 x 128); o0/o1 are [B,32,H,W], x is [B,64,H/2,W/2]      */
+  int32_t precision;        /* TPSPP_HEAD_TC                                                     */
+  int32_t flags;            /* TPSPP_HEAD_FLAG_WEIGHTS_CACHED: folded BN + weight images in `workspace` still valid */
+} tpspp_stage_cfg;
+
+/* params table = the stage's slice of the reference state_dict, in its order, without the int64 num_batches_tracked
+ * buffers: conv1.{weight,bias}, bn1.{weight,bias,running_mean,running_var}, then per block conv1.weight, bn1 x4,
+ * conv2.weight, bn2 x4 and, for layer2.0, downsample.0.weight, downsample.1 x4. */
+enum {
+  TPSPP_SP_CONV1_W = 0, TPSPP_SP_CONV1_B, TPSPP_SP_BN1_W, TPSPP_SP_BN1_B, TPSPP_SP_BN1_MEAN, TPSPP_SP_BN1_VAR,
+  TPSPP_SP_LAYER1 = 6,      /* 3 blocks x 10 tensors  */
+  TPSPP_SP_LAYER2 = 36,     /* 15 tensors (with downsample) + 3 blocks x 10 */
+  TPSPP_SP_COUNT = 81
+};
+
+TPSPP_API size_t tpspp_stage_workspace_bytes(const tpspp_stage_cfg* cfg);
+/* img [B,3,H,W] fp32 NCHW -> o0 (stem output) and o1 (layer1 output) [B,32,H,W], x (layer2 output) [B,64,H/2,W/2]:
+ * exactly the tensors tpspp_head_fwd / tpspp_warp_fwd take.  params: HOST array of TPSPP_SP_COUNT DEVICE pointers.
+ * workspace: 256-byte aligned, >= tpspp_stage_workspace_bytes(cfg). */
+TPSPP_API int tpspp_stage_fwd(const tpspp_stage_cfg* cfg, const float* img, const float* const* params, float* o0, float* o1,
+                              float* x, void* workspace, tpspp_stream_t stream);
+
 /* Number of kernel launches the most recent call on this host thread enqueued
  * (bench.py uses it to report gpu_launches). */
 TPSPP_API int tpspp_last_launch_count(void);

@@ -257,6 +257,7 @@ def main():
     oc = O.classical_localization(sdc, torch.from_numpy(img))
     check("classical C'", _mx(oc, rc), 1e-6)
     nrtr_fixture(write=not args.check)
+    backbone_fixture(write=not args.check)
     print('all oracle checks passed' + ('' if args.check else f'; fixtures written to {GOLD}'))
 
 
@@ -335,6 +336,50 @@ def nrtr_fixture(write: bool, batch: int = 2):
     # the drop-in module under the same seed must hold the stock weights bit-for-bit (so the fixture need not carry them)
     if write:
         np.savez_compressed(os.path.join(GOLD, 'nrtr_argmax.npz'), **out)
+
+
+BACKBONE_SUBSAMPLE = 61
+
+
+def backbone_fixture(write: bool, batch: int = 2):
+    """the backbone stage in front of the call.  Runs the unmodified reference
+    ``ResNetABI_v2_large(strides=[1,2,2,1,2])`` (eval) with the deterministic stage weights of
+    ``O.trained_like_backbone_state`` on ``O.synthetic_images`` and captures what it hands to ``tpsnet(x, outs)``
+    (resnet_v2_large.py:189-191); pins ``O.backbone_stage_forward`` against it (full tensors here, a strided subsample in
+    the committed fixture: 1.3 MB per image would not be a small fixture)."""
+    import contextlib
+    import io
+    from . import nrtr_loader as L
+    print('backbone stage fixture (stem + layer1 + layer2)')
+    ns = L.load_nrtr()
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        bb = ns.ResNetABI_v2_large(arch_settings=[3, 4, 6, 6, 3], strides=[1, 2, 2, 1, 2])
+    bb.eval()
+    sd = O.trained_like_backbone_state(5)
+    ref_keys = [k for k in bb.state_dict().keys() if k.split('.')[0] in ('conv1', 'bn1', 'layer1', 'layer2')]
+    check('stage state_dict keys == reference keys (order included)', float(ref_keys != [k for k, _ in O.backbone_stage_keys()]), 0.0)
+    missing, unexpected = bb.load_state_dict(sd, strict=False)
+    check('no unexpected keys', float(len(unexpected)), 0.0)
+    img = O.synthetic_images(batch)
+    cap = {}
+
+    def tap(x, outs, **kw):
+        cap.update(x=x.detach().clone(), o0=outs[0].detach().clone(), o1=outs[1].detach().clone())
+        return {}
+    with torch.no_grad():
+        bb(torch.from_numpy(img), tap, True)
+    x32, outs32 = O.backbone_stage_forward(sd, img, torch.float32)
+    x64, outs64 = O.backbone_stage_forward(sd, img, torch.float64)
+    for nm, ours, ref, tw in (('x', x32, cap['x'], x64), ('o0', outs32[0], cap['o0'], outs64[0]), ('o1', outs32[1], cap['o1'], outs64[1])):
+        check(f'backbone stage {nm}: oracle fp32 vs reference (scale {float(ref.abs().max()):.2f})', _mx(ours, ref), 2e-5)
+        print(f'    {nm}: reference fp32 vs oracle fp64 twin: {_mx(ref, tw):.3e}')
+    if write:
+        S = BACKBONE_SUBSAMPLE
+        np.savez_compressed(os.path.join(GOLD, 'backbone_stage.npz'), batch=np.array(batch), stride=np.array(S),
+                            x=cap['x'].numpy().reshape(-1)[::S], o0=cap['o0'].numpy().reshape(-1)[::S],
+                            o1=cap['o1'].numpy().reshape(-1)[::S],
+                            state_digest=np.array([float(v.double().abs().sum()) for v in sd.values()]))
 
 
 if __name__ == '__main__':

@@ -561,6 +561,88 @@ def synthetic_tpspp_inputs(batch: int, seed: int = 0, h: int = 16, w: int = 64):
     return x, o0, o1
 
 
+# --------------------------------------------------------------------------
+# Backbone stage in front of the call: stem + layer1 + layer2 of ResNetABI_v2_large --------------
+# --------------------------------------------------------------------------
+# (layer, blocks, in planes, planes, stride of the first block) for strides=[1,2,...] (the only setting under
+# which TPS_PP's shape contract holds); backbones/resnet_v2_large.py:44-96
+BACKBONE_STAGE_LAYERS = (('layer1', 3, 32, 32, 1), ('layer2', 4, 32, 64, 2))
+BN_EPS = 1e-5   # nn.BatchNorm2d default
+
+
+def backbone_stage_keys():
+    """state_dict keys/shapes of the stage, in the reference module's order (resnet_v2_large.py:131-135,109-129;
+    layers/conv_layer.py:12-33 on top of mmcv BasicBlock: conv1 = 1x1 stride 1, conv2 = 3x3 with the block's stride)."""
+    def bn(prefix, c):
+        return [(prefix + '.weight', (c,)), (prefix + '.bias', (c,)), (prefix + '.running_mean', (c,)),
+                (prefix + '.running_var', (c,)), (prefix + '.num_batches_tracked', ())]
+    keys = [('conv1.weight', (32, 3, 3, 3)), ('conv1.bias', (32,))] + bn('bn1', 32)
+    for layer, blocks, cin, planes, stride in BACKBONE_STAGE_LAYERS:
+        for i in range(blocks):
+            p = f'{layer}.{i}.'
+            ci = cin if i == 0 else planes
+            keys += [(p + 'conv1.weight', (planes, ci, 1, 1))] + bn(p + 'bn1', planes)
+            keys += [(p + 'conv2.weight', (planes, planes, 3, 3))] + bn(p + 'bn2', planes)
+            if i == 0 and (stride != 1 or ci != planes):
+                keys += [(p + 'downsample.0.weight', (planes, ci, 1, 1))] + bn(p + 'downsample.1', planes)
+    return keys
+
+
+def trained_like_backbone_state(seed: int = 5) -> Dict[str, torch.Tensor]:
+    """Deterministic (numpy legacy RNG) weights for the stage: He-uniform convolutions, BatchNorm with non-trivial
+    affine parameters and running statistics so that folding BN into the convolution is actually exercised."""
+    rs = np.random.RandomState(seed)
+    st: Dict[str, torch.Tensor] = {}
+    for name, shape in backbone_stage_keys():
+        if name.endswith('num_batches_tracked'):
+            st[name] = torch.tensor(100, dtype=torch.int64)
+        elif name.endswith('running_var'):
+            st[name] = torch.from_numpy(rs.uniform(0.5, 1.5, shape).astype(np.float32))
+        elif name.endswith('running_mean'):
+            st[name] = torch.from_numpy((0.1 * rs.standard_normal(shape)).astype(np.float32))
+        elif len(shape) == 4:
+            bound = math.sqrt(6.0 / int(np.prod(shape[1:])))
+            st[name] = torch.from_numpy(rs.uniform(-bound, bound, shape).astype(np.float32))
+        elif name.endswith('.weight'):      # BN gamma; the residual branch (bn2) is damped so activations stay O(1..10)
+            lo, hi = (0.1, 0.3) if '.bn2.' in name else (0.6, 1.4)
+            st[name] = torch.from_numpy(rs.uniform(lo, hi, shape).astype(np.float32))
+        else:                               # conv1.bias, BN beta
+            st[name] = torch.from_numpy((0.1 * rs.standard_normal(shape)).astype(np.float32))
+    return st
+
+
+def synthetic_images(batch: int, seed: int = 1234, h: int = 32, w: int = 128) -> np.ndarray:
+    """img [B,3,32,128] ~ N(0,1) (BASELINE configs 1/5), numpy legacy RNG."""
+    return np.random.RandomState(seed).standard_normal((batch, 3, h, w)).astype(np.float32)
+
+
+def _bn_eval(state, prefix, x):
+    return F.batch_norm(x, _t(state, prefix + '.running_mean', x.dtype), _t(state, prefix + '.running_var', x.dtype),
+                        _t(state, prefix + '.weight', x.dtype), _t(state, prefix + '.bias', x.dtype), False, 0.0, BN_EPS)
+
+
+def backbone_stage_forward(state, img, dtype=torch.float32):
+    """What ``ResNetABI_v2_large.forward`` computes before it calls ``tpsnet(x, outs)`` (resnet_v2_large.py:176-191), eval
+    mode: stem conv+BN+ReLU, then layer1 and layer2; ``outs`` = [stem output, layer1 output].  Block = mmcv BasicBlock
+    forward with the reference's 1x1/3x3 pair (conv_layer.py:30-33): relu(bn1(conv1 x)) -> bn2(conv2 .) -> + identity
+    (through ``downsample`` = 1x1 stride-s conv + BN when present) -> relu.  Returns (x, [o0, o1])."""
+    x = torch.as_tensor(np.asarray(img)).to(dtype)
+    x = F.relu(_bn_eval(state, 'bn1', F.conv2d(x, _t(state, 'conv1.weight', dtype), _t(state, 'conv1.bias', dtype), padding=1)))
+    outs = []
+    for layer, blocks, cin, planes, stride in BACKBONE_STAGE_LAYERS:
+        outs.append(x)
+        for i in range(blocks):
+            p = f'{layer}.{i}.'
+            s = stride if i == 0 else 1
+            out = F.relu(_bn_eval(state, p + 'bn1', F.conv2d(x, _t(state, p + 'conv1.weight', dtype))))
+            out = _bn_eval(state, p + 'bn2', F.conv2d(out, _t(state, p + 'conv2.weight', dtype), stride=s, padding=1))
+            idn = x
+            if (p + 'downsample.0.weight') in state:
+                idn = _bn_eval(state, p + 'downsample.1', F.conv2d(x, _t(state, p + 'downsample.0.weight', dtype), stride=s))
+            x = F.relu(out + idn)
+    return x, outs
+
+
 def head_intermediates(state, x, outs, dtype=torch.float32, p_stride=2):
     """Every intermediate of the head, named like the native workspace slots (include/tpspp.h TPSPP_WS_*),
     computed with the same stage functions as :func:`tps_pp_forward` (tps_pp.py:581-594, 156-169;

@@ -131,3 +131,19 @@ def test_nrtr_fixture_weights_are_reproducible(golden):
     assert np.allclose(digest, g["trained_state_digest"], rtol=1e-6, atol=0)
     assert g["x"].shape == (2, 64, 16, 64) and g["o0"].shape == (2, 32, 32, 128)
     assert float(g["stock_safe_delta"]) >= 1e-3 and float(g["trained_safe_delta"]) >= 1e-3 and int(g["stock_flips"][0]) == 0 and int(g["trained_flips"][0]) == 0
+
+
+def test_backbone_stage_vs_reference(golden):
+    """the oracle's stem + layer1 + layer2 against what the unmodified reference backbone handed to
+    ``tpsnet(x, outs)`` (strided subsample of the full tensors, oracle/make_golden.py::backbone_fixture)."""
+    g = golden("backbone_stage.npz")
+    sd = O.trained_like_backbone_state(5)
+    digest = [float(v.double().abs().sum()) for v in sd.values()]
+    assert np.allclose(digest, g["state_digest"], rtol=0, atol=0)
+    img = O.synthetic_images(int(g["batch"]))
+    x, outs = O.backbone_stage_forward(sd, img, torch.float32)
+    s = int(g["stride"])
+    assert mx(x.numpy().reshape(-1)[::s], g["x"]) < 2e-5
+    assert mx(outs[0].numpy().reshape(-1)[::s], g["o0"]) < 2e-5
+    assert mx(outs[1].numpy().reshape(-1)[::s], g["o1"]) < 2e-5
+    assert tuple(x.shape) == (2, 64, 16, 64) and tuple(outs[0].shape) == tuple(outs[1].shape) == (2, 32, 32, 128)

@@ -36,6 +36,12 @@ class HeadCfg(Structure):
     ]
 
 
+class StageCfg(Structure):
+    """Mirror of ``tpspp_stage_cfg`` (include/tpspp.h)."""
+    _fields_ = [("batch", c_int32), ("height", c_int32), ("width", c_int32), ("precision", c_int32), ("flags", c_int32)]
+
+
+SP_COUNT = 81
 HEAD_FP32, HEAD_TC, HEAD_BF16 = 0, 1, 2
 HEAD_FLAG_WEIGHTS_CACHED = 1
 HEAD_FLAG_UNFUSED_DOWN = 2
@@ -61,6 +67,9 @@ _SIGNATURES = {
     "tpspp_head_workspace_offsets": (c_int, [POINTER(HeadCfg), POINTER(c_size_t)]),
     "tpspp_head_fwd": (c_int, [POINTER(HeadCfg), c_void_p, c_void_p, c_void_p, POINTER(c_void_p),
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tpspp_stage_workspace_bytes": (c_size_t, [POINTER(StageCfg)]),
+    "tpspp_stage_fwd": (c_int, [POINTER(StageCfg), c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
 }
 _OPTIONAL = {}
 

@@ -22,6 +22,7 @@ struct ConvArgs {
   float act_scale;       // tanh(scale * x)
   int Cout;              // channels of the output tensor (column blocks of NT go to grid.y)
   long long wimg_stride; // floats between per-image weight images (0: weights shared by all images)
+  int skip_pre;          // 1: `skip` is added before the activation (residual block), 0: after it (MSFA decoder)
 };
 enum { CONV_ACT_RELU = 0, CONV_ACT_NONE = 1, CONV_ACT_GELU = 2, CONV_ACT_TANH = 3 };
 // operand mode of a tensor-core convolution (head_tc.cu): 3xTF32 | single-pass bf16 | tf32 main term + bf16 corrections
@@ -48,6 +49,7 @@ struct WPrepLayer {
   const float* w;   // [N][Ctot][KS*KS]
   float* out;
   int Ctot, taps, N, NT;
+  const float* scale; // per-output-row factor applied before the split (BatchNorm folding), or null
   int bf16;         // CM_*: 1 = single bf16 image [chunk][4 k-groups][64][8], 2 = tf32 hi | bf16 w | bf16 lo, 0 = fp32 hi|lo pair
 };
 constexpr int WPREP_MAX_LAYERS = 20;

@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
     mbar_init(&fbars[0], TC_PRODUCERS / 32); mbar_init(&fbars[1], TC_PRODUCERS / 32);
     fence_barrier_init();
   }
-  if (tid < NT) bias_s[tid] = a.bias != nullptr ? __ldg(a.bias + tid) : 0.f;
+  if (tid < NT) bias_s[tid] = (a.bias != nullptr && tid < a.Cout) ? __ldg(a.bias + tid) : 0.f;
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -618,6 +618,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
           const float4 bs = b4[j >> 2];
           acc[j] += bs.x; acc[j + 1] += bs.y; acc[j + 2] += bs.z; acc[j + 3] += bs.w;
         }
+        const size_t o0 = ((size_t)b * a.Cout + cb) * HoWo + rem;
+        if (cb >= a.Cout) continue;
+        if (a.skip != nullptr && a.skip_pre) {
+          const float* sk = a.skip + o0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += __ldg(sk + (size_t)j * HoWo);
+        }
         if (a.act == CONV_ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = fmaxf(acc[j], 0.f);
@@ -625,8 +632,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = tc_act(acc[j], a.act, a.act_scale);
         }
-        const size_t o0 = ((size_t)b * a.Cout + cb) * HoWo + rem;
-        if (a.skip != nullptr) {
+        if (a.skip != nullptr && !a.skip_pre) {
           const float* sk = a.skip + o0;
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] += __ldg(sk + (size_t)j * HoWo);
@@ -656,6 +662,7 @@ struct ConvTmaArgs {
   ConvTcArgs t;
   CUtensorMap tmap[3];
   int TW, TH, BW, BH;      // tile and box (halo) extent in pixels; CHS = BW * BH floats per channel
+  int TX, TPI;             // tiles per image row, tiles per image
   int S;                   // convolution stride (1, or 2 for 3x3: one box per filter row, rows strided by the tensor map)
 };
 constexpr int TM_XH = 4;   // x halo of a 3x3 box: the innermost TMA coordinate must be 16-byte aligned (probed: x = -1 traps)
@@ -707,7 +714,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
     mbar_init(d_empty, TC_PRODUCERS / 32);
     fence_barrier_init();
   }
-  if (tid < NT) bias_s[tid] = a.bias != nullptr ? __ldg(a.bias + tid) : 0.f;
+  if (tid < NT) bias_s[tid] = (a.bias != nullptr && tid < a.Cout) ? __ldg(a.bias + tid) : 0.f;
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
@@ -729,10 +736,10 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
   // (channel-group counter gcc and chunk counter gch run across tiles and drive the mbarrier phases)
   const int S = g.S, NG = (KS == 3 && S == 2) ? 3 : 1, TG = T / NG;   // tile loads per channel group, taps per load
   auto issue_tile = [&](int tile, int cc, int grp, int gcc) {
-    const long long m_base = (long long)tile * TC_TM;
-    const int img = (int)(m_base / HoWo);
-    const int rem0 = (int)(m_base - (long long)img * HoWo);
-    const int oy0 = rem0 / a.Wo, ox0 = rem0 - oy0 * a.Wo;
+    const int img = tile / g.TPI;
+    const int trem = tile - img * g.TPI;
+    const int tyy = trem / g.TX;
+    const int oy0 = tyy * g.TH, ox0 = (trem - tyy * g.TX) * g.TW;
     int s = 0, c0 = cc * TC_KC;
     if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { c0 -= a.src[1].C; s = 2; } }
     const int up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
@@ -833,10 +840,10 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
     const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     int gch = 0, gcc = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const long long m_base = (long long)tile * TC_TM;
-      const int img = (int)(m_base / HoWo);
-      const int rem0 = (int)(m_base - (long long)img * HoWo);
-      const int oy0 = rem0 / a.Wo, ox0 = rem0 - oy0 * a.Wo;
+      const int img = tile / g.TPI;
+      const int trem = tile - img * g.TPI;
+      const int tyy = trem / g.TX;
+      const int oy0 = tyy * g.TH, ox0 = (trem - tyy * g.TX) * g.TW;      // tile = TH x TW rectangle (tiles row-major in the image)
       for (int cc = 0; cc < ncc; ++cc)
       for (int grp = 0; grp < NG; ++grp, ++gcc) {
         const int tb = gcc % NTB;
@@ -913,6 +920,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
       const bool relu = a.act == CONV_ACT_RELU;
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
+        const int cb = half * 32 + pass * 16;
+        if (cb >= a.Cout) break;                 // 32-channel layers run on a 64-row weight image padded with zeros
         float acc[16], part[16];
         const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * 32 + pass * 16);
         tmem_ld_cols<16>(taddr, acc);
@@ -922,12 +931,16 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         } else {
           tmem_ld_cols<16>(taddr + 64, part);
         }
-        const int cb = half * 32 + pass * 16;
         const float4* b4 = reinterpret_cast<const float4*>(bias_s + cb);       // warp-uniform: broadcast loads
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const float4 bs = b4[j >> 2];
           acc[j] += part[j] + bs.x; acc[j + 1] += part[j + 1] + bs.y; acc[j + 2] += part[j + 2] + bs.z; acc[j + 3] += part[j + 3] + bs.w;
+        }
+        if (a.skip != nullptr && a.skip_pre) {   // residual block: the identity is added BEFORE the activation
+          const float* sk = a.skip + ((size_t)img * a.Cout + cb) * HoWo + (size_t)oy * a.Wo + ox;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += __ldg(sk + (size_t)j * HoWo);
         }
         if (relu) {
 #pragma unroll
@@ -937,7 +950,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           for (int j = 0; j < 16; ++j) acc[j] = tc_act(acc[j], a.act, a.act_scale);
         }
         const size_t o0 = ((size_t)img * a.Cout + cb) * HoWo + (size_t)oy * a.Wo + ox;
-        if (a.skip != nullptr) {
+        if (a.skip != nullptr && !a.skip_pre) {
           const float* sk = a.skip + o0;
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] += __ldg(sk + (size_t)j * HoWo);
@@ -1010,10 +1023,12 @@ static bool tmap_cached(CUtensorMap* out, int rank, const void* ptr, const cuuin
 
 // NCHW convolution whose tile is a rectangle of one image, every source either full or half resolution
 static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g) {
-  if (a.sh != a.sw || (a.sh != 1 && !(a.sh == 2 && KS == 3)) || a.out_nhwc || a.wimg_stride != 0 || a.Cout != 64) return false;
+  if (a.sh != a.sw || (a.sh != 1 && !(a.sh == 2 && KS == 3)) || a.out_nhwc || a.wimg_stride != 0 || (a.Cout != 64 && a.Cout != 32)) return false;
   if (a.pad != (KS == 3 ? 1 : 0)) return false;
   const int S = a.sh;
-  const int TW = a.Wo < 128 ? a.Wo : 128;
+  // 1x1: whole rows (up to 128 pixels); 3x3: at most 64 columns so that the halo box of 32 channels fits the tile buffer
+  const int TWmax = KS == 3 ? 64 : 128;
+  const int TW = a.Wo < TWmax ? a.Wo : TWmax;
   if (TW < 16 || 128 % TW || a.Wo % TW) return false;
   const int TH = 128 / TW;
   if (a.Ho % TH) return false;
@@ -1035,6 +1050,7 @@ static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g) {
     if (!tmap_cached(&g->tmap[s], 4, sc.ptr, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
   }
   g->TW = TW; g->TH = TH; g->BW = BW; g->BH = BH; g->S = S;
+  g->TX = a.Wo / TW; g->TPI = (a.Wo / TW) * (a.Ho / TH);
   return true;
 }
 
@@ -2139,12 +2155,14 @@ struct WPrepArgs {
 __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
   const WPrepLayer L = a.L[blockIdx.y];
   const int Ktot = L.Ctot * L.taps;
-  const int total = L.N * Ktot;
+  const int Npad = ((L.N + L.NT - 1) / L.NT) * L.NT;      // rows N .. Npad-1 of the last column block are zero
+  const int total = Npad * Ktot;
   const int nchunks = Ktot >> 5;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
     const int n = i / Ktot, k = i - n * Ktot;
     const int tap = k / L.Ctot, cin = k - tap * L.Ctot;
-    const float w = __ldg(L.w + (size_t)n * Ktot + cin * L.taps + tap);
+    float w = n < L.N ? __ldg(L.w + (size_t)n * Ktot + cin * L.taps + tap) : 0.f;
+    if (L.scale != nullptr && n < L.N) w *= __ldg(L.scale + n);         // BatchNorm folded into the convolution (stage.cu)
     const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
     if (L.bf16 == CM_MIX) {   // per chunk: hi tf32 [8 k-groups][64 n][4] | w bf16 [4 k-groups][64 n][8] | lo bf16 (same)
       // weights are prepared once, so the tf32 part is rounded to nearest (|lo| <= 2^-11 |w|)
@@ -2179,7 +2197,7 @@ bool conv_tc_eligible(const ConvArgs& a, int KS) {
   return true;
 }
 
-size_t conv_tc_wprep_floats(int Ctot, int KS, int N) { return (size_t)2 * N * Ctot * KS * KS; }
+size_t conv_tc_wprep_floats(int Ctot, int KS, int N) { return (size_t)2 * N * Ctot * KS * KS; }   // N already padded to NT
 
 int conv_tc_prepare_weights(const WPrepLayer* layers, int nlayers, cudaStream_t st) {
   TPSPP_REQUIRE(nlayers <= WPREP_MAX_LAYERS, "too many layers for wprep");
@@ -2335,7 +2353,7 @@ int run_score_fused(const float* de2, const float* w0img, const float* w1img, co
 int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStream_t st, int mode) {
   const bool bf16 = mode == CM_BF16;
   TPSPP_REQUIRE(NT == 64 || NT == 32, "conv_tc: column tile must be 32 or 64");
-  TPSPP_REQUIRE(a.Cout % NT == 0, "conv_tc: Cout %d is not a multiple of the column tile %d", a.Cout, NT);
+  TPSPP_REQUIRE(a.Cout % NT == 0 || (NT == 64 && a.Cout == 32), "conv_tc: Cout %d is not a multiple of the column tile %d", a.Cout, NT);
   TPSPP_REQUIRE(KS == 1 || NT == 64, "conv_tc: 3x3 kernels are instantiated for 64-column tiles only");
   // the TMA-staged kernels are the product path: without the driver's tensor-map encoder fail loudly instead of
   // silently dropping to the (2x slower) gather-fed kernels
@@ -2344,9 +2362,9 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
   t.c = a;
   t.wprep = wprep;
   const long long M = (long long)a.B * a.Ho * a.Wo;
-  dim3 grid((unsigned)((M + TC_TM - 1) / TC_TM), (unsigned)(a.Cout / NT));
+  dim3 grid((unsigned)((M + TC_TM - 1) / TC_TM), (unsigned)((a.Cout + NT - 1) / NT));
   const bool nhwc = a.src[0].nhwc != 0;
-  if (!nhwc && NT == 64 && a.Cout == 64 && a.wimg_stride == 0) {    // convolutions: A operand through TMEM
+  if (!nhwc && NT == 64 && (a.Cout == 64 || a.Cout == 32) && a.wimg_stride == 0) {    // convolutions: A operand through TMEM
     int dev = 0;
     TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
     ConvTmaArgs g;

@@ -238,3 +238,57 @@ def head_forward(x: torch.Tensor, o0: torch.Tensor, o1: torch.Tensor, params, po
         N.check(N.lib().tpspp_head_fwd(ctypes.byref(cfg), _ptr(x), _ptr(o0), _ptr(o1), table, _ptr(feat_grid),
                                        _ptr(c_prime), _ptr(score), _ptr(workspace), _stream(x)), "tpspp_head_fwd")
     return feat_grid, c_prime, score, workspace
+
+
+def stage_param_shapes():
+    """Shapes of the 81 tensors ``tpspp_stage_fwd`` takes (include/tpspp.h TPSPP_SP_*): the stage's slice of the reference
+    ``ResNetABI_v2_large`` state_dict without the int64 ``num_batches_tracked`` buffers."""
+    def bn(c):
+        return [(c,)] * 4
+    shapes = [(32, 3, 3, 3), (32,)] + bn(32)
+    for cin, planes, blocks, down in ((32, 32, 3, False), (32, 64, 4, True)):
+        for i in range(blocks):
+            ci = cin if i == 0 else planes
+            shapes += [(planes, ci, 1, 1)] + bn(planes) + [(planes, planes, 3, 3)] + bn(planes)
+            if i == 0 and down:
+                shapes += [(planes, ci, 1, 1)] + bn(planes)
+    return shapes
+
+
+def stage_forward(img: torch.Tensor, params, workspace: Optional[torch.Tensor] = None, weights_cached: bool = False):
+    """Native backbone stage in front of the rectifier (reference backbones/resnet_v2_large.py:176-191 up to the
+    ``tpsnet(x, outs)`` call; eval-mode BatchNorm folded into the convolutions), inference only.
+
+    ``img`` [B,3,H,128] fp32 CUDA; ``params``: the 81 stage tensors in state_dict order (``stage_param_shapes``).
+    Returns ``(o0 [B,32,H,W], o1 [B,32,H,W], x [B,64,H/2,W/2], workspace)``."""
+    _require_cuda("img", img, torch.float32)
+    img = img.contiguous()
+    b, c, h, w = img.shape
+    if c != 3:
+        raise RuntimeError(f"tps_pp_b200: the backbone stage takes 3-channel images, got {tuple(img.shape)}")
+    params = list(params)
+    shapes = stage_param_shapes()
+    if len(params) != N.SP_COUNT:
+        raise RuntimeError(f"tps_pp_b200: expected {N.SP_COUNT} stage tensors, got {len(params)}")
+    table = (ctypes.c_void_p * N.SP_COUNT)()
+    for i, (p, shp) in enumerate(zip(params, shapes)):
+        _require_cuda(f"stage param[{i}]", p, torch.float32)
+        if not p.is_contiguous() or tuple(p.shape) != shp:
+            raise RuntimeError(f"tps_pp_b200: stage param[{i}] must be a contiguous {shp} tensor, got {tuple(p.shape)}")
+        table[i] = p.data_ptr()
+    cfg = N.StageCfg(b, h, w, N.HEAD_TC, 0)
+    with torch.cuda.device(img.device):
+        nbytes = int(N.lib().tpspp_stage_workspace_bytes(ctypes.byref(cfg)))
+        if nbytes == 0 and b > 0:
+            raise RuntimeError("tpspp_stage_workspace_bytes failed: " + N.last_error())
+        if workspace is None or workspace.numel() < nbytes or workspace.device != img.device:
+            workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=img.device)
+            weights_cached = False
+        if weights_cached:
+            cfg.flags |= N.HEAD_FLAG_WEIGHTS_CACHED
+        o0 = torch.empty((b, 32, h, w), dtype=torch.float32, device=img.device)
+        o1 = torch.empty((b, 32, h, w), dtype=torch.float32, device=img.device)
+        x = torch.empty((b, 64, h // 2, w // 2), dtype=torch.float32, device=img.device)
+        N.check(N.lib().tpspp_stage_fwd(ctypes.byref(cfg), _ptr(img), table, _ptr(o0), _ptr(o1), _ptr(x), _ptr(workspace),
+                                        _stream(img)), "tpspp_stage_fwd")
+    return o0, o1, x, workspace
