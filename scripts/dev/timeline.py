@@ -1,6 +1,6 @@
-"""Dev tool: prints the clock64 timeline written by an INSTRUMENTED build of libtpspp.so (-DTPSPP_TIMELINE: conv_pair_kernel
-records events of CTA 0 for global chunk steps 128..191 into g_tl; `tpspp_dbg_read` copies it out).  The last
-conv_pair_kernel launch of the forward (dec3) is what remains in the buffer.  Not part of the shipped library."""
+"""Dev tool: prints the clock64 timeline written by an INSTRUMENTED build of libtpspp.so (a temporary g_tl device array +
+tpspp_dbg_read export patched into conv_tma_kernel by hand; see profiles/r02_conv_experiments.md).  The last conv_tma launch
+of the forward (dec3: 18 chunks per tile) is what remains in the buffer.  It does not work against the shipped library."""
 import sys, ctypes, torch, numpy as np
 sys.path.insert(0, '/root/repo')
 import tps_pp_b200 as T
@@ -14,11 +14,11 @@ with torch.no_grad():
     for _ in range(3): m(x, [o0, o1])
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 2048)()
-lib = N.lib()
+lib = ctypes.CDLL(N.LIB_PATH)
 print('rc', lib.tpspp_dbg_read(buf))
 a = np.array(buf[:]).reshape(64, 32)
 t0 = a[0, 0]
-print('step | MMA: top waited issued | P warp0: lds a_empty st_issued st_waited arrived | P warp15: same')
-for i in range(0, 40):
+print('chunk | MMA: top a_full w_full issued (probe bits) | P warp0: lds_done split_done a_empty st_issued arrived | TMA: top a_empty')
+for i in range(0, 44):
     r = a[i] - t0
-    print(128 + i, r[0:3].tolist(), '|', r[8:13].tolist(), '|', r[16:21].tolist())
+    print(128 + i, r[0:4].tolist(), int(a[i, 30]), '|', r[8:13].tolist(), '|', r[16:18].tolist())

@@ -342,6 +342,52 @@ __device__ __forceinline__ void mix_mma_chunk(uint32_t tmem_d, uint32_t a_base, 
     umma_ts_tf32(tmem_d, a_base + j * 8, dbh, idesc_tf, (first && j == 0) ? 0u : 1u);
   }
 }
+// The MMAs of one chunk in the CM_MIX form, the commit that releases the stage, and -- hidden behind them -- the probes of
+// the NEXT chunk's two barriers, as ONE asm block.  A barrier check costs the issuing thread ~200-250 cycles of latency even
+// when the phase completed long ago (clock64 timeline, profiles/r02_conv_experiments.md); issued as separate statements each
+// check is followed by the selp that consumes its predicate and the in-order thread stalls there, so two checks per chunk
+// were ~500 of the MMA warp's ~900 cycles per chunk -- and that loop is the critical path of the 3x3 convolutions.  Here both
+// test_wait go out back to back, the eight UTCHMMA and the UTCBAR follow without depending on them, and the predicates are
+// read only after the issue (which blocks for the MMAs' ~270 cycles anyway).
+__device__ __forceinline__ void mix_mma_chunk_probed(uint32_t d, uint32_t a_base, uint64_t bdesc0, uint32_t idesc_tf, uint32_t idesc_bf,
+                                                     uint32_t accumulate, uint32_t commit_bar, uint32_t next_a_bar, uint32_t next_w_bar,
+                                                     uint32_t next_parity, uint32_t& ok_a, uint32_t& ok_w) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pa, pw, pf, pt;\n"
+      ".reg .b64 dsc;\n"
+      ".reg .b32 ta, tc;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 pa, [%2], %4;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%3], %4;\n"
+      "setp.ne.b32 pf, %9, 0;\n"
+      "setp.eq.u32 pt, %4, %4;\n"
+      "add.u32 tc, %5, 64;\n"
+      // corrections (kind::f16, bf16 operands, K = 16 each): lo(A) x bf16(W) and bf16(A) x lo(W), k-halves 0 and 1
+      "add.u32 ta, %6, 32;\n add.u64 dsc, %7, 512;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [tc], [ta], dsc, %11, pf;\n"
+      "add.u32 ta, %6, 48;\n add.u64 dsc, %7, 768;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [tc], [ta], dsc, %11, pt;\n"
+      "add.u32 ta, %6, 40;\n add.u64 dsc, %7, 640;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [tc], [ta], dsc, %11, pt;\n"
+      "add.u32 ta, %6, 56;\n add.u64 dsc, %7, 896;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [tc], [ta], dsc, %11, pt;\n"
+      // main term (kind::tf32, K = 8 each)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%5], [%6], %7, %10, pf;\n"
+      "add.u32 ta, %6, 8;\n add.u64 dsc, %7, 128;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%5], [ta], dsc, %10, pt;\n"
+      "add.u32 ta, %6, 16;\n add.u64 dsc, %7, 256;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%5], [ta], dsc, %10, pt;\n"
+      "add.u32 ta, %6, 24;\n add.u64 dsc, %7, 384;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%5], [ta], dsc, %10, pt;\n"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n"
+      "selp.u32 %0, 1, 0, pa;\n"
+      "selp.u32 %1, 1, 0, pw;\n"
+      "}\n"
+      : "=r"(ok_a), "=r"(ok_w)
+      : "r"(next_a_bar), "r"(next_w_bar), "r"(next_parity), "r"(d), "r"(a_base), "l"(bdesc0), "r"(commit_bar), "r"(accumulate),
+        "r"(idesc_tf), "r"(idesc_bf)
+      : "memory");
+}
 // producer thread: its 16 channels (half kh of the chunk) -> the three parts of the A stage
 __device__ __forceinline__ void mix_split(const float (&v)[16], float (&hi)[16], uint32_t (&lo2)[8], uint32_t (&a2)[8]) {
 #pragma unroll
@@ -767,12 +813,25 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         const uint32_t ph = (uint32_t)((gch >> 1) & 1);
         if (!ok_a) mbar_wait_bounded(&a_full[buf], ph);
         if (!ok_w) mbar_wait_bounded(&w_full[buf], ph);
-        {
-          const uint32_t ph1 = (uint32_t)(((gch + 1) >> 1) & 1);
+        const uint32_t ph1 = (uint32_t)(((gch + 1) >> 1) & 1);
+        if (!MIX) {
           ok_a = __shfl_sync(0xffffffffu, mbar_test_wait(&a_full[buf ^ 1], ph1) ? 1 : 0, 0);
           ok_w = __shfl_sync(0xffffffffu, mbar_test_wait(&w_full[buf ^ 1], ph1) ? 1 : 0, 0);
         }
         tc_fence_after();
+        if (MIX) {
+          uint32_t pa = 0, pw = 0;
+          if (elect_one_sync()) {
+            const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE);
+            mix_mma_chunk_probed(tmem_d, tmem_d + 128 + (uint32_t)(buf * 64), umma_smem_desc(b_hi, NT * 16, 128), IDESC, IDESC_BF,
+                                 ch != 0 ? 1u : 0u, smem_u32(&a_empty[buf]), smem_u32(&a_full[buf ^ 1]), smem_u32(&w_full[buf ^ 1]),
+                                 ph1, pa, pw);
+          }
+          // the probing lane is the elected one: OR-reduce so that every lane of the warp holds its answer
+          ok_a = __any_sync(0xffffffffu, pa != 0) ? 1 : 0;
+          ok_w = __any_sync(0xffffffffu, pw != 0) ? 1 : 0;
+          continue;
+        }
         if (elect_one_sync()) {
           const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE), b_lo = b_hi + TS_B_BYTES;
           const uint32_t a_hi = tmem_d + 128 + (uint32_t)(buf * 64), a_lo = a_hi + 32;

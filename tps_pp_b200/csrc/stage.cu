@@ -44,8 +44,8 @@ struct StemArgs {
   int B, H, W;
 };
 __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
-  __shared__ float ws[27 * 32];      // [k = cin*9 + tap][cout]
-  __shared__ float bs[32];
+  __shared__ __align__(16) float ws[27 * 32];      // [k = cin*9 + tap][cout]
+  __shared__ __align__(16) float bs[32];
   for (int i = threadIdx.x; i < 27 * 32; i += 256) {
     const int k = i >> 5, n = i & 31;
     ws[i] = __ldg(a.w + n * 27 + k) * __ldg(a.scale + n);
@@ -69,12 +69,23 @@ __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
           v[c * 9 + dy * 3 + dx] = ok ? __ldg(a.img + ((size_t)b * 3 + c) * HW + (size_t)yy * a.W + xx) : 0.f;
         }
     float* po = a.out + (size_t)b * 32 * HW + r;
-#pragma unroll 4
-    for (int n = 0; n < 32; ++n) {
-      float acc = bs[n];
+    // four output channels per shared-memory load (warp-uniform LDS.128): with one LDS per FMA the kernel was bound by the
+    // shared-memory pipe (97 us at B = 256 against a 23 us HBM floor)
+    const float4* ws4 = reinterpret_cast<const float4*>(ws);
+    const float4* bs4 = reinterpret_cast<const float4*>(bs);
+#pragma unroll 1
+    for (int n4 = 0; n4 < 8; ++n4) {
+      float4 acc = bs4[n4];
 #pragma unroll
-      for (int k = 0; k < 27; ++k) acc = fmaf(v[k], ws[k * 32 + n], acc);
-      po[(size_t)n * HW] = fmaxf(acc, 0.f);
+      for (int k = 0; k < 27; ++k) {
+        const float4 w4 = ws4[k * 8 + n4];
+        acc.x = fmaf(v[k], w4.x, acc.x); acc.y = fmaf(v[k], w4.y, acc.y);
+        acc.z = fmaf(v[k], w4.z, acc.z); acc.w = fmaf(v[k], w4.w, acc.w);
+      }
+      po[(size_t)(4 * n4) * HW] = fmaxf(acc.x, 0.f);
+      po[(size_t)(4 * n4 + 1) * HW] = fmaxf(acc.y, 0.f);
+      po[(size_t)(4 * n4 + 2) * HW] = fmaxf(acc.z, 0.f);
+      po[(size_t)(4 * n4 + 3) * HW] = fmaxf(acc.w, 0.f);
     }
   }
 }
