@@ -323,7 +323,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(ConvTcArgs t) {
 //   A stage in tensor memory (64 columns): hi tf32 [0,32) | lo bf16x2 [32,48) | a bf16x2 [48,64)
 //   weight image of a chunk (16 KB):       hi tf32 8 KB    | w bf16 4 KB      | lo bf16 4 KB   (k-group-major, see wprep_kernel)
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t MIX_B_BF = 8192, MIX_B_LO = 12288;    // byte offsets of the bf16 images inside a chunk's weight image
+// byte offsets of the bf16 images inside a chunk's weight image (NT output rows: hi tf32 NT*128 B | w bf16 NT*64 B | lo bf16 NT*64 B)
+__host__ __device__ constexpr uint32_t mix_b_bf(int NT) { return (uint32_t)NT * 128u; }
+__host__ __device__ constexpr uint32_t mix_b_lo(int NT) { return (uint32_t)NT * 192u; }
+constexpr uint32_t MIX_B_BF = mix_b_bf(64), MIX_B_LO = mix_b_lo(64);
 
 // one elected lane: the 8 MMAs of a chunk (a_base = first TMEM column of the A stage, b_base = shared address of the image)
 template <int NT>
@@ -331,8 +334,8 @@ __device__ __forceinline__ void mix_mma_chunk(uint32_t tmem_d, uint32_t a_base, 
                                               bool first) {
 #pragma unroll
   for (int j = 0; j < TC_KC / 16; ++j) {        // corrections: K = 16 bf16 per MMA = two 16-byte k-groups
-    const uint64_t dbw = umma_smem_desc(b_base + MIX_B_BF + j * 2 * (NT * 16), NT * 16, 128);
-    const uint64_t dbl = umma_smem_desc(b_base + MIX_B_LO + j * 2 * (NT * 16), NT * 16, 128);
+    const uint64_t dbw = umma_smem_desc(b_base + mix_b_bf(NT) + j * 2 * (NT * 16), NT * 16, 128);
+    const uint64_t dbl = umma_smem_desc(b_base + mix_b_lo(NT) + j * 2 * (NT * 16), NT * 16, 128);
     umma_ts_f16(tmem_d + 64, a_base + 32 + j * 8, dbw, idesc_bf, (first && j == 0) ? 0u : 1u);
     umma_ts_f16(tmem_d + 64, a_base + 48 + j * 8, dbl, idesc_bf, 1u);
   }
@@ -349,9 +352,12 @@ __device__ __forceinline__ void mix_mma_chunk(uint32_t tmem_d, uint32_t a_base, 
 // were ~500 of the MMA warp's ~900 cycles per chunk -- and that loop is the critical path of the 3x3 convolutions.  Here both
 // test_wait go out back to back, the eight UTCHMMA and the UTCBAR follow without depending on them, and the predicates are
 // read only after the issue (which blocks for the MMAs' ~270 cycles anyway).
+template <int NT>
 __device__ __forceinline__ void mix_mma_chunk_probed(uint32_t d, uint32_t a_base, uint64_t bdesc0, uint32_t idesc_tf, uint32_t idesc_bf,
                                                      uint32_t accumulate, uint32_t commit_bar, uint32_t next_a_bar, uint32_t next_w_bar,
                                                      uint32_t next_parity, uint32_t& ok_a, uint32_t& ok_w) {
+  // descriptor address field is in 16-byte units: one MMA's two k-groups are 2 * NT * 16 bytes apart
+  constexpr int KS2 = 2 * NT, BW0 = 8 * NT, BL0 = 12 * NT;
   asm volatile(
       "{\n"
       ".reg .pred pa, pw, pf, pt;\n"
@@ -363,21 +369,21 @@ __device__ __forceinline__ void mix_mma_chunk_probed(uint32_t d, uint32_t a_base
       "setp.eq.u32 pt, %4, %4;\n"
       "add.u32 tc, %5, 64;\n"
       // corrections (kind::f16, bf16 operands, K = 16 each): lo(A) x bf16(W) and bf16(A) x lo(W), k-halves 0 and 1
-      "add.u32 ta, %6, 32;\n add.u64 dsc, %7, 512;\n"
+      "add.u32 ta, %6, 32;\n add.u64 dsc, %7, %12;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [tc], [ta], dsc, %11, pf;\n"
-      "add.u32 ta, %6, 48;\n add.u64 dsc, %7, 768;\n"
+      "add.u32 ta, %6, 48;\n add.u64 dsc, %7, %13;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [tc], [ta], dsc, %11, pt;\n"
-      "add.u32 ta, %6, 40;\n add.u64 dsc, %7, 640;\n"
+      "add.u32 ta, %6, 40;\n add.u64 dsc, %7, %14;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [tc], [ta], dsc, %11, pt;\n"
-      "add.u32 ta, %6, 56;\n add.u64 dsc, %7, 896;\n"
+      "add.u32 ta, %6, 56;\n add.u64 dsc, %7, %15;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [tc], [ta], dsc, %11, pt;\n"
       // main term (kind::tf32, K = 8 each)
       "tcgen05.mma.cta_group::1.kind::tf32 [%5], [%6], %7, %10, pf;\n"
-      "add.u32 ta, %6, 8;\n add.u64 dsc, %7, 128;\n"
+      "add.u32 ta, %6, 8;\n add.u64 dsc, %7, %16;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%5], [ta], dsc, %10, pt;\n"
-      "add.u32 ta, %6, 16;\n add.u64 dsc, %7, 256;\n"
+      "add.u32 ta, %6, 16;\n add.u64 dsc, %7, %17;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%5], [ta], dsc, %10, pt;\n"
-      "add.u32 ta, %6, 24;\n add.u64 dsc, %7, 384;\n"
+      "add.u32 ta, %6, 24;\n add.u64 dsc, %7, %18;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%5], [ta], dsc, %10, pt;\n"
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n"
       "selp.u32 %0, 1, 0, pa;\n"
@@ -385,7 +391,7 @@ __device__ __forceinline__ void mix_mma_chunk_probed(uint32_t d, uint32_t a_base
       "}\n"
       : "=r"(ok_a), "=r"(ok_w)
       : "r"(next_a_bar), "r"(next_w_bar), "r"(next_parity), "r"(d), "r"(a_base), "l"(bdesc0), "r"(commit_bar), "r"(accumulate),
-        "r"(idesc_tf), "r"(idesc_bf)
+        "r"(idesc_tf), "r"(idesc_bf), "n"(BW0), "n"(BL0), "n"(BW0 + KS2), "n"(BL0 + KS2), "n"(KS2), "n"(2 * KS2), "n"(3 * KS2)
       : "memory");
 }
 // producer thread: its 16 channels (half kh of the chunk) -> the three parts of the A stage
@@ -729,12 +735,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, in
 
 // BF16 = true: single-pass bf16 operands (kind::f16, fp32 accumulate) -- the opt-in TPSPP_HEAD_BF16 mode: A packs two
 // channels per TMEM column, the weight image is bf16, no correction accumulator.
-template <int KS, int MODE>
+template <int KS, int MODE, int NT = 64>
 __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_constant__ ConvTmaArgs g) {
   constexpr bool BF16 = MODE == CM_BF16, MIX = MODE == CM_MIX;
-  constexpr int NT = 64, T = KS * KS;
+  constexpr int T = KS * KS;
+  static_assert(NT == 64 || NT == 32, "64 or 32 output channels per tile");
   constexpr int XH = KS == 3 ? TM_XH : 0;
-  constexpr int W_BYTES = BF16 ? NT * TC_KC * 2 : 2 * TS_B_BYTES;
+  constexpr int W_BYTES = BF16 ? NT * TC_KC * 2 : 2 * tc_b_bytes(NT);      // weight image bytes per chunk
   constexpr int TILE_BYTES = tm_tile_bytes(KS);
   constexpr int NTB = tm_tile_bufs(KS);                          // activation tile buffers in flight
   extern __shared__ unsigned char smem_raw[];
@@ -823,7 +830,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           uint32_t pa = 0, pw = 0;
           if (elect_one_sync()) {
             const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE);
-            mix_mma_chunk_probed(tmem_d, tmem_d + 128 + (uint32_t)(buf * 64), umma_smem_desc(b_hi, NT * 16, 128), IDESC, IDESC_BF,
+            mix_mma_chunk_probed<NT>(tmem_d, tmem_d + 128 + (uint32_t)(buf * 64), umma_smem_desc(b_hi, NT * 16, 128), IDESC, IDESC_BF,
                                  ch != 0 ? 1u : 0u, smem_u32(&a_empty[buf]), smem_u32(&a_full[buf ^ 1]), smem_u32(&w_full[buf ^ 1]),
                                  ph1, pa, pw);
           }
@@ -833,7 +840,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           continue;
         }
         if (elect_one_sync()) {
-          const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE), b_lo = b_hi + TS_B_BYTES;
+          const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE), b_lo = b_hi + tc_b_bytes(NT);
           const uint32_t a_hi = tmem_d + 128 + (uint32_t)(buf * 64), a_lo = a_hi + 32;
           if (BF16) {
 #pragma unroll
@@ -978,11 +985,11 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
       const int oy = oy0 + pr, ox = ox0 + pc;
       const bool relu = a.act == CONV_ACT_RELU;
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const int cb = half * 32 + pass * 16;
-        if (cb >= a.Cout) break;                 // 32-channel layers run on a 64-row weight image padded with zeros
+      for (int pass = 0; pass < NT / 32; ++pass) {
+        const int cb = half * (NT / 2) + pass * 16;
+        if (cb >= a.Cout) break;                 // a 32-channel layer on a 64-row weight image padded with zeros
         float acc[16], part[16];
-        const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * 32 + pass * 16);
+        const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)cb;
         tmem_ld_cols<16>(taddr, acc);
         if (BF16) {
 #pragma unroll
@@ -2223,14 +2230,14 @@ __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
     float w = n < L.N ? __ldg(L.w + (size_t)n * Ktot + cin * L.taps + tap) : 0.f;
     if (L.scale != nullptr && n < L.N) w *= __ldg(L.scale + n);         // BatchNorm folded into the convolution (stage.cu)
     const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
-    if (L.bf16 == CM_MIX) {   // per chunk: hi tf32 [8 k-groups][64 n][4] | w bf16 [4 k-groups][64 n][8] | lo bf16 (same)
+    if (L.bf16 == CM_MIX) {   // per chunk: hi tf32 [8 k-groups][NT n][4] | w bf16 [4 k-groups][NT n][8] | lo bf16 (same)
       // weights are prepared once, so the tf32 part is rounded to nearest (|lo| <= 2^-11 |w|)
       const float whi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
-      unsigned char* oc = reinterpret_cast<unsigned char*>(L.out) + (size_t)(k >> 5) * 16384;
-      reinterpret_cast<float*>(oc)[((k >> 2) & 7) * (64 * 4) + n * 4 + (k & 3)] = whi;
-      const int o16 = ((k >> 3) & 3) * (64 * 8) + n * 8 + (k & 7);
-      reinterpret_cast<__nv_bfloat16*>(oc + MIX_B_BF)[o16] = __float2bfloat16_rn(w);
-      reinterpret_cast<__nv_bfloat16*>(oc + MIX_B_LO)[o16] = __float2bfloat16_rn(w - whi);
+      unsigned char* oc = reinterpret_cast<unsigned char*>(L.out) + (size_t)(k >> 5) * (size_t)(L.NT * 256);
+      reinterpret_cast<float*>(oc)[((k >> 2) & 7) * (L.NT * 4) + n * 4 + (k & 3)] = whi;
+      const int o16 = ((k >> 3) & 3) * (L.NT * 8) + n * 8 + (k & 7);
+      reinterpret_cast<__nv_bfloat16*>(oc + mix_b_bf(L.NT))[o16] = __float2bfloat16_rn(w);
+      reinterpret_cast<__nv_bfloat16*>(oc + mix_b_lo(L.NT))[o16] = __float2bfloat16_rn(w - whi);
       continue;
     }
     if (L.bf16) {   // [chunk][4 k-groups][64 n][8 bf16]
@@ -2413,7 +2420,8 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
   const bool bf16 = mode == CM_BF16;
   TPSPP_REQUIRE(NT == 64 || NT == 32, "conv_tc: column tile must be 32 or 64");
   TPSPP_REQUIRE(a.Cout % NT == 0 || (NT == 64 && a.Cout == 32), "conv_tc: Cout %d is not a multiple of the column tile %d", a.Cout, NT);
-  TPSPP_REQUIRE(KS == 1 || NT == 64, "conv_tc: 3x3 kernels are instantiated for 64-column tiles only");
+  TPSPP_REQUIRE(KS == 1 || NT == 64 || (a.Cout == 32 && mode == CM_MIX && !a.out_nhwc),
+                "conv_tc: 3x3 kernels with a 32-column tile exist for the 32-channel NCHW layers in the mixed operand mode only");
   // the TMA-staged kernels are the product path: without the driver's tensor-map encoder fail loudly instead of
   // silently dropping to the (2x slower) gather-fed kernels
   TPSPP_REQUIRE(tmap_encoder() != nullptr, "conv_tc: cuTensorMapEncodeTiled is not available from this CUDA driver");
@@ -2423,7 +2431,8 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
   const long long M = (long long)a.B * a.Ho * a.Wo;
   dim3 grid((unsigned)((M + TC_TM - 1) / TC_TM), (unsigned)((a.Cout + NT - 1) / NT));
   const bool nhwc = a.src[0].nhwc != 0;
-  if (!nhwc && NT == 64 && (a.Cout == 64 || a.Cout == 32) && a.wimg_stride == 0) {    // convolutions: A operand through TMEM
+  if (!nhwc && a.wimg_stride == 0 && ((NT == 64 && (a.Cout == 64 || a.Cout == 32)) || (NT == 32 && a.Cout == 32 && !a.out_nhwc))) {
+    // convolutions: A operand through TMEM
     int dev = 0;
     TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
     ConvTmaArgs g;
@@ -2437,9 +2446,19 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
         TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, CM_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
         TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1, CM_MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
         TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, CM_MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1, CM_TF32X3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(1)));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3, CM_MIX, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(3)));
         tma_dev = dev;
       }
       dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()));
+      if (NT == 32) {       // 32-channel layers of the backbone stage: half the weight bytes and half the B-operand reads per chunk
+        TPSPP_REQUIRE((KS == 1 && mode == CM_TF32X3) || (KS == 3 && mode == CM_MIX), "conv_tc: the 32-column tile exists for 1x1/3xTF32 and 3x3/mixed only");
+        if (KS == 1) conv_tma_kernel<1, CM_TF32X3, 32><<<pgrid, TM_THREADS, tm_smem_bytes(1), st>>>(g);
+        else conv_tma_kernel<3, CM_MIX, 32><<<pgrid, TM_THREADS, tm_smem_bytes(3), st>>>(g);
+        count_launch();
+        TPSPP_CHECK_CUDA(cudaGetLastError());
+        return TPSPP_OK;
+      }
       auto kern = KS == 1 ? (mode == CM_BF16 ? conv_tma_kernel<1, CM_BF16> : mode == CM_MIX ? conv_tma_kernel<1, CM_MIX> : conv_tma_kernel<1, CM_TF32X3>)
                           : (mode == CM_BF16 ? conv_tma_kernel<3, CM_BF16> : mode == CM_MIX ? conv_tma_kernel<3, CM_MIX> : conv_tma_kernel<3, CM_TF32X3>);
       kern<<<pgrid, TM_THREADS, tm_smem_bytes(KS), st>>>(g);
@@ -2447,6 +2466,7 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
       TPSPP_CHECK_CUDA(cudaGetLastError());
       return TPSPP_OK;
     }
+    TPSPP_REQUIRE(NT == 64, "conv_tc: the 32-column convolution tile needs a TMA-stageable geometry");
     static thread_local int ts_dev = -1;
     if (ts_dev != dev) {
       TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, CM_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));

@@ -9,8 +9,8 @@
 // itself (49 KB): o0, o1 and x are written straight into the buffers tpspp_head_fwd / tpspp_warp_fwd read.
 //   stem          3 -> 32, 3x3: 27 inputs per pixel, CUDA cores in fp32 (stem_kernel; 7 MFLOP per image)
 //   15 more convs 1x1 / 3x3, 32 or 64 channels: the head's tcgen05 engine (conv_tma_kernel / conv_ts_kernel, head_tc.cu):
-//                 split-fp32 operands (tf32 main term + bf16 corrections), 32-channel layers on a weight image padded to 64
-//                 rows, residual added before the ReLU in the epilogue (ConvArgs::skip_pre)
+//                 split-fp32 operands (tf32 main term + bf16 corrections), 32-channel layers on 32-column MMAs (half the weight
+//                 bytes per chunk), residual added before the ReLU in the epilogue (ConvArgs::skip_pre)
 #include "head.cuh"
 
 #include <string.h>
@@ -125,7 +125,7 @@ static void stage_offsets(const StageDims& d, size_t* off, size_t* total) {
   size_t sz[SW_COUNT];
   sz[SW_FOLD] = STAGE_CONVS * 128;
   size_t wp = 0;
-  for (int i = 0; i < STAGE_CONVS - 1; ++i) wp += conv_tc_wprep_floats(kStage[i].Cin, kStage[i].KS, 64);
+  for (int i = 0; i < STAGE_CONVS - 1; ++i) wp += conv_tc_wprep_floats(kStage[i].Cin, kStage[i].KS, kStage[i].Cout);
   sz[SW_WPREP] = wp;
   sz[SW_T1] = big32; sz[SW_YA] = big32; sz[SW_YB] = big32; sz[SW_T2] = big64;
   sz[SW_IDN] = small64; sz[SW_T3] = small64; sz[SW_ZA] = small64; sz[SW_ZB] = small64;
@@ -175,7 +175,7 @@ extern "C" int tpspp_stage_fwd(const tpspp_stage_cfg* cfg, const float* img, con
     float* cur = W(SW_WPREP);
     for (int i = 0; i < STAGE_CONVS - 1; ++i) {
       wp[i] = cur;
-      cur += conv_tc_wprep_floats(kStage[i].Cin, kStage[i].KS, 64);
+      cur += conv_tc_wprep_floats(kStage[i].Cin, kStage[i].KS, kStage[i].Cout);
     }
   }
   if (!(cfg->flags & TPSPP_HEAD_FLAG_WEIGHTS_CACHED)) {
@@ -194,7 +194,7 @@ extern "C" int tpspp_stage_fwd(const tpspp_stage_cfg* cfg, const float* img, con
     WPrepLayer L[STAGE_CONVS - 1];
     for (int i = 0; i < STAGE_CONVS - 1; ++i) {
       L[i].w = P[kStage[i].w_idx]; L[i].out = const_cast<float*>(wp[i]); L[i].Ctot = kStage[i].Cin;
-      L[i].taps = kStage[i].KS * kStage[i].KS; L[i].N = kStage[i].Cout; L[i].NT = 64;
+      L[i].taps = kStage[i].KS * kStage[i].KS; L[i].N = kStage[i].Cout; L[i].NT = kStage[i].Cout;     // 32-row images for the 32-channel layers
       L[i].bf16 = kStage[i].KS == 3 ? CM_MIX : CM_TF32X3;
       L[i].scale = fold + 128 * (i + 1);
     }
@@ -222,7 +222,7 @@ extern "C" int tpspp_stage_fwd(const tpspp_stage_cfg* cfg, const float* img, con
     a.B = d.B; a.Ho = Hin / c.stride; a.Wo = Win / c.stride; a.Ctot = c.Cin; a.sh = c.stride; a.sw = c.stride;
     a.pad = c.KS == 3 ? 1 : 0; a.out_nhwc = 0; a.act = relu ? CONV_ACT_RELU : CONV_ACT_NONE; a.act_scale = 1.f;
     a.Cout = c.Cout; a.wimg_stride = 0;
-    return run_conv_tc(c.KS, a, wp[i], 64, st, c.KS == 3 ? CM_MIX : CM_TF32X3);
+    return run_conv_tc(c.KS, a, wp[i], c.Cout, st, c.KS == 3 ? CM_MIX : CM_TF32X3);
   };
 #define CONV(...) do { rc = conv(__VA_ARGS__); if (rc != TPSPP_OK) return rc; } while (0)
   const int H = d.H, Wd = d.W, h = d.h, w = d.w;
