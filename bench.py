@@ -75,6 +75,14 @@ def _launch_names(n):
     return None
 
 
+def _split_ceiling(head):
+    """Tensor ceiling of the fp32-parity operand modes, TFLOP/s of algorithmic work: a product costs three tf32 MMAs in the
+    all-tf32 3xTF32 form (nominal dense tf32 1125 / 3 = 375) and one tf32 + two bf16 MMAs -- two tf32-equivalents -- in the
+    default mixed form (1125 / 2 = 562)."""
+    return {"tc": (562.5, "tf32 main term + two bf16 correction MMAs = 2 tf32-equivalents per product: nominal dense tf32 1125 / 2"),
+            "tc3x": (TF32X3_CEILING, "three tf32 MMAs per product: nominal dense tf32 1125 / 3")}.get(head, (None, None))
+
+
 def _dominant(launch_ms, batch, tpeak, tpeak_src, step_ms, head):
     names = _launch_names(len(launch_ms)) if launch_ms else None
     if names is None:
@@ -82,14 +90,26 @@ def _dominant(launch_ms, batch, tpeak, tpeak_src, step_ms, head):
     i = max(range(len(launch_ms)), key=lambda k: launch_ms[k])
     out = {"kernel": names[i], "avg_launch_ms": launch_ms[i], "share_of_step": launch_ms[i] / step_ms,
            "per_launch_ms": dict(zip(names, [round(v, 4) for v in launch_ms]))}
-    if names[i] == "enc0":
+    ceil, ceil_what = _split_ceiling(head)
+
+    def enc0_entry(ms):
         gflop = 2 * 1024 * 1728 * 64 * batch / 1e9
-        ach = gflop / launch_ms[i]                       # GFLOP / ms = TFLOP/s
-        out.update({"what": "conv_tma_kernel<3>: 3x3 conv 192->64 at 16x64", "bound": "tensor", "achieved": ach, "peak": tpeak,
-                    "unit": "TFLOP/s", "frac": ach / tpeak, "peak_source": tpeak_src, "gflop_per_launch": gflop,
-                    "frac_of_3xtf32_ceiling": ach / TF32X3_CEILING if head == "tc" else None,
-                    "ceiling_3xtf32": "nominal dense tf32 1125 TFLOP/s / 3 MMAs per product = 375 TFLOP/s (the measured cuBLAS "
-                                      "bf16 figure / 6 would be 242: this kernel exceeds it)"})
+        ach = gflop / ms                                 # GFLOP / ms = TFLOP/s
+        return {"what": "conv_tma_kernel<3>: 3x3 conv 192->64 at 16x64 (enc0)", "bound": "tensor", "avg_launch_ms": ms, "achieved": ach,
+                "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "peak_source": tpeak_src, "gflop_per_launch": gflop,
+                "frac_of_split_fp32_ceiling": ach / ceil if ceil else None, "split_fp32_ceiling": ceil, "split_fp32_ceiling_is": ceil_what}
+    if names[i] == "enc0":
+        out.update(enc0_entry(launch_ms[i]))
+    elif names[i].startswith("down_fused"):
+        # o0 + o1 + x read once, f0 / f1 / f2 / feat_grid written once: 4,718,592 B per image
+        nbytes = batch * 4 * (2 * 32 * 4096 + 64 * 1024 + 2 * 64 * 4096 + 64 * 1024 + 64 * 4096)
+        peak, peak_src = _peaks()
+        ach = nbytes / (launch_ms[i] * 1e-3) / 1e9
+        out.update({"what": "down_fused_kernel: down0 + down1 + down2 + down_feat in one pass (four 1x1 convolutions, TMEM-chained)",
+                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                    "bytes_per_launch": nbytes})
+    if "enc0" in names and names[i] != "enc0":
+        out["largest_tensor_bound_kernel"] = enc0_entry(launch_ms[names.index("enc0")])
     return out
 
 
@@ -481,13 +501,14 @@ def run_ours(args):
                          "bytes_per_launch": warp_bytes, "avg_launch_ms": warp_mean_ms,
                          "warp_only_img_per_s": B / (warp_mean_ms * 1e-3)},
             # everything before the warp (convs, DGAB, localization, score): SURVEY 8(d) counts 0.82 GFLOP/img of
-            # dense contractions.  The fp32-parity mode spends three TF32 MMAs per product (3xTF32) at half the
-            # bf16 rate: its own ceiling is the nominal tf32 rate / 3 (375 TFLOP/s); both fractions are reported.
+            # dense contractions.  The fp32-parity modes spend several MMAs per product (split operands, _split_ceiling):
+            # the fraction of the measured bf16 peak and the fraction of the mode's own ceiling are both reported.
             "roofline_head": {"kernels": "conv_tma_kernel / conv_ts_kernel / lin_tma_kernel / conv_tc_kernel / dgab_warp_kernel / loc_p1_kernel / cbam_kernel",
                               "bound": "tensor", "achieved": HEAD_GFLOP_PER_IMG * B / head_ms, "peak": tpeak,
                               "unit": "TFLOP/s", "frac": HEAD_GFLOP_PER_IMG * B / head_ms / tpeak,
-                              "frac_of_3xtf32_ceiling": (HEAD_GFLOP_PER_IMG * B / head_ms / TF32X3_CEILING
-                                                         if args.head == "tc" else None),
+                              "frac_of_split_fp32_ceiling": (HEAD_GFLOP_PER_IMG * B / head_ms / _split_ceiling(args.head)[0]
+                                                             if _split_ceiling(args.head)[0] else None),
+                              "split_fp32_ceiling": _split_ceiling(args.head)[0], "split_fp32_ceiling_is": _split_ceiling(args.head)[1],
                               "peak_source": tpeak_src, "gflop_per_img": HEAD_GFLOP_PER_IMG,
                               "avg_head_ms": head_ms, "share_of_step": head_ms / (total_ms / args.steps)},
             # the single largest kernel of the step, timed live (see above): enc0 = 3x3 conv 192 -> 64 at 16x64,
