@@ -264,6 +264,24 @@ TPSPP_API size_t tpspp_stage_workspace_bytes(const tpspp_stage_cfg* cfg);
 TPSPP_API int tpspp_stage_fwd(const tpspp_stage_cfg* cfg, const float* img, const float* const* params, float* o0, float* o1,
                               float* x, void* workspace, tpspp_stream_t stream);
 
+/* ---- Training-path convolution: forward and backward of one ConvModule (conv + bias + ReLU; reference
+ * tps_pp.py:126-131,149-154,538-548), so that autograd of the rectifier's convolutions runs on native kernels
+ * (north_star (4); the reference side is torch autograd of nn.Conv2d + ReLU).  NCHW fp32, 64 output channels. */
+typedef struct {
+  int32_t batch, cin;       /* cin: 32 or a multiple of 64                                        */
+  int32_t height, width;    /* input size; output = input / stride                                */
+  int32_t ksize;            /* 1 (stride 1) or 3 (pad 1)                                          */
+  int32_t stride_h, stride_w; /* (1,1), (2,2) or (2,1)                                            */
+  int32_t relu;             /* 1: y = relu(conv + b), 0: y = conv + b                             */
+} tpspp_conv_cfg;
+TPSPP_API size_t tpspp_conv_workspace_bytes(const tpspp_conv_cfg* cfg);   /* covers both calls */
+/* y [B,64,H/sh,W/sw] = act(conv(x [B,cin,H,W], w [64,cin,k,k]) + bias [64]) */
+TPSPP_API int tpspp_conv_fwd(const tpspp_conv_cfg* cfg, const float* x, const float* w, const float* bias, float* y,
+                             void* workspace, tpspp_stream_t stream);
+/* gradients of the above given y (the saved output) and gy: gx [B,cin,H,W], gw [64,cin,k,k], gb [64]; each may be NULL */
+TPSPP_API int tpspp_conv_bwd(const tpspp_conv_cfg* cfg, const float* x, const float* w, const float* y, const float* gy,
+                             float* gx, float* gw, float* gb, void* workspace, tpspp_stream_t stream);
+
 /* Number of kernel launches the most recent call on this host thread enqueued
  * (bench.py uses it to report gpu_launches). */
 TPSPP_API int tpspp_last_launch_count(void);

@@ -115,16 +115,27 @@ def test_tps_pp_random_init_matches_oracle(native_lib):
     assert mx(r["mp_img"], r64["mp_img"]) <= max(1e-5, FLOOR_K * mx(r32["mp_img"], r64["mp_img"]))
 
 
-def test_tps_pp_autograd_reaches_every_parameter(native_lib):
-    """Training contract: grads flow to batch_img, outs[*] and every parameter."""
+@pytest.mark.parametrize("train_convs,batch", [("native", 4), ("native", 2), ("library", 2)])
+def test_tps_pp_autograd_reaches_every_parameter(native_lib, train_convs, batch):
+    """Training contract: grads flow to batch_img, outs[*] and every parameter -- with the 14 ConvModules on the
+    native forward/backward kernels (batch 4: all of them; batch 2: the deepest layers fall back to cuDNN) and on cuDNN."""
     sd = O.trained_like_state(3)
     m = T.TPS_PP().to(DEV)
     m.load_state_dict(sd, strict=True)
-    x, o0, o1 = O.synthetic_tpspp_inputs(2, 1)
+    m.train_convs = train_convs
+    x, o0, o1 = O.synthetic_tpspp_inputs(batch, 1)
     tx = torch.from_numpy(x).to(DEV).requires_grad_()
     t0 = torch.from_numpy(o0).to(DEV).requires_grad_()
     t1 = torch.from_numpy(o1).to(DEV).requires_grad_()
     r = m(tx, [t0, t1])
+    ts = m.training_stages
+    assert ts["convs_native"] + ts["convs_library"] == 14
+    if train_convs == "library":
+        assert ts["convs_native"] == 0
+    elif batch == 4:
+        assert ts["convs_library"] == 0, ts
+    else:
+        assert ts["convs_native"] >= 10, ts
     r["output"].square().mean().backward()
     for name, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
@@ -154,12 +165,20 @@ def test_tps_pp_autograd_reaches_every_parameter(native_lib):
         run().square().mean().backward()
     finally:
         O._t = orig
+    worst = ("", 0.0)
     for name, p in m.named_parameters():
         ref = st[name].grad
         scale = max(float(ref.abs().max()), 1e-12)
-        # fp32 head + the TPS solve's 1e2-1e3x rounding amplification: percent-level agreement
-        assert mx(p.grad, ref) <= 3e-2 * scale + 1e-9, name
-    assert mx(tx.grad, px.grad) <= 3e-2 * float(px.grad.abs().max())
+        ratio = mx(p.grad, ref) / scale
+        if ratio > worst[1]:
+            worst = (name, ratio)
+    print(f"autograd [{train_convs}, batch {batch}]: worst parameter-gradient error {worst[1]:.3e} of its scale ({worst[0]}); "
+          f"d batch_img {mx(tx.grad, px.grad) / float(px.grad.abs().max()):.3e}")
+    # fp32 head + the TPS solve's 1e2-1e3x rounding amplification + ReLU masks that differ between an fp32 and an
+    # fp64 forward at pixels within rounding of zero: percent-level agreement (each convolution alone is checked to 1e-4 in
+    # tests/test_conv_train_gpu.py)
+    assert worst[1] <= 5e-2, worst
+    assert mx(tx.grad, px.grad) <= 5e-2 * float(px.grad.abs().max())
 
 
 def test_tps_preprocessor_like_reference_test(native_lib):

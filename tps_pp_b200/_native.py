@@ -41,6 +41,12 @@ class StageCfg(Structure):
     _fields_ = [("batch", c_int32), ("height", c_int32), ("width", c_int32), ("precision", c_int32), ("flags", c_int32)]
 
 
+class ConvCfg(Structure):
+    """Mirror of ``tpspp_conv_cfg`` (include/tpspp.h)."""
+    _fields_ = [("batch", c_int32), ("cin", c_int32), ("height", c_int32), ("width", c_int32), ("ksize", c_int32),
+                ("stride_h", c_int32), ("stride_w", c_int32), ("relu", c_int32)]
+
+
 SP_COUNT = 81
 HEAD_FP32, HEAD_TC, HEAD_BF16 = 0, 1, 2
 HEAD_FLAG_WEIGHTS_CACHED = 1
@@ -67,6 +73,9 @@ _SIGNATURES = {
     "tpspp_head_workspace_offsets": (c_int, [POINTER(HeadCfg), POINTER(c_size_t)]),
     "tpspp_head_fwd": (c_int, [POINTER(HeadCfg), c_void_p, c_void_p, c_void_p, POINTER(c_void_p),
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tpspp_conv_workspace_bytes": (c_size_t, [POINTER(ConvCfg)]),
+    "tpspp_conv_fwd": (c_int, [POINTER(ConvCfg)] + [c_void_p] * 6),
+    "tpspp_conv_bwd": (c_int, [POINTER(ConvCfg)] + [c_void_p] * 9),
     "tpspp_stage_workspace_bytes": (c_size_t, [POINTER(StageCfg)]),
     "tpspp_stage_fwd": (c_int, [POINTER(StageCfg), c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),

@@ -1090,7 +1090,7 @@ static int run_conv(int KS, ConvSrc s0, ConvSrc s1, ConvSrc s2, const float* w, 
                     const float* wprep = nullptr, int mode = CM_TF32X3) {
   ConvArgs a;
   a.out_nhwc = out_nhwc;
-  a.act = CONV_ACT_RELU; a.act_scale = 1.f; a.Cout = 64; a.wimg_stride = 0; a.skip_pre = 0;
+  a.act = CONV_ACT_RELU; a.act_scale = 1.f; a.Cout = 64; a.wimg_stride = 0; a.skip_pre = 0; a.out_cstride = 0; a.zi = 0;
   a.src[0] = s0; a.src[1] = s1; a.src[2] = s2;
   a.weight = w; a.bias = bias; a.skip = skip; a.out = out;
   a.B = B; a.Ho = Ho; a.Wo = Wo; a.Ctot = s0.C + s1.C + s2.C; a.sh = sh; a.sw = sw; a.pad = (KS == 3) ? 1 : 0;
@@ -1187,7 +1187,7 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     float* cur = W(TPSPP_WS_WPREP);
     for (int i = 0; i < kNumTcLayers; ++i) {
       L[i].w = P[kConvLayers[i].w_idx]; L[i].out = cur; L[i].Ctot = kConvLayers[i].Ctot;
-      L[i].taps = kConvLayers[i].KS * kConvLayers[i].KS; L[i].N = kConvLayers[i].N; L[i].NT = kConvLayers[i].NT; L[i].scale = nullptr;
+      L[i].taps = kConvLayers[i].KS * kConvLayers[i].KS; L[i].N = kConvLayers[i].N; L[i].NT = kConvLayers[i].NT; L[i].scale = nullptr; L[i].dg_cin = 0; L[i].dg_ci0 = 0;
       L[i].bf16 = i < 14 ? cmode[i] : CM_TF32X3;
       wp[i] = cur;
       cur += conv_tc_wprep_floats(kConvLayers[i].Ctot, kConvLayers[i].KS, kConvLayers[i].N);

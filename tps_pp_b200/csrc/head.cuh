@@ -23,6 +23,8 @@ struct ConvArgs {
   int Cout;              // channels of the output tensor (column blocks of NT go to grid.y)
   long long wimg_stride; // floats between per-image weight images (0: weights shared by all images)
   int skip_pre;          // 1: `skip` is added before the activation (residual block), 0: after it (MSFA decoder)
+  int out_cstride;       // channels per image of the out / skip tensors when this launch writes a channel slice (0: = Cout)
+  int zi;                // 1: up-sampled sources are ZERO-INSERTED instead of nearest (data gradient of a strided convolution)
 };
 enum { CONV_ACT_RELU = 0, CONV_ACT_NONE = 1, CONV_ACT_GELU = 2, CONV_ACT_TANH = 3 };
 // operand mode of a tensor-core convolution (head_tc.cu): 3xTF32 | single-pass bf16 | tf32 main term + bf16 corrections
@@ -50,6 +52,7 @@ struct WPrepLayer {
   float* out;
   int Ctot, taps, N, NT;
   const float* scale; // per-output-row factor applied before the split (BatchNorm folding), or null
+  int dg_cin, dg_ci0; // dgrad image of a forward weight [Ctot out][dg_cin in][taps]: rows = input channels dg_ci0.. (dg_cin = 0: forward)
   int bf16;         // CM_*: 1 = single bf16 image [chunk][4 k-groups][64][8], 2 = tf32 hi | bf16 w | bf16 lo, 0 = fp32 hi|lo pair
 };
 constexpr int WPREP_MAX_LAYERS = 20;

@@ -560,7 +560,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
     auto gather = [&](float (&v)[16]) {
       const int dy = tap / KS, dx = tap - dy * KS;
       const int iy = gq.y + dy, ix = gq.z + dx;
-      const bool ok = gq.w && iy >= 0 && ix >= 0 && iy < lim_y && ix < lim_x;
+      bool ok = gq.w && iy >= 0 && ix >= 0 && iy < lim_y && ix < lim_x;
+      // zero insertion (the data gradient of a strided convolution is a stride-1 convolution over the gradient with zeros
+      // between its pixels): only even positions of an up-sampled axis carry data
+      if (a.zi && (((s_uh == 2) && (iy & 1)) || ((s_uw == 2) && (ix & 1)))) ok = false;
       const int sy = (s_uh == 2) ? (iy >> 1) : iy, sx = (s_uw == 2) ? (ix >> 1) : ix;
       const float* q = t_base + (size_t)c_in * s_plane + (ok ? sy * s_W + sx : 0);
       // the 16 channel planes are a compile-time stride apart for the plane sizes of this network: one LDG with an
@@ -670,7 +673,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
           const float4 bs = b4[j >> 2];
           acc[j] += bs.x; acc[j + 1] += bs.y; acc[j + 2] += bs.z; acc[j + 3] += bs.w;
         }
-        const size_t o0 = ((size_t)b * a.Cout + cb) * HoWo + rem;
+        const size_t o0 = ((size_t)b * (a.out_cstride ? a.out_cstride : a.Cout) + cb) * HoWo + rem;
         if (cb >= a.Cout) continue;
         if (a.skip != nullptr && a.skip_pre) {
           const float* sk = a.skip + o0;
@@ -926,6 +929,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           const int tap = grp * TG + tg;
           const int dy = tap / KS, dx = tap - dy * KS;
           int iy = oy0 + pr + dy - a.pad, ix = S * (ox0 + pc) + dx - a.pad;
+          const bool zero = a.zi && up && ((iy | ix) & 1);       // zero-inserted source (data gradient of a stride-2 convolution)
           if (up) { iy >>= 1; ix >>= 1; }
           // stride 2: the box of this filter row already holds input rows 2 oy + dy - pad, one per tile row
           // 32-bit shared-memory addresses: with generic pointers the 16 channel loads cost ~6 instructions each
@@ -934,6 +938,10 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(qa + (uint32_t)i * cstride));
+          if (zero) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
           // split first, wait second: only the tcgen05.st sit between "stage free" and "stage full"
           float mhi[16];
           uint32_t mlo2[8], ma2[8];
@@ -1004,7 +1012,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           acc[j] += part[j] + bs.x; acc[j + 1] += part[j + 1] + bs.y; acc[j + 2] += part[j + 2] + bs.z; acc[j + 3] += part[j + 3] + bs.w;
         }
         if (a.skip != nullptr && a.skip_pre) {   // residual block: the identity is added BEFORE the activation
-          const float* sk = a.skip + ((size_t)img * a.Cout + cb) * HoWo + (size_t)oy * a.Wo + ox;
+          const float* sk = a.skip + ((size_t)img * (a.out_cstride ? a.out_cstride : a.Cout) + cb) * HoWo + (size_t)oy * a.Wo + ox;
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] += __ldg(sk + (size_t)j * HoWo);
         }
@@ -1015,7 +1023,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = tc_act(acc[j], a.act, a.act_scale);
         }
-        const size_t o0 = ((size_t)img * a.Cout + cb) * HoWo + (size_t)oy * a.Wo + ox;
+        const size_t o0 = ((size_t)img * (a.out_cstride ? a.out_cstride : a.Cout) + cb) * HoWo + (size_t)oy * a.Wo + ox;
         if (a.skip != nullptr && !a.skip_pre) {
           const float* sk = a.skip + o0;
 #pragma unroll
@@ -2227,7 +2235,13 @@ __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
   for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
     const int n = i / Ktot, k = i - n * Ktot;
     const int tap = k / L.Ctot, cin = k - tap * L.Ctot;
-    float w = n < L.N ? __ldg(L.w + (size_t)n * Ktot + cin * L.taps + tap) : 0.f;
+    float w = 0.f;
+    if (n < L.N) {
+      // forward: row n = output channel, k = tap * Ctot + cin.  dgrad (data gradient as a convolution over the output gradient):
+      // row n = INPUT channel dg_ci0 + n of the forward layer, contraction over its Ctot OUTPUT channels, taps mirrored
+      w = L.dg_cin == 0 ? __ldg(L.w + (size_t)n * Ktot + cin * L.taps + tap)
+                        : __ldg(L.w + ((size_t)cin * L.dg_cin + L.dg_ci0 + n) * L.taps + (L.taps - 1 - tap));
+    }
     if (L.scale != nullptr && n < L.N) w *= __ldg(L.scale + n);         // BatchNorm folded into the convolution (stage.cu)
     const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
     if (L.bf16 == CM_MIX) {   // per chunk: hi tf32 [8 k-groups][NT n][4] | w bf16 [4 k-groups][NT n][8] | lo bf16 (same)

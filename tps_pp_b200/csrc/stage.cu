@@ -196,7 +196,7 @@ extern "C" int tpspp_stage_fwd(const tpspp_stage_cfg* cfg, const float* img, con
       L[i].w = P[kStage[i].w_idx]; L[i].out = const_cast<float*>(wp[i]); L[i].Ctot = kStage[i].Cin;
       L[i].taps = kStage[i].KS * kStage[i].KS; L[i].N = kStage[i].Cout; L[i].NT = kStage[i].Cout;     // 32-row images for the 32-channel layers
       L[i].bf16 = kStage[i].KS == 3 ? CM_MIX : CM_TF32X3;
-      L[i].scale = fold + 128 * (i + 1);
+      L[i].scale = fold + 128 * (i + 1); L[i].dg_cin = 0; L[i].dg_ci0 = 0;
     }
     rc = conv_tc_prepare_weights(L, STAGE_CONVS - 1, st);
     if (rc != TPSPP_OK) return rc;

@@ -292,3 +292,72 @@ def stage_forward(img: torch.Tensor, params, workspace: Optional[torch.Tensor] =
         N.check(N.lib().tpspp_stage_fwd(ctypes.byref(cfg), _ptr(img), table, _ptr(o0), _ptr(o1), _ptr(x), _ptr(workspace),
                                         _stream(img)), "tpspp_stage_fwd")
     return o0, o1, x, workspace
+
+
+class _ConvRelu(torch.autograd.Function):
+    """One ``ConvModule`` (conv + bias + ReLU, reference tps_pp.py:126-131,149-154,538-548) with native forward AND backward
+    (``tpspp_conv_fwd`` / ``tpspp_conv_bwd``): the training-path counterpart of the fused inference head."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, relu):
+        _require_cuda("x", x, torch.float32)
+        _require_cuda("weight", weight, torch.float32)
+        _require_cuda("bias", bias, torch.float32)
+        x = x.contiguous(); weight = weight.contiguous(); bias = bias.contiguous()
+        b, cin, h, w = x.shape
+        k = weight.shape[-1]
+        if weight.shape[0] != 64 or weight.shape[1] != cin or weight.shape[2] != k:
+            raise RuntimeError(f"tps_pp_b200: conv weight must be [64,{cin},k,k], got {tuple(weight.shape)}")
+        sh, sw = (stride, stride) if isinstance(stride, int) else stride
+        cfg = N.ConvCfg(b, cin, h, w, k, sh, sw, 1 if relu else 0)
+        with torch.cuda.device(x.device):
+            nbytes = int(N.lib().tpspp_conv_workspace_bytes(ctypes.byref(cfg)))
+            if nbytes == 0 and b > 0:
+                raise RuntimeError("tpspp_conv_workspace_bytes failed: " + N.last_error())
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+            y = torch.empty((b, 64, h // sh, w // sw), dtype=torch.float32, device=x.device)
+            N.check(N.lib().tpspp_conv_fwd(ctypes.byref(cfg), _ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(ws), _stream(x)),
+                    "tpspp_conv_fwd")
+        ctx.save_for_backward(x, weight, y)
+        ctx.cfg = (b, cin, h, w, k, sh, sw, 1 if relu else 0)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        cfg = N.ConvCfg(*ctx.cfg)
+        gy = gy.contiguous()
+        need = ctx.needs_input_grad
+        gx = torch.empty_like(x) if need[0] else None
+        gw = torch.empty_like(weight) if need[1] else None
+        gb = torch.empty(64, dtype=torch.float32, device=x.device) if need[2] else None
+        with torch.cuda.device(x.device):
+            nbytes = int(N.lib().tpspp_conv_workspace_bytes(ctypes.byref(cfg)))
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+            N.check(N.lib().tpspp_conv_bwd(ctypes.byref(cfg), _ptr(x), _ptr(weight), _ptr(y), _ptr(gy), _ptr(gx), _ptr(gw),
+                                           _ptr(gb), _ptr(ws), _stream(x)), "tpspp_conv_bwd")
+        return gx, gw, gb, None, None
+
+
+def conv_relu_supported(x: torch.Tensor, weight: torch.Tensor, stride=1) -> bool:
+    """Geometry the native training convolution covers (include/tpspp.h ``tpspp_conv_cfg``)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 4 and weight.dim() == 4):
+        return False
+    b, cin, h, w = x.shape
+    k = weight.shape[-1]
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    if weight.shape[0] != 64 or weight.shape[1] != cin or weight.shape[2] != k or k not in (1, 3):
+        return False
+    if cin % 32 or (cin > 64 and cin % 64) or cin > 512:
+        return False
+    if (sh, sw) != (1, 1) and not (k == 3 and sh == 2 and sw in (1, 2)):
+        return False
+    if h % sh or w % sw:
+        return False
+    ho, wo = h // sh, w // sw
+    return b > 0 and (b * ho * wo) % 128 == 0 and (b * h * w) % 128 == 0 and (ho * wo) % 32 == 0 and (h * w) % 4 == 0
+
+
+def conv_relu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride=1, relu: bool = True) -> torch.Tensor:
+    """``relu(conv2d(x, weight, bias, stride, padding=k//2))`` with 64 output channels on the native kernels, differentiable."""
+    return _ConvRelu.apply(x, weight, bias, stride, relu)

@@ -155,6 +155,9 @@ class TPS_PP(_BaseModule):
         # "auto": native kernels whenever autograd is not recording (inference); the library-op head is kept
         # for training, where its backward comes from torch autograd (the warp's backward is native either way)
         self.head_impl = "auto"
+        # convolutions of the TRAINING path (autograd recording): "native" = tpspp_conv_fwd/bwd, "library" = cuDNN
+        self.train_convs = "native"
+        self._train_native_convs = self._train_library_convs = 0
         self._last_head_native = None
         # tcgen05 3xTF32 convolutions (fp32-level accuracy); N.HEAD_FP32 = CUDA-core only
         self.head_precision = N.HEAD_TC
@@ -169,8 +172,14 @@ class TPS_PP(_BaseModule):
         return self.get_parameter(name)
 
     def _conv_relu(self, prefix: str, x, stride=1, padding=0):
-        return F.relu(F.conv2d(x, self._p(prefix + ".conv.weight"), self._p(prefix + ".conv.bias"),
-                               stride=stride, padding=padding))
+        w, b = self._p(prefix + ".conv.weight"), self._p(prefix + ".conv.bias")
+        # training path: native forward AND backward of the ConvModule (tpspp_conv_fwd / tpspp_conv_bwd) where its geometry
+        # is covered; cuDNN otherwise (tiny batches of the deepest layers)
+        if self.train_convs == "native" and w.shape[0] == 64 and TF.conv_relu_supported(x, w, stride):
+            self._train_native_convs += 1
+            return TF.conv_relu(x, w, b, stride)
+        self._train_library_convs += 1
+        return F.relu(F.conv2d(x, w, b, stride=stride, padding=padding))
 
     def _down(self, x, o0, o1):
         """tps_pp.py:581-585 (+ :560-562)."""
@@ -254,6 +263,11 @@ class TPS_PP(_BaseModule):
         nat = self._last_head_native if self._last_head_native is not None else self._use_native_head(None)
         return {"warp": True, "down": nat, "msfa": nat, "cbam": nat, "dgab": nat, "localization": nat, "score": nat}
 
+    @property
+    def training_stages(self):
+        """What the last autograd-recording forward ran its 14 ConvModules on: (native launches, cuDNN launches)."""
+        return {"convs_native": self._train_native_convs, "convs_library": self._train_library_convs}
+
     def _use_native_head(self, batch_img) -> bool:
         if self.head_impl == "native":
             return True
@@ -285,6 +299,7 @@ class TPS_PP(_BaseModule):
             self._last_head_launches = N.last_launch_count()
             return fg, cp, sc
         self._last_head_launches = 0
+        self._train_native_convs = self._train_library_convs = 0
         # library stages must not drop to TF32: C' feeds a solve that amplifies rounding 1e2-1e3x
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False), _matmul_fp32():
             feat_cat, feat_grid = self._down(batch_img, outs[0], outs[1])
