@@ -23,8 +23,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, steps, warm = 128, 10, 3
+    convs = "library" if "--library-convs" in sys.argv else "native"
     m = T.TPS_PP().to(dev).train()
+    m.train_convs = convs
     _trained_like_(m)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     bucket = PAR.GradBucket(m.parameters())
     opt = torch.optim.Adam(m.parameters(), lr=1e-4)      # schedule_adam_step_12e.py:1
     g = torch.Generator(device=dev).manual_seed(rank)
@@ -32,8 +36,8 @@ def main():
     o0 = torch.randn((B, 32, 32, 128), device=dev, generator=g)
     o1 = torch.randn((B, 32, 32, 128), device=dev, generator=g)
     tgt = torch.randn((B, 64, 16, 64), device=dev, generator=g)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    t_total = t_ar = 0.0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    t_total = t_ar = t_fwd = 0.0
     for it in range(warm + steps):
         if world > 1:
             dist.barrier()
@@ -42,6 +46,7 @@ def main():
         bucket.zero()
         r = m(x, [o0, o1])
         loss = (r["output"] - tgt).square().mean()
+        ev[4].record()
         loss.backward()
         ev[1].record()
         bucket.all_reduce_mean()
@@ -50,15 +55,16 @@ def main():
         ev[3].record()
         torch.cuda.synchronize()
         if it >= warm:
-            t_total += ev[0].elapsed_time(ev[3]); t_ar += ev[1].elapsed_time(ev[2])
-    t = torch.tensor([t_total / steps, t_ar / steps], device=dev, dtype=torch.float64)
+            t_total += ev[0].elapsed_time(ev[3]); t_ar += ev[1].elapsed_time(ev[2]); t_fwd += ev[0].elapsed_time(ev[4])
+    t = torch.tensor([t_total / steps, t_ar / steps, t_fwd / steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"metric": "tps_pp_train_step", "n_gpus": world, "batch_per_gpu": B, "ms_per_step": t[0].item(),
-                          "allreduce_ms": t[1].item(), "img_per_s": world * B / (t[0].item() * 1e-3),
-                          "grad_bucket_bytes": bucket.flat.numel() * 4, "loss": float(loss),
-                          "head": "library ops + autograd (fp32), warp fwd/bwd native"}))
+                          "allreduce_ms": t[1].item(), "forward_ms": t[2].item(), "img_per_s": world * B / (t[0].item() * 1e-3),
+                          "grad_bucket_bytes": bucket.flat.numel() * 4, "loss": float(loss), "training_stages": m.training_stages,
+                          "head": f"14 ConvModules: {convs} forward+backward (fp32-level); CBAM/DGAB/localisation/score: torch ops + autograd "
+                                  "(fp32, TF32 off); warp fwd/bwd native"}))
     if world > 1:
         dist.destroy_process_group()
 

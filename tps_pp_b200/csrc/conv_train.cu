@@ -8,11 +8,13 @@
 //                                                             weight image transposed and mirrored (wprep dg_*), 64 input
 //                                                             channels per launch; a strided forward becomes a convolution
 //                                                             over the ZERO-INSERTED gradient (ConvArgs::zi)
-//             gw[co][ci][t] = sum_{b,p} g[b,co,p] x[b,ci,p+t]  wgrad_kernel: fp32 FMA outer products (64 x 64 tile per tap and
-//                                                             pixel split, deterministic two-stage reduction)
+//             gw[co][ci][t] = sum_{b,p} g[b,co,p] x[b,ci,p+t]  wgrad_kernel: warp-level tf32 MMAs with the 3xTF32 split (64 x 64 tile
+//                                                             per tap and pixel split, deterministic two-stage reduction)
 // Geometry: NCHW fp32, Cout = 64, Cin a multiple of 32, 1x1 (stride 1) or 3x3 (pad 1; stride 1, 2 or (2,1)).
 #include "head.cuh"
+#include "tc.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace tpspp {
@@ -53,16 +55,26 @@ __global__ void bias_finalize_kernel(const float* __restrict__ part, float* __re
   gb[c] = acc;
 }
 
-// ---- weight gradient: one block = one (tap, 64-input-channel block, pixel split): a 64 x 64 tile of outer products over its
-//      32-pixel chunks.  Shared tiles are stored pixel-major ([k][channel], pitch 68) so that a thread reads the four output
-//      and the four input channels of its 4 x 4 register tile with one LDS.128 each per pixel: 2 loads per 16 FMAs. ----
+// ---- weight gradient: one block = one (tap, 64-input-channel block, pixel split): a 64 x 64 tile gw[co][ci] += g[co][p] x[ci][p]
+//      over its 32-pixel chunks, on the warp-level tensor-core path (mma.sync m16n8k8 tf32, fp32 accumulators in registers)
+//      with the 3xTF32 split of both operands done on the fragments (hi*hi + lo*hi + hi*lo).  The first version (fp32 FMA outer
+//      products, 4 x 4 register tiles) was bound by shared-memory loads: 5.6 ms of a 14.8 ms training step at batch 128.
+//      Shared tiles are pixel-major [k][channel ^ f(k)] with f(k) = (k % 4) * 8 + k / 4: the staging stores of a warp (32 pixels
+//      of one channel) and its fragment loads (8 channels x 4 pixels) both fall into 32 distinct banks.  tcgen05 is not used here on purpose: K = pixels would need the transposed A staging and its own
+//      hand-off pipeline for 1 % of the training step's FLOP budget. ----
 struct WgradArgs {
   const float *g, *x;          // g [B,64,Ho,Wo], x [B,Cin,H,W]
   float* part;                 // [splits][T * Cin * 64] as [tap][ci][co]
   int B, Cin, H, W, Ho, Wo, KS, sh, sw, splits;
 };
-constexpr int WG_PITCH = 68;
-__global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
+constexpr int WG_PITCH = 64;
+__device__ __forceinline__ int wg_swz(int k) { return ((k & 3) << 3) | (k >> 2); }
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__global__ void __launch_bounds__(256, 3) wgrad_kernel(WgradArgs a) {
   __shared__ __align__(16) float Gs[32 * WG_PITCH];
   __shared__ __align__(16) float Xs[32 * WG_PITCH];
   const int T = a.KS * a.KS;
@@ -72,14 +84,18 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
   const long long nchunks = (long long)a.B * HoWo / 32;
   const long long c0 = nchunks * sp / a.splits, c1 = nchunks * (sp + 1) / a.splits;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int co4 = (tid >> 4) * 4, ci4 = (tid & 15) * 4;
   const int cw = a.Cin - cib * 64 < 64 ? a.Cin - cib * 64 : 64;     // input channels of this block (32 for the 32-channel layers)
+  // warp tile: 16 output channels x 32 input channels (four n-tiles of 8); fragment coordinates g = lane / 4, t = lane % 4
+  const int co0 = (warp & 3) * 16, ci0 = (warp >> 2) * 32;
+  const int fg = lane >> 2, ft = lane & 3;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (long long ch = c0; ch < c1; ++ch) {
+  // global loads of chunk ch + 1 are issued before the MMAs of chunk ch (registers), so their latency hides behind them
+  float gr[8], xr[8];
+  auto fetch = [&](long long ch) {
     const long long p0 = ch * 32;
     const int b = (int)(p0 / HoWo);
     const int p = (int)(p0 - (long long)b * HoWo) + lane;       // this lane's output pixel
@@ -88,39 +104,267 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
     const bool ok = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
     const float* gp = a.g + (size_t)b * 64 * HoWo + p;
     const float* xp = a.x + ((size_t)b * a.Cin + cib * 64) * HW + (ok ? iy * a.W + ix : 0);
-    __syncthreads();                                             // the previous chunk's tiles are no longer read
 #pragma unroll
     for (int r = 0; r < 8; ++r) {                                // warp w stages channels w, w + 8, ...: lanes = pixels, coalesced
       const int c = warp + 8 * r;
-      Gs[lane * WG_PITCH + c] = __ldg(gp + (size_t)c * HoWo);
-      Xs[lane * WG_PITCH + c] = (ok && c < cw) ? __ldg(xp + (size_t)c * HW) : 0.f;
+      gr[r] = __ldg(gp + (size_t)c * HoWo);
+      xr[r] = (ok && c < cw) ? __ldg(xp + (size_t)c * HW) : 0.f;
+    }
+  };
+  if (c0 < c1) fetch(c0);
+  for (long long ch = c0; ch < c1; ++ch) {
+    __syncthreads();                                             // the previous chunk's tiles are no longer read
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int c = warp + 8 * r;
+      Gs[lane * WG_PITCH + (c ^ wg_swz(lane))] = gr[r];
+      Xs[lane * WG_PITCH + (c ^ wg_swz(lane))] = xr[r];
     }
     __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      const float4 gv = *reinterpret_cast<const float4*>(Gs + k * WG_PITCH + co4);
-      const float4 xv = *reinterpret_cast<const float4*>(Xs + k * WG_PITCH + ci4);
-      const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (ch + 1 < c1) fetch(ch + 1);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int ks = 0; ks < 4; ++ks) {                             // 8 pixels per mma
+      const int k0 = ks * 8 + ft, k1 = k0 + 4;
+      const int s0 = wg_swz(k0), s1 = wg_swz(k1);
+      const float* g0 = Gs + k0 * WG_PITCH;
+      const float* g1 = Gs + k1 * WG_PITCH;
+      const float av[4] = {g0[(co0 + fg) ^ s0], g0[(co0 + fg + 8) ^ s0], g1[(co0 + fg) ^ s1], g1[(co0 + fg + 8) ^ s1]};   // (g,t) (g+8,t) (g,t+4) (g+8,t+4)
+      uint32_t ah[4], al[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gg[i], xx[j], acc[i][j]);
+      for (int i = 0; i < 4; ++i) {
+        ah[i] = __float_as_uint(av[i]) & 0xFFFFE000u;
+        al[i] = __float_as_uint(av[i] - __uint_as_float(ah[i]));
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int cc = ci0 + nt * 8 + fg;
+        const float bv[2] = {Xs[k0 * WG_PITCH + (cc ^ s0)], Xs[k1 * WG_PITCH + (cc ^ s1)]};   // (k = t, n = g), (k = t + 4, n = g)
+        uint32_t bh[2], bl[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          bh[i] = __float_as_uint(bv[i]) & 0xFFFFE000u;
+          bl[i] = __float_as_uint(bv[i] - __uint_as_float(bh[i]));
+        }
+        mma_tf32(acc[nt], al, bh);
+        mma_tf32(acc[nt], ah, bl);
+        mma_tf32(acc[nt], ah, bh);
+      }
     }
   }
+  // accumulator fragment: c0 (row g, col 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1); rows = co, cols = ci
   float* o = a.part + ((size_t)sp * T + tap) * a.Cin * 64 + (size_t)(cib * 64) * 64;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (ci4 + j < cw) *reinterpret_cast<float4*>(o + (size_t)(ci4 + j) * 64 + co4) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+  for (int nt = 0; nt < 4; ++nt) {
+    const int ci = ci0 + nt * 8 + 2 * ft, co = co0 + fg;
+    if (ci < cw) { o[(size_t)ci * 64 + co] = acc[nt][0]; o[(size_t)ci * 64 + co + 8] = acc[nt][2]; }
+    if (ci + 1 < cw) { o[(size_t)(ci + 1) * 64 + co] = acc[nt][1]; o[(size_t)(ci + 1) * 64 + co + 8] = acc[nt][3]; }
+  }
 }
-// gw[co][ci][tap] = sum over splits of part[split][tap][ci][co]
+// gw[co][ci][tap] = sum over splits of part[split][tap][ci][co]: threads walk the partials' layout (coalesced reads; the
+// strided writes are 64 * Cin * T floats in total)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw, int Cin, int T, int splits) {
   const int total = 64 * Cin * T;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-    const int co = i / (Cin * T), r = i - co * (Cin * T), ci = r / T, tap = r - ci * T;
+    const int tap = i / (Cin * 64), r = i - tap * (Cin * 64), ci = r >> 6, co = r & 63;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += __ldg(part + ((size_t)s * T + tap) * Cin * 64 + (size_t)ci * 64 + co);
-    gw[i] = acc;
+    for (int s = 0; s < splits; ++s) acc += __ldg(part + (size_t)s * total + i);
+    gw[((size_t)co * Cin + ci) * T + tap] = acc;
   }
+}
+
+// ---- weight gradient on tcgen05 (the product path; the mma.sync kernel above is kept for geometries this one does not take).
+//      gw[co][(tap, ci)] = sum over pixels: a GEMM whose contraction axis is the PIXEL axis, so the TS scheme of the forward
+//      engine is used transposed: a CTA owns one pair of filter taps x 64 input channels = 128 A rows (TMEM lane = (tap, ci)),
+//      a chunk's 32 pixels are the K columns, B = the 64 x 32 tile of the masked output gradient in the canonical shared-memory
+//      layout.  3xTF32 on both operands (hi*hi into D_main, lo*hi + hi*lo into D_corr), accumulators persistent over the CTA's
+//      pixel range, one epilogue at the end (partials per pixel split, reduced deterministically by wgrad_reduce_kernel).
+//      Per chunk all 8 producer warps first stage x (two shifted rows per input channel) and g with coalesced loads
+//      (lane = pixel) into padded shared tiles; then warps 0-3 read their A row (conflict-free, pitch 33), split it and store
+//      it to tensor memory, warps 4-7 do the same for B into the operand images; one MMA warp issues. ----
+constexpr int WT_THREADS = 288, WT_PITCH = 33;
+constexpr int WT_XS = 128 * WT_PITCH * 4, WT_GS = 64 * WT_PITCH * 4;              // raw staging tiles (bytes)
+constexpr int WT_RING = 3;                                                         // raw-tile ring: chunk i+2 is in flight while chunk i is consumed
+constexpr int WT_SMEM = 2 * 16384 /* B images */ + WT_RING * (WT_XS + WT_GS) + 64 + 1024;
+// 4-byte asynchronous global -> shared copy; src_bytes = 0 writes a zero (padding, channels beyond the tensor)
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool ok) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+__global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, int npairs) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* bimg = smem;                                             // 2 stages x (hi 8 KB | lo 8 KB)
+  float* xs = reinterpret_cast<float*>(smem + 2 * 16384);                       // WT_RING x [128][33]
+  float* gs = reinterpret_cast<float*>(smem + 2 * 16384 + WT_RING * WT_XS);     // WT_RING x [64][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * 16384 + WT_RING * (WT_XS + WT_GS));
+  uint64_t* s_empty = bars;          // [2] the MMAs that read stage s completed
+  uint64_t* s_full = bars + 2;       // [2] all 8 producer warps filled stage s (A in tensor memory, B images in shared memory)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (tid == 0) {
+    mbar_init(&s_empty[0], 1); mbar_init(&s_empty[1], 1);
+    mbar_init(&s_full[0], 8); mbar_init(&s_full[1], 8);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int T = a.KS * a.KS, pad = a.KS / 2;
+  const int pair = blockIdx.x % npairs, cib = blockIdx.x / npairs, sp = blockIdx.y;
+  const int cw = a.Cin - cib * 64 < 64 ? a.Cin - cib * 64 : 64;
+  const int HoWo = a.Ho * a.Wo, HW = a.H * a.W;
+  const long long nchunks = (long long)a.B * HoWo / 32;
+  const long long c0 = nchunks * sp / a.splits, c1 = nchunks * (sp + 1) / a.splits;
+  const int nmy = (int)(c1 - c0);
+  constexpr uint32_t IDESC = umma_instr_desc(128, 64, 2);
+
+  if (warp == 8) {
+    // ===== MMA issuer =====
+    for (int i = 0; i < nmy; ++i) {
+      const int st = i & 1;
+      mbar_wait_bounded(&s_full[st], (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t b_hi = smem_u32(bimg) + (uint32_t)(st * 16384), b_lo = b_hi + 8192;
+        const uint32_t a_hi = tmem_d + 128 + (uint32_t)(st * 64), a_lo = a_hi + 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (64 * 16), 64 * 16, 128);
+          const uint64_t dbl = umma_smem_desc(b_lo + j * 2 * (64 * 16), 64 * 16, 128);
+          umma_ts_tf32(tmem_d + 64, a_lo + j * 8, dbh, IDESC, (i | j) != 0 ? 1u : 0u);
+          umma_ts_tf32(tmem_d + 64, a_hi + j * 8, dbl, IDESC, 1u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t dbh = umma_smem_desc(b_hi + j * 2 * (64 * 16), 64 * 16, 128);
+          umma_ts_tf32(tmem_d, a_hi + j * 8, dbh, IDESC, (i | j) != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== producer warps =====
+    // staging map: lane = pixel of the chunk; warp w loads A rows w, w + 8, ... (rows 0-63: first tap of the pair, 64-127: second)
+    // and g rows w, w + 8, ...
+    const int tap0 = 2 * pair, tap1 = 2 * pair + 1;
+    const bool t1ok = tap1 < T;
+    const int dy0 = tap0 / a.KS, dx0 = tap0 - dy0 * a.KS, dy1 = tap1 / a.KS, dx1 = tap1 - dy1 * a.KS;
+    // asynchronous 4-byte copies (LDGSTS) straight into the raw-tile ring, two chunks ahead: a register prefetch of one chunk
+    // left every chunk waiting for a full memory round trip (3300 cycles per chunk measured)
+    auto fetch = [&](long long ch, int slot) {
+      const long long p0 = ch * 32;
+      const int b = (int)(p0 / HoWo);
+      const int p = (int)(p0 - (long long)b * HoWo) + lane;
+      const int oy = p / a.Wo, ox = p - oy * a.Wo;
+      const int iy0 = oy * a.sh + dy0 - pad, ix0 = ox * a.sw + dx0 - pad;
+      const int iy1 = oy * a.sh + dy1 - pad, ix1 = ox * a.sw + dx1 - pad;
+      const bool ok0 = iy0 >= 0 && iy0 < a.H && ix0 >= 0 && ix0 < a.W;
+      const bool ok1 = t1ok && iy1 >= 0 && iy1 < a.H && ix1 >= 0 && ix1 < a.W;
+      const float* xb = a.x + ((size_t)b * a.Cin + cib * 64) * HW;
+      const float* x0 = xb + (ok0 ? iy0 * a.W + ix0 : 0);
+      const float* x1 = xb + (ok1 ? iy1 * a.W + ix1 : 0);
+      const float* gp = a.g + (size_t)b * 64 * HoWo + p;
+      float* xt = xs + slot * (128 * WT_PITCH);
+      float* gt = gs + slot * (64 * WT_PITCH);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = warp + 8 * j;
+        const bool cv = c < cw;
+        cp_async4(xt + c * WT_PITCH + lane, x0 + (size_t)(cv ? c : 0) * HW, ok0 && cv);
+        cp_async4(xt + (64 + c) * WT_PITCH + lane, x1 + (size_t)(cv ? c : 0) * HW, ok1 && cv);
+        cp_async4(gt + c * WT_PITCH + lane, gp + (size_t)c * HoWo, true);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    if (nmy > 0) fetch(c0, 0);
+    if (nmy > 1) fetch(c0 + 1, 1);
+    for (int i = 0; i < nmy; ++i) {
+      const int st = i & 1, slot = i % WT_RING;
+      float* xt = xs + slot * (128 * WT_PITCH);
+      float* gt = gs + slot * (64 * WT_PITCH);
+      if (i + 1 < nmy) asm volatile("cp.async.wait_group 1;" ::: "memory");      // chunk i has landed (chunk i+1 may be in flight)
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      named_bar_sync(1, 256);                       // every producer thread's copies of chunk i are visible; chunk i-1 is consumed
+      if (i + 2 < nmy) fetch(c0 + i + 2, (i + 2) % WT_RING);
+      if (warp < 4) {
+        // A: row = this thread's (tap, input channel), 32 pixels -> hi | lo columns of the stage in tensor memory
+        const float* row = xt + (warp * 32 + lane) * WT_PITCH;
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = row[k];
+        float hi[32], lo[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          hi[k] = __uint_as_float(__float_as_uint(v[k]) & 0xFFFFE000u);
+          lo[k] = v[k] - hi[k];
+        }
+        if (i >= 2) {
+          mbar_wait_bounded(&s_empty[st], (uint32_t)(((i >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t col = lane_addr + 128u + (uint32_t)(st * 64);
+        tmem_st16(col, hi); tmem_st16(col + 16, hi + 16);
+        tmem_st16(col + 32, lo); tmem_st16(col + 48, lo + 16);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        // B: thread = (output channel, half of the chunk's pixels) -> canonical operand images [k-group of 4 pixels][co][16 B]
+        const int t = tid - 128, co = t & 63, half = t >> 6;
+        const float* row = gt + co * WT_PITCH + half * 16;
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = row[k];
+        if (i >= 2) mbar_wait_bounded(&s_empty[st], (uint32_t)(((i >> 1) - 1) & 1));
+        unsigned char* img = bimg + st * 16384;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 h, l;
+          split_tf32(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), h, l);
+          const int kg = half * 4 + q;
+          *reinterpret_cast<float4*>(img + kg * 1024 + co * 16) = h;
+          *reinterpret_cast<float4*>(img + 8192 + kg * 1024 + co * 16) = l;
+        }
+        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async proxy
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[st]);
+    }
+    // ---- epilogue: D_main + D_corr -> partials [split][tap][ci][co] ----
+    if (nmy > 0) {
+      const int last = nmy - 1;
+      mbar_wait_bounded(&s_empty[last & 1], (uint32_t)((last >> 1) & 1));
+      tc_fence_after();
+    }
+    const int r = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int tap = 2 * pair + (r >> 6), ci = r & 63;
+    const bool valid = tap < T && ci < cw;
+    float* o = a.part + (((size_t)sp * T + (valid ? tap : 0)) * a.Cin + cib * 64 + ci) * 64 + half * 32;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      float acc[16], part[16];
+      if (nmy > 0) {
+        tmem_ld_cols<16>(lane_addr + (uint32_t)(half * 32 + pass * 16), acc);
+        tmem_ld_cols<16>(lane_addr + 64u + (uint32_t)(half * 32 + pass * 16), part);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { acc[j] = 0.f; part[j] = 0.f; }
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(o + pass * 16 + j) =
+              make_float4(acc[j] + part[j], acc[j + 1] + part[j + 1], acc[j + 2] + part[j + 2], acc[j + 3] + part[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 256);
 }
 
 struct ConvDims { int B, Cin, H, W, KS, sh, sw, Ho, Wo, relu, T, slices, splits; };
@@ -137,13 +381,13 @@ static int conv_dims(const tpspp_conv_cfg* c, ConvDims* d) {
   TPSPP_REQUIRE(d->B == 0 || ((long long)d->B * d->Ho * d->Wo) % 128 == 0, "batch * output pixels must be a multiple of 128");
   TPSPP_REQUIRE((d->Ho * d->Wo) % 32 == 0 && (d->H * d->W) % 4 == 0, "output plane must be a multiple of 32 pixels");
   d->slices = (d->Cin + 63) / 64;
-  // pixel splits of the weight gradient: enough blocks for ~2 waves, at least 8 chunks of 32 pixels per block
+  // pixel splits of the weight gradient: one resident wave of CTAs (two per SM), at least 8 chunks of 32 pixels per CTA
   long long chunks = (long long)d->B * d->Ho * d->Wo / 32;
-  long long blocks_per_split = (long long)d->T * d->slices;
-  long long sp = (2LL * sm_count() * 2 + blocks_per_split - 1) / blocks_per_split;
+  long long blocks_per_split = (long long)((d->T + 1) / 2) * d->slices;
+  long long sp = (2LL * sm_count()) / blocks_per_split;
   if (sp > chunks / 8) sp = chunks / 8;
   if (sp < 1) sp = 1;
-  if (sp > 64) sp = 64;
+  if (sp > 296) sp = 296;
   d->splits = (int)sp;
   return TPSPP_OK;
 }
@@ -258,10 +502,23 @@ extern "C" int tpspp_conv_bwd(const tpspp_conv_cfg* cfg, const float* x, const f
   // 3. weight gradient
   if (gw != nullptr) {
     WgradArgs wa{W(CW_G), x, W(CW_WPART), d.B, d.Cin, d.H, d.W, d.Ho, d.Wo, d.KS, d.sh, d.sw, d.splits};
-    wgrad_kernel<<<dim3(d.T * d.slices, d.splits), 256, 0, st>>>(wa);
+    static const bool use_mma_sync = getenv("TPSPP_WGRAD_MMASYNC") != nullptr;
+    if (!use_mma_sync) {
+      static thread_local int wt_dev = -1;
+      int dev = 0;
+      TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+      if (wt_dev != dev) {
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+        wt_dev = dev;
+      }
+      const int npairs = (d.T + 1) / 2;
+      wgrad_tc_kernel<<<dim3(npairs * d.slices, d.splits), WT_THREADS, WT_SMEM, st>>>(wa, npairs);
+    } else {
+      wgrad_kernel<<<dim3(d.T * d.slices, d.splits), 256, 0, st>>>(wa);
+    }
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
-    wgrad_reduce_kernel<<<64, 256, 0, st>>>(W(CW_WPART), gw, d.Cin, d.T, d.splits);
+    wgrad_reduce_kernel<<<(64 * d.Cin * d.T + 255) / 256, 256, 0, st>>>(W(CW_WPART), gw, d.Cin, d.T, d.splits);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
   }

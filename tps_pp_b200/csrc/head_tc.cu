@@ -69,26 +69,6 @@ __device__ __forceinline__ float tc_act(float x, int act, float scale) {
   }
 }
 
-template <int N>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
-  if constexpr (N == 32) {
-    tmem_ld32(taddr, v);
-  } else {
-    static_assert(N == 16, "16 or 32 columns");
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-  }
-}
-
 template <int KS, bool NHWC_SRC, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(ConvTcArgs t) {
   constexpr int B_BYTES = tc_b_bytes(NT), STAGE = tc_stage_bytes(NT), HC = NT / 2;
