@@ -273,6 +273,9 @@ typedef struct {
   int32_t ksize;            /* 1 (stride 1) or 3 (pad 1)                                          */
   int32_t stride_h, stride_w; /* (1,1), (2,2) or (2,1)                                            */
   int32_t relu;             /* 1: y = relu(conv + b), 0: y = conv + b                             */
+  /* torch.cat / F.interpolate fused into the convolution (tps_pp.py:159-168,583-585); all zero = one plain source */
+  int32_t nsrc;             /* 0/1: one source; 2/3: the input is the channel concatenation of nsrc 64-channel sources (cin = 64 nsrc) */
+  int32_t up_h[3], up_w[3]; /* nearest-upsample factor of each source (0/1 or 2): source s is stored [B, C, height/up_h, width/up_w] */
 } tpspp_conv_cfg;
 TPSPP_API size_t tpspp_conv_workspace_bytes(const tpspp_conv_cfg* cfg);   /* covers both calls */
 /* y [B,64,H/sh,W/sw] = act(conv(x [B,cin,H,W], w [64,cin,k,k]) + bias [64]) */
@@ -281,6 +284,32 @@ TPSPP_API int tpspp_conv_fwd(const tpspp_conv_cfg* cfg, const float* x, const fl
 /* gradients of the above given y (the saved output) and gy: gx [B,cin,H,W], gw [64,cin,k,k], gb [64]; each may be NULL */
 TPSPP_API int tpspp_conv_bwd(const tpspp_conv_cfg* cfg, const float* x, const float* w, const float* y, const float* gy,
                              float* gx, float* gw, float* gb, void* workspace, tpspp_stream_t stream);
+
+/* ---- Training-path linear layers: forward and backward of the reference's nn.Linear / torch.bmm calls (DGAB.py:11-23,
+ * 28-36,52; tps_pp.py:250-273 localization_fc1/fc2, p_linear, feat_linear; :293-299 the einsum of atten_score), so that
+ * autograd of the rectifier's dense layers runs on native kernels instead of cuBLAS.  Row-major fp32:
+ *   y [rows, out] = x [rows, in] . w[out, in]^T + bias          (weight_batches == 1: nn.Linear)
+ *   y_b = x_b . w_b^T for weight_batches equal groups of rows     (weight_batches  > 1: torch.bmm(x, w.transpose(1, 2)))
+ * tcgen05 3xTF32 kernels when rows (per batch) % 128 == 0 and in/out features % 32 == 0 (out <= 256, and in <= 64 or out <= 64);
+ * fp32 CUDA-core kernels for every other shape.  No activation: the caller applies it (and its derivative). */
+typedef struct {
+  int64_t rows;             /* product of the leading dimensions                                  */
+  int32_t in_features, out_features;
+  int32_t weight_batches;   /* 1, or the number of [out, in] weights (rows % weight_batches == 0)  */
+} tpspp_linear_cfg;
+TPSPP_API size_t tpspp_linear_workspace_bytes(const tpspp_linear_cfg* cfg);   /* covers both calls */
+TPSPP_API int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias /* or NULL */,
+                               float* y, void* workspace, tpspp_stream_t stream);
+/* gx [rows, in] (or NULL), gw [batches, out, in] (or NULL), gb [out] (or NULL; needs gw) from gy [rows, out] */
+TPSPP_API int tpspp_linear_bwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* gy, float* gx,
+                               float* gw, float* gb, void* workspace, tpspp_stream_t stream);
+
+/* The same pair for a ConvModule whose input is torch.cat(sources, dim=1) and/or F.interpolate(source, mode="nearest"):
+ * xs / gxs are arrays of cfg->nsrc pointers (gxs entries may be NULL); gxs[s] has the STORED (low-resolution) shape of source s. */
+TPSPP_API int tpspp_convcat_fwd(const tpspp_conv_cfg* cfg, const float* const* xs, const float* w, const float* bias, float* y,
+                                void* workspace, tpspp_stream_t stream);
+TPSPP_API int tpspp_convcat_bwd(const tpspp_conv_cfg* cfg, const float* const* xs, const float* w, const float* y, const float* gy,
+                                float* const* gxs, float* gw, float* gb, void* workspace, tpspp_stream_t stream);
 
 /* Number of kernel launches the most recent call on this host thread enqueued
  * (bench.py uses it to report gpu_launches). */

@@ -26,6 +26,7 @@ def main():
     convs = "library" if "--library-convs" in sys.argv else "native"
     m = T.TPS_PP().to(dev).train()
     m.train_convs = convs
+    m.train_linears = "library" if ("--library-linears" in sys.argv or convs == "library") else "native"
     _trained_like_(m)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -56,6 +57,24 @@ def main():
         torch.cuda.synchronize()
         if it >= warm:
             t_total += ev[0].elapsed_time(ev[3]); t_ar += ev[1].elapsed_time(ev[2]); t_fwd += ev[0].elapsed_time(ev[4])
+    if "--profile" in sys.argv and rank == 0:
+        # per-kernel device time of one training step (CUPTI, not ncu: warm caches, real overlap) -> stdout table
+        from torch.profiler import profile, ProfilerActivity
+        nprof = 4
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(nprof):
+                bucket.zero()
+                r = m(x, [o0, o1])
+                loss = (r["output"] - tgt).square().mean()
+                loss.backward()
+                opt.step()
+            torch.cuda.synchronize()
+        rows = sorted(((e.key, e.self_device_time_total / nprof, e.count // nprof) for e in prof.key_averages()),
+                      key=lambda r: -r[1])
+        tot = sum(r[1] for r in rows)
+        print("# per-step device time %.1f us over %d kernel names" % (tot, len(rows)))
+        for k, us, n in rows[:70]:
+            print("%9.1f us %4d x  %s" % (us, n, k[:150]))
     t = torch.tensor([t_total / steps, t_ar / steps, t_fwd / steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -63,8 +82,8 @@ def main():
         print(json.dumps({"metric": "tps_pp_train_step", "n_gpus": world, "batch_per_gpu": B, "ms_per_step": t[0].item(),
                           "allreduce_ms": t[1].item(), "forward_ms": t[2].item(), "img_per_s": world * B / (t[0].item() * 1e-3),
                           "grad_bucket_bytes": bucket.flat.numel() * 4, "loss": float(loss), "training_stages": m.training_stages,
-                          "head": f"14 ConvModules: {convs} forward+backward (fp32-level); CBAM/DGAB/localisation/score: torch ops + autograd "
-                                  "(fp32, TF32 off); warp fwd/bwd native"}))
+                          "head": f"14 ConvModules: {convs} forward+backward (fp32-level); 16 dense layers (CBAM/DGAB/localisation/score): "
+                                  f"{m.train_linears} forward+backward; LayerNorm/softmax/GELU/elementwise: torch ops; warp fwd/bwd native"}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,0 +1,73 @@
+"""Native forward / backward of the head's dense layers (tpspp_linear_fwd / tpspp_linear_bwd, include/tpspp.h) against fp64
+torch autograd on the device.  Shapes = every nn.Linear / bmm of the rectifier's training path at a small batch
+(DGAB.py:11-23,28-36,52; tps_pp.py:250-273,293-299) plus ragged ones that must take the CUDA-core kernels."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# (leading shape, in, out, bias, what)
+CASES = [
+    ((4, 64, 16), 64, 64, True, "DGAB attn.proj"),
+    ((4, 64, 16), 64, 256, True, "Mlp fc1"),
+    ((4, 64, 16), 256, 64, True, "Mlp fc2"),
+    ((4, 1024), 64, 32, True, "feat_linear.0"),
+    ((4, 1024), 32, 128, True, "feat_linear.1"),
+    ((4, 32), 64, 256, True, "localization_fc1.0 (rows = 128)"),
+    ((4, 32), 256, 2, True, "localization_fc1.2 (odd width)"),
+    ((4,), 64, 64, True, "localization_fc2 (4 rows)"),
+    ((4, 64), 96, 65, False, "DGAB mlp_w (odd width, no bias)"),
+    ((4, 64), 48, 17, False, "DGAB mlp_h"),
+    ((8, 4, 64, 16), 64, 256, True, "Mlp fc1, 32768 rows"),
+    ((3, 37), 50, 7, True, "ragged"),
+]
+
+
+def _rel(a, b):
+    return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("lead,k,n,bias,what", CASES, ids=[c[4] for c in CASES])
+def test_linear_fwd_bwd_vs_fp64(lead, k, n, bias, what):
+    from tps_pp_b200 import functional as TF
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(hash(what) % 1000)
+    x = torch.randn(lead + (k,), device=dev, generator=g, requires_grad=True)
+    w = (torch.randn((n, k), device=dev, generator=g) / k ** 0.5).requires_grad_()
+    b = torch.randn((n,), device=dev, generator=g).requires_grad_() if bias else None
+    gy = torch.randn(lead + (n,), device=dev, generator=g)
+    y = TF.linear(x, w, b)
+    y.backward(gy)
+    xd, wd = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
+    bd = b.detach().double().requires_grad_() if bias else None
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    yd.backward(gy.double())
+    assert _rel(y.detach(), yd.detach()) <= 2e-6, what
+    assert _rel(x.grad, xd.grad) <= 2e-6, what
+    assert _rel(w.grad, wd.grad) <= 5e-6, what
+    if bias:
+        assert _rel(b.grad, bd.grad) <= 5e-6, what
+
+
+@pytest.mark.parametrize("bsz,rows,k,n", [(4, 1024, 128, 32), (3, 100, 20, 5)], ids=["score QK^T", "ragged"])
+def test_bmm_nt_fwd_bwd_vs_fp64(bsz, rows, k, n):
+    from tps_pp_b200 import functional as TF
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(rows)
+    x = torch.randn((bsz, rows, k), device=dev, generator=g, requires_grad=True)
+    w = (torch.randn((bsz, n, k), device=dev, generator=g) / k ** 0.5).requires_grad_()
+    gy = torch.randn((bsz, rows, n), device=dev, generator=g)
+    y = TF.bmm_nt(x, w)
+    y.backward(gy)
+    xd, wd = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
+    yd = torch.bmm(xd, wd.transpose(1, 2))
+    yd.backward(gy.double())
+    assert _rel(y.detach(), yd.detach()) <= 2e-6
+    assert _rel(x.grad, xd.grad) <= 2e-6
+    assert _rel(w.grad, wd.grad) <= 5e-6
+
+
+def test_linear_rejects_cpu_tensors():
+    from tps_pp_b200 import functional as TF
+    with pytest.raises(RuntimeError):
+        TF.linear(torch.zeros(4, 8), torch.zeros(3, 8), None)

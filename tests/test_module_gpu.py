@@ -123,6 +123,7 @@ def test_tps_pp_autograd_reaches_every_parameter(native_lib, train_convs, batch)
     m = T.TPS_PP().to(DEV)
     m.load_state_dict(sd, strict=True)
     m.train_convs = train_convs
+    m.train_linears = train_convs            # the dense layers (CBAM, DGAB, localisation, score) follow the same switch
     x, o0, o1 = O.synthetic_tpspp_inputs(batch, 1)
     tx = torch.from_numpy(x).to(DEV).requires_grad_()
     t0 = torch.from_numpy(o0).to(DEV).requires_grad_()
@@ -130,6 +131,8 @@ def test_tps_pp_autograd_reaches_every_parameter(native_lib, train_convs, batch)
     r = m(tx, [t0, t1])
     ts = m.training_stages
     assert ts["convs_native"] + ts["convs_library"] == 14
+    assert ts["linears_native" if train_convs == "native" else "linears_library"] == (16 if train_convs == "native" else 13), ts
+    assert ts["linears_library" if train_convs == "native" else "linears_native"] == 0, ts
     if train_convs == "library":
         assert ts["convs_native"] == 0
     elif batch == 4:

@@ -44,7 +44,13 @@ class StageCfg(Structure):
 class ConvCfg(Structure):
     """Mirror of ``tpspp_conv_cfg`` (include/tpspp.h)."""
     _fields_ = [("batch", c_int32), ("cin", c_int32), ("height", c_int32), ("width", c_int32), ("ksize", c_int32),
-                ("stride_h", c_int32), ("stride_w", c_int32), ("relu", c_int32)]
+                ("stride_h", c_int32), ("stride_w", c_int32), ("relu", c_int32), ("nsrc", c_int32),
+                ("up_h", c_int32 * 3), ("up_w", c_int32 * 3)]
+
+
+class LinearCfg(Structure):
+    """Mirror of ``tpspp_linear_cfg`` (include/tpspp.h)."""
+    _fields_ = [("rows", ctypes.c_int64), ("in_features", c_int32), ("out_features", c_int32), ("weight_batches", c_int32)]
 
 
 SP_COUNT = 81
@@ -76,6 +82,11 @@ _SIGNATURES = {
     "tpspp_conv_workspace_bytes": (c_size_t, [POINTER(ConvCfg)]),
     "tpspp_conv_fwd": (c_int, [POINTER(ConvCfg)] + [c_void_p] * 6),
     "tpspp_conv_bwd": (c_int, [POINTER(ConvCfg)] + [c_void_p] * 9),
+    "tpspp_convcat_fwd": (c_int, [POINTER(ConvCfg), POINTER(c_void_p)] + [c_void_p] * 5),
+    "tpspp_convcat_bwd": (c_int, [POINTER(ConvCfg), POINTER(c_void_p)] + [c_void_p] * 3 + [POINTER(c_void_p)] + [c_void_p] * 4),
+    "tpspp_linear_workspace_bytes": (c_size_t, [POINTER(LinearCfg)]),
+    "tpspp_linear_fwd": (c_int, [POINTER(LinearCfg)] + [c_void_p] * 6),
+    "tpspp_linear_bwd": (c_int, [POINTER(LinearCfg)] + [c_void_p] * 8),
     "tpspp_stage_workspace_bytes": (c_size_t, [POINTER(StageCfg)]),
     "tpspp_stage_fwd": (c_int, [POINTER(StageCfg), c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),

@@ -66,6 +66,14 @@ struct WgradArgs {
   const float *g, *x;          // g [B,64,Ho,Wo], x [B,Cin,H,W]
   float* part;                 // [splits][T * Cin * 64] as [tap][ci][co]
   int B, Cin, H, W, Ho, Wo, KS, sh, sw, splits;
+  // conv mode, fused torch.cat / F.interpolate: nsrc > 1: 64-channel slice s of the input is its own tensor xs[s]; su/sv = log2 of
+  // the slice's nearest-upsample factor (the tensor is stored [B, C, H >> su, W >> sv])
+  const float* xs[3];
+  int nsrc, su[3], sv[3];
+  // row-major mode (wgrad_tc_kernel<true>, linear layers): g [R, N], x [R, K]; part [splits][K][Npad]; bpart [splits][2][Npad] or null
+  long long R;
+  int K, N, Npad;
+  float* bpart;
 };
 constexpr int WG_PITCH = 64;
 __device__ __forceinline__ int wg_swz(int k) { return ((k & 3) << 3) | (k >> 2); }
@@ -189,6 +197,11 @@ constexpr int WT_SMEM = 2 * 16384 /* B images */ + WT_RING * (WT_XS + WT_GS) + 6
 __device__ __forceinline__ void cp_async4(void* dst, const void* src, bool ok) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
 }
+// ROWS = true: the same engine for a row-major linear layer y[R,N] = x[R,K] w^T: gw[n][k] = sum_r gy[r][n] x[r][k] -- the
+// contraction axis is the ROW axis, A rows = 128 input features (blockIdx.x), B columns = 64 output features (blockIdx.z),
+// a chunk = 32 rows; only the staging differs (lane = feature: coalesced 4-byte copies of a row's features into the
+// transposed raw tiles).  The B-staging threads also keep the column sums of gy (bias gradient) when bpart is given.
+template <bool ROWS>
 __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, int npairs) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -213,10 +226,10 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
   const uint32_t tmem_d = *tmem_slot;
 
   const int T = a.KS * a.KS, pad = a.KS / 2;
-  const int pair = blockIdx.x % npairs, cib = blockIdx.x / npairs, sp = blockIdx.y;
+  const int pair = ROWS ? 0 : blockIdx.x % npairs, cib = ROWS ? 0 : blockIdx.x / npairs, sp = blockIdx.y;
   const int cw = a.Cin - cib * 64 < 64 ? a.Cin - cib * 64 : 64;
   const int HoWo = a.Ho * a.Wo, HW = a.H * a.W;
-  const long long nchunks = (long long)a.B * HoWo / 32;
+  const long long nchunks = ROWS ? a.R / 32 : (long long)a.B * HoWo / 32;
   const long long c0 = nchunks * sp / a.splits, c1 = nchunks * (sp + 1) / a.splits;
   const int nmy = (int)(c1 - c0);
   constexpr uint32_t IDESC = umma_instr_desc(128, 64, 2);
@@ -256,6 +269,30 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
     // asynchronous 4-byte copies (LDGSTS) straight into the raw-tile ring, two chunks ahead: a register prefetch of one chunk
     // left every chunk waiting for a full memory round trip (3300 cycles per chunk measured)
     auto fetch = [&](long long ch, int slot) {
+      if (ROWS) {
+        const long long r0 = ch * 32;
+        const int k0 = blockIdx.x * 128, n0 = blockIdx.z * 64;
+        float* xt = xs + slot * (128 * WT_PITCH);
+        float* gt = gs + slot * (64 * WT_PITCH);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rl = warp + 8 * j;
+          const float* xr = a.x + (size_t)(r0 + rl) * a.K;
+          const float* gr = a.g + (size_t)(r0 + rl) * a.N;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k = k0 + lane + 32 * q;
+            cp_async4(xt + (lane + 32 * q) * WT_PITCH + rl, xr + (k < a.K ? k : 0), k < a.K);
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int n = n0 + lane + 32 * q;
+            cp_async4(gt + (lane + 32 * q) * WT_PITCH + rl, gr + (n < a.N ? n : 0), n < a.N);
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        return;
+      }
       const long long p0 = ch * 32;
       const int b = (int)(p0 / HoWo);
       const int p = (int)(p0 - (long long)b * HoWo) + lane;
@@ -264,9 +301,10 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
       const int iy1 = oy * a.sh + dy1 - pad, ix1 = ox * a.sw + dx1 - pad;
       const bool ok0 = iy0 >= 0 && iy0 < a.H && ix0 >= 0 && ix0 < a.W;
       const bool ok1 = t1ok && iy1 >= 0 && iy1 < a.H && ix1 >= 0 && ix1 < a.W;
-      const float* xb = a.x + ((size_t)b * a.Cin + cib * 64) * HW;
-      const float* x0 = xb + (ok0 ? iy0 * a.W + ix0 : 0);
-      const float* x1 = xb + (ok1 ? iy1 * a.W + ix1 : 0);
+      const int si = a.nsrc > 1 ? cib : 0, su = a.su[si], sv = a.sv[si], Ws = a.W >> sv, HWs = (a.H >> su) * Ws;
+      const float* xb = a.nsrc > 1 ? a.xs[cib] + (size_t)b * 64 * HWs : a.x + ((size_t)b * a.Cin + cib * 64) * HWs;
+      const float* x0 = xb + (ok0 ? (iy0 >> su) * Ws + (ix0 >> sv) : 0);
+      const float* x1 = xb + (ok1 ? (iy1 >> su) * Ws + (ix1 >> sv) : 0);
       const float* gp = a.g + (size_t)b * 64 * HoWo + p;
       float* xt = xs + slot * (128 * WT_PITCH);
       float* gt = gs + slot * (64 * WT_PITCH);
@@ -274,13 +312,14 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
       for (int j = 0; j < 8; ++j) {
         const int c = warp + 8 * j;
         const bool cv = c < cw;
-        cp_async4(xt + c * WT_PITCH + lane, x0 + (size_t)(cv ? c : 0) * HW, ok0 && cv);
-        cp_async4(xt + (64 + c) * WT_PITCH + lane, x1 + (size_t)(cv ? c : 0) * HW, ok1 && cv);
+        cp_async4(xt + c * WT_PITCH + lane, x0 + (size_t)(cv ? c : 0) * HWs, ok0 && cv);
+        cp_async4(xt + (64 + c) * WT_PITCH + lane, x1 + (size_t)(cv ? c : 0) * HWs, ok1 && cv);
         cp_async4(gt + c * WT_PITCH + lane, gp + (size_t)c * HoWo, true);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    float bsum = 0.f;                               // ROWS: column sum of gy over this CTA's rows (this thread's half of each chunk)
     if (nmy > 0) fetch(c0, 0);
     if (nmy > 1) fetch(c0 + 1, 1);
     for (int i = 0; i < nmy; ++i) {
@@ -319,6 +358,10 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
         float v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = row[k];
+        if (ROWS) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) bsum += v[k];
+        }
         if (i >= 2) mbar_wait_bounded(&s_empty[st], (uint32_t)(((i >> 1) - 1) & 1));
         unsigned char* img = bimg + st * 16384;
 #pragma unroll
@@ -342,8 +385,13 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
     }
     const int r = (warp & 3) * 32 + lane, half = warp >> 2;
     const int tap = 2 * pair + (r >> 6), ci = r & 63;
-    const bool valid = tap < T && ci < cw;
-    float* o = a.part + (((size_t)sp * T + (valid ? tap : 0)) * a.Cin + cib * 64 + ci) * 64 + half * 32;
+    const bool valid = ROWS ? ((int)blockIdx.x * 128 + r < a.K) : (tap < T && ci < cw);
+    float* o = ROWS ? a.part + ((size_t)sp * a.K + (valid ? blockIdx.x * 128 + r : 0)) * a.Npad + blockIdx.z * 64 + half * 32
+                    : a.part + (((size_t)sp * T + (valid ? tap : 0)) * a.Cin + cib * 64 + ci) * 64 + half * 32;
+    if (ROWS && a.bpart != nullptr && blockIdx.x == 0 && warp >= 4) {
+      const int t = tid - 128;                       // (column, half of the chunk) as in the B staging
+      a.bpart[((size_t)sp * 2 + (t >> 6)) * a.Npad + blockIdx.z * 64 + (t & 63)] = bsum;
+    }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       float acc[16], part[16];
@@ -367,7 +415,94 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
   if (warp == 0) tmem_dealloc(tmem_d, 256);
 }
 
-struct ConvDims { int B, Cin, H, W, KS, sh, sw, Ho, Wo, relu, T, slices, splits; };
+// gw[n][k] = sum over splits of part[split][k][n];  gb[n] = sum over splits and halves of bpart (fixed order: deterministic)
+__global__ void __launch_bounds__(256) wgrad_rows_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bpart,
+                                                                float* __restrict__ gw, float* __restrict__ gb, int K, int N, int Npad,
+                                                                int splits, int batched) {
+  const int total = K * Npad;
+  if (batched) {          // one split per weight batch (torch.bmm): gw[b][n][k] = part[b][k][n], nothing to sum
+    for (long long i = blockIdx.x * 256 + threadIdx.x; i < (long long)total * splits; i += (long long)gridDim.x * 256) {
+      const int b = (int)(i / total), r = (int)(i - (long long)b * total), k = r / Npad, n = r - k * Npad;
+      if (n < N) gw[((size_t)b * N + n) * K + k] = __ldg(part + i);
+    }
+    return;
+  }
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int k = i / Npad, n = i - k * Npad;
+    if (n >= N) continue;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += __ldg(part + (size_t)s * total + i);
+    gw[(size_t)n * K + k] = acc;
+  }
+  if (gb != nullptr && blockIdx.x == 0) {
+    for (int n = threadIdx.x; n < N; n += 256) {
+      float acc = 0.f;
+      for (int s = 0; s < 2 * splits; ++s) acc += __ldg(bpart + (size_t)s * Npad + n);
+      gb[n] = acc;
+    }
+  }
+}
+
+int wgrad_rows_splits(long long R, int K, int N, int batches) {
+  if (batches > 1) return batches;
+  const long long blocks = (long long)((K + 127) / 128) * ((N + 63) / 64);
+  long long sp = (2LL * sm_count()) / blocks;
+  if (sp > R / 32 / 8) sp = R / 32 / 8;
+  if (sp < 1) sp = 1;
+  return (int)sp;
+}
+size_t wgrad_rows_ws_floats(long long R, int K, int N, int batches) {
+  const int Npad = (N + 63) / 64 * 64;
+  const int sp = wgrad_rows_splits(R, K, N, batches);
+  return (size_t)sp * K * Npad + (size_t)sp * 2 * Npad;
+}
+// weight (and bias) gradient of a row-major linear layer on tcgen05; R % 32 == 0; ws >= wgrad_rows_ws_floats(R, K, N) floats
+int run_wgrad_rows(const float* gy, const float* x, float* gw, float* gb, long long R, int K, int N, int batches, float* ws,
+                   cudaStream_t st) {
+  TPSPP_REQUIRE(R > 0 && R % 32 == 0, "wgrad_rows: rows must be a positive multiple of 32");
+  TPSPP_REQUIRE(batches <= 1 || (R % batches == 0 && (R / batches) % 32 == 0 && gb == nullptr && batches <= 65535),
+                "wgrad_rows: batched weights need rows per batch that are a multiple of 32 and no bias");
+  const int Npad = (N + 63) / 64 * 64;
+  const int sp = wgrad_rows_splits(R, K, N, batches);
+  WgradArgs wa;
+  memset(&wa, 0, sizeof(wa));
+  wa.g = gy; wa.x = x; wa.part = ws; wa.KS = 1; wa.splits = sp; wa.R = R; wa.K = K; wa.N = N; wa.Npad = Npad;
+  wa.Cin = 64; wa.Ho = wa.Wo = wa.H = wa.W = 1;
+  wa.bpart = gb != nullptr ? ws + (size_t)sp * K * Npad : nullptr;
+  static thread_local int wr_dev = -1;
+  int dev = 0;
+  TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (wr_dev != dev) {
+    TPSPP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    wr_dev = dev;
+  }
+  wgrad_tc_kernel<true><<<dim3((K + 127) / 128, sp, Npad / 64), WT_THREADS, WT_SMEM, st>>>(wa, 1);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  const long long rtotal = (long long)K * Npad * (batches > 1 ? sp : 1);
+  wgrad_rows_reduce_kernel<<<(unsigned)min((rtotal + 255) / 256, 4096LL), 256, 0, st>>>(ws, wa.bpart, gw, gb, K, N, Npad, sp, batches > 1);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
+// data gradient of a nearest-upsampled source: gx[b][c][y][x] = sum over the uh x uw block of the full-resolution gradient
+__global__ void __launch_bounds__(256) upsum_kernel(const float* __restrict__ gfull, float* __restrict__ gx, long long planes, int Hs,
+                                                    int Ws, int uh, int uw) {
+  const long long total = planes * Hs * Ws;
+  const int Wf = Ws * uw;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long pl = i / (Hs * Ws);
+    const int r = (int)(i - pl * (Hs * Ws)), y = r / Ws, x = r - y * Ws;
+    const float* q = gfull + (pl * Hs * uh + (long long)y * uh) * Wf + (long long)x * uw;
+    float acc = 0.f;
+    for (int dy = 0; dy < uh; ++dy)
+      for (int dx = 0; dx < uw; ++dx) acc += __ldg(q + (size_t)dy * Wf + dx);
+    gx[i] = acc;
+  }
+}
+
+struct ConvDims { int B, Cin, H, W, KS, sh, sw, Ho, Wo, relu, T, slices, splits, nsrc, uh[3], uw[3], anyup; };
 static int conv_dims(const tpspp_conv_cfg* c, ConvDims* d) {
   TPSPP_REQUIRE(c != nullptr, "conv cfg is NULL");
   TPSPP_REQUIRE(c->batch >= 0, "batch must be >= 0");
@@ -381,6 +516,17 @@ static int conv_dims(const tpspp_conv_cfg* c, ConvDims* d) {
   TPSPP_REQUIRE(d->B == 0 || ((long long)d->B * d->Ho * d->Wo) % 128 == 0, "batch * output pixels must be a multiple of 128");
   TPSPP_REQUIRE((d->Ho * d->Wo) % 32 == 0 && (d->H * d->W) % 4 == 0, "output plane must be a multiple of 32 pixels");
   d->slices = (d->Cin + 63) / 64;
+  d->nsrc = c->nsrc < 1 ? 1 : c->nsrc;
+  TPSPP_REQUIRE(d->nsrc <= 3 && (d->nsrc == 1 || d->Cin == 64 * d->nsrc), "nsrc must be 1..3 with 64 channels per concatenated source");
+  d->anyup = 0;
+  for (int s = 0; s < 3; ++s) {
+    d->uh[s] = (s < d->nsrc && c->up_h[s] > 1) ? c->up_h[s] : 1;
+    d->uw[s] = (s < d->nsrc && c->up_w[s] > 1) ? c->up_w[s] : 1;
+    TPSPP_REQUIRE(d->uh[s] <= 2 && d->uw[s] <= 2 && d->H % d->uh[s] == 0 && d->W % d->uw[s] == 0, "upsample factors must be 1 or 2 and divide the input size");
+    TPSPP_REQUIRE(((d->H / d->uh[s]) * (d->W / d->uw[s])) % 4 == 0, "source plane must be a multiple of 4 pixels");
+    if (d->uh[s] > 1 || d->uw[s] > 1) d->anyup = 1;
+  }
+  TPSPP_REQUIRE(!d->anyup || (d->sh == 1 && d->sw == 1), "an upsampled source needs a stride-1 convolution");
   // pixel splits of the weight gradient: one resident wave of CTAs (two per SM), at least 8 chunks of 32 pixels per CTA
   long long chunks = (long long)d->B * d->Ho * d->Wo / 32;
   long long blocks_per_split = (long long)((d->T + 1) / 2) * d->slices;
@@ -391,7 +537,7 @@ static int conv_dims(const tpspp_conv_cfg* c, ConvDims* d) {
   d->splits = (int)sp;
   return TPSPP_OK;
 }
-enum { CW_WFWD = 0, CW_WDG, CW_G, CW_BPART, CW_WPART, CW_COUNT };
+enum { CW_WFWD = 0, CW_WDG, CW_G, CW_BPART, CW_WPART, CW_UPTMP, CW_COUNT };
 static void conv_offsets(const ConvDims& d, size_t* off, size_t* total) {
   size_t sz[CW_COUNT];
   sz[CW_WFWD] = conv_tc_wprep_floats(d.Cin, d.KS, 64);
@@ -399,6 +545,7 @@ static void conv_offsets(const ConvDims& d, size_t* off, size_t* total) {
   sz[CW_G] = (size_t)d.B * 64 * d.Ho * d.Wo;
   sz[CW_BPART] = MB_SPLITS * 64;
   sz[CW_WPART] = (size_t)d.splits * d.T * d.Cin * 64;
+  sz[CW_UPTMP] = d.anyup ? (size_t)d.B * (d.nsrc > 1 ? 64 : d.Cin) * d.H * d.W : 0;     // full-resolution data gradient of an upsampled source
   size_t cur = 0;
   for (int i = 0; i < CW_COUNT; ++i) {
     off[i] = cur;
@@ -421,13 +568,22 @@ extern "C" size_t tpspp_conv_workspace_bytes(const tpspp_conv_cfg* cfg) {
 
 extern "C" int tpspp_conv_fwd(const tpspp_conv_cfg* cfg, const float* x, const float* w, const float* bias, float* y,
                               void* workspace, tpspp_stream_t stream) {
+  TPSPP_REQUIRE(cfg != nullptr && cfg->nsrc <= 1, "tpspp_conv_fwd: concatenated sources go through tpspp_convcat_fwd");
+  const float* xs[3] = {x, nullptr, nullptr};
+  return tpspp_convcat_fwd(cfg, xs, w, bias, y, workspace, stream);
+}
+
+extern "C" int tpspp_convcat_fwd(const tpspp_conv_cfg* cfg, const float* const* xs, const float* w, const float* bias, float* y,
+                                 void* workspace, tpspp_stream_t stream) {
   reset_launch_count();
   ConvDims d;
   int rc = conv_dims(cfg, &d);
   if (rc != TPSPP_OK) return rc;
   if (d.B == 0) return TPSPP_OK;
-  TPSPP_REQUIRE(x && w && y && workspace, "tpspp_conv_fwd: null pointer");
-  TPSPP_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)workspace) & 15) == 0, "tpspp_conv_fwd: buffers must be 16-byte aligned");
+  TPSPP_REQUIRE(xs && w && y && workspace, "tpspp_conv_fwd: null pointer");
+  for (int s = 0; s < d.nsrc; ++s)
+    TPSPP_REQUIRE(xs[s] != nullptr && ((uintptr_t)xs[s] & 15) == 0, "tpspp_conv_fwd: source %d is NULL or not 16-byte aligned", s);
+  TPSPP_REQUIRE((((uintptr_t)y | (uintptr_t)workspace) & 15) == 0, "tpspp_conv_fwd: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   size_t off[CW_COUNT], total;
   conv_offsets(d, off, &total);
@@ -440,8 +596,11 @@ extern "C" int tpspp_conv_fwd(const tpspp_conv_cfg* cfg, const float* x, const f
   if (rc != TPSPP_OK) return rc;
   ConvArgs a;
   memset(&a, 0, sizeof(a));
-  a.src[0].ptr = x; a.src[0].C = d.Cin; a.src[0].H = d.H; a.src[0].W = d.W; a.src[0].uh = 1; a.src[0].uw = 1;
   a.src[1].H = a.src[1].W = a.src[1].uh = a.src[1].uw = 1; a.src[2] = a.src[1];
+  for (int s = 0; s < d.nsrc; ++s) {
+    a.src[s].ptr = xs[s]; a.src[s].C = d.Cin / d.nsrc; a.src[s].H = d.H / d.uh[s]; a.src[s].W = d.W / d.uw[s];
+    a.src[s].uh = d.uh[s]; a.src[s].uw = d.uw[s];
+  }
   a.weight = w; a.bias = bias; a.out = y; a.B = d.B; a.Ho = d.Ho; a.Wo = d.Wo; a.Ctot = d.Cin; a.sh = d.sh; a.sw = d.sw;
   a.pad = d.KS / 2; a.act = d.relu ? CONV_ACT_RELU : CONV_ACT_NONE; a.act_scale = 1.f; a.Cout = 64;
   return run_conv_tc(d.KS, a, wimg, 64, st, mode);
@@ -449,14 +608,26 @@ extern "C" int tpspp_conv_fwd(const tpspp_conv_cfg* cfg, const float* x, const f
 
 extern "C" int tpspp_conv_bwd(const tpspp_conv_cfg* cfg, const float* x, const float* w, const float* y, const float* gy,
                               float* gx, float* gw, float* gb, void* workspace, tpspp_stream_t stream) {
+  TPSPP_REQUIRE(cfg != nullptr && cfg->nsrc <= 1, "tpspp_conv_bwd: concatenated sources go through tpspp_convcat_bwd");
+  const float* xs[3] = {x, nullptr, nullptr};
+  float* gxs[3] = {gx, nullptr, nullptr};
+  return tpspp_convcat_bwd(cfg, xs, w, y, gy, gxs, gw, gb, workspace, stream);
+}
+
+extern "C" int tpspp_convcat_bwd(const tpspp_conv_cfg* cfg, const float* const* xs, const float* w, const float* y, const float* gy,
+                                 float* const* gxs, float* gw, float* gb, void* workspace, tpspp_stream_t stream) {
   reset_launch_count();
   ConvDims d;
   int rc = conv_dims(cfg, &d);
   if (rc != TPSPP_OK) return rc;
   if (d.B == 0) return TPSPP_OK;
-  TPSPP_REQUIRE(x && w && y && gy && workspace, "tpspp_conv_bwd: null pointer");
-  TPSPP_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gy | (uintptr_t)gx | (uintptr_t)workspace) & 15) == 0,
-                "tpspp_conv_bwd: buffers must be 16-byte aligned");
+  TPSPP_REQUIRE(xs && gxs && w && y && gy && workspace, "tpspp_conv_bwd: null pointer");
+  for (int s = 0; s < d.nsrc; ++s)
+    TPSPP_REQUIRE(xs[s] != nullptr && (((uintptr_t)xs[s] | (uintptr_t)gxs[s]) & 15) == 0, "tpspp_conv_bwd: source %d is NULL or misaligned", s);
+  TPSPP_REQUIRE((((uintptr_t)y | (uintptr_t)gy | (uintptr_t)workspace) & 15) == 0, "tpspp_conv_bwd: buffers must be 16-byte aligned");
+  const float* x = xs[0];
+  bool any_gx = false;
+  for (int s = 0; s < d.nsrc; ++s) any_gx = any_gx || gxs[s] != nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   size_t off[CW_COUNT], total;
   conv_offsets(d, off, &total);
@@ -472,7 +643,7 @@ extern "C" int tpspp_conv_bwd(const tpspp_conv_cfg* cfg, const float* x, const f
     TPSPP_CHECK_CUDA(cudaGetLastError());
   }
   // 2. data gradient: one stride-1 convolution over g (zero-inserted when the forward was strided) per 64 input channels
-  if (gx != nullptr) {
+  if (any_gx) {
     const int mode = d.KS == 3 ? CM_MIX : CM_TF32X3;
     WPrepLayer L[8];
     TPSPP_REQUIRE(d.slices <= 8, "too many input-channel slices");
@@ -487,32 +658,53 @@ extern "C" int tpspp_conv_bwd(const tpspp_conv_cfg* cfg, const float* x, const f
     if (rc != TPSPP_OK) return rc;
     for (int s = 0; s < d.slices; ++s) {
       const int n = d.Cin - s * 64 < 64 ? d.Cin - s * 64 : 64;
+      const int si = d.nsrc > 1 ? s : 0;                       // the source this 64-channel slice belongs to
+      float* gdst = gxs[si];
+      if (gdst == nullptr) continue;
+      const bool up = d.uh[si] > 1 || d.uw[si] > 1;
+      // an upsampled source: full-resolution gradient into the scratch tensor, then the uh x uw block sums
+      float* full = up ? W(CW_UPTMP) : gdst;
       ConvArgs a;
       memset(&a, 0, sizeof(a));
       a.src[0].ptr = W(CW_G); a.src[0].C = 64; a.src[0].H = d.Ho; a.src[0].W = d.Wo; a.src[0].uh = d.sh; a.src[0].uw = d.sw;
       a.src[1].H = a.src[1].W = a.src[1].uh = a.src[1].uw = 1; a.src[2] = a.src[1];
       a.zi = (d.sh == 2 || d.sw == 2) ? 1 : 0;
-      a.out = gx + (size_t)s * 64 * d.H * d.W; a.out_cstride = d.Cin; a.Cout = n;
+      if (d.nsrc > 1) { a.out = full; a.out_cstride = 0; }
+      else { a.out = full + (size_t)s * 64 * d.H * d.W; a.out_cstride = d.Cin; }
+      a.Cout = n;
       a.B = d.B; a.Ho = d.H; a.Wo = d.W; a.Ctot = 64; a.sh = 1; a.sw = 1; a.pad = d.KS / 2;
       a.act = CONV_ACT_NONE; a.act_scale = 1.f;
       rc = run_conv_tc(d.KS, a, W(CW_WDG) + (size_t)s * per, 64, st, mode);
       if (rc != TPSPP_OK) return rc;
+      if (up && (d.nsrc > 1 || s == d.slices - 1)) {
+        const long long planes = (long long)d.B * (d.nsrc > 1 ? 64 : d.Cin);
+        const int Hs = d.H / d.uh[si], Ws = d.W / d.uw[si];
+        const long long tot = planes * Hs * Ws;
+        upsum_kernel<<<(unsigned)min((tot + 255) / 256, 8192LL), 256, 0, st>>>(full, gdst, planes, Hs, Ws, d.uh[si], d.uw[si]);
+        count_launch();
+        TPSPP_CHECK_CUDA(cudaGetLastError());
+      }
     }
   }
   // 3. weight gradient
   if (gw != nullptr) {
-    WgradArgs wa{W(CW_G), x, W(CW_WPART), d.B, d.Cin, d.H, d.W, d.Ho, d.Wo, d.KS, d.sh, d.sw, d.splits};
-    static const bool use_mma_sync = getenv("TPSPP_WGRAD_MMASYNC") != nullptr;
+    WgradArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.g = W(CW_G); wa.x = x; wa.part = W(CW_WPART); wa.B = d.B; wa.Cin = d.Cin; wa.H = d.H; wa.W = d.W; wa.Ho = d.Ho; wa.Wo = d.Wo;
+    wa.KS = d.KS; wa.sh = d.sh; wa.sw = d.sw; wa.splits = d.splits; wa.nsrc = d.nsrc;
+    for (int s = 0; s < 3; ++s) { wa.xs[s] = s < d.nsrc ? xs[s] : nullptr; wa.su[s] = d.uh[s] == 2; wa.sv[s] = d.uw[s] == 2; }
+    static const bool env_mma_sync = getenv("TPSPP_WGRAD_MMASYNC") != nullptr;
+    const bool use_mma_sync = env_mma_sync && d.nsrc == 1 && !d.anyup;
     if (!use_mma_sync) {
       static thread_local int wt_dev = -1;
       int dev = 0;
       TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
       if (wt_dev != dev) {
-        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+        TPSPP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
         wt_dev = dev;
       }
       const int npairs = (d.T + 1) / 2;
-      wgrad_tc_kernel<<<dim3(npairs * d.slices, d.splits), WT_THREADS, WT_SMEM, st>>>(wa, npairs);
+      wgrad_tc_kernel<false><<<dim3(npairs * d.slices, d.splits), WT_THREADS, WT_SMEM, st>>>(wa, npairs);
     } else {
       wgrad_kernel<<<dim3(d.T * d.slices, d.splits), 256, 0, st>>>(wa);
     }

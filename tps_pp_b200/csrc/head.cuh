@@ -56,6 +56,11 @@ struct WPrepLayer {
   int bf16;         // CM_*: 1 = single bf16 image [chunk][4 k-groups][64][8], 2 = tf32 hi | bf16 w | bf16 lo, 0 = fp32 hi|lo pair
 };
 constexpr int WPREP_MAX_LAYERS = 20;
+// weight (+ bias) gradient of row-major linear layers on tcgen05 (conv_train.cu): gw[n][k] = sum_r gy[r][n] x[r][k]; batches > 1 =
+// torch.bmm semantics (rows split evenly into groups with their own weight, gw [batches][N][K])
+size_t wgrad_rows_ws_floats(long long R, int K, int N, int batches);
+int run_wgrad_rows(const float* gy, const float* x, float* gw, float* gb, long long R, int K, int N, int batches, float* ws,
+                   cudaStream_t st);
 int conv_tc_prepare_weights(const WPrepLayer* layers, int nlayers, cudaStream_t st);
 
 }  // namespace tpspp

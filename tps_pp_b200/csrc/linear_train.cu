@@ -1,0 +1,233 @@
+// Training-path linear layers of the head (north_star (4), SURVEY K-p): forward and backward of the reference's
+// `nn.Linear` / `torch.bmm` calls (DGAB.py:11-23,28-36,52; tps_pp.py:250-273,293-312) as native kernels, so that autograd of
+// the rectifier's dense layers no longer goes through cuBLAS.
+//
+//   forward   y = x w^T + b                 row-major [R,K] x [N,K]^T: lin_tma_kernel (tcgen05, 3xTF32 split)
+//   backward  gx = gy w                     the same kernel over the transposed weight image
+//             gw[n][k] = sum_r gy[r][n] x[r][k],  gb[n] = sum_r gy[r][n]      wgrad_tc_kernel<ROWS> (conv_train.cu)
+//   weight_batches > 1: torch.bmm(x, w^T) with one [N,K] weight per group of rows (the QK^T score of get_score).
+// Shapes the tensor-core kernels do not take (R not a multiple of 128, K or N not a multiple of 32: DGAB's axial mlp_w /
+// mlp_h, localization_fc1.2, CBAM's channel MLP) run on the fp32 CUDA-core kernels below -- they are < 1 % of the FLOPs.
+#include "head.cuh"
+#include "tc.cuh"
+
+#include <string.h>
+
+namespace tpspp {
+
+constexpr int TC_TM = 128, TC_KC = 32;      // row tile and k chunk of the tcgen05 linear kernel (head_tc.cu)
+
+// ---- operand image of a row-major weight for the tcgen05 linear kernel (same layout as wprep_kernel's fp32 hi|lo pair):
+//      image row n' / column k' = w[n'][k'] (forward) or w[k'][n'] (transposed: the data-gradient GEMM), one image per batch ----
+__global__ void __launch_bounds__(256) lin_wprep_kernel(const float* __restrict__ w, float* __restrict__ out, int Nn, int Kk, int NT,
+                                                        int transposed, int batches) {
+  const int Npad = (Nn + NT - 1) / NT * NT;
+  const int per = Npad * Kk, nchunks = Kk >> 5;
+  const long long total = (long long)per * batches;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int b = (int)(i / per), r = (int)(i - (long long)b * per), n = r / Kk, k = r - n * Kk;
+    const float* wb = w + (size_t)b * Nn * Kk;
+    float v = 0.f;
+    if (n < Nn) v = transposed ? __ldg(wb + (size_t)k * Nn + n) : __ldg(wb + (size_t)n * Kk + k);
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const int blk = n / NT, nn = n - blk * NT;
+    float* o = out + (size_t)b * 2 * per + ((size_t)(blk * nchunks + (k >> 5)) * 2) * (NT * 32) + ((k >> 2) & 7) * (NT * 4) + nn * 4 + (k & 3);
+    o[0] = hi;
+    o[NT * 32] = v - hi;
+  }
+}
+
+// ---- fp32 CUDA-core kernels for the small / odd shapes ----
+// y[r][n] = sum_k x[r][k] w[b][n][k] (+ bias): 32 x 32 output tile per block, 32-wide k chunks through padded shared tiles
+// (coalesced global reads for either weight orientation), thread = one column x four rows
+__global__ void __launch_bounds__(256) lin_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int K, int N,
+                                                            long long rows_per_batch, int transposed) {
+  // transposed = 0: y = x w^T (w [N][K]);  1: y = x w (w [K][N], the data gradient with K/N swapped by the caller)
+  __shared__ float Xs[32][33], Ws[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int b = blockIdx.z, n0 = blockIdx.x * 32;
+  const long long rb = (long long)b * rows_per_batch, r0 = rb + (long long)blockIdx.y * 32, rend = rb + rows_per_batch;
+  const float* wb = w + (size_t)b * N * K;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = ty + 8 * j;
+      Xs[rr][tx] = (r0 + rr < rend && k0 + tx < K) ? __ldg(x + (size_t)(r0 + rr) * K + k0 + tx) : 0.f;
+      if (!transposed) Ws[rr][tx] = (n0 + rr < N && k0 + tx < K) ? __ldg(wb + (size_t)(n0 + rr) * K + k0 + tx) : 0.f;
+      else Ws[tx][rr] = (n0 + tx < N && k0 + rr < K) ? __ldg(wb + (size_t)(k0 + rr) * N + n0 + tx) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float wv = Ws[tx][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(Xs[ty + 8 * j][k], wv, acc[j]);
+    }
+    __syncthreads();
+  }
+  if (n0 + tx >= N) return;
+  const float bv = bias != nullptr ? __ldg(bias + n0 + tx) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (r0 + ty + 8 * j < rend) y[(size_t)(r0 + ty + 8 * j) * N + n0 + tx] = acc[j] + bv;
+}
+// gw[b][n][k] = sum over the batch's rows of gy[r][n] x[r][k]; gb[n] = sum_r gy[r][n] (column K of the same grid).
+// block = 32 features (k) x 8 row lanes for one output feature n; fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) lin_small_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                              float* __restrict__ gw, float* __restrict__ gb, long long rows_per_batch,
+                                                              int K, int N) {
+  const int n = blockIdx.y, b = blockIdx.z;
+  const int kx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + kx;                       // k == K: the bias column
+  const long long r0 = (long long)b * rows_per_batch;
+  float acc = 0.f;
+  if (k <= K) {
+    for (long long r = r0 + ry; r < r0 + rows_per_batch; r += 8) {
+      const float g = __ldg(gy + (size_t)r * N + n);
+      acc = fmaf(g, k < K ? __ldg(x + (size_t)r * K + k) : 1.f, acc);
+    }
+  }
+  __shared__ float red[8][33];
+  red[ry][kx] = acc;
+  __syncthreads();
+  if (ry == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][kx];
+    if (k < K) gw[((size_t)b * N + n) * K + k] = s;
+    else if (k == K && gb != nullptr) gb[n] = s;
+  }
+}
+
+struct LinDims { long long R; int K, N, batches; long long rpb; bool tc_fwd, tc_dx, tc_wg; int nt_fwd, nt_dx; };
+static bool lin_tc_shape(long long R, int K, int N, long long rpb, int* NT) {
+  if (R % TC_TM || rpb % TC_TM || K % TC_KC || N % 32 || N > 256 || R > 0x7fffffffLL) return false;
+  *NT = N % 64 == 0 ? 64 : 32;
+  if (K > 64 && N != *NT) return false;       // lin_tma_plan: A stays in tensor memory across column blocks only for K <= 64
+  return true;
+}
+static int lin_dims(const tpspp_linear_cfg* c, LinDims* d) {
+  TPSPP_REQUIRE(c != nullptr, "linear cfg is NULL");
+  TPSPP_REQUIRE(c->rows >= 0 && c->in_features > 0 && c->out_features > 0, "linear: rows >= 0, in/out features > 0");
+  TPSPP_REQUIRE(c->weight_batches >= 1 && c->weight_batches <= 65535, "linear: weight_batches must be in 1..65535");
+  TPSPP_REQUIRE(c->rows % c->weight_batches == 0, "linear: rows must split evenly over the weight batches");
+  TPSPP_REQUIRE(c->rows / c->weight_batches < 65535LL * 32, "linear: too many rows per weight batch");
+  TPSPP_REQUIRE(c->rows * (long long)(c->in_features > c->out_features ? c->in_features : c->out_features) < (1LL << 40), "linear: too large");
+  d->R = c->rows; d->K = c->in_features; d->N = c->out_features; d->batches = c->weight_batches;
+  d->rpb = d->batches > 0 && d->R > 0 ? d->R / d->batches : 1;
+  d->nt_fwd = d->nt_dx = 64;
+  d->tc_fwd = d->R > 0 && lin_tc_shape(d->R, d->K, d->N, d->rpb, &d->nt_fwd);
+  d->tc_dx = d->R > 0 && lin_tc_shape(d->R, d->N, d->K, d->rpb, &d->nt_dx);
+  d->tc_wg = d->R >= 2048 && d->rpb % 32 == 0 && d->K <= 1024 && d->N <= 1024 && (d->batches == 1 || d->rpb >= 256);
+  return TPSPP_OK;
+}
+enum { LW_WFWD = 0, LW_WDX, LW_WG, LW_COUNT };
+static void lin_offsets(const LinDims& d, size_t* off, size_t* total) {
+  size_t sz[LW_COUNT];
+  const int npf = (d.N + d.nt_fwd - 1) / d.nt_fwd * d.nt_fwd, npx = (d.K + d.nt_dx - 1) / d.nt_dx * d.nt_dx;
+  sz[LW_WFWD] = d.tc_fwd ? (size_t)2 * npf * d.K * d.batches : 0;
+  sz[LW_WDX] = d.tc_dx ? (size_t)2 * npx * d.N * d.batches : 0;
+  sz[LW_WG] = d.tc_wg ? wgrad_rows_ws_floats(d.R, d.K, d.N, d.batches) : 0;
+  size_t cur = 0;
+  for (int i = 0; i < LW_COUNT; ++i) {
+    off[i] = cur;
+    cur += (sz[i] * sizeof(float) + 255) / 256 * 256;
+  }
+  *total = cur + 256;
+}
+
+// out[R, Nn] = in[R, Kk] . img^T (+ bias) through the tcgen05 row-major linear kernel
+static int lin_tc_run(const float* in, const float* wimg, const float* bias, float* out, const LinDims& d, int Kk, int Nn, int NT,
+                      cudaStream_t st) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src[0].ptr = in; a.src[0].C = Kk; a.src[0].H = 1; a.src[0].W = (int)d.rpb; a.src[0].uh = a.src[0].uw = 1; a.src[0].nhwc = 1;
+  a.src[1].H = a.src[1].W = a.src[1].uh = a.src[1].uw = 1; a.src[2] = a.src[1];
+  a.bias = bias; a.out = out; a.B = d.batches; a.Ho = 1; a.Wo = (int)d.rpb; a.Ctot = Kk; a.sh = a.sw = 1; a.pad = 0;
+  a.out_nhwc = 1; a.act = CONV_ACT_NONE; a.act_scale = 1.f; a.Cout = Nn;
+  a.wimg_stride = d.batches > 1 ? (long long)2 * ((Nn + NT - 1) / NT * NT) * Kk : 0;
+  return run_conv_tc(1, a, wimg, NT, st, CM_TF32X3);
+}
+
+}  // namespace tpspp
+
+using namespace tpspp;
+
+extern "C" size_t tpspp_linear_workspace_bytes(const tpspp_linear_cfg* cfg) {
+  LinDims d;
+  if (lin_dims(cfg, &d) != TPSPP_OK) return 0;
+  size_t off[LW_COUNT], total;
+  lin_offsets(d, off, &total);
+  return total;
+}
+
+extern "C" int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias, float* y,
+                                void* workspace, tpspp_stream_t stream) {
+  reset_launch_count();
+  LinDims d;
+  int rc = lin_dims(cfg, &d);
+  if (rc != TPSPP_OK) return rc;
+  if (d.R == 0) return TPSPP_OK;
+  TPSPP_REQUIRE(x && w && y && workspace, "tpspp_linear_fwd: null pointer");
+  TPSPP_REQUIRE(d.batches == 1 || bias == nullptr, "tpspp_linear_fwd: batched weights (bmm) take no bias");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t off[LW_COUNT], total;
+  lin_offsets(d, off, &total);
+  if (d.tc_fwd && !(((uintptr_t)x | (uintptr_t)y | (uintptr_t)workspace) & 15)) {
+    float* img = reinterpret_cast<float*>((char*)workspace + off[LW_WFWD]);
+    const long long tot = (long long)((d.N + d.nt_fwd - 1) / d.nt_fwd * d.nt_fwd) * d.K * d.batches;
+    lin_wprep_kernel<<<(unsigned)min((tot + 255) / 256, 2048LL), 256, 0, st>>>(w, img, d.N, d.K, d.nt_fwd, 0, d.batches);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+    return lin_tc_run(x, img, bias, y, d, d.K, d.N, d.nt_fwd, st);
+  }
+  lin_small_fwd_kernel<<<dim3((d.N + 31) / 32, (unsigned)((d.rpb + 31) / 32), d.batches), 256, 0, st>>>(x, w, bias, y, d.K, d.N, d.rpb, 0);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}
+
+extern "C" int tpspp_linear_bwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* gy, float* gx, float* gw,
+                                float* gb, void* workspace, tpspp_stream_t stream) {
+  reset_launch_count();
+  LinDims d;
+  int rc = lin_dims(cfg, &d);
+  if (rc != TPSPP_OK) return rc;
+  if (d.R == 0) return TPSPP_OK;
+  TPSPP_REQUIRE(x && w && gy && workspace, "tpspp_linear_bwd: null pointer");
+  TPSPP_REQUIRE(d.batches == 1 || gb == nullptr, "tpspp_linear_bwd: batched weights (bmm) have no bias gradient");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t off[LW_COUNT], total;
+  lin_offsets(d, off, &total);
+  if (gx != nullptr) {
+    if (d.tc_dx && !(((uintptr_t)gy | (uintptr_t)gx | (uintptr_t)workspace) & 15)) {
+      float* img = reinterpret_cast<float*>((char*)workspace + off[LW_WDX]);
+      const long long tot = (long long)((d.K + d.nt_dx - 1) / d.nt_dx * d.nt_dx) * d.N * d.batches;
+      lin_wprep_kernel<<<(unsigned)min((tot + 255) / 256, 2048LL), 256, 0, st>>>(w, img, d.K, d.N, d.nt_dx, 1, d.batches);
+      count_launch();
+      TPSPP_CHECK_CUDA(cudaGetLastError());
+      rc = lin_tc_run(gy, img, nullptr, gx, d, d.N, d.K, d.nt_dx, st);
+      if (rc != TPSPP_OK) return rc;
+    } else {
+      // gx[r][k] = sum_n gy[r][n] w[n][k]: the forward kernel with the roles of K and N swapped and the weight read transposed
+      lin_small_fwd_kernel<<<dim3((d.K + 31) / 32, (unsigned)((d.rpb + 31) / 32), d.batches), 256, 0, st>>>(gy, w, nullptr, gx, d.N, d.K, d.rpb, 1);
+      count_launch();
+      TPSPP_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+  if (gw != nullptr) {
+    if (d.tc_wg && !(((uintptr_t)workspace) & 15)) {
+      rc = run_wgrad_rows(gy, x, gw, gb, d.R, d.K, d.N, d.batches, reinterpret_cast<float*>((char*)workspace + off[LW_WG]), st);
+      if (rc != TPSPP_OK) return rc;
+    } else {
+      lin_small_wgrad_kernel<<<dim3((d.K + 1 + 31) / 32, d.N, d.batches), 256, 0, st>>>(gy, x, gw, gb, d.rpb, d.K, d.N);
+      count_launch();
+      TPSPP_CHECK_CUDA(cudaGetLastError());
+    }
+  } else if (gb != nullptr) {
+    TPSPP_REQUIRE(false, "tpspp_linear_bwd: the bias gradient comes with the weight gradient (pass gw)");
+  }
+  return TPSPP_OK;
+}

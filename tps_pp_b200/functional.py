@@ -294,56 +294,95 @@ def stage_forward(img: torch.Tensor, params, workspace: Optional[torch.Tensor] =
     return o0, o1, x, workspace
 
 
+def _conv_cfg(b, cin, h, w, k, sh, sw, relu, ups):
+    cfg = N.ConvCfg(b, cin, h, w, k, sh, sw, 1 if relu else 0, len(ups))
+    for i, (uh, uw) in enumerate(ups):
+        cfg.up_h[i] = uh
+        cfg.up_w[i] = uw
+    return cfg
+
+
+def _ptr_array(ts):
+    arr = (ctypes.c_void_p * 3)()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
 class _ConvRelu(torch.autograd.Function):
     """One ``ConvModule`` (conv + bias + ReLU, reference tps_pp.py:126-131,149-154,538-548) with native forward AND backward
-    (``tpspp_conv_fwd`` / ``tpspp_conv_bwd``): the training-path counterpart of the fused inference head."""
+    (``tpspp_convcat_fwd`` / ``tpspp_convcat_bwd``): the training-path counterpart of the fused inference head.  The input is
+    ``torch.cat([F.interpolate(x_s, scale_factor=ups[s]) for s], dim=1)`` without either being materialised
+    (tps_pp.py:159-168,583-585)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, relu):
-        _require_cuda("x", x, torch.float32)
+    def forward(ctx, weight, bias, stride, relu, ups, *xs):
         _require_cuda("weight", weight, torch.float32)
         _require_cuda("bias", bias, torch.float32)
-        x = x.contiguous(); weight = weight.contiguous(); bias = bias.contiguous()
-        b, cin, h, w = x.shape
+        xs = [x.contiguous() for x in xs]
+        for x in xs:
+            _require_cuda("x", x, torch.float32)
+        weight = weight.contiguous(); bias = bias.contiguous()
+        b = xs[0].shape[0]
+        h, w = xs[0].shape[2] * ups[0][0], xs[0].shape[3] * ups[0][1]
+        cin = sum(x.shape[1] for x in xs)
+        for x, (uh, uw) in zip(xs, ups):
+            if x.shape[0] != b or (x.shape[2] * uh, x.shape[3] * uw) != (h, w) or (len(xs) > 1 and x.shape[1] != 64):
+                raise RuntimeError("tps_pp_b200: concatenated conv sources must share batch and (upsampled) size, 64 channels each")
         k = weight.shape[-1]
         if weight.shape[0] != 64 or weight.shape[1] != cin or weight.shape[2] != k:
             raise RuntimeError(f"tps_pp_b200: conv weight must be [64,{cin},k,k], got {tuple(weight.shape)}")
         sh, sw = (stride, stride) if isinstance(stride, int) else stride
-        cfg = N.ConvCfg(b, cin, h, w, k, sh, sw, 1 if relu else 0)
-        with torch.cuda.device(x.device):
+        cfg = _conv_cfg(b, cin, h, w, k, sh, sw, relu, ups)
+        dev = xs[0].device
+        with torch.cuda.device(dev):
             nbytes = int(N.lib().tpspp_conv_workspace_bytes(ctypes.byref(cfg)))
             if nbytes == 0 and b > 0:
                 raise RuntimeError("tpspp_conv_workspace_bytes failed: " + N.last_error())
-            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
-            y = torch.empty((b, 64, h // sh, w // sw), dtype=torch.float32, device=x.device)
-            N.check(N.lib().tpspp_conv_fwd(ctypes.byref(cfg), _ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(ws), _stream(x)),
-                    "tpspp_conv_fwd")
-        ctx.save_for_backward(x, weight, y)
-        ctx.cfg = (b, cin, h, w, k, sh, sw, 1 if relu else 0)
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+            y = torch.empty((b, 64, h // sh, w // sw), dtype=torch.float32, device=dev)
+            N.check(N.lib().tpspp_convcat_fwd(ctypes.byref(cfg), _ptr_array(xs), _ptr(weight), _ptr(bias), _ptr(y), _ptr(ws),
+                                              _stream(y)), "tpspp_convcat_fwd")
+        ctx.save_for_backward(weight, y, *xs)
+        ctx.cfg = (b, cin, h, w, k, sh, sw, relu, tuple(ups))
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight, y = ctx.saved_tensors
-        cfg = N.ConvCfg(*ctx.cfg)
+        weight, y, *xs = ctx.saved_tensors
+        cfg = _conv_cfg(*ctx.cfg)
         gy = gy.contiguous()
         need = ctx.needs_input_grad
-        gx = torch.empty_like(x) if need[0] else None
-        gw = torch.empty_like(weight) if need[1] else None
-        gb = torch.empty(64, dtype=torch.float32, device=x.device) if need[2] else None
-        with torch.cuda.device(x.device):
+        gxs = [torch.empty_like(x) if need[5 + i] else None for i, x in enumerate(xs)]
+        gw = torch.empty_like(weight) if need[0] else None
+        gb = torch.empty(64, dtype=torch.float32, device=y.device) if need[1] else None
+        with torch.cuda.device(y.device):
             nbytes = int(N.lib().tpspp_conv_workspace_bytes(ctypes.byref(cfg)))
-            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
-            N.check(N.lib().tpspp_conv_bwd(ctypes.byref(cfg), _ptr(x), _ptr(weight), _ptr(y), _ptr(gy), _ptr(gx), _ptr(gw),
-                                           _ptr(gb), _ptr(ws), _stream(x)), "tpspp_conv_bwd")
-        return gx, gw, gb, None, None
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=y.device)
+            N.check(N.lib().tpspp_convcat_bwd(ctypes.byref(cfg), _ptr_array(xs), _ptr(weight), _ptr(y), _ptr(gy), _ptr_array(gxs),
+                                              _ptr(gw), _ptr(gb), _ptr(ws), _stream(y)), "tpspp_convcat_bwd")
+        return (gw, gb, None, None, None, *gxs)
 
 
-def conv_relu_supported(x: torch.Tensor, weight: torch.Tensor, stride=1) -> bool:
-    """Geometry the native training convolution covers (include/tpspp.h ``tpspp_conv_cfg``)."""
-    if not (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 4 and weight.dim() == 4):
+def conv_relu_supported(x, weight: torch.Tensor, stride=1, ups=None) -> bool:
+    """Geometry the native training convolution covers (include/tpspp.h ``tpspp_conv_cfg``).  ``x``: one tensor or a sequence
+    of up to three 64-channel tensors (fused ``torch.cat``); ``ups``: per-source nearest-upsample factors (fused ``F.interpolate``)."""
+    xs = [x] if isinstance(x, torch.Tensor) else list(x)
+    ups = _norm_ups(ups, len(xs))
+    if not 1 <= len(xs) <= 3 or weight.dim() != 4 or weight.dtype != torch.float32:
         return False
-    b, cin, h, w = x.shape
+    for t, (uh, uw) in zip(xs, ups):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4) or uh not in (1, 2) or uw not in (1, 2):
+            return False
+        if len(xs) > 1 and t.shape[1] != 64:
+            return False
+        if (t.shape[2] * t.shape[3]) % 4:
+            return False
+    b = xs[0].shape[0]
+    h, w = xs[0].shape[2] * ups[0][0], xs[0].shape[3] * ups[0][1]
+    if any(t.shape[0] != b or (t.shape[2] * u[0], t.shape[3] * u[1]) != (h, w) for t, u in zip(xs, ups)):
+        return False
+    cin = sum(t.shape[1] for t in xs)
     k = weight.shape[-1]
     sh, sw = (stride, stride) if isinstance(stride, int) else stride
     if weight.shape[0] != 64 or weight.shape[1] != cin or weight.shape[2] != k or k not in (1, 3):
@@ -352,12 +391,90 @@ def conv_relu_supported(x: torch.Tensor, weight: torch.Tensor, stride=1) -> bool
         return False
     if (sh, sw) != (1, 1) and not (k == 3 and sh == 2 and sw in (1, 2)):
         return False
+    if (sh, sw) != (1, 1) and any(u != (1, 1) for u in ups):
+        return False
     if h % sh or w % sw:
         return False
     ho, wo = h // sh, w // sw
     return b > 0 and (b * ho * wo) % 128 == 0 and (b * h * w) % 128 == 0 and (ho * wo) % 32 == 0 and (h * w) % 4 == 0
 
 
-def conv_relu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride=1, relu: bool = True) -> torch.Tensor:
-    """``relu(conv2d(x, weight, bias, stride, padding=k//2))`` with 64 output channels on the native kernels, differentiable."""
-    return _ConvRelu.apply(x, weight, bias, stride, relu)
+def _norm_ups(ups, n):
+    if ups is None:
+        return [(1, 1)] * n
+    out = []
+    for u in ups:
+        out.append((int(u), int(u)) if isinstance(u, int) else (int(u[0]), int(u[1])))
+    if len(out) != n:
+        raise RuntimeError("tps_pp_b200: one upsample factor per conv source")
+    return out
+
+
+def conv_relu(x, weight: torch.Tensor, bias: torch.Tensor, stride=1, relu: bool = True, ups=None) -> torch.Tensor:
+    """``relu(conv2d(cat([interpolate(x_s, ups[s]) ...], 1), weight, bias, stride, padding=k//2))`` with 64 output channels on the
+    native kernels, differentiable.  ``x``: one tensor or a sequence of up to three 64-channel tensors."""
+    xs = [x] if isinstance(x, torch.Tensor) else list(x)
+    return _ConvRelu.apply(weight, bias, stride, relu, _norm_ups(ups, len(xs)), *xs)
+
+
+class _Linear(torch.autograd.Function):
+    """``nn.Linear`` / ``torch.bmm(x, w^T)`` of the head's dense stages with native forward AND backward
+    (``tpspp_linear_fwd`` / ``tpspp_linear_bwd``; reference DGAB.py:11-23,28-36,52, tps_pp.py:250-273,293-299)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda("x", x, torch.float32)
+        _require_cuda("weight", weight, torch.float32)
+        _require_cuda("bias", bias, torch.float32)
+        batches = weight.shape[0] if weight.dim() == 3 else 1
+        n, k = weight.shape[-2], weight.shape[-1]
+        if x.shape[-1] != k:
+            raise RuntimeError(f"tps_pp_b200: linear input features {x.shape[-1]} != weight in_features {k}")
+        if batches > 1 and (bias is not None or x.shape[0] != batches):
+            raise RuntimeError("tps_pp_b200: batched linear (bmm) needs x [batches, rows, in] and no bias")
+        x2 = x.contiguous()
+        weight = weight.contiguous()
+        bias = bias.contiguous() if bias is not None else None
+        rows = x2.numel() // k
+        cfg = N.LinearCfg(rows, k, n, batches)
+        y = torch.empty(x.shape[:-1] + (n,), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            nbytes = int(N.lib().tpspp_linear_workspace_bytes(ctypes.byref(cfg)))
+            if nbytes == 0:
+                raise RuntimeError("tpspp_linear_workspace_bytes failed: " + N.last_error())
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            N.check(N.lib().tpspp_linear_fwd(ctypes.byref(cfg), _ptr(x2), _ptr(weight), _ptr(bias), _ptr(y), _ptr(ws), _stream(x)),
+                    "tpspp_linear_fwd")
+        ctx.save_for_backward(x2, weight)
+        ctx.cfg = (rows, k, n, batches)
+        ctx.has_bias = bias is not None
+        ctx.x_shape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight = ctx.saved_tensors
+        cfg = N.LinearCfg(*ctx.cfg)
+        gy = gy.contiguous()
+        need = ctx.needs_input_grad
+        want_w = need[1] or (ctx.has_bias and need[2])
+        gx = torch.empty_like(x2) if need[0] else None
+        gw = torch.empty_like(weight) if want_w else None
+        gb = torch.empty(ctx.cfg[2], dtype=torch.float32, device=gy.device) if (ctx.has_bias and need[2]) else None
+        with torch.cuda.device(gy.device):
+            nbytes = int(N.lib().tpspp_linear_workspace_bytes(ctypes.byref(cfg)))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=gy.device)
+            N.check(N.lib().tpspp_linear_bwd(ctypes.byref(cfg), _ptr(x2), _ptr(weight), _ptr(gy), _ptr(gx), _ptr(gw), _ptr(gb),
+                                             _ptr(ws), _stream(gy)), "tpspp_linear_bwd")
+        return (gx.view(ctx.x_shape) if gx is not None else None), (gw if need[1] else None), gb
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear(x, weight, bias)`` on the native kernels, differentiable (any leading shape, fp32)."""
+    return _Linear.apply(x, weight, bias)
+
+
+def bmm_nt(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``torch.bmm(x, w.transpose(1, 2))`` -- x [B, rows, K], w [B, N, K] -> [B, rows, N] -- on the native kernels, differentiable
+    (the einsum of ``atten_score``, tps_pp.py:293-299)."""
+    return _Linear.apply(x, w, None)

@@ -157,7 +157,11 @@ class TPS_PP(_BaseModule):
         self.head_impl = "auto"
         # convolutions of the TRAINING path (autograd recording): "native" = tpspp_conv_fwd/bwd, "library" = cuDNN
         self.train_convs = "native"
+        # dense layers of the TRAINING path (nn.Linear / bmm of CBAM, DGAB, localisation, score): "native" =
+        # tpspp_linear_fwd/bwd, "library" = cuBLAS
+        self.train_linears = "native"
         self._train_native_convs = self._train_library_convs = 0
+        self._train_native_linears = self._train_library_linears = 0
         self._last_head_native = None
         # tcgen05 3xTF32 convolutions (fp32-level accuracy); N.HEAD_FP32 = CUDA-core only
         self.head_precision = N.HEAD_TC
@@ -171,24 +175,39 @@ class TPS_PP(_BaseModule):
     def _p(self, name: str) -> torch.Tensor:
         return self.get_parameter(name)
 
-    def _conv_relu(self, prefix: str, x, stride=1, padding=0):
+    def _conv_relu(self, prefix: str, x, stride=1, padding=0, ups=None):
+        """``x``: a tensor, or a sequence of tensors that the reference concatenates along the channels first; ``ups``: the
+        nearest-upsample factor the reference applies to each of them first (``F.interpolate`` / ``nn.Upsample``)."""
         w, b = self._p(prefix + ".conv.weight"), self._p(prefix + ".conv.bias")
-        # training path: native forward AND backward of the ConvModule (tpspp_conv_fwd / tpspp_conv_bwd) where its geometry
-        # is covered; cuDNN otherwise (tiny batches of the deepest layers)
-        if self.train_convs == "native" and w.shape[0] == 64 and TF.conv_relu_supported(x, w, stride):
+        # training path: native forward AND backward of the ConvModule (tpspp_convcat_fwd / tpspp_convcat_bwd) where its
+        # geometry is covered -- cat and upsampling fused into the convolution; cuDNN otherwise (tiny batches of the deepest layers)
+        if self.train_convs == "native" and w.shape[0] == 64 and TF.conv_relu_supported(x, w, stride, ups):
             self._train_native_convs += 1
-            return TF.conv_relu(x, w, b, stride)
+            return TF.conv_relu(x, w, b, stride, True, ups)
         self._train_library_convs += 1
+        xs = [x] if isinstance(x, torch.Tensor) else list(x)
+        if ups is not None:
+            xs = [t if u in (1, (1, 1)) else F.interpolate(t, scale_factor=u, mode="nearest") for t, u in zip(xs, ups)]
+        x = xs[0] if len(xs) == 1 else torch.cat(xs, dim=1)
         return F.relu(F.conv2d(x, w, b, stride=stride, padding=padding))
+
+    def _lin(self, x, wname: str, bname: Optional[str] = None):
+        """``F.linear`` of the training path: native forward and backward (tpspp_linear_fwd / tpspp_linear_bwd) or cuBLAS."""
+        w = self._p(wname) if isinstance(wname, str) else wname
+        b = self._p(bname) if bname is not None else None
+        if self.train_linears == "native":
+            self._train_native_linears += 1
+            return TF.linear(x, w, b)
+        self._train_library_linears += 1
+        return F.linear(x, w, b)
 
     def _down(self, x, o0, o1):
         """tps_pp.py:581-585 (+ :560-562)."""
         f0 = self._conv_relu("down0", o0)
         f1 = self._conv_relu("down1", o1)
         f2 = self._conv_relu("down2", x)
-        feat_cat = torch.cat((self._conv_relu("down0_1", f0, 2, 1), self._conv_relu("down1_1", f1, 2, 1), f2), dim=1)
-        up = F.interpolate(f2, scale_factor=2, mode="nearest")
-        feat_grid = self._conv_relu("down_feat", torch.cat((f0, f1, up), dim=1))
+        feat_cat = (self._conv_relu("down0_1", f0, 2, 1), self._conv_relu("down1_1", f1, 2, 1), f2)   # concatenated by enc0
+        feat_grid = self._conv_relu("down_feat", (f0, f1, f2), ups=(1, 1, 2))
         return feat_cat, feat_grid
 
     def _cbam(self, x):
@@ -196,12 +215,24 @@ class TPS_PP(_BaseModule):
         w0 = self._p("MSFA.conv.atten.channel_attention.shared_MLP.0.weight")
         w2 = self._p("MSFA.conv.atten.channel_attention.shared_MLP.2.weight")
         pooled = torch.cat([x.mean(dim=(2, 3), keepdim=True), x.amax(dim=(2, 3), keepdim=True)], dim=0)
-        z = F.conv2d(F.relu(F.conv2d(pooled, w0)), w2)
         b = x.shape[0]
+        if self.train_linears == "native":
+            # the two 1x1 convolutions of shared_MLP act on pooled [2B,64,1,1]: dense layers; the 3x3 spatial-attention
+            # convolution (2 -> 1 channels on a 2x16 map) as unfold + dense layer
+            z = self._lin(F.relu(self._lin(pooled.flatten(1), w0.flatten(1))), w2.flatten(1))[:, :, None, None]
+        else:
+            z = F.conv2d(F.relu(F.conv2d(pooled, w0)), w2)
         out = torch.sigmoid(z[:b] + z[b:]) * x
         sp = torch.cat([out.mean(dim=1, keepdim=True), out.amax(dim=1, keepdim=True)], dim=1)
-        gate = F.conv2d(sp, self._p("MSFA.conv.atten.spatial_attention.conv2d.weight"),
-                        self._p("MSFA.conv.atten.spatial_attention.conv2d.bias"), padding=1)
+        wsp, bsp = self._p("MSFA.conv.atten.spatial_attention.conv2d.weight"), self._p("MSFA.conv.atten.spatial_attention.conv2d.bias")
+        if self.train_linears == "native":
+            hh, ww = sp.shape[2], sp.shape[3]
+            spp = F.pad(sp, (1, 1, 1, 1))                                           # im2col by shifted views: [B, h*w, 2*9]
+            cols = torch.stack([spp[:, :, dy:dy + hh, dx:dx + ww] for dy in range(3) for dx in range(3)], dim=2).flatten(1, 2)
+            cols = cols.flatten(2).transpose(1, 2)
+            gate = self._lin(cols, wsp.flatten(1), "MSFA.conv.atten.spatial_attention.conv2d.bias").transpose(1, 2).reshape(b, 1, *sp.shape[2:])
+        else:
+            gate = F.conv2d(sp, wsp, bsp, padding=1)
         return torch.sigmoid(gate) * out
 
     def _msfa(self, feat_cat):
@@ -215,9 +246,7 @@ class TPS_PP(_BaseModule):
         en_feat = skips[-1]
         k = self._cbam(en_feat)
         for i, sc in enumerate(((2, 1), self.p_stride, 2, 1)):
-            if sc != 1:
-                k = F.interpolate(k, scale_factor=sc, mode="nearest")
-            k = self._conv_relu(f"MSFA.conv.k_decoder.{i}.1", k, 1, 1)
+            k = self._conv_relu(f"MSFA.conv.k_decoder.{i}.1", k, 1, 1, ups=(sc,))
             if i < 3:
                 k = k + skips[2 - i]
         return en_feat, k
@@ -228,15 +257,14 @@ class TPS_PP(_BaseModule):
         h, w = x.shape[2], x.shape[3]
         u = F.layer_norm(x, (h, w), self._p(pre + "norm1.weight"), self._p(pre + "norm1.bias"))
         yt = en.transpose(1, 2)
-        lw = F.linear(torch.cat([u.mean(2), yt], 2), self._p(pre + "attn.mlp_w.0.weight"))
-        lh = F.linear(torch.cat([u.mean(3), yt], 2), self._p(pre + "attn.mlp_h.0.weight"))
+        lw = self._lin(torch.cat([u.mean(2), yt], 2), pre + "attn.mlp_w.0.weight")
+        lh = self._lin(torch.cat([u.mean(3), yt], 2), pre + "attn.mlp_h.0.weight")
         v_w = lw[:, :, :-1].softmax(dim=-1).unsqueeze(2) * lw[:, :, -1, None, None]
         v_h = lh[:, :, :-1].softmax(dim=-1).unsqueeze(3) * lh[:, :, -1, None, None]
         a = u * (v_h + v_w)
-        x = x + F.linear(a, self._p(pre + "attn.proj.weight"), self._p(pre + "attn.proj.bias"))
+        x = x + self._lin(a, pre + "attn.proj.weight", pre + "attn.proj.bias")
         v = F.layer_norm(x, (h, w), self._p(pre + "norm2.weight"), self._p(pre + "norm2.bias"))
-        v = F.linear(F.gelu(F.linear(v, self._p(pre + "mlp.fc1.weight"), self._p(pre + "mlp.fc1.bias"))),
-                     self._p(pre + "mlp.fc2.weight"), self._p(pre + "mlp.fc2.bias"))
+        v = self._lin(F.gelu(self._lin(v, pre + "mlp.fc1.weight", pre + "mlp.fc1.bias")), pre + "mlp.fc2.weight", pre + "mlp.fc2.bias")
         return x + v
 
     def _tpe(self, en_feat, de_feat):
@@ -244,16 +272,18 @@ class TPS_PP(_BaseModule):
         b = en_feat.shape[0]
         en = en_feat.flatten(2).transpose(1, 2)
         de = self._dgab(de_feat, en)
-        z = F.relu(F.linear(F.relu(F.linear(en, self._p("TPE.localization_fc1.0.weight"), self._p("TPE.localization_fc1.0.bias"))),
-                            self._p("TPE.localization_fc1.2.weight"), self._p("TPE.localization_fc1.2.bias")))
-        c_prime = F.linear(z.reshape(b, -1), self._p("TPE.localization_fc2.weight"),
-                           self._p("TPE.localization_fc2.bias")).view(b, self.num_fiducial, 2)
-        p1 = F.linear(F.linear(en, self._p("TPE.p_linear.0.weight"), self._p("TPE.p_linear.0.bias")),
-                      self._p("TPE.p_linear.1.weight"), self._p("TPE.p_linear.1.bias"))
+        z = F.relu(self._lin(F.relu(self._lin(en, "TPE.localization_fc1.0.weight", "TPE.localization_fc1.0.bias")),
+                             "TPE.localization_fc1.2.weight", "TPE.localization_fc1.2.bias"))
+        c_prime = self._lin(z.reshape(b, -1), "TPE.localization_fc2.weight", "TPE.localization_fc2.bias").view(b, self.num_fiducial, 2)
+        p1 = self._lin(self._lin(en, "TPE.p_linear.0.weight", "TPE.p_linear.0.bias"), "TPE.p_linear.1.weight", "TPE.p_linear.1.bias")
         feat = de.flatten(2).transpose(1, 2)
-        f = F.linear(F.linear(feat, self._p("TPE.feat_linear.0.weight"), self._p("TPE.feat_linear.0.bias")),
-                     self._p("TPE.feat_linear.1.weight"), self._p("TPE.feat_linear.1.bias"))
-        score = torch.tanh(torch.bmm(f, p1.transpose(1, 2)) * self.scale)
+        f = self._lin(self._lin(feat, "TPE.feat_linear.0.weight", "TPE.feat_linear.0.bias"), "TPE.feat_linear.1.weight", "TPE.feat_linear.1.bias")
+        if self.train_linears == "native":
+            self._train_native_linears += 1
+            score = torch.tanh(TF.bmm_nt(f, p1) * self.scale)
+        else:
+            self._train_library_linears += 1
+            score = torch.tanh(torch.bmm(f, p1.transpose(1, 2)) * self.scale)
         return c_prime, score
 
     # ------------------------------------------------------------------ forward
@@ -266,7 +296,8 @@ class TPS_PP(_BaseModule):
     @property
     def training_stages(self):
         """What the last autograd-recording forward ran its 14 ConvModules on: (native launches, cuDNN launches)."""
-        return {"convs_native": self._train_native_convs, "convs_library": self._train_library_convs}
+        return {"convs_native": self._train_native_convs, "convs_library": self._train_library_convs,
+                "linears_native": self._train_native_linears, "linears_library": self._train_library_linears}
 
     def _use_native_head(self, batch_img) -> bool:
         if self.head_impl == "native":
@@ -300,6 +331,7 @@ class TPS_PP(_BaseModule):
             return fg, cp, sc
         self._last_head_launches = 0
         self._train_native_convs = self._train_library_convs = 0
+        self._train_native_linears = self._train_library_linears = 0
         # library stages must not drop to TF32: C' feeds a solve that amplifies rounding 1e2-1e3x
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False), _matmul_fp32():
             feat_cat, feat_grid = self._down(batch_img, outs[0], outs[1])
