@@ -171,11 +171,25 @@ __global__ void __launch_bounds__(256, 3) wgrad_kernel(WgradArgs a) {
 // gw[co][ci][tap] = sum over splits of part[split][tap][ci][co]: threads walk the partials' layout (coalesced reads; the
 // strided writes are 64 * Cin * T floats in total)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw, int Cin, int T, int splits) {
+  // block = 32 outputs x 8 split lanes: with one thread per output the 1x1 layers (2048 outputs, 296 splits) were a serial chain of
+  // 296 dependent loads on 8 blocks (40 us); fixed lane assignment + fixed tree = deterministic
+  __shared__ float red[8][33];
   const int total = 64 * Cin * T;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-    const int tap = i / (Cin * 64), r = i - tap * (Cin * 64), ci = r >> 6, co = r & 63;
+  const int ox = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ox;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < total) {
+    int s = sl;
+    for (; s + 8 < splits; s += 16) { a0 += __ldg(part + (size_t)s * total + i); a1 += __ldg(part + (size_t)(s + 8) * total + i); }
+    if (s < splits) a0 += __ldg(part + (size_t)s * total + i);
+  }
+  red[sl][ox] = a0 + a1;
+  __syncthreads();
+  if (sl == 0 && i < total) {
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += __ldg(part + (size_t)s * total + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += red[j][ox];
+    const int tap = i / (Cin * 64), r = i - tap * (Cin * 64), ci = r >> 6, co = r & 63;
     gw[((size_t)co * Cin + ci) * T + tap] = acc;
   }
 }
@@ -189,13 +203,22 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 //      Per chunk all 8 producer warps first stage x (two shifted rows per input channel) and g with coalesced loads
 //      (lane = pixel) into padded shared tiles; then warps 0-3 read their A row (conflict-free, pitch 33), split it and store
 //      it to tensor memory, warps 4-7 do the same for B into the operand images; one MMA warp issues. ----
-constexpr int WT_THREADS = 288, WT_PITCH = 33;
-constexpr int WT_XS = 128 * WT_PITCH * 4, WT_GS = 64 * WT_PITCH * 4;              // raw staging tiles (bytes)
+constexpr int WT_THREADS = 288;
+// raw-tile row pitch in floats.  Convolutions: 36 -- rows start 16-byte aligned, so g (and x of a 1x1 layer) arrive by 16-byte
+// copies and are read back with LDS.128 (a quarter warp's rows fall into distinct bank groups: conflict-free).  Row-major
+// linear layers: 33 -- the copies TRANSPOSE (lane = feature), which needs an odd pitch; reads are scalar.
+// The x tile of a 3x3 layer keeps pitch 33 (its taps are misaligned: 4-byte copies, scalar reads; 36 would not fit two CTAs per SM);
+// a 1x1 layer uses only 64 of the 128 rows, which leaves room for pitch 36 there.
+template <bool ROWS> struct WtPitch { static constexpr int v = ROWS ? 33 : 36; };
+constexpr int WT_XS = 128 * 33 * 4, WT_GS = 64 * 36 * 4;                          // raw staging tiles (bytes)
 constexpr int WT_RING = 3;                                                         // raw-tile ring: chunk i+2 is in flight while chunk i is consumed
 constexpr int WT_SMEM = 2 * 16384 /* B images */ + WT_RING * (WT_XS + WT_GS) + 64 + 1024;
 // 4-byte asynchronous global -> shared copy; src_bytes = 0 writes a zero (padding, channels beyond the tensor)
 __device__ __forceinline__ void cp_async4(void* dst, const void* src, bool ok) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 // ROWS = true: the same engine for a row-major linear layer y[R,N] = x[R,K] w^T: gw[n][k] = sum_r gy[r][n] x[r][k] -- the
 // contraction axis is the ROW axis, A rows = 128 input features (blockIdx.x), B columns = 64 output features (blockIdx.z),
@@ -203,10 +226,12 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src, bool ok) {
 // transposed raw tiles).  The B-staging threads also keep the column sums of gy (bias gradient) when bpart is given.
 template <bool ROWS>
 __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, int npairs) {
+  constexpr int WT_PITCH = WtPitch<ROWS>::v;              // g tile (and both tiles of the row-major mode)
+  const int XP = (ROWS || a.KS != 1) ? 33 : 36;           // x tile
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* bimg = smem;                                             // 2 stages x (hi 8 KB | lo 8 KB)
-  float* xs = reinterpret_cast<float*>(smem + 2 * 16384);                       // WT_RING x [128][33]
+  float* xs = reinterpret_cast<float*>(smem + 2 * 16384);                       // WT_RING x [128][pitch]
   float* gs = reinterpret_cast<float*>(smem + 2 * 16384 + WT_RING * WT_XS);     // WT_RING x [64][33]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * 16384 + WT_RING * (WT_XS + WT_GS));
   uint64_t* s_empty = bars;          // [2] the MMAs that read stage s completed
@@ -219,6 +244,8 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
     mbar_init(&s_full[0], 8); mbar_init(&s_full[1], 8);
     fence_barrier_init();
   }
+  if (!ROWS && a.KS == 1)                      // 1x1 layers copy only the valid A rows (16-byte path): the others stay zero
+    for (int i = tid; i < WT_RING * (WT_XS / 4); i += WT_THREADS) xs[i] = 0.f;
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
@@ -272,8 +299,8 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
       if (ROWS) {
         const long long r0 = ch * 32;
         const int k0 = blockIdx.x * 128, n0 = blockIdx.z * 64;
-        float* xt = xs + slot * (128 * WT_PITCH);
-        float* gt = gs + slot * (64 * WT_PITCH);
+        float* xt = xs + slot * (WT_XS / 4);
+        float* gt = gs + slot * (WT_GS / 4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int rl = warp + 8 * j;
@@ -306,15 +333,31 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
       const float* x0 = xb + (ok0 ? (iy0 >> su) * Ws + (ix0 >> sv) : 0);
       const float* x1 = xb + (ok1 ? (iy1 >> su) * Ws + (ix1 >> sv) : 0);
       const float* gp = a.g + (size_t)b * 64 * HoWo + p;
-      float* xt = xs + slot * (128 * WT_PITCH);
-      float* gt = gs + slot * (64 * WT_PITCH);
+      float* xt = xs + slot * (WT_XS / 4);
+      float* gt = gs + slot * (WT_GS / 4);
+      // g: the chunk's 32 pixels are contiguous and 16-byte aligned in every channel plane: 64 rows x 8 segments of 16 bytes
+      const int ptid = warp * 32 + lane;
+      const float* gch = gp - lane;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = warp + 8 * j;
-        const bool cv = c < cw;
-        cp_async4(xt + c * WT_PITCH + lane, x0 + (size_t)(cv ? c : 0) * HWs, ok0 && cv);
-        cp_async4(xt + (64 + c) * WT_PITCH + lane, x1 + (size_t)(cv ? c : 0) * HWs, ok1 && cv);
-        cp_async4(gt + c * WT_PITCH + lane, gp + (size_t)c * HoWo, true);
+      for (int j = 0; j < 2; ++j) {
+        const int idx = ptid + 256 * j, row = idx >> 3, seg = idx & 7;
+        cp_async16(gt + row * WT_PITCH + seg * 4, gch + (size_t)row * HoWo + seg * 4);
+      }
+      if (a.KS == 1 && su == 0 && sv == 0) {           // 1x1, plain source: the same for the cw valid rows of x
+        const float* xch = xb + (p - lane);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int idx = ptid + 256 * j, row = idx >> 3, seg = idx & 7;
+          if (row < cw) cp_async16(xt + row * XP + seg * 4, xch + (size_t)row * HWs + seg * 4);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = warp + 8 * j;
+          const bool cv = c < cw;
+          cp_async4(xt + c * XP + lane, x0 + (size_t)(cv ? c : 0) * HWs, ok0 && cv);
+          if (t1ok) cp_async4(xt + (64 + c) * XP + lane, x1 + (size_t)(cv ? c : 0) * HWs, ok1 && cv);
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -324,18 +367,26 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
     if (nmy > 1) fetch(c0 + 1, 1);
     for (int i = 0; i < nmy; ++i) {
       const int st = i & 1, slot = i % WT_RING;
-      float* xt = xs + slot * (128 * WT_PITCH);
-      float* gt = gs + slot * (64 * WT_PITCH);
+      float* xt = xs + slot * (WT_XS / 4);
+      float* gt = gs + slot * (WT_GS / 4);
       if (i + 1 < nmy) asm volatile("cp.async.wait_group 1;" ::: "memory");      // chunk i has landed (chunk i+1 may be in flight)
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
       named_bar_sync(1, 256);                       // every producer thread's copies of chunk i are visible; chunk i-1 is consumed
       if (i + 2 < nmy) fetch(c0 + i + 2, (i + 2) % WT_RING);
       if (warp < 4) {
         // A: row = this thread's (tap, input channel), 32 pixels -> hi | lo columns of the stage in tensor memory
-        const float* row = xt + (warp * 32 + lane) * WT_PITCH;
+        const float* row = xt + (warp * 32 + lane) * XP;
         float v[32];
+        if (ROWS || a.KS != 1) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = row[k];
+          for (int k = 0; k < 32; ++k) v[k] = row[k];
+        } else if (warp < 2) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(v + 4 * k) = *reinterpret_cast<const float4*>(row + 4 * k);
+        } else {                 // rows 64-127 = the pair's second tap, which a 1x1 filter does not have
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = 0.f;
+        }
         float hi[32], lo[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
@@ -356,8 +407,13 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradArgs a, in
         const int t = tid - 128, co = t & 63, half = t >> 6;
         const float* row = gt + co * WT_PITCH + half * 16;
         float v[16];
+        if (ROWS) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = row[k];
+          for (int k = 0; k < 16; ++k) v[k] = row[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(v + 4 * k) = *reinterpret_cast<const float4*>(row + 4 * k);
+        }
         if (ROWS) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) bsum += v[k];
@@ -427,17 +483,35 @@ __global__ void __launch_bounds__(256) wgrad_rows_reduce_kernel(const float* __r
     }
     return;
   }
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-    const int k = i / Npad, n = i - k * Npad;
-    if (n >= N) continue;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += __ldg(part + (size_t)s * total + i);
-    gw[(size_t)n * K + k] = acc;
-  }
-  if (gb != nullptr && blockIdx.x == 0) {
-    for (int n = threadIdx.x; n < N; n += 256) {
+  __shared__ float red[8][33];
+  const int ox = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  for (int i0 = blockIdx.x * 32; i0 < total; i0 += gridDim.x * 32) {       // block = 32 outputs x 8 split lanes (see wgrad_reduce_kernel)
+    const int i = i0 + ox;
+    float a0 = 0.f;
+    if (i < total)
+      for (int s = sl; s < splits; s += 8) a0 += __ldg(part + (size_t)s * total + i);
+    red[sl][ox] = a0;
+    __syncthreads();
+    if (sl == 0 && i < total) {
       float acc = 0.f;
-      for (int s = 0; s < 2 * splits; ++s) acc += __ldg(bpart + (size_t)s * Npad + n);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += red[j][ox];
+      const int k = i / Npad, n = i - k * Npad;
+      if (n < N) gw[(size_t)n * K + k] = acc;
+    }
+    __syncthreads();
+  }
+  if (gb != nullptr && blockIdx.x * 32 < N) {
+    const int n = blockIdx.x * 32 + ox;
+    float a0 = 0.f;
+    if (n < N)
+      for (int s = sl; s < 2 * splits; s += 8) a0 += __ldg(bpart + (size_t)s * Npad + n);
+    red[sl][ox] = a0;
+    __syncthreads();
+    if (sl == 0 && n < N) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += red[j][ox];
       gb[n] = acc;
     }
   }
@@ -480,7 +554,7 @@ int run_wgrad_rows(const float* gy, const float* x, float* gw, float* gb, long l
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   const long long rtotal = (long long)K * Npad * (batches > 1 ? sp : 1);
-  wgrad_rows_reduce_kernel<<<(unsigned)min((rtotal + 255) / 256, 4096LL), 256, 0, st>>>(ws, wa.bpart, gw, gb, K, N, Npad, sp, batches > 1);
+  wgrad_rows_reduce_kernel<<<(unsigned)min(batches > 1 ? (rtotal + 255) / 256 : (rtotal + 31) / 32, 4096LL), 256, 0, st>>>(ws, wa.bpart, gw, gb, K, N, Npad, sp, batches > 1);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;
@@ -710,7 +784,7 @@ extern "C" int tpspp_convcat_bwd(const tpspp_conv_cfg* cfg, const float* const* 
     }
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
-    wgrad_reduce_kernel<<<(64 * d.Cin * d.T + 255) / 256, 256, 0, st>>>(W(CW_WPART), gw, d.Cin, d.T, d.splits);
+    wgrad_reduce_kernel<<<(64 * d.Cin * d.T + 31) / 32, 256, 0, st>>>(W(CW_WPART), gw, d.Cin, d.T, d.splits);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
   }
