@@ -1081,15 +1081,15 @@ static void head_offsets(const HeadDims& d, size_t* off, size_t* total) {
   *total = cur + 256;
 }
 
-static ConvSrc mk_src(const float* p, int C, int H, int W, int nhwc, int uh = 1, int uw = 1) {
-  ConvSrc s; s.ptr = p; s.C = C; s.H = H; s.W = W; s.uh = uh; s.uw = uw; s.nhwc = nhwc; return s;
+static ConvSrc mk_src(const float* p, int C, int H, int W, int nhwc, int uh = 1, int uw = 1, int bf16 = 0) {
+  ConvSrc s; s.ptr = p; s.C = C; s.H = H; s.W = W; s.uh = uh; s.uw = uw; s.nhwc = nhwc; s.bf16 = bf16; return s;
 }
 
 static int run_conv(int KS, ConvSrc s0, ConvSrc s1, ConvSrc s2, const float* w, const float* bias, const float* skip,
                     float* out, int out_nhwc, int B, int Ho, int Wo, int sh, int sw, cudaStream_t st,
-                    const float* wprep = nullptr, int mode = CM_TF32X3) {
+                    const float* wprep = nullptr, int mode = CM_TF32X3, int out_bf16 = 0, int skip_bf16 = 0) {
   ConvArgs a;
-  a.out_nhwc = out_nhwc;
+  a.out_nhwc = out_nhwc; a.out_bf16 = out_bf16; a.skip_bf16 = skip_bf16;
   a.act = CONV_ACT_RELU; a.act_scale = 1.f; a.Cout = 64; a.wimg_stride = 0; a.skip_pre = 0; a.out_cstride = 0; a.zi = 0;
   a.src[0] = s0; a.src[1] = s1; a.src[2] = s2;
   a.weight = w; a.bias = bias; a.skip = skip; a.out = out;
@@ -1180,8 +1180,10 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   int cmode[14];
   for (int i = 0; i < 14; ++i) {
     const bool one = kConvLayers[i].KS == 1;
-    cmode[i] = bf16 ? CM_BF16 : ((one || (cfg->flags & TPSPP_HEAD_FLAG_TF32X3_CONV)) ? CM_TF32X3 : CM_MIX);
+    cmode[i] = (bf16 && !one) ? CM_BF16 : ((one || (cfg->flags & TPSPP_HEAD_FLAG_TF32X3_CONV)) ? CM_TF32X3 : CM_MIX);
   }
+  // (bf16 mode: the four 1x1 layers stay 3xTF32 inside the fused down kernel -- it is HBM-bound, so rounding its operands
+  //  buys nothing; run unfused they took 0.34 ms against the fused kernel's 0.27)
   if (tc) {
     WPrepLayer L[kNumTcLayers];
     float* cur = W(TPSPP_WS_WPREP);
@@ -1201,28 +1203,32 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   // down0/1/2 + grid()/down_feat (tps_pp.py:581-583,585,560-562): one fused tensor-core kernel in the 3xTF32 mode; f0/f1/f2
   // are still written (once) for the stride-2 convolutions and the MSFA encoder
   bool fused_down = false;
-  if (tc && !bf16 && !(cfg->flags & TPSPP_HEAD_FLAG_UNFUSED_DOWN)) {
+  if (tc && !(cfg->flags & TPSPP_HEAD_FLAG_UNFUSED_DOWN)) {
     rc = run_down_fused(x, o0, o1, wp[0], wp[1], wp[2], wp[5], P[TPSPP_P_DOWN0_B], P[TPSPP_P_DOWN1_B], P[TPSPP_P_DOWN2_B],
-                        P[TPSPP_P_DOWNFEAT_B], W(TPSPP_WS_F0), W(TPSPP_WS_F1), W(TPSPP_WS_F2), feat_grid, B, h, w, st);
+                        P[TPSPP_P_DOWNFEAT_B], W(TPSPP_WS_F0), W(TPSPP_WS_F1), W(TPSPP_WS_F2), feat_grid, B, h, w, st, bf16 ? 1 : 0);
     if (rc < 0) return rc;
     fused_down = rc == TPSPP_OK;
+    TPSPP_REQUIRE(fused_down || !bf16, "head: the bf16 mode needs the fused down kernel's geometry (width 64, 16-byte aligned inputs)");
   }
+  // bf16 mode: the LARGE head-internal activations are stored as bf16 (f0, f1, f2, a0, a1, e0, d2 -- 85 % of the intermediate
+  // bytes); the small deep maps (e1, e2, e3, cbam, d0, d1), de (DGAB's input) and everything after it stay fp32
+  const int bs = (bf16 && fused_down) ? 1 : 0;
   if (!fused_down) {
   RUN(1, mk_src(o0, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_W], P[TPSPP_P_DOWN0_B], nullptr, W(TPSPP_WS_F0), NCHW, B, H2, W2, 1, 1, st, wp[0], cmode[0]);
   RUN(1, mk_src(o1, 32, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_W], P[TPSPP_P_DOWN1_B], nullptr, W(TPSPP_WS_F1), NCHW, B, H2, W2, 1, 1, st, wp[1], cmode[1]);
   RUN(1, mk_src(x, 64, h, w, NCHW), none, none, P[TPSPP_P_DOWN2_W], P[TPSPP_P_DOWN2_B], nullptr, W(TPSPP_WS_F2), NCHW, B, h, w, 1, 1, st, wp[2], cmode[2]);
   }
   // down0_1 / down1_1: 3x3 stride 2 (tps_pp.py:584)
-  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), NCHW, B, h, w, 2, 2, st, wp[3], cmode[3]);
-  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), NCHW, B, h, w, 2, 2, st, wp[4], cmode[4]);
+  RUN(3, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW, 1, 1, bs), none, none, P[TPSPP_P_DOWN0_1_W], P[TPSPP_P_DOWN0_1_B], nullptr, W(TPSPP_WS_A0), NCHW, B, h, w, 2, 2, st, wp[3], cmode[3], bs);
+  RUN(3, mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW, 1, 1, bs), none, none, P[TPSPP_P_DOWN1_1_W], P[TPSPP_P_DOWN1_1_B], nullptr, W(TPSPP_WS_A1), NCHW, B, h, w, 2, 2, st, wp[4], cmode[4], bs);
   // grid(): down_feat(cat(f0, f1, up2(f2))) (tps_pp.py:560-562,585) -> feat_grid in the boundary layout (warp input)
   if (!fused_down)
   RUN(1, mk_src(W(TPSPP_WS_F0), 64, H2, W2, NCHW), mk_src(W(TPSPP_WS_F1), 64, H2, W2, NCHW), mk_src(W(TPSPP_WS_F2), 64, h, w, NCHW, 2, 2),
       P[TPSPP_P_DOWNFEAT_W], P[TPSPP_P_DOWNFEAT_B], nullptr, feat_grid, NCHW, B, H2, W2, 1, 1, st, wp[5], cmode[5]);
   // MSFA encoder (tps_pp.py:158-160): cat(a0, a1, f2) -> e0 -> e1 -> e2 -> e3
-  RUN(3, mk_src(W(TPSPP_WS_A0), 64, h, w, NCHW), mk_src(W(TPSPP_WS_A1), 64, h, w, NCHW), mk_src(W(TPSPP_WS_F2), 64, h, w, NCHW),
-      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), NCHW, B, h, w, 1, 1, st, wp[6], cmode[6]);
-  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w, NCHW), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), NCHW, B, d.h1, d.w1, 2, 2, st, wp[7], cmode[7]);
+  RUN(3, mk_src(W(TPSPP_WS_A0), 64, h, w, NCHW, 1, 1, bs), mk_src(W(TPSPP_WS_A1), 64, h, w, NCHW, 1, 1, bs), mk_src(W(TPSPP_WS_F2), 64, h, w, NCHW, 1, 1, bs),
+      P[TPSPP_P_ENC0_W], P[TPSPP_P_ENC0_B], nullptr, W(TPSPP_WS_E0), NCHW, B, h, w, 1, 1, st, wp[6], cmode[6], bs);
+  RUN(3, mk_src(W(TPSPP_WS_E0), 64, h, w, NCHW, 1, 1, bs), none, none, P[TPSPP_P_ENC1_W], P[TPSPP_P_ENC1_B], nullptr, W(TPSPP_WS_E1), NCHW, B, d.h1, d.w1, 2, 2, st, wp[7], cmode[7]);
   RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1, NCHW), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), NCHW, B, d.h2, d.w2, d.ps, d.ps, st, wp[8], cmode[8]);
   RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2, NCHW), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), NCHW, B, d.py, d.px, 2, 1, st, wp[9], cmode[9]);
   // CBAM on the deepest map (tps_pp.py:163)
@@ -1233,8 +1239,8 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   // decoder (tps_pp.py:165-168): upsample + conv + skip
   RUN(3, mk_src(W(TPSPP_WS_CBAM), 64, d.py, d.px, NCHW, 2, 1), none, none, P[TPSPP_P_DEC0_W], P[TPSPP_P_DEC0_B], W(TPSPP_WS_E2), W(TPSPP_WS_D0), NCHW, B, d.h2, d.w2, 1, 1, st, wp[10], cmode[10]);
   RUN(3, mk_src(W(TPSPP_WS_D0), 64, d.h2, d.w2, NCHW, d.ps, d.ps), none, none, P[TPSPP_P_DEC1_W], P[TPSPP_P_DEC1_B], W(TPSPP_WS_E1), W(TPSPP_WS_D1), NCHW, B, d.h1, d.w1, 1, 1, st, wp[11], cmode[11]);
-  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, NCHW, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), NCHW, B, h, w, 1, 1, st, wp[12], cmode[12]);
-  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w, NCHW), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), NCHW, B, h, w, 1, 1, st, wp[13], cmode[13]);
+  RUN(3, mk_src(W(TPSPP_WS_D1), 64, d.h1, d.w1, NCHW, 2, 2), none, none, P[TPSPP_P_DEC2_W], P[TPSPP_P_DEC2_B], W(TPSPP_WS_E0), W(TPSPP_WS_D2), NCHW, B, h, w, 1, 1, st, wp[12], cmode[12], bs, bs);
+  RUN(3, mk_src(W(TPSPP_WS_D2), 64, h, w, NCHW, 1, 1, bs), none, none, P[TPSPP_P_DEC3_W], P[TPSPP_P_DEC3_B], nullptr, W(TPSPP_WS_DE), NCHW, B, h, w, 1, 1, st, wp[13], cmode[13]);
 #undef RUN
   // localisation + p_linear (tps_pp.py:321-323, 305)
   {

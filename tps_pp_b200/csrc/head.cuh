@@ -8,6 +8,7 @@ struct ConvSrc {
   const float* ptr;
   int C, H, W, uh, uw;   // stored size and integer nearest-upsample factors (1 or 2)
   int nhwc;              // 0: [B,C,H,W] (the reference's layout, used at the boundary), 1: [B,H,W,C] (internal)
+  int bf16;              // 1: the tensor is stored as bf16 (head-internal activations of the bf16 mode; 3x3 TMA kernel only)
 };
 struct ConvArgs {
   ConvSrc src[3];
@@ -25,6 +26,7 @@ struct ConvArgs {
   int skip_pre;          // 1: `skip` is added before the activation (residual block), 0: after it (MSFA decoder)
   int out_cstride;       // channels per image of the out / skip tensors when this launch writes a channel slice (0: = Cout)
   int zi;                // 1: up-sampled sources are ZERO-INSERTED instead of nearest (data gradient of a strided convolution)
+  int out_bf16, skip_bf16; // 1: out / skip are stored as bf16 (bf16 mode of the head, 3x3 TMA kernel only)
 };
 enum { CONV_ACT_RELU = 0, CONV_ACT_NONE = 1, CONV_ACT_GELU = 2, CONV_ACT_TANH = 3 };
 // operand mode of a tensor-core convolution (head_tc.cu): 3xTF32 | single-pass bf16 | tf32 main term + bf16 corrections
@@ -41,7 +43,7 @@ int run_mlp_fused(const float* v, const float* x1, const float* w1img, const flo
 // down0 + down1 + down2 + down_feat in one kernel (tps_pp.py:538-540,548,560-562,581-585); returns 1 if not applicable
 int run_down_fused(const float* x, const float* o0, const float* o1, const float* w0img, const float* w1img, const float* w2img,
                    const float* wfimg, const float* b0, const float* b1, const float* b2, const float* bf, float* f0, float* f1,
-                   float* f2, float* fg, int B, int h, int w, cudaStream_t st);
+                   float* f2, float* fg, int B, int h, int w, cudaStream_t st, int out_bf16 = 0);
 // feat_linear.0 -> feat_linear.1 -> tanh(QK^T / 8) in one kernel (tps_pp.py:258-261,293-312); returns 1 if not applicable
 int run_score_fused(const float* de2, const float* w0img, const float* w1img, const float* p1img, const float* b0, const float* b1,
                     float* score, int B, int h, int w, int F, float scale, cudaStream_t st);

@@ -699,12 +699,15 @@ struct ConvTmaArgs {
   int TW, TH, BW, BH;      // tile and box (halo) extent in pixels; CHS = BW * BH floats per channel
   int TX, TPI;             // tiles per image row, tiles per image
   int S;                   // convolution stride (1, or 2 for 3x3: one box per filter row, rows strided by the tensor map)
+  int XH;                  // x halo of the box in elements (3x3: 4 floats or 8 bf16 = 16 bytes; 1x1: 0)
 };
 constexpr int TM_XH = 4;   // x halo of a 3x3 box: the innermost TMA coordinate must be 16-byte aligned (probed: x = -1 traps)
 constexpr int TM_TILE_MAX = 32 * (4 * 72) * 4;                            // 3x3 at TW = 64: 4 rows x 72 columns
+constexpr int TM_TILE_BF = 24576;      // bf16-stored source: 32 ch x 4 x 80 x 2 B = 20 KB; three buffers in the room of two fp32 ones
 __host__ __device__ constexpr int tm_tile_bytes(int KS) { return KS == 3 ? ((TM_TILE_MAX + 1023) / 1024) * 1024 : 16384; }
 __host__ __device__ constexpr int tm_tile_bufs(int KS) { return KS == 3 ? 2 : 4; }
-__host__ __device__ constexpr int tm_smem_bytes(int KS) { return tm_tile_bufs(KS) * tm_tile_bytes(KS) + 2 * TS_STAGE + 512 + 1024; }
+// (3x3: + 4 KB so that the bf16 kernel's three 12 KB weight stages fit where the other modes keep two 16 KB stages)
+__host__ __device__ constexpr int tm_smem_bytes(int KS) { return tm_tile_bufs(KS) * tm_tile_bytes(KS) + 2 * TS_STAGE + (KS == 3 ? 4096 : 0) + 512 + 1024; }
 constexpr int TM_THREADS = TC_THREADS + 32;                                // 8 producer warps, MMA warp, TMA warp
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar,
@@ -723,29 +726,44 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
   constexpr bool BF16 = MODE == CM_BF16, MIX = MODE == CM_MIX;
   constexpr int T = KS * KS;
   static_assert(NT == 64 || NT == 32, "64 or 32 output channels per tile");
-  constexpr int XH = KS == 3 ? TM_XH : 0;
-  constexpr int W_BYTES = BF16 ? NT * TC_KC * 2 : 2 * tc_b_bytes(NT);      // weight image bytes per chunk
+  const int XH = g.XH;
+  // bf16-STORED activations (bf16 mode of the head, this kernel's <3, CM_BF16> form only): 2-byte tiles -- three tile buffers
+  // in the room of two, half the L2 / HBM bytes per tile (with fp32 tiles the bf16 kernel was bound by its tile loads)
+  const bool SBF = (BF16 && KS == 3) && g.t.c.src[0].bf16 != 0;
+  const int ntb_rt = SBF ? 3 : tm_tile_bufs(KS);
+  const int tile_stride = SBF ? TM_TILE_BF : tm_tile_bytes(KS);
+  // bf16 3x3: a chunk is one FILTER ROW (3 taps x 32 channels, K = 96) -- a third of the stage hand-offs, which is what bounds
+  // this kernel once the operands need a single MMA pass (profiles/r02_conv_experiments.md: 780 cycles per hand-off);
+  // the A stage holds 3 x 16 packed columns, the weight stage the three taps' 4 KB images
+  constexpr int CT = (BF16 && KS == 3) ? 3 : 1;                  // taps per chunk
+  constexpr int W_TAP = BF16 ? NT * TC_KC * 2 : 2 * tc_b_bytes(NT);        // weight image bytes per (tap, channel group)
+  constexpr int W_BYTES = CT * W_TAP;                                      // ... per chunk
+  // ... and, with a single 64-column accumulator, tensor memory has room for THREE 48-column A stages (columns 64..207) and
+  // shared memory for three 12 KB weight stages: one more chunk in flight per CTA
+  constexpr int NS = (BF16 && KS == 3) ? 3 : 2;                  // A / weight stages
+  constexpr int A_BASE = NS == 3 ? 64 : 128, A_STRIDE = NS == 3 ? 48 : 64;       // TMEM columns of the A ring
+  constexpr int WS_STRIDE = NS == 3 ? 12288 : TS_STAGE;          // bytes between weight stages
   constexpr int TILE_BYTES = tm_tile_bytes(KS);
   constexpr int NTB = tm_tile_bufs(KS);                          // activation tile buffers in flight
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* tiles = smem;                                   // NTB activation tiles [32 ch][BH][BW]
   unsigned char* wst = smem + NTB * TILE_BYTES;                  // 2 weight stages (hi | lo image of a chunk)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + 2 * TS_STAGE);
-  uint64_t* a_empty = bars;          // [2] MMAs that read A stage / weight stage completed
-  uint64_t* a_full = bars + 2;       // [2] all 8 producer warps stored their part of the chunk
-  uint64_t* w_full = bars + 4;       // [2] weight image landed
-  uint64_t* t_full = bars + 6;       // [4] activation tile landed
-  uint64_t* t_empty = bars + 10;     // [4] all 8 producer warps are done reading the tile
-  uint64_t* d_empty = bars + 14;     // [1] the epilogue has drained the accumulator
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-  float* bias_s = reinterpret_cast<float*>(bars + 16);          // [64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (NS == 3 ? 3 * 12288 : 2 * TS_STAGE));
+  uint64_t* a_empty = bars;          // [NS] MMAs that read A stage / weight stage completed
+  uint64_t* a_full = bars + 3;       // [NS] all 8 producer warps stored their part of the chunk
+  uint64_t* w_full = bars + 6;       // [NS] weight image landed
+  uint64_t* t_full = bars + 9;       // [4] activation tile landed
+  uint64_t* t_empty = bars + 13;     // [4] all 8 producer warps are done reading the tile
+  uint64_t* d_empty = bars + 17;     // [1] the epilogue has drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* bias_s = reinterpret_cast<float*>(bars + 20);          // [64]
   const ConvArgs& a = g.t.c;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_empty[i], 1); mbar_init(&a_full[i], TC_PRODUCERS / 32); mbar_init(&w_full[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&a_empty[i], 1); mbar_init(&a_full[i], TC_PRODUCERS / 32); mbar_init(&w_full[i], 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TC_PRODUCERS / 32); }
     mbar_init(d_empty, TC_PRODUCERS / 32);
     fence_barrier_init();
@@ -760,9 +778,9 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
   const int HoWo = a.Ho * a.Wo;
   const int ntiles = (int)(((long long)a.B * HoWo) / TC_TM);
   const int ncc = a.Ctot / TC_KC;
-  const int nchunks = ncc * T;
+  const int nchunks = ncc * T / CT;
   const int CHS = g.BW * g.BH;
-  const uint32_t tile_tx = (uint32_t)(CHS * TC_KC * 4);
+  const uint32_t tile_tx = (uint32_t)(CHS * TC_KC * (SBF ? 2 : 4));
   const unsigned char* wimg = reinterpret_cast<const unsigned char*>(g.t.wprep);
   constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, BF16 ? 1 : 2);
   constexpr uint32_t IDESC_BF = umma_instr_desc(TC_TM, NT, 1);
@@ -780,9 +798,9 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
     if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { c0 -= a.src[1].C; s = 2; } }
     const int up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
     const int y0 = S * oy0 - a.pad + grp;
-    const int tb = gcc % NTB;
+    const int tb = gcc % ntb_rt;
     mbar_arrive_expect_tx(&t_full[tb], tile_tx);
-    tma_load_4d(tiles + tb * TILE_BYTES, &g.tmap[s], up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH), up ? (y0 >> 1) : y0, c0, img,
+    tma_load_4d(tiles + tb * tile_stride, &g.tmap[s], up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH), up ? (y0 >> 1) : y0, c0, img,
                 &t_full[tb], policy_evict_first());
   };
 
@@ -799,22 +817,22 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         tc_fence_after();
       }
       for (int ch = 0; ch < nchunks; ++ch, ++gch) {
-        const int buf = gch & 1;
-        const uint32_t ph = (uint32_t)((gch >> 1) & 1);
+        const int buf = gch % NS, nbuf = (gch + 1) % NS;
+        const uint32_t ph = (uint32_t)((gch / NS) & 1);
         if (!ok_a) mbar_wait_bounded(&a_full[buf], ph);
         if (!ok_w) mbar_wait_bounded(&w_full[buf], ph);
-        const uint32_t ph1 = (uint32_t)(((gch + 1) >> 1) & 1);
+        const uint32_t ph1 = (uint32_t)(((gch + 1) / NS) & 1);
         if (!MIX) {
-          ok_a = __shfl_sync(0xffffffffu, mbar_test_wait(&a_full[buf ^ 1], ph1) ? 1 : 0, 0);
-          ok_w = __shfl_sync(0xffffffffu, mbar_test_wait(&w_full[buf ^ 1], ph1) ? 1 : 0, 0);
+          ok_a = __shfl_sync(0xffffffffu, mbar_test_wait(&a_full[nbuf], ph1) ? 1 : 0, 0);
+          ok_w = __shfl_sync(0xffffffffu, mbar_test_wait(&w_full[nbuf], ph1) ? 1 : 0, 0);
         }
         tc_fence_after();
         if (MIX) {
           uint32_t pa = 0, pw = 0;
           if (elect_one_sync()) {
-            const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE);
-            mix_mma_chunk_probed<NT>(tmem_d, tmem_d + 128 + (uint32_t)(buf * 64), umma_smem_desc(b_hi, NT * 16, 128), IDESC, IDESC_BF,
-                                 ch != 0 ? 1u : 0u, smem_u32(&a_empty[buf]), smem_u32(&a_full[buf ^ 1]), smem_u32(&w_full[buf ^ 1]),
+            const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * WS_STRIDE);
+            mix_mma_chunk_probed<NT>(tmem_d, tmem_d + A_BASE + (uint32_t)(buf * A_STRIDE), umma_smem_desc(b_hi, NT * 16, 128), IDESC, IDESC_BF,
+                                 ch != 0 ? 1u : 0u, smem_u32(&a_empty[buf]), smem_u32(&a_full[nbuf]), smem_u32(&w_full[nbuf]),
                                  ph1, pa, pw);
           }
           // the probing lane is the elected one: OR-reduce so that every lane of the warp holds its answer
@@ -823,14 +841,16 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           continue;
         }
         if (elect_one_sync()) {
-          const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * TS_STAGE), b_lo = b_hi + tc_b_bytes(NT);
-          const uint32_t a_hi = tmem_d + 128 + (uint32_t)(buf * 64), a_lo = a_hi + 32;
+          const uint32_t b_hi = smem_u32(wst) + (uint32_t)(buf * WS_STRIDE), b_lo = b_hi + tc_b_bytes(NT);
+          const uint32_t a_hi = tmem_d + A_BASE + (uint32_t)(buf * A_STRIDE), a_lo = a_hi + 32;
           if (BF16) {
 #pragma unroll
-            for (int j = 0; j < TC_KC / 16; ++j) {     // one MMA = K 16 = two 16-byte k-groups of 8 bf16
-              const uint64_t db = umma_smem_desc(b_hi + j * 2 * (NT * 16), NT * 16, 128);
-              umma_ts_f16(tmem_d, a_hi + j * 8, db, IDESC, (ch | j) != 0 ? 1u : 0u);
-            }
+            for (int t = 0; t < CT; ++t)
+#pragma unroll
+              for (int j = 0; j < TC_KC / 16; ++j) {   // one MMA = K 16 = two 16-byte k-groups of 8 bf16
+                const uint64_t db = umma_smem_desc(b_hi + t * W_TAP + j * 2 * (NT * 16), NT * 16, 128);
+                umma_ts_f16(tmem_d, a_hi + t * 16 + j * 8, db, IDESC, (ch | t | j) != 0 ? 1u : 0u);
+              }
           } else if (MIX) {
             mix_mma_chunk<NT>(tmem_d, a_hi, b_hi, IDESC, IDESC_BF, ch == 0);
           } else {
@@ -858,25 +878,27 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
     int l_tile = blockIdx.x, l_cc = 0, l_grp = 0, l_idx = 0;      // cursor of the next tile load to issue
     auto issue_next_tile = [&]() {
       if (l_idx >= nloads) return;
-      if (l_idx >= NTB) mbar_wait_bounded(&t_empty[l_idx % NTB], (uint32_t)(((l_idx / NTB) - 1) & 1));
+      if (l_idx >= ntb_rt) mbar_wait_bounded(&t_empty[l_idx % ntb_rt], (uint32_t)(((l_idx / ntb_rt) - 1) & 1));
       if (elect_one_sync()) issue_tile(l_tile, l_cc, l_grp, l_idx);
       __syncwarp();
       ++l_idx;
       if (++l_grp == NG) { l_grp = 0; if (++l_cc == ncc) { l_cc = 0; l_tile += gridDim.x; } }
     };
-    for (int i = 0; i < NTB - 1; ++i) issue_next_tile();
+    for (int i = 0; i < ntb_rt - 1; ++i) issue_next_tile();
     int gch = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
       for (int cc = 0; cc < ncc; ++cc)
         for (int grp = 0; grp < NG; ++grp) {
           issue_next_tile();
-          for (int tg = 0; tg < TG; ++tg, ++gch) {
-            const int buf = gch & 1;
-            if (gch >= 2) mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch >> 1) - 1) & 1));
+          for (int tg = 0; tg < TG; tg += CT, ++gch) {
+            const int buf = gch % NS;
+            if (gch >= NS) mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch / NS) - 1) & 1));
             if (elect_one_sync()) {
               mbar_arrive_expect_tx(&w_full[buf], W_BYTES);
-              bulk_g2s(wst + buf * TS_STAGE, wimg + (size_t)((grp * TG + tg) * ncc + cc) * W_BYTES, W_BYTES, &w_full[buf],
-                       policy_evict_last());
+#pragma unroll
+              for (int t = 0; t < CT; ++t)
+                bulk_g2s(wst + buf * WS_STRIDE + t * W_TAP, wimg + (size_t)((grp * TG + tg + t) * ncc + cc) * W_TAP, W_TAP, &w_full[buf],
+                         policy_evict_last());
             }
             __syncwarp();
           }
@@ -895,17 +917,62 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
       const int oy0 = tyy * g.TH, ox0 = (trem - tyy * g.TX) * g.TW;      // tile = TH x TW rectangle (tiles row-major in the image)
       for (int cc = 0; cc < ncc; ++cc)
       for (int grp = 0; grp < NG; ++grp, ++gcc) {
-        const int tb = gcc % NTB;
+        const int tb = gcc % ntb_rt;
         int s = 0, c0 = cc * TC_KC;
         if (c0 >= a.src[0].C) { c0 -= a.src[0].C; s = 1; if (c0 >= a.src[1].C) { s = 2; } }
         const bool up = (s == 0 ? a.src[0].uh : (s == 1 ? a.src[1].uh : a.src[2].uh)) == 2;
         const int by = up ? ((oy0 - a.pad) >> 1) : (oy0 - a.pad), bx = up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH);
-        const uint32_t cstride = 4u * (uint32_t)CHS;
-        const uint32_t tile_a = smem_u32(tiles + tb * TILE_BYTES) + (uint32_t)(kh * 16) * cstride;
-        mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc / NTB) & 1));
+        const uint32_t esz = SBF ? 2u : 4u;
+        const uint32_t cstride = esz * (uint32_t)CHS;
+        const uint32_t tile_a = smem_u32(tiles + tb * tile_stride) + (uint32_t)(kh * 16) * cstride;
+        mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc / ntb_rt) & 1));
 #pragma unroll 1
-        for (int tg = 0; tg < TG; ++tg, ++gch) {
-          const int buf = gch & 1;
+        for (int tg = 0; tg < TG; tg += CT, ++gch) {
+          const int buf = gch % NS;
+          if constexpr (CT == 3) {
+            // bf16 filter-row chunk: the three taps of row dy read the same halo rows at column offsets 0, 1, 2
+            uint32_t pk[3][8];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const int tap = grp * TG + tg + t;
+              const int dy = tap / KS, dx = tap - dy * KS;
+              int iy = oy0 + pr + dy - a.pad, ix = S * (ox0 + pc) + dx - a.pad;
+              const bool zero = a.zi && up && ((iy | ix) & 1);
+              if (up) { iy >>= 1; ix >>= 1; }
+              const uint32_t qa = tile_a + esz * (uint32_t)((S == 2 ? pr : iy - by) * g.BW + (ix - bx));
+              if (SBF) {          // the tile already holds bf16: two 2-byte loads per packed column
+                unsigned short u[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u[i]) : "r"(qa + (uint32_t)i * cstride));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pk[t][i] = zero ? 0u : ((uint32_t)u[2 * i] | ((uint32_t)u[2 * i + 1] << 16));
+              } else {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(qa + (uint32_t)i * cstride));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(zero ? 0.f : v[2 * i], zero ? 0.f : v[2 * i + 1]);
+                  pk[t][i] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+              }
+            }
+            if (gch >= NS) {
+              mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch / NS) - 1) & 1));
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int t = 0; t < 3; ++t) tmem_st8(lane_addr + (uint32_t)(A_BASE + buf * A_STRIDE + t * 16 + kh * 8), pk[t]);
+            if (tg + CT >= TG) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&t_empty[tb]);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[buf]);
+            continue;
+          }
           const int tap = grp * TG + tg;
           const int dy = tap / KS, dx = tap - dy * KS;
           int iy = oy0 + pr + dy - a.pad, ix = S * (ox0 + pc) + dx - a.pad;
@@ -926,8 +993,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           float mhi[16];
           uint32_t mlo2[8], ma2[8];
           if (MIX) mix_split(v, mhi, mlo2, ma2);
-          if (gch >= 2) {
-            mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch >> 1) - 1) & 1));   // MMAs of chunk gch-2 have read the stage
+          if (gch >= NS) {
+            mbar_wait_bounded(&a_empty[buf], (uint32_t)(((gch / NS) - 1) & 1));   // MMAs of chunk gch-NS have read the stage
             tc_fence_after();
           }
           if (BF16) {
@@ -937,9 +1004,9 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
               const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);   // .x (low half) = even channel
               pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
             }
-            tmem_st8(lane_addr + (uint32_t)(128 + buf * 64 + kh * 8), pk);
+            tmem_st8(lane_addr + (uint32_t)(A_BASE + buf * A_STRIDE + kh * 8), pk);
           } else if (MIX) {
-            const uint32_t sa = lane_addr + (uint32_t)(128 + buf * 64);
+            const uint32_t sa = lane_addr + (uint32_t)(A_BASE + buf * A_STRIDE);
             tmem_st16(sa + (uint32_t)(kh * 16), mhi);
             tmem_st8(sa + (uint32_t)(32 + kh * 8), mlo2);
             tmem_st8(sa + (uint32_t)(48 + kh * 8), ma2);
@@ -950,7 +1017,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
               hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
               lo[i] = v[i] - hi[i];
             }
-            const uint32_t col = (uint32_t)(128 + buf * 64 + kh * 16);
+            const uint32_t col = (uint32_t)(A_BASE + buf * A_STRIDE + kh * 16);
             tmem_st16(lane_addr + col, hi);
             tmem_st16(lane_addr + col + 32, lo);
           }
@@ -965,7 +1032,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         }
       }
       const int last = gch - 1;
-      mbar_wait_bounded(&a_empty[last & 1], (uint32_t)((last >> 1) & 1));
+      mbar_wait_bounded(&a_empty[last % NS], (uint32_t)((last / NS) & 1));
       tc_fence_after();
 
       // ---- epilogue (NCHW): lane = pixel, coalesced per channel ----
@@ -1005,9 +1072,21 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         }
         const size_t o0 = ((size_t)img * (a.out_cstride ? a.out_cstride : a.Cout) + cb) * HoWo + (size_t)oy * a.Wo + ox;
         if (a.skip != nullptr && !a.skip_pre) {
-          const float* sk = a.skip + o0;
+          if (BF16 && a.skip_bf16) {
+            const __nv_bfloat16* sk = reinterpret_cast<const __nv_bfloat16*>(a.skip) + o0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] += __ldg(sk + (size_t)j * HoWo);
+            for (int j = 0; j < 16; ++j) acc[j] += __bfloat162float(sk[(size_t)j * HoWo]);
+          } else {
+            const float* sk = a.skip + o0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] += __ldg(sk + (size_t)j * HoWo);
+          }
+        }
+        if (BF16 && a.out_bf16) {
+          __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(a.out) + o0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) po[(size_t)j * HoWo] = __float2bfloat16_rn(acc[j]);
+          continue;
         }
         float* po = a.out + o0;
 #pragma unroll
@@ -1048,17 +1127,17 @@ struct TmapKey {
   const void* ptr;
   cuuint64_t dims[4], strides[3];
   cuuint32_t box[4], es[4];
-  int rank, swizzle;
+  int rank, swizzle, bf16;
 };
 static bool tmap_cached(CUtensorMap* out, int rank, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,
-                        const cuuint32_t* box, const cuuint32_t* es, CUtensorMapSwizzle swz) {
+                        const cuuint32_t* box, const cuuint32_t* es, CUtensorMapSwizzle swz, bool bf16 = false) {
   constexpr int CAP = 96;
   struct Entry { TmapKey k; CUtensorMap m; };
   static thread_local Entry cache[CAP];
   static thread_local int used = 0, next = 0;
   TmapKey k;
   memset(&k, 0, sizeof(k));
-  k.ptr = ptr; k.rank = rank; k.swizzle = (int)swz;
+  k.ptr = ptr; k.rank = rank; k.swizzle = (int)swz; k.bf16 = bf16 ? 1 : 0;
   for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.es[i] = es[i]; }
   for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
   for (int i = 0; i < used; ++i)
@@ -1066,7 +1145,7 @@ static bool tmap_cached(CUtensorMap* out, int rank, const void* ptr, const cuuin
   tmap_encode_fn enc = tmap_encoder();
   if (enc == nullptr) return false;
   CUtensorMap m;
-  if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es,
+  if (enc(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es,
           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
   const int slot = used < CAP ? used++ : (next++ % CAP);
@@ -1076,7 +1155,11 @@ static bool tmap_cached(CUtensorMap* out, int rank, const void* ptr, const cuuin
 }
 
 // NCHW convolution whose tile is a rectangle of one image, every source either full or half resolution
-static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g) {
+static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g, int mode = CM_TF32X3) {
+  // bf16-stored activations (bf16 mode of the head): 3x3 bf16-operand kernel only, every source of the launch bf16, no up-sampling
+  const bool sbf = a.src[0].bf16 != 0;
+  if ((sbf || a.out_bf16 || a.skip_bf16) && !(KS == 3 && mode == CM_BF16 && a.Cout == 64)) return false;
+  const int XH = KS == 3 ? (sbf ? 8 : TM_XH) : 0;
   if (a.sh != a.sw || (a.sh != 1 && !(a.sh == 2 && KS == 3)) || a.out_nhwc || a.wimg_stride != 0 || (a.Cout != 64 && a.Cout != 32)) return false;
   if (a.pad != (KS == 3 ? 1 : 0)) return false;
   const int S = a.sh;
@@ -1089,21 +1172,23 @@ static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g) {
   // stride 1: one halo box serves all taps.  stride 2: one box per filter row -- full-width input rows 2 oy + dy - 1
   // (the tensor map walks rows with element stride 2; TMA cannot stride the innermost dimension, so the threads read
   // columns 2 ox + dx - 1 themselves)
-  const int BW = KS == 3 ? S * TW + 2 * TM_XH : TW, BH = (KS == 3 && S == 1) ? TH + 2 : TH;
-  if (BW > 256 || BH > 256 || (size_t)BW * BH * TC_KC * 4 > (size_t)tm_tile_bytes(KS)) return false;
+  const int BW = KS == 3 ? S * TW + 2 * XH : TW, BH = (KS == 3 && S == 1) ? TH + 2 : TH;
+  if (BW > 256 || BH > 256 || (size_t)BW * BH * TC_KC * (sbf ? 2 : 4) > (size_t)(sbf ? TM_TILE_BF : tm_tile_bytes(KS))) return false;
   for (int s = 0; s < 3; ++s) {
     const ConvSrc& sc = a.src[s];
     if (sc.C == 0) continue;
     if (sc.nhwc || sc.C % TC_KC || sc.uh != sc.uw || (sc.uh != 1 && sc.uh != 2) || (S == 2 && sc.uh != 1)) return false;
+    if ((sc.bf16 != 0) != sbf || (sbf && sc.uh != 1)) return false;
     if (sc.H * sc.uh != a.Ho * S || sc.W * sc.uw != a.Wo * S) return false;
-    if ((sc.W * 4) % 16 || ((uintptr_t)sc.ptr & 15)) return false;
+    const cuuint64_t esz = sbf ? 2 : 4;
+    if ((sc.W * esz) % 16 || ((uintptr_t)sc.ptr & 15)) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)sc.W, (cuuint64_t)sc.H, (cuuint64_t)sc.C, (cuuint64_t)a.B};
-    const cuuint64_t strides[3] = {(cuuint64_t)sc.W * 4, (cuuint64_t)sc.W * sc.H * 4, (cuuint64_t)sc.W * sc.H * sc.C * 4};
+    const cuuint64_t strides[3] = {(cuuint64_t)sc.W * esz, (cuuint64_t)sc.W * sc.H * esz, (cuuint64_t)sc.W * sc.H * sc.C * esz};
     const cuuint32_t box[4] = {(cuuint32_t)BW, (cuuint32_t)(BH * S), (cuuint32_t)TC_KC, 1};
     const cuuint32_t es[4] = {1, (cuuint32_t)S, 1, 1};
-    if (!tmap_cached(&g->tmap[s], 4, sc.ptr, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+    if (!tmap_cached(&g->tmap[s], 4, sc.ptr, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE, sbf)) return false;
   }
-  g->TW = TW; g->TH = TH; g->BW = BW; g->BH = BH; g->S = S;
+  g->TW = TW; g->TH = TH; g->BW = BW; g->BH = BH; g->S = S; g->XH = XH;
   g->TX = a.Wo / TW; g->TPI = (a.Wo / TW) * (a.Ho / TH);
   return true;
 }
@@ -1614,6 +1699,7 @@ struct DownFusedArgs {
   const float *b0, *b1, *b2, *bf;
   float *f0, *f1, *f2, *fg;
   int B, h;                            // h = rows of x (the outs have 2h rows, 128 columns)
+  int out_bf16;                        // 1: f0 / f1 / f2 are stored as bf16 (feat_grid stays fp32: it is the warp's input)
 };
 constexpr int DF_WARPS = 16;
 constexpr int DF_THREADS = (DF_WARPS + 2) * 32;
@@ -1859,15 +1945,29 @@ __global__ void __launch_bounds__(DF_THREADS, 1) down_fused_kernel(const __grid_
       const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
       const int r = rem >> 1, c0 = rem & 1;
       if (j < 2) {
-        float* po = (j == 0 ? g.f0 : g.f1) + (((size_t)img * 64 + p * 16) * H2 + (2 * r + ty)) * W2 + 64 * c0 + tx;
+        const size_t o = (((size_t)img * 64 + p * 16) * H2 + (2 * r + ty)) * W2 + 64 * c0 + tx;
         const size_t plane = (size_t)H2 * W2;
+        if (g.out_bf16) {                                   // bf16 mode of the head: f0 / f1 / f2 are stored as bf16
+          __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(j == 0 ? g.f0 : g.f1) + o;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = acc[i];
+          for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = __float2bfloat16_rn(acc[i]);
+        } else {
+          float* po = (j == 0 ? g.f0 : g.f1) + o;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = acc[i];
+        }
       } else if (ty == 0 && (tx & 1) == 0) {              // f2 lives at half resolution: one writer per 2x2 block
-        float* po = g.f2 + (((size_t)img * 64 + p * 16) * g.h + r) * 64 + 32 * c0 + (tx >> 1);
+        const size_t o = (((size_t)img * 64 + p * 16) * g.h + r) * 64 + 32 * c0 + (tx >> 1);
         const size_t plane = (size_t)g.h * 64;
+        if (g.out_bf16) {
+          __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(g.f2) + o;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = acc[i];
+          for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = __float2bfloat16_rn(acc[i]);
+        } else {
+          float* po = g.f2 + o;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = acc[i];
+        }
       }
     };
     if (n_my > 0) { produce_a1(0, 0); produce_a1(0, 1); }
@@ -2342,7 +2442,7 @@ int run_mlp_fused(const float* v, const float* x1, const float* w1img, const flo
 // separate convolutions instead: other widths, misaligned pointers)
 int run_down_fused(const float* x, const float* o0, const float* o1, const float* w0img, const float* w1img, const float* w2img,
                    const float* wfimg, const float* b0, const float* b1, const float* b2, const float* bf, float* f0, float* f1,
-                   float* f2, float* fg, int B, int h, int w, cudaStream_t st) {
+                   float* f2, float* fg, int B, int h, int w, cudaStream_t st, int out_bf16) {
   if (w != 64 || h < 1 || B < 1) return 1;
   if ((((uintptr_t)x | (uintptr_t)o0 | (uintptr_t)o1 | (uintptr_t)w0img | (uintptr_t)w1img | (uintptr_t)w2img | (uintptr_t)wfimg) & 15) != 0)
     return 1;
@@ -2365,7 +2465,7 @@ int run_down_fused(const float* x, const float* o0, const float* o1, const float
   }
   g.w0img = w0img; g.w1img = w1img; g.w2img = w2img; g.wfimg = wfimg;
   g.b0 = b0; g.b1 = b1; g.b2 = b2; g.bf = bf;
-  g.f0 = f0; g.f1 = f1; g.f2 = f2; g.fg = fg; g.B = B; g.h = h;
+  g.f0 = f0; g.f1 = f1; g.f2 = f2; g.fg = fg; g.B = B; g.h = h; g.out_bf16 = out_bf16;
   static thread_local int df_dev = -1;
   int dev = 0;
   TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
@@ -2430,7 +2530,7 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
     int dev = 0;
     TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
     ConvTmaArgs g;
-    if (conv_tma_plan(KS, a, &g)) {               // rectangular tiles: activations staged by TMA
+    if (conv_tma_plan(KS, a, &g, mode)) {         // rectangular tiles: activations staged by TMA
       g.t = t;
       static thread_local int tma_dev = -1;
       if (tma_dev != dev) {
@@ -2461,6 +2561,7 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
       return TPSPP_OK;
     }
     TPSPP_REQUIRE(NT == 64, "conv_tc: the 32-column convolution tile needs a TMA-stageable geometry");
+    TPSPP_REQUIRE(!a.src[0].bf16 && !a.out_bf16 && !a.skip_bf16, "conv_tc: bf16-stored activations need the TMA-staged 3x3 bf16 kernel");
     static thread_local int ts_dev = -1;
     if (ts_dev != dev) {
       TPSPP_CHECK_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, CM_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
