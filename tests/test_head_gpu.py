@@ -44,7 +44,8 @@ def _run_native(sd, x, o0, o1, precision=N.HEAD_FP32, flags=0):
     for name, shp in shapes.items():
         n = int(np.prod(shp))
         if name in as_bf16:
-            got[name] = ws[off[name]: off[name] + 2 * n].view(torch.bfloat16).float().view(shp).cpu()
+            got[name] = (ws[off[name]: off[name] + 2 * n].view(torch.bfloat16).float()
+                         .view(shp[0], shp[2], shp[3], shp[1]).permute(0, 3, 1, 2).contiguous().cpu())    # stored [B,H,W,C]
             continue
         flat = ws[off[name]: off[name] + 4 * n].view(torch.float32)
         if name in nhwc:

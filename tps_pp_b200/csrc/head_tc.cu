@@ -703,7 +703,7 @@ struct ConvTmaArgs {
 };
 constexpr int TM_XH = 4;   // x halo of a 3x3 box: the innermost TMA coordinate must be 16-byte aligned (probed: x = -1 traps)
 constexpr int TM_TILE_MAX = 32 * (4 * 72) * 4;                            // 3x3 at TW = 64: 4 rows x 72 columns
-constexpr int TM_TILE_BF = 24576;      // bf16-stored source: 32 ch x 4 x 80 x 2 B = 20 KB; three buffers in the room of two fp32 ones
+constexpr int TM_TILE_BF = 17408;      // bf16 NHWC source: 66 x 4 pixels x 32 ch x 2 B = 16.5 KB (1 KB aligned); four buffers in the room of two fp32 ones
 __host__ __device__ constexpr int tm_tile_bytes(int KS) { return KS == 3 ? ((TM_TILE_MAX + 1023) / 1024) * 1024 : 16384; }
 __host__ __device__ constexpr int tm_tile_bufs(int KS) { return KS == 3 ? 2 : 4; }
 // (3x3: + 4 KB so that the bf16 kernel's three 12 KB weight stages fit where the other modes keep two 16 KB stages)
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
   // bf16-STORED activations (bf16 mode of the head, this kernel's <3, CM_BF16> form only): 2-byte tiles -- three tile buffers
   // in the room of two, half the L2 / HBM bytes per tile (with fp32 tiles the bf16 kernel was bound by its tile loads)
   const bool SBF = (BF16 && KS == 3) && g.t.c.src[0].bf16 != 0;
-  const int ntb_rt = SBF ? 3 : tm_tile_bufs(KS);
+  const int ntb_rt = SBF ? 4 : tm_tile_bufs(KS);
   const int tile_stride = SBF ? TM_TILE_BF : tm_tile_bytes(KS);
   // bf16 3x3: a chunk is one FILTER ROW (3 taps x 32 channels, K = 96) -- a third of the stage hand-offs, which is what bounds
   // this kernel once the operands need a single MMA pass (profiles/r02_conv_experiments.md: 780 cycles per hand-off);
@@ -800,8 +800,11 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
     const int y0 = S * oy0 - a.pad + grp;
     const int tb = gcc % ntb_rt;
     mbar_arrive_expect_tx(&t_full[tb], tile_tx);
-    tma_load_4d(tiles + tb * tile_stride, &g.tmap[s], up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH), up ? (y0 >> 1) : y0, c0, img,
-                &t_full[tb], policy_evict_first());
+    if (SBF)      // [B,H,W,64] bf16: coordinates (channel, x, y, image)
+      tma_load_4d(tiles + tb * tile_stride, &g.tmap[s], c0, S * ox0 - XH, y0, img, &t_full[tb], policy_evict_first());
+    else
+      tma_load_4d(tiles + tb * tile_stride, &g.tmap[s], up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH), up ? (y0 >> 1) : y0, c0, img,
+                  &t_full[tb], policy_evict_first());
   };
 
   if (warp == TC_PRODUCERS / 32) {
@@ -924,7 +927,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         const int by = up ? ((oy0 - a.pad) >> 1) : (oy0 - a.pad), bx = up ? ((ox0 - 2 * XH) >> 1) : (S * ox0 - XH);
         const uint32_t esz = SBF ? 2u : 4u;
         const uint32_t cstride = esz * (uint32_t)CHS;
-        const uint32_t tile_a = smem_u32(tiles + tb * tile_stride) + (uint32_t)(kh * 16) * cstride;
+        const uint32_t tile_b = smem_u32(tiles + tb * tile_stride);
+        const uint32_t tile_a = tile_b + (uint32_t)(kh * 16) * cstride;
         mbar_wait_bounded(&t_full[tb], (uint32_t)((gcc / ntb_rt) & 1));
 #pragma unroll 1
         for (int tg = 0; tg < TG; tg += CT, ++gch) {
@@ -940,12 +944,17 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
               const bool zero = a.zi && up && ((iy | ix) & 1);
               if (up) { iy >>= 1; ix >>= 1; }
               const uint32_t qa = tile_a + esz * (uint32_t)((S == 2 ? pr : iy - by) * g.BW + (ix - bx));
-              if (SBF) {          // the tile already holds bf16: two 2-byte loads per packed column
-                unsigned short u[16];
+              if (SBF) {
+                // pixel-major bf16 tile (64-byte rows, SWIZZLE_64B): this thread's 16 channels are two 16-byte pieces that are
+                // already the packed TMEM columns -- 2 LDS.128 per tap instead of 16 scalar loads + 8 conversions
+                const uint32_t r = (uint32_t)((S == 2 ? pr : iy - by) * g.BW + (ix - bx));
+                const uint32_t sw = (r >> 1) & 3u;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u[i]) : "r"(qa + (uint32_t)i * cstride));
-#pragma unroll
-                for (int i = 0; i < 8; ++i) pk[t][i] = zero ? 0u : ((uint32_t)u[2 * i] | ((uint32_t)u[2 * i + 1] << 16));
+                for (int q = 0; q < 2; ++q) {
+                  const uint32_t ad = tile_b + r * 64u + ((((uint32_t)(kh * 2 + q)) ^ sw) << 4);
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(pk[t][4 * q]), "=r"(pk[t][4 * q + 1]), "=r"(pk[t][4 * q + 2]), "=r"(pk[t][4 * q + 3]) : "r"(ad));
+                }
               } else {
                 float v[16];
 #pragma unroll
@@ -1072,10 +1081,19 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
         }
         const size_t o0 = ((size_t)img * (a.out_cstride ? a.out_cstride : a.Cout) + cb) * HoWo + (size_t)oy * a.Wo + ox;
         if (a.skip != nullptr && !a.skip_pre) {
-          if (BF16 && a.skip_bf16) {
-            const __nv_bfloat16* sk = reinterpret_cast<const __nv_bfloat16*>(a.skip) + o0;
+          if (BF16 && a.skip_bf16) {          // [B,Ho,Wo,64] bf16: this pixel's 16 channels are 32 contiguous bytes
+            const uint4* sk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.skip) +
+                                                             (((size_t)img * a.Ho + oy) * a.Wo + ox) * 64 + cb);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] += __bfloat162float(sk[(size_t)j * HoWo]);
+            for (int q = 0; q < 2; ++q) {
+              const uint4 u = __ldg(sk + q);
+              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                acc[8 * q + 2 * i] += __uint_as_float(w4[i] << 16);
+                acc[8 * q + 2 * i + 1] += __uint_as_float(w4[i] & 0xFFFF0000u);
+              }
+            }
           } else {
             const float* sk = a.skip + o0;
 #pragma unroll
@@ -1083,9 +1101,17 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
           }
         }
         if (BF16 && a.out_bf16) {
-          __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(a.out) + o0;
+          uint4* po = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + (((size_t)img * a.Ho + oy) * a.Wo + ox) * 64 + cb);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) po[(size_t)j * HoWo] = __float2bfloat16_rn(acc[j]);
+          for (int q = 0; q < 2; ++q) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[8 * q + 2 * i], acc[8 * q + 2 * i + 1]);
+              w4[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            po[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
           continue;
         }
         float* po = a.out + o0;
@@ -1159,7 +1185,7 @@ static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g, int mode = 
   // bf16-stored activations (bf16 mode of the head): 3x3 bf16-operand kernel only, every source of the launch bf16, no up-sampling
   const bool sbf = a.src[0].bf16 != 0;
   if ((sbf || a.out_bf16 || a.skip_bf16) && !(KS == 3 && mode == CM_BF16 && a.Cout == 64)) return false;
-  const int XH = KS == 3 ? (sbf ? 8 : TM_XH) : 0;
+  const int XH = KS == 3 ? (sbf ? 1 : TM_XH) : 0;       // bf16 sources are NHWC: x is not the innermost TMA coordinate, no alignment halo
   if (a.sh != a.sw || (a.sh != 1 && !(a.sh == 2 && KS == 3)) || a.out_nhwc || a.wimg_stride != 0 || (a.Cout != 64 && a.Cout != 32)) return false;
   if (a.pad != (KS == 3 ? 1 : 0)) return false;
   const int S = a.sh;
@@ -1174,19 +1200,29 @@ static bool conv_tma_plan(int KS, const ConvArgs& a, ConvTmaArgs* g, int mode = 
   // columns 2 ox + dx - 1 themselves)
   const int BW = KS == 3 ? S * TW + 2 * XH : TW, BH = (KS == 3 && S == 1) ? TH + 2 : TH;
   if (BW > 256 || BH > 256 || (size_t)BW * BH * TC_KC * (sbf ? 2 : 4) > (size_t)(sbf ? TM_TILE_BF : tm_tile_bytes(KS))) return false;
+  if ((a.out_bf16 || a.skip_bf16) && a.Cout != 64) return false;
   for (int s = 0; s < 3; ++s) {
     const ConvSrc& sc = a.src[s];
     if (sc.C == 0) continue;
     if (sc.nhwc || sc.C % TC_KC || sc.uh != sc.uw || (sc.uh != 1 && sc.uh != 2) || (S == 2 && sc.uh != 1)) return false;
-    if ((sc.bf16 != 0) != sbf || (sbf && sc.uh != 1)) return false;
+    if ((sc.bf16 != 0) != sbf || (sbf && (sc.uh != 1 || sc.C != 64))) return false;
     if (sc.H * sc.uh != a.Ho * S || sc.W * sc.uw != a.Wo * S) return false;
-    const cuuint64_t esz = sbf ? 2 : 4;
-    if ((sc.W * esz) % 16 || ((uintptr_t)sc.ptr & 15)) return false;
+    if (sbf) {
+      // [B, H, W, 64] bf16: box = 32 channels (64 bytes, SWIZZLE_64B: a thread's 32-byte reads are conflict-free) x BW x BH rows
+      if ((uintptr_t)sc.ptr & 15) return false;
+      const cuuint64_t dims[4] = {(cuuint64_t)sc.C, (cuuint64_t)sc.W, (cuuint64_t)sc.H, (cuuint64_t)a.B};
+      const cuuint64_t strides[3] = {(cuuint64_t)sc.C * 2, (cuuint64_t)sc.W * sc.C * 2, (cuuint64_t)sc.W * sc.H * sc.C * 2};
+      const cuuint32_t box[4] = {(cuuint32_t)TC_KC, (cuuint32_t)BW, (cuuint32_t)(BH * S), 1};
+      const cuuint32_t es[4] = {1, 1, (cuuint32_t)S, 1};
+      if (!tmap_cached(&g->tmap[s], 4, sc.ptr, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_64B, true)) return false;
+      continue;
+    }
+    if ((sc.W * 4) % 16 || ((uintptr_t)sc.ptr & 15)) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)sc.W, (cuuint64_t)sc.H, (cuuint64_t)sc.C, (cuuint64_t)a.B};
-    const cuuint64_t strides[3] = {(cuuint64_t)sc.W * esz, (cuuint64_t)sc.W * sc.H * esz, (cuuint64_t)sc.W * sc.H * sc.C * esz};
+    const cuuint64_t strides[3] = {(cuuint64_t)sc.W * 4, (cuuint64_t)sc.W * sc.H * 4, (cuuint64_t)sc.W * sc.H * sc.C * 4};
     const cuuint32_t box[4] = {(cuuint32_t)BW, (cuuint32_t)(BH * S), (cuuint32_t)TC_KC, 1};
     const cuuint32_t es[4] = {1, (cuuint32_t)S, 1, 1};
-    if (!tmap_cached(&g->tmap[s], 4, sc.ptr, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE, sbf)) return false;
+    if (!tmap_cached(&g->tmap[s], 4, sc.ptr, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
   }
   g->TW = TW; g->TH = TH; g->BW = BW; g->BH = BH; g->S = S; g->XH = XH;
   g->TX = a.Wo / TW; g->TPI = (a.Wo / TW) * (a.Ho / TH);
@@ -1693,6 +1729,21 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const __grid_c
 //   smem   W0, W1, W2 images resident (64 KB), Wf chunks through a 4-stage ring, two sets of input boxes (o0 | o1 | x)
 //   warps  0-15 workers (lane quarter q = TMEM lanes = pixels, part p = 8 / 16 of the channels), 16 MMA issuer, 17 TMA
 // ------------------------------------------------------------------------------------------------
+// 16 consecutive channels of one pixel -> 32 contiguous bytes of a [.., 64] bf16 row
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float (&acc)[16]) {
+  uint4* po = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t w4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[8 * q + 2 * i], acc[8 * q + 2 * i + 1]);
+      w4[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    po[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  }
+}
+
 struct DownFusedArgs {
   CUtensorMap tm_o0, tm_o1, tm_x;      // o0/o1 [B,32,2h,128] box 64 x 2 x 32; x [B,64,h,64] box 32 x 1 x 64
   const float *w0img, *w1img, *w2img, *wfimg;
@@ -1947,10 +1998,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) down_fused_kernel(const __grid_
       if (j < 2) {
         const size_t o = (((size_t)img * 64 + p * 16) * H2 + (2 * r + ty)) * W2 + 64 * c0 + tx;
         const size_t plane = (size_t)H2 * W2;
-        if (g.out_bf16) {                                   // bf16 mode of the head: f0 / f1 / f2 are stored as bf16
-          __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(j == 0 ? g.f0 : g.f1) + o;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = __float2bfloat16_rn(acc[i]);
+        if (g.out_bf16) {                                   // bf16 mode of the head: f0 / f1 / f2 are stored as [B,H,W,64] bf16
+          const size_t on = (((size_t)img * H2 + (2 * r + ty)) * W2 + 64 * c0 + tx) * 64 + p * 16;
+          store_bf16x16(reinterpret_cast<__nv_bfloat16*>(j == 0 ? g.f0 : g.f1) + on, acc);
         } else {
           float* po = (j == 0 ? g.f0 : g.f1) + o;
 #pragma unroll
@@ -1960,9 +2010,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) down_fused_kernel(const __grid_
         const size_t o = (((size_t)img * 64 + p * 16) * g.h + r) * 64 + 32 * c0 + (tx >> 1);
         const size_t plane = (size_t)g.h * 64;
         if (g.out_bf16) {
-          __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(g.f2) + o;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) po[(size_t)i * plane] = __float2bfloat16_rn(acc[i]);
+          const size_t on = (((size_t)img * g.h + r) * 64 + 32 * c0 + (tx >> 1)) * 64 + p * 16;
+          store_bf16x16(reinterpret_cast<__nv_bfloat16*>(g.f2) + on, acc);
         } else {
           float* po = g.f2 + o;
 #pragma unroll
