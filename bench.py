@@ -488,7 +488,8 @@ def run_ours(args):
             "metric": "tps_pp_rectified_img_per_s", "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-            "dtype": "bf16 conv operands / f32 elsewhere" if args.head == "bf16" else "f32",
+            "dtype": ("bf16 operands + bf16 storage of the large intermediates in the ten 3x3 convolutions / f32 (3xTF32) elsewhere"
+                      if args.head == "bf16" else "f32"),
             "data": "synthetic",
             "config": {"workload": (WORKLOAD if B == BATCH_PER_GPU and not strong else
                                     WORKLOAD.replace("batch 256/GPU", f"global batch {gB} split over {world} GPU(s) (BASELINE configs[4] shard)"

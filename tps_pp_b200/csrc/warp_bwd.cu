@@ -724,7 +724,9 @@ static size_t bwd_csr_smem() { return BS_CSR_BYTES + (size_t)BS_MAX_N * sizeof(d
 
 int bwd_nsplit(const tpspp_warp_cfg* cfg) {
   const int n = cfg->out_h * cfg->out_w;
-  int ns = (2 * 148 + cfg->batch - 1) / (cfg->batch > 0 ? cfg->batch : 1);
+  // pixel splits of grid_bwd_reduce_kernel: ~8 CTAs per SM.  (With 2 per SM every warp walked 64 pixel rows, four loads in flight
+  // at a time: 16 dependent memory round trips -- 47 us at B = 128 for 34 MB of traffic.)
+  int ns = (8 * 148 + cfg->batch - 1) / (cfg->batch > 0 ? cfg->batch : 1);
   const int maxs = (n + 63) / 64;
   if (ns > maxs) ns = maxs;
   if (ns < 1) ns = 1;
