@@ -623,6 +623,17 @@ def _classical_cpu(F_, steps, warmup, batch):
     return batch / med, med * 1e3, cores
 
 
+class _no_tf32_matmul:
+    """cuBLAS fp32 without TF32 (the reference's numerics) for the library arm of a comparison."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 def run_classical(args):
     """BASELINE configs[3]: high-res classical TPS rectification, 64x256x3 input, F = 20 / 40, batch 1024 per GPU: the
     fused grid generator + bilinear warp alone (the localisation network is not part of the north_star path)."""
@@ -719,6 +730,33 @@ def run_classical(args):
         f1.record()
         barrier()
         e2e_ms = f0.elapsed_time(f1)
+    # the whole drop-in module: TPSPreprocessor.forward = localisation network + the warp above, device-
+    # resident images, with the native localisation network (tpspp_locnet_fwd) and with the cuDNN / cuBLAS fp32 stack
+    module = None
+    if rank == 0 and world == 1:
+        import tps_pp_b200 as T
+        torch.manual_seed(0)
+        tp = T.TPSPreprocessor(num_fiducial=F_, img_size=(64, 256), rectified_img_size=(64, 256), num_img_channel=3).to(dev).eval()
+        module = {"what": "TPSPreprocessor.forward(img[B,3,64,256]) = LocalizationNetwork (1.87 GFLOP/img) + GridGenerator + grid_sample, "
+                          "device-resident images, random-init weights, eval mode"}
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False), _no_tf32_matmul():
+            for impl, nst in (("auto", 5), ("library", 3)):
+                tp.locnet_impl = impl
+                for _ in range(2):
+                    tp(img)
+                torch.cuda.synchronize()
+                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                m0.record()
+                for _ in range(nst):
+                    tp(img)
+                m1.record()
+                torch.cuda.synchronize()
+                ms = m0.elapsed_time(m1) / nst
+                name = "native" if impl == "auto" else "library"
+                module[name + "_locnet_ms_per_step"] = ms
+                module[name + "_locnet_img_per_s"] = B / (ms * 1e-3)
+                if impl == "auto":
+                    module["locnet_native"] = bool(tp._last_locnet_native)
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -747,7 +785,7 @@ def run_classical(args):
                          "fp64_fma_per_launch": dfma,
                          "note": "the grid P_hat.T is evaluated in fp64 (pixel parity 1e-5 needs coordinates to ~1e-8): "
                                  f"{dfma / 1e9:.2f} G DFMA per launch is a second floor next to the HBM one"},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "module": module,
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "img/s", "h2d_bytes_per_step": himg.numel() * 4 + hcp.numel() * 4,
                     "d2h_bytes_per_step": hout.numel() * 4, "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks}), flush=True)

@@ -264,6 +264,26 @@ TPSPP_API size_t tpspp_stage_workspace_bytes(const tpspp_stage_cfg* cfg);
 TPSPP_API int tpspp_stage_fwd(const tpspp_stage_cfg* cfg, const float* img, const float* const* params, float* o0, float* o1,
                               float* x, void* workspace, tpspp_stream_t stream);
 
+/* ---- Classical (RARE) localisation network -------------------------------------------
+ * Replaces `TPSPreprocessor.LocalizationNetwork.forward` (preprocessor/tps_preprocessor.py:96-156), eval mode: four
+ * conv3x3 + BatchNorm + ReLU blocks (C -> 64 -> 128 -> 256 -> 512, MaxPool2d(2) after the first three, AdaptiveAvgPool2d(1)
+ * after the last), localization_fc1 (512 -> 256, ReLU), localization_fc2 (256 -> 2F) -> C' [B, F, 2], which
+ * tpspp_warp_fwd (classical mode) takes.  The reference-side binding is `tps_pp_b200/classical.py::TPSPreprocessor.localize`. */
+typedef struct {
+  int32_t batch, channels;  /* channels: 1 or 3                                                              */
+  int32_t height, width;    /* multiples of 8 whose /2, /4, /8 maps tile into 128-pixel rectangles: 64x256, 64x128, 32x256, ... */
+  int32_t num_fiducial;
+  int32_t flags;            /* TPSPP_HEAD_FLAG_WEIGHTS_CACHED: folded BN + weight images in `workspace` still valid */
+} tpspp_locnet_cfg;
+/* params table = the LocalizationNetwork slice of the reference state_dict, in its order, without num_batches_tracked:
+ * conv.{0,4,8,12}.weight each followed by its BatchNorm's weight, bias, running_mean, running_var; then
+ * localization_fc1.0.{weight,bias}, localization_fc2.{weight,bias}. */
+enum { TPSPP_LP_FC1_W = 20, TPSPP_LP_FC1_B, TPSPP_LP_FC2_W, TPSPP_LP_FC2_B, TPSPP_LP_COUNT = 24 };
+TPSPP_API size_t tpspp_locnet_workspace_bytes(const tpspp_locnet_cfg* cfg);   /* 0: unsupported geometry (tpspp_last_error) */
+/* img [B,C,H,W] fp32 -> c_prime [B, F, 2].  params: HOST array of TPSPP_LP_COUNT DEVICE pointers. */
+TPSPP_API int tpspp_locnet_fwd(const tpspp_locnet_cfg* cfg, const float* img, const float* const* params, float* c_prime,
+                               void* workspace, tpspp_stream_t stream);
+
 /* ---- Training-path convolution: forward and backward of one ConvModule (conv + bias + ReLU; reference
  * tps_pp.py:126-131,149-154,538-548), so that autograd of the rectifier's convolutions runs on native kernels
  * (north_star (4); the reference side is torch autograd of nn.Conv2d + ReLU).  NCHW fp32, 64 output channels. */

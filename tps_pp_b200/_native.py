@@ -48,6 +48,15 @@ class ConvCfg(Structure):
                 ("up_h", c_int32 * 3), ("up_w", c_int32 * 3)]
 
 
+class LocnetCfg(Structure):
+    """Mirror of ``tpspp_locnet_cfg`` (include/tpspp.h)."""
+    _fields_ = [("batch", c_int32), ("channels", c_int32), ("height", c_int32), ("width", c_int32), ("num_fiducial", c_int32),
+                ("flags", c_int32)]
+
+
+LP_COUNT = 24
+
+
 class LinearCfg(Structure):
     """Mirror of ``tpspp_linear_cfg`` (include/tpspp.h)."""
     _fields_ = [("rows", ctypes.c_int64), ("in_features", c_int32), ("out_features", c_int32), ("weight_batches", c_int32)]
@@ -84,6 +93,8 @@ _SIGNATURES = {
     "tpspp_conv_bwd": (c_int, [POINTER(ConvCfg)] + [c_void_p] * 9),
     "tpspp_convcat_fwd": (c_int, [POINTER(ConvCfg), POINTER(c_void_p)] + [c_void_p] * 5),
     "tpspp_convcat_bwd": (c_int, [POINTER(ConvCfg), POINTER(c_void_p)] + [c_void_p] * 3 + [POINTER(c_void_p)] + [c_void_p] * 4),
+    "tpspp_locnet_workspace_bytes": (c_size_t, [POINTER(LocnetCfg)]),
+    "tpspp_locnet_fwd": (c_int, [POINTER(LocnetCfg), c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
     "tpspp_linear_workspace_bytes": (c_size_t, [POINTER(LinearCfg)]),
     "tpspp_linear_fwd": (c_int, [POINTER(LinearCfg)] + [c_void_p] * 6),
     "tpspp_linear_bwd": (c_int, [POINTER(LinearCfg)] + [c_void_p] * 8),

@@ -294,6 +294,51 @@ def stage_forward(img: torch.Tensor, params, workspace: Optional[torch.Tensor] =
     return o0, o1, x, workspace
 
 
+def locnet_param_keys():
+    """state_dict keys (relative to ``LocalizationNetwork.``) in the order ``tpspp_locnet_fwd`` takes them (TPSPP_LP_*)."""
+    keys = []
+    for ci in (0, 4, 8, 12):
+        keys.append(f"conv.{ci}.weight")
+        keys += [f"conv.{ci + 1}.{n}" for n in ("weight", "bias", "running_mean", "running_var")]
+    return keys + ["localization_fc1.0.weight", "localization_fc1.0.bias", "localization_fc2.weight", "localization_fc2.bias"]
+
+
+def locnet_supported(channels: int, height: int, width: int, num_fiducial: int) -> bool:
+    """Whether the native localisation network takes this geometry (include/tpspp.h ``tpspp_locnet_cfg``)."""
+    cfg = N.LocnetCfg(1, channels, height, width, num_fiducial, 0)
+    return int(N.lib().tpspp_locnet_workspace_bytes(ctypes.byref(cfg))) > 0
+
+
+def locnet_forward(img: torch.Tensor, params, num_fiducial: int, workspace: Optional[torch.Tensor] = None,
+                   weights_cached: bool = False):
+    """``LocalizationNetwork.forward`` of the classical preprocessor (tps_preprocessor.py:143-156), eval mode, on the native
+    kernels: img [B,C,H,W] fp32 -> (C' [B,F,2], workspace).  ``params``: the 24 tensors of :func:`locnet_param_keys`."""
+    _require_cuda("img", img, torch.float32)
+    if len(params) != N.LP_COUNT:
+        raise RuntimeError(f"tps_pp_b200: the localisation network takes {N.LP_COUNT} parameter tensors, got {len(params)}")
+    for i, t in enumerate(params):
+        _require_cuda(f"params[{i}]", t, torch.float32)
+        if not t.is_contiguous():
+            raise RuntimeError(f"tps_pp_b200: params[{i}] must be contiguous")
+    img = img.contiguous()
+    b, c, h, w = img.shape
+    cfg = N.LocnetCfg(b, c, h, w, num_fiducial, 0)
+    table = (ctypes.c_void_p * N.LP_COUNT)(*[t.data_ptr() for t in params])
+    with torch.cuda.device(img.device):
+        nbytes = int(N.lib().tpspp_locnet_workspace_bytes(ctypes.byref(cfg)))
+        if nbytes == 0 and b > 0:
+            raise RuntimeError("tpspp_locnet_workspace_bytes failed: " + N.last_error())
+        if workspace is None or workspace.numel() < nbytes or workspace.device != img.device:
+            workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=img.device)
+            weights_cached = False
+        if weights_cached:
+            cfg.flags |= N.HEAD_FLAG_WEIGHTS_CACHED
+        cp = torch.empty((b, num_fiducial, 2), dtype=torch.float32, device=img.device)
+        N.check(N.lib().tpspp_locnet_fwd(ctypes.byref(cfg), _ptr(img), table, _ptr(cp), _ptr(workspace), _stream(img)),
+                "tpspp_locnet_fwd")
+    return cp, workspace
+
+
 def _conv_cfg(b, cin, h, w, k, sh, sw, relu, ups):
     cfg = N.ConvCfg(b, cin, h, w, k, sh, sw, 1 if relu else 0, len(ups))
     for i, (uh, uw) in enumerate(ups):
