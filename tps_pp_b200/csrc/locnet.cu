@@ -8,7 +8,7 @@
 //             (locnet_stem_kernel: thread = pooled pixel, 4 x 4 input patch and 4 pixels x 4 channels of accumulators in registers)
 //   blocks 2-4 the head's tcgen05 engine (conv_tma_kernel, tf32 main term + bf16 corrections = fp32-level), 64 output channels
 //             per launch written as a channel slice of the layer's output (ConvArgs::out_cstride)
-//   pools     maxpool2_kernel; the global average pool is fused with the two dense layers (locnet_fc_kernel, one CTA per image)
+//   pools     maxpool2_kernel, locnet_avgpool_kernel (one warp per plane); the two dense layers in locnet_fc_kernel (8 images per CTA)
 #include "head.cuh"
 
 #include <string.h>
@@ -122,42 +122,65 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__
 
 // ---- AdaptiveAvgPool2d(1) + localization_fc1 (512 -> 256, ReLU) + localization_fc2 (256 -> 2F): one CTA per image ----
 struct LocFcArgs {
-  const float *feat;                    // [B, 512, hw]
+  const float *feat;                    // pooled features [B, 512]
   const float *w1, *b1, *w2, *b2;       // [256, 512], [256], [2F, 256], [2F]
   float* c_prime;                       // [B, 2F]
   int hw, nout;
 };
-__global__ void __launch_bounds__(256) locnet_fc_kernel(LocFcArgs a) {
-  __shared__ float pooled[512];
-  __shared__ float hid[256];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // mean over the plane: one warp per channel, fixed lane assignment + shuffle tree (deterministic)
-  for (int c = warp; c < 512; c += 8) {
-    const float* q = a.feat + ((size_t)b * 512 + c) * a.hw;
-    float s = 0.f;
-    for (int i = lane; i < a.hw; i += 32) s += __ldg(q + i);
+// AdaptiveAvgPool2d(1): one warp per (image, channel) plane, fixed lane assignment + shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) locnet_avgpool_kernel(const float* __restrict__ feat, float* __restrict__ pooled, long long planes,
+                                                             int hw) {
+  const int lane = threadIdx.x & 31;
+  const long long pl = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pl >= planes) return;
+  const float4* q = reinterpret_cast<const float4*>(feat + pl * hw);
+  float s = 0.f;
+  for (int k = lane; k < (hw >> 2); k += 32) {
+    const float4 v = __ldg(q + k);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) pooled[c] = s / (float)a.hw;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) pooled[pl] = s / (float)hw;
+}
+constexpr int FC_IMGS = 8;        // images per CTA: every weight row read from L2 feeds eight dot products
+__global__ void __launch_bounds__(256) locnet_fc_kernel(LocFcArgs a, int B) {
+  __shared__ __align__(16) float pooled[FC_IMGS][512];
+  __shared__ float hid[FC_IMGS][256];
+  const int b0 = blockIdx.x * FC_IMGS, tid = threadIdx.x;
+  const int nb = min(FC_IMGS, B - b0);
+  for (int u = tid; u < FC_IMGS * 512; u += 256) {
+    const int i = u >> 9;
+    pooled[i][u & 511] = i < nb ? __ldg(a.feat + (size_t)b0 * 512 + u) : 0.f;      // a.feat = pooled features [B, 512]
   }
   __syncthreads();
   {
     const float4* w = reinterpret_cast<const float4*>(a.w1 + (size_t)tid * 512);
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
+    float acc[FC_IMGS];
+#pragma unroll
+    for (int i = 0; i < FC_IMGS; ++i) acc[i] = 0.f;
+#pragma unroll 2
     for (int k = 0; k < 128; ++k) {
       const float4 w4 = __ldg(w + k);
-      a0 = fmaf(w4.x, pooled[4 * k], a0); a1 = fmaf(w4.y, pooled[4 * k + 1], a1);
-      a0 = fmaf(w4.z, pooled[4 * k + 2], a0); a1 = fmaf(w4.w, pooled[4 * k + 3], a1);
+#pragma unroll
+      for (int i = 0; i < FC_IMGS; ++i) {
+        const float4 p4 = *reinterpret_cast<const float4*>(&pooled[i][4 * k]);     // warp-uniform: broadcast
+        acc[i] = fmaf(w4.x, p4.x, acc[i]); acc[i] = fmaf(w4.y, p4.y, acc[i]);
+        acc[i] = fmaf(w4.z, p4.z, acc[i]); acc[i] = fmaf(w4.w, p4.w, acc[i]);
+      }
     }
-    hid[tid] = fmaxf(a0 + a1 + __ldg(a.b1 + tid), 0.f);
+    const float bb = __ldg(a.b1 + tid);
+#pragma unroll
+    for (int i = 0; i < FC_IMGS; ++i) hid[i][tid] = fmaxf(acc[i] + bb, 0.f);
   }
   __syncthreads();
-  for (int o = tid; o < a.nout; o += 256) {
-    const float* w = a.w2 + (size_t)o * 256;
+  for (int o = tid; o < a.nout * FC_IMGS; o += 256) {
+    const int i = o / a.nout, n = o - i * a.nout;
+    if (i >= nb) continue;
+    const float* w = a.w2 + (size_t)n * 256;
     float acc = 0.f;
-    for (int k = 0; k < 256; ++k) acc = fmaf(__ldg(w + k), hid[k], acc);
-    a.c_prime[(size_t)b * a.nout + o] = acc + __ldg(a.b2 + o);
+    for (int k = 0; k < 256; ++k) acc = fmaf(__ldg(w + k), hid[i][k], acc);
+    a.c_prime[(size_t)(b0 + i) * a.nout + n] = acc + __ldg(a.b2 + n);
   }
 }
 
@@ -310,8 +333,13 @@ extern "C" int tpspp_locnet_fwd(const tpspp_locnet_cfg* cfg, const float* img, c
   rc = pool(W(LW_C3), W(LW_P3), 256, H4, W4);     if (rc != TPSPP_OK) return rc;
   rc = conv_block(3, W(LW_P3), H8, W8, W(LW_C4)); if (rc != TPSPP_OK) return rc;
   {
-    LocFcArgs fa{W(LW_C4), P[TPSPP_LP_FC1_W], P[TPSPP_LP_FC1_B], P[TPSPP_LP_FC2_W], P[TPSPP_LP_FC2_B], c_prime, H8 * W8, 2 * d.F};
-    locnet_fc_kernel<<<d.B, 256, 0, st>>>(fa);
+    // the pooled [B, 512] features reuse the (dead by now) P3 buffer
+    const long long planes = (long long)d.B * 512;
+    locnet_avgpool_kernel<<<(unsigned)((planes + 7) / 8), 256, 0, st>>>(W(LW_C4), W(LW_P3), planes, H8 * W8);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+    LocFcArgs fa{W(LW_P3), P[TPSPP_LP_FC1_W], P[TPSPP_LP_FC1_B], P[TPSPP_LP_FC2_W], P[TPSPP_LP_FC2_B], c_prime, H8 * W8, 2 * d.F};
+    locnet_fc_kernel<<<(d.B + FC_IMGS - 1) / FC_IMGS, 256, 0, st>>>(fa, d.B);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
   }
