@@ -116,6 +116,46 @@ __global__ void __launch_bounds__(32 * GB_ROWS) grid_bwd_reduce_kernel(WarpParam
   for (int i = 0; i < GB_MAXI; ++i) { ax[i] = 0.0; ay[i] = 0.0; }
   double a0x = 0, a0y = 0, a1x = 0, a1y = 0, a2x = 0, a2y = 0;   // affine columns (attention, lane 0)
   const float th = p.theta;
+  if (MODE == 0 && p.F <= 32) {
+    // TPS++ geometry (F <= 32: one column per lane).  The inputs of FOUR pixel rows are loaded before anything is stored: with
+    // the plain loop below the compiler may not move a row's loads above the previous row's g_score store (the pointers can
+    // alias), so a warp had one row -- 384 bytes -- in flight and the kernel sat on the long scoreboard (ncu: 14 of 22 warp
+    // cycles per issue, 5 % of the DRAM bandwidth, 85 us at B = 256 for 70 MB).
+    const int k = lane;
+    const bool kv = k < p.F;
+    const double t3x = kv ? Tsm[2 * (3 + k)] : 0.0, t3y = kv ? Tsm[2 * (3 + k) + 1] : 0.0;
+    for (int pix0 = p_lo + row; pix0 < p_hi; pix0 += 4 * GB_ROWS) {
+      float2 gg[4], pp[4];
+      float hh[4], ss[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pix = pix0 + j * GB_ROWS;
+        const bool ok = pix < p_hi;
+        const size_t r = (size_t)b * p.n + (ok ? pix : p_lo);
+        gg[j] = ok ? __ldg(reinterpret_cast<const float2*>(p.g_grid + r * 2)) : make_float2(0.f, 0.f);
+        hh[j] = (ok && kv) ? __ldg(p.P_hat + (size_t)pix * p.F + k) : 0.f;
+        ss[j] = (ok && kv) ? __ldg(p.score + r * p.F + k) : 0.f;
+        pp[j] = (ok && lane == 0) ? __ldg(reinterpret_cast<const float2*>(p.P + 2 * pix)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pix = pix0 + j * GB_ROWS;
+        if (pix >= p_hi) break;
+        const double dgx = (double)gg[j].x, dgy = (double)gg[j].y, h = (double)hh[j];
+        const double phi = h * (1.0 + (double)th * (double)ss[j]);
+        ax[0] = fma(phi, dgx, ax[0]);
+        ay[0] = fma(phi, dgy, ay[0]);
+        if (p.g_score != nullptr && kv)
+          __stcs(p.g_score + ((size_t)b * p.n + pix) * p.F + k, (float)((double)th * h * (dgx * t3x + dgy * t3y)));
+        if (lane == 0) {
+          const double px = (double)pp[j].x, py = (double)pp[j].y;
+          a0x += dgx; a0y += dgy;
+          a1x = fma(px, dgx, a1x); a1y = fma(px, dgy, a1y);
+          a2x = fma(py, dgx, a2x); a2y = fma(py, dgy, a2y);
+        }
+      }
+    }
+  } else
   // independent pixel rows: unrolled so that the loads of four rows are in flight together (the loop is latency-bound)
 #pragma unroll 4
   for (int pix = p_lo + row; pix < p_hi; pix += GB_ROWS) {
