@@ -117,10 +117,10 @@ __global__ void __launch_bounds__(32 * GB_ROWS) grid_bwd_reduce_kernel(WarpParam
   double a0x = 0, a0y = 0, a1x = 0, a1y = 0, a2x = 0, a2y = 0;   // affine columns (attention, lane 0)
   const float th = p.theta;
   if (MODE == 0 && p.F <= 32) {
-    // TPS++ geometry (F <= 32: one column per lane).  The inputs of FOUR pixel rows are loaded before anything is stored: with
-    // the plain loop below the compiler may not move a row's loads above the previous row's g_score store (the pointers can
-    // alias), so a warp had one row -- 384 bytes -- in flight and the kernel sat on the long scoreboard (ncu: 14 of 22 warp
-    // cycles per issue, 5 % of the DRAM bandwidth, 85 us at B = 256 for 70 MB).
+    // TPS++ geometry (F <= 32: one column per lane): the inputs of FOUR pixel rows are loaded before anything is stored (the
+    // pointers may alias, so the compiler keeps a row's loads behind the previous row's g_score store), T's columns 3.. stay
+    // in registers.  Same summation order as the generic loop below.  (ncu at B = 256: 85 us for 70 MB -- ~70 instructions
+    // per pixel row, a third of them the lane-0 affine columns under a divergent branch; not yet restructured.)
     const int k = lane;
     const bool kv = k < p.F;
     const double t3x = kv ? Tsm[2 * (3 + k)] : 0.0, t3y = kv ? Tsm[2 * (3 + k) + 1] : 0.0;
@@ -764,8 +764,7 @@ static size_t bwd_csr_smem() { return BS_CSR_BYTES + (size_t)BS_MAX_N * sizeof(d
 
 int bwd_nsplit(const tpspp_warp_cfg* cfg) {
   const int n = cfg->out_h * cfg->out_w;
-  // pixel splits of grid_bwd_reduce_kernel: ~8 CTAs per SM.  (With 2 per SM every warp walked 64 pixel rows, four loads in flight
-  // at a time: 16 dependent memory round trips -- 47 us at B = 128 for 34 MB of traffic.)
+  // pixel splits of grid_bwd_reduce_kernel: ~8 CTAs per SM
   int ns = (8 * 148 + cfg->batch - 1) / (cfg->batch > 0 ? cfg->batch : 1);
   const int maxs = (n + 63) / 64;
   if (ns > maxs) ns = maxs;
