@@ -116,45 +116,85 @@ __global__ void __launch_bounds__(32 * GB_ROWS) grid_bwd_reduce_kernel(WarpParam
   for (int i = 0; i < GB_MAXI; ++i) { ax[i] = 0.0; ay[i] = 0.0; }
   double a0x = 0, a0y = 0, a1x = 0, a1y = 0, a2x = 0, a2y = 0;   // affine columns (attention, lane 0)
   const float th = p.theta;
-  if (MODE == 0 && p.F <= 32) {
-    // TPS++ geometry (F <= 32: one column per lane): the inputs of FOUR pixel rows are loaded before anything is stored (the
-    // pointers may alias, so the compiler keeps a row's loads behind the previous row's g_score store), T's columns 3.. stay
-    // in registers.  Same summation order as the generic loop below.  (ncu at B = 256: 85 us for 70 MB -- ~70 instructions
-    // per pixel row, a third of them the lane-0 affine columns under a divergent branch; not yet restructured.)
-    const int k = lane;
-    const bool kv = k < p.F;
-    const double t3x = kv ? Tsm[2 * (3 + k)] : 0.0, t3y = kv ? Tsm[2 * (3 + k) + 1] : 0.0;
-    for (int pix0 = p_lo + row; pix0 < p_hi; pix0 += 4 * GB_ROWS) {
-      float2 gg[4], pp[4];
-      float hh[4], ss[4];
+  if (MODE == 0 && p.F == 32 &&
+      (((uintptr_t)p.P_hat | (uintptr_t)p.score | (uintptr_t)p.g_score | (uintptr_t)p.P) & 15) == 0) {
+    // TPS++ geometry (F = 32), 16-byte aligned tensors.  A warp takes FOUR consecutive pixel rows per step: lane = (row, column quad), so a row's 32
+    // scores / P_hat entries / score gradients are one 16-byte access per lane (the rows are contiguous: 512 bytes per warp
+    // access), and each lane keeps fp64 column sums for its four columns.  Two steps are loaded before anything is stored (the
+    // pointers may alias).  ~13 instead of ~70 instructions per pixel row (the one-column-per-lane loop below paid address
+    // arithmetic, conversions and a divergent lane-0 branch for the affine columns per row: 85 us at B = 256 for 70 MB).
+    const int rg = lane >> 3, cq = lane & 7;
+    double t3x[4], t3y[4], sx[4], sy[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int pix = pix0 + j * GB_ROWS;
+    for (int i = 0; i < 4; ++i) {
+      t3x[i] = Tsm[2 * (3 + 4 * cq + i)]; t3y[i] = Tsm[2 * (3 + 4 * cq + i) + 1];
+      sx[i] = 0.0; sy[i] = 0.0;
+    }
+    const double thd = (double)th;
+    for (int pix0 = p_lo + 4 * row; pix0 < p_hi; pix0 += 8 * GB_ROWS) {
+      float4 s4[2], h4[2];
+      float2 gg[2], pp[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int pix = pix0 + j * 4 * GB_ROWS + rg;
         const bool ok = pix < p_hi;
         const size_t r = (size_t)b * p.n + (ok ? pix : p_lo);
+        s4[j] = ok ? __ldg(reinterpret_cast<const float4*>(p.score + r * 32) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        h4[j] = ok ? __ldg(reinterpret_cast<const float4*>(p.P_hat + (size_t)pix * 32) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
         gg[j] = ok ? __ldg(reinterpret_cast<const float2*>(p.g_grid + r * 2)) : make_float2(0.f, 0.f);
-        hh[j] = (ok && kv) ? __ldg(p.P_hat + (size_t)pix * p.F + k) : 0.f;
-        ss[j] = (ok && kv) ? __ldg(p.score + r * p.F + k) : 0.f;
-        pp[j] = (ok && lane == 0) ? __ldg(reinterpret_cast<const float2*>(p.P + 2 * pix)) : make_float2(0.f, 0.f);
+        pp[j] = (ok && cq == 0) ? __ldg(reinterpret_cast<const float2*>(p.P + 2 * pix)) : make_float2(0.f, 0.f);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int pix = pix0 + j * GB_ROWS;
-        if (pix >= p_hi) break;
-        const double dgx = (double)gg[j].x, dgy = (double)gg[j].y, h = (double)hh[j];
-        const double phi = h * (1.0 + (double)th * (double)ss[j]);
-        ax[0] = fma(phi, dgx, ax[0]);
-        ay[0] = fma(phi, dgy, ay[0]);
-        if (p.g_score != nullptr && kv)
-          __stcs(p.g_score + ((size_t)b * p.n + pix) * p.F + k, (float)((double)th * h * (dgx * t3x + dgy * t3y)));
-        if (lane == 0) {
-          const double px = (double)pp[j].x, py = (double)pp[j].y;
-          a0x += dgx; a0y += dgy;
-          a1x = fma(px, dgx, a1x); a1y = fma(px, dgy, a1y);
-          a2x = fma(py, dgx, a2x); a2y = fma(py, dgy, a2y);
+      for (int j = 0; j < 2; ++j) {
+        const int pix = pix0 + j * 4 * GB_ROWS + rg;
+        const bool ok = pix < p_hi;
+        const double dgx = (double)gg[j].x, dgy = (double)gg[j].y;       // zero for rows past the end: they add nothing
+        const float sv[4] = {s4[j].x, s4[j].y, s4[j].z, s4[j].w}, hv[4] = {h4[j].x, h4[j].y, h4[j].z, h4[j].w};
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double h = (double)hv[i];
+          const double phi = h * (1.0 + thd * (double)sv[i]);
+          sx[i] = fma(phi, dgx, sx[i]);
+          sy[i] = fma(phi, dgy, sy[i]);
+          o[i] = (float)(thd * h * (dgx * t3x[i] + dgy * t3y[i]));
         }
+        if (ok && p.g_score != nullptr)
+          __stcs(reinterpret_cast<float4*>(p.g_score + ((size_t)b * p.n + pix) * 32) + cq, make_float4(o[0], o[1], o[2], o[3]));
+        // affine columns: the quad-0 lane of each row (predicated: pp and dg are zero elsewhere / past the end)
+        const double px = (double)pp[j].x, py = (double)pp[j].y, m = cq == 0 ? 1.0 : 0.0;
+        a0x = fma(m, dgx, a0x); a0y = fma(m, dgy, a0y);
+        a1x = fma(px, dgx, a1x); a1y = fma(px, dgy, a1y);
+        a2x = fma(py, dgx, a2x); a2y = fma(py, dgy, a2y);
       }
     }
+    // fold the four row groups (lanes l, l ^ 8, l ^ 16, l ^ 24): fixed butterfly = deterministic
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sx[i] += __shfl_xor_sync(0xffffffffu, sx[i], off);
+        sy[i] += __shfl_xor_sync(0xffffffffu, sy[i], off);
+      }
+      a0x += __shfl_xor_sync(0xffffffffu, a0x, off); a0y += __shfl_xor_sync(0xffffffffu, a0y, off);
+      a1x += __shfl_xor_sync(0xffffffffu, a1x, off); a1y += __shfl_xor_sync(0xffffffffu, a1y, off);
+      a2x += __shfl_xor_sync(0xffffffffu, a2x, off); a2y += __shfl_xor_sync(0xffffffffu, a2y, off);
+    }
+    double* mine = red + (size_t)row * 2 * p.K;
+    if (rg == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { mine[2 * (3 + 4 * cq + i)] = sx[i]; mine[2 * (3 + 4 * cq + i) + 1] = sy[i]; }
+      if (cq == 0) { mine[0] = a0x; mine[1] = a0y; mine[2] = a1x; mine[3] = a1y; mine[4] = a2x; mine[5] = a2y; }
+    }
+    __syncthreads();
+    double* outp = partial + ((size_t)b * nsplit + split) * 2 * p.K;
+    for (int o = threadIdx.x; o < 2 * p.K; o += blockDim.x) {
+      double acc = 0.0;
+#pragma unroll
+      for (int r = 0; r < GB_ROWS; ++r) acc += red[(size_t)r * 2 * p.K + o];
+      outp[o] = acc;
+    }
+    return;
   } else
   // independent pixel rows: unrolled so that the loads of four rows are in flight together (the loop is latency-bound)
 #pragma unroll 4
