@@ -369,7 +369,7 @@ __device__ __forceinline__ void staged_grid_phase(const WarpParams& p, const dou
 }
 
 // ---- K-B1c ----
-__global__ void __launch_bounds__(BS_CONSUMERS, 1) warp_bwd_csr_kernel(BwdStagedArgs a) {
+__global__ void __launch_bounds__(BS_CONSUMERS, 2) warp_bwd_csr_kernel(BwdStagedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const WarpParams& p = a.p;
   BwdCsr csr0, csr1;
