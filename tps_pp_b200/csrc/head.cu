@@ -4,7 +4,7 @@
 //   down0/1/2, down0_1/1_1, grid()/down_feat        :538-548,560-562,581-585   -> conv_ffma_kernel
 //   Encoder_Decoder_Feature_Extractor.forward       :156-169                   -> conv_ffma_kernel (+skip)
 //   CBAM / ChannelAttention / SpatialAttention      :27-82                     -> cbam_kernel
-//   DGAB.forward / DGAB_Block.forward (DGAB.py:39-55,74-77), LayerNorm(H,W)    -> dgab_plane_kernel
+//   DGAB.forward / DGAB_Block.forward (DGAB.py:39-55,74-77), LayerNorm(H,W)    -> dgab_warp_kernel
 //   Mlp.forward (DGAB.py:17-23) + residual                                     -> dgab_mlp_kernel
 //   localization_fc1/fc2 -> C' (:321-323), p_linear (:305)                     -> loc_p1_kernel
 //   feat_linear + atten_score = tanh(f p1^T * 64^-0.5) (:293-312)              -> score_kernel
@@ -399,212 +399,11 @@ struct DgabArgs {
   int H, F;
 };
 
-__device__ __forceinline__ float block_sum_256(float v, float* red) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = 0.f;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) t += red[w];
-  return t;
-}
-
 constexpr int DG_MAXH = 32;
 
-// dot product of a shared-memory weight row with a shared-memory vector, split over G consecutive lanes
-template <int G>
-__device__ __forceinline__ float group_dot(const float* row, const float* vec, int len, int part) {
-  // four independent partial sums: the dependent LDS->FFMA chain is what bounds this kernel
-  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-  int i = part;
-  for (; i + 3 * G < len; i += 4 * G) {
-    t0 = __fmaf_rn(row[i], vec[i], t0);
-    t1 = __fmaf_rn(row[i + G], vec[i + G], t1);
-    t2 = __fmaf_rn(row[i + 2 * G], vec[i + 2 * G], t2);
-    t3 = __fmaf_rn(row[i + 3 * G], vec[i + 3 * G], t3);
-  }
-  for (; i < len; i += G) t0 = __fmaf_rn(row[i], vec[i], t0);
-  float t = (t0 + t1) + (t2 + t3);
-#pragma unroll
-  for (int m = 1; m < G; m <<= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
-  return t;
-}
-
-// Persistent: every CTA keeps the DGAB weights (proj^T, mlp_w, mlp_h, both LayerNorm affines) in shared
-// memory and walks planes blockIdx.x, blockIdx.x + gridDim.x, ...; the next plane's pixels are prefetched
-// into registers while the current one is processed.
-template <int PER>   // H/4 plane elements per thread
-__global__ void __launch_bounds__(256, 2) dgab_plane_kernel(DgabArgs a, int nplanes) {
-  extern __shared__ __align__(16) float dsm[];
-  const int H = a.H, F = a.F, tid = threadIdx.x;
-  const int n = H * 64;
-  const int LW = 64 + F + 1, LH = H + F + 1;        // padded row strides (conflict-free group_dot)
-  float* as = dsm;                       // [H][64]   (float4 reads: keep the 16-byte aligned arrays first)
-  float* us = as + n;                    // [H][64]
-  float* n1w = us + n;                   // [n] x4
-  float* n1b = n1w + n;
-  float* n2w = n1b + n;
-  float* n2b = n2w + n;
-  float* wpT = n2b + n;                  // [64][65]
-  float* wws = wpT + 64 * 65;            // [65][LW]
-  float* whs = wws + 65 * LW;            // [H+1][LH]
-  float* vecw = whs + (H + 1) * LH;      // [64+F] = colmean | y
-  float* vech = vecw + 64 + F;           // [H+F]  = rowmean | y
-  float* lw = vech + H + F;              // [65]
-  float* lh = lw + 65;                   // [H+1]
-  float* vw = lh + H + 1;                // [64]
-  float* vh = vw + 64;                   // [H]
-  float* red = vh + H;                   // [8]
-
-  for (int i = tid; i < 4096; i += 256) wpT[(i & 63) * 65 + (i >> 6)] = __ldg(a.wp + i);
-  for (int i = tid; i < 65 * (64 + F); i += 256) { const int r = i / (64 + F); wws[r * LW + (i - r * (64 + F))] = __ldg(a.ww + i); }
-  for (int i = tid; i < (H + 1) * (H + F); i += 256) { const int r = i / (H + F); whs[r * LH + (i - r * (H + F))] = __ldg(a.wh + i); }
-  for (int i = tid; i < n; i += 256) {
-    n1w[i] = __ldg(a.n1w + i); n1b[i] = __ldg(a.n1b + i); n2w[i] = __ldg(a.n2w + i); n2b[i] = __ldg(a.n2b + i);
-  }
-  const float bproj = __ldg(a.bp + (tid & 63));
-
-  float xn[PER];
-  int pl = blockIdx.x;
-  if (pl < nplanes) {
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      xn[i] = __ldg(a.x + (size_t)pl * n + tid + 256 * i);
-  }
-  for (; pl < nplanes; pl += gridDim.x) {
-    const size_t plane = (size_t)pl * n;
-    float xv[PER];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      { xv[i] = xn[i]; s += xv[i]; }
-    if (pl + (int)gridDim.x < nplanes) {      // prefetch the next plane of this CTA
-#pragma unroll
-      for (int i = 0; i < PER; ++i)
-        xn[i] = __ldg(a.x + (size_t)(pl + gridDim.x) * n + tid + 256 * i);
-    }
-    if (tid < F) { const float y = __ldg(a.e3 + (size_t)pl * F + tid); vecw[64 + tid] = y; vech[H + tid] = y; }
-    const float mean = block_sum_256(s, red) / (float)n;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      { const float d = xv[i] - mean; q = __fmaf_rn(d, d, q); }
-    const float rstd = rsqrtf(block_sum_256(q, red) / (float)n + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      {
-        const int idx = tid + 256 * i;
-        us[idx] = (xv[i] - mean) * rstd * n1w[idx] + n1b[idx];
-      }
-    __syncthreads();
-    if (tid < 64) {
-      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-      for (int h = 0; h < H; h += 4) {       // H is a multiple of 8
-        t0 += us[h * 64 + tid]; t1 += us[(h + 1) * 64 + tid]; t2 += us[(h + 2) * 64 + tid]; t3 += us[(h + 3) * 64 + tid];
-      }
-      vecw[tid] = ((t0 + t1) + (t2 + t3)) / (float)H;
-    } else if (tid < 64 + 4 * H) {           // 4 lanes per row
-      const int h = (tid - 64) >> 2, q = (tid - 64) & 3;
-      float t0 = 0.f, t1 = 0.f;
-      for (int w = q * 16; w < q * 16 + 16; w += 2) { t0 += us[h * 64 + w]; t1 += us[h * 64 + w + 1]; }
-      float t = t0 + t1;
-      t += __shfl_xor_sync(0xffffffffu, t, 1);
-      t += __shfl_xor_sync(0xffffffffu, t, 2);
-      if (q == 0) vech[h] = t / 64.f;
-    }
-    __syncthreads();
-    {  // width logits 0..63: 4 lanes each;   then logit 64 and the H+1 height logits: 8 lanes each
-      const float t = group_dot<4>(wws + (tid >> 2) * LW, vecw, 64 + F, tid & 3);
-      if ((tid & 3) == 0) lw[tid >> 2] = t;
-      const int o = tid >> 3;                 // 0: lw[64]; 1..H+1: lh[o-1]
-      const bool act = o < H + 2;             // inactive groups run an empty loop: shuffles stay warp-uniform
-      const float* row = !act ? wws : (o == 0) ? (wws + 64 * LW) : (whs + (o - 1) * LH);
-      const float* vec = (o == 0) ? vecw : vech;
-      const float t2 = group_dot<8>(row, vec, !act ? 0 : (o == 0) ? 64 + F : H + F, tid & 7);
-      if (act && (tid & 7) == 0) { if (o == 0) lw[64] = t2; else lh[o - 1] = t2; }
-    }
-    __syncthreads();
-    if (tid < 32) {            // softmax over the 64 width logits
-      const float v0 = lw[tid], v1 = lw[tid + 32];
-      float m = fmaxf(v0, v1);
-#pragma unroll
-      for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
-      const float e0 = expf(v0 - m), e1 = expf(v1 - m);
-      float t = e0 + e1;
-#pragma unroll
-      for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
-      vw[tid] = e0 / t;
-      vw[tid + 32] = e1 / t;
-    } else if (tid < 64) {     // softmax over the H height logits
-      const int l = tid - 32;
-      const float v0 = l < H ? lh[l] : -INFINITY;
-      float m = v0;
-#pragma unroll
-      for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
-      const float e0 = l < H ? expf(v0 - m) : 0.f;
-      float t = e0;
-#pragma unroll
-      for (int k = 16; k >= 1; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
-      if (l < H) vh[l] = e0 / t;
-    }
-    __syncthreads();
-    {
-      const float hl = lh[H], wl = lw[64];
-#pragma unroll
-      for (int i = 0; i < PER; ++i)
-        {
-          const int idx = tid + 256 * i, h = idx >> 6, w = idx & 63;
-          const float u = us[idx];
-          as[idx] = (vh[h] * u) * hl + (vw[w] * u) * wl;   // same association as DGAB.py:50
-        }
-    }
-    __syncthreads();
-    // proj over the width axis + residual; thread -> column j = tid&63, rows (tid>>6) + 4*i
-    float o[PER];
-    {
-      const int j = tid & 63, h0 = tid >> 6;
-#pragma unroll
-      for (int i = 0; i < PER; ++i) o[i] = 0.f;
-#pragma unroll 2
-      for (int w = 0; w < 64; w += 4) {
-        const float w0 = wpT[(w + 0) * 65 + j], w1 = wpT[(w + 1) * 65 + j];
-        const float w2 = wpT[(w + 2) * 65 + j], w3 = wpT[(w + 3) * 65 + j];
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-          const float4 av = *reinterpret_cast<const float4*>(as + (h0 + 4 * i) * 64 + w);   // warp-wide broadcast
-          o[i] = __fmaf_rn(av.x, w0, o[i]); o[i] = __fmaf_rn(av.y, w1, o[i]);
-          o[i] = __fmaf_rn(av.z, w2, o[i]); o[i] = __fmaf_rn(av.w, w3, o[i]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < PER; ++i) o[i] = xv[i] + (o[i] + bproj);    // idx = tid + 256*i <-> (h0+4i, j)
-    }
-    float s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      { a.x1[plane + tid + 256 * i] = o[i]; s2 += o[i]; }
-    const float mean2 = block_sum_256(s2, red) / (float)n;
-    float q2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      { const float d = o[i] - mean2; q2 = __fmaf_rn(d, d, q2); }
-    const float rstd2 = rsqrtf(block_sum_256(q2, red) / (float)n + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      {
-        const int idx = tid + 256 * i;
-        a.v[plane + idx] = (o[i] - mean2) * rstd2 * n2w[idx] + n2b[idx];
-      }
-    // the next iteration's first shared-memory writes (vecw/vech tails, us) are ordered behind the
-    // block_sum_256 barriers above, after every read of this plane's us / as / vw / vh
-  }
-}
-
-// Warp-per-plane form of the same block: a [H,64] plane is 2H elements per lane, so LayerNorm statistics, the two
-// gate soft-maxes and the row/column means are warp shuffles and the whole plane needs no block barrier (the
-// block-per-plane kernel above spends most of its 5.7 us per plane waiting in ~13 __syncthreads).  16 warps per CTA,
+// DGAB gating block, one warp per plane: a [H,64] plane is 2H elements per lane, so LayerNorm statistics, the two
+// gate soft-maxes and the row/column means are warp shuffles and the whole plane needs no block barrier (the round-1
+// block-per-plane kernel spent most of its 5.7 us per plane waiting in ~13 __syncthreads; removed).  16 warps per CTA,
 // one CTA per SM, weights shared in shared memory, per-warp scratch for the gated plane.
 constexpr int DW_WARPS = 16;
 template <int H>
@@ -774,11 +573,6 @@ static size_t dgab_warp_smem(int H, int F) {
                                   DW_WARPS * (n + (64 + F) + (H + F) + 4) + 8);
 }
 
-static size_t dgab_plane_smem(int H, int F) {
-  const int n = H * 64;
-  return sizeof(float) * (size_t)(64 * 65 + 65 * (64 + F + 1) + (H + 1) * (H + F + 1) + 6 * n + (64 + F) + (H + F) + 65 +
-                                  (H + 1) + 64 + H + 8 + 16);
-}
 
 // =====================================================================================
 // DGAB part 2: x2 = x1 + fc2(GELU(fc1(v))) over the width axis; rows = (b, c, h), K = 64
@@ -1263,24 +1057,14 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     a.n1w = P[TPSPP_P_NORM1_W]; a.n1b = P[TPSPP_P_NORM1_B]; a.n2w = P[TPSPP_P_NORM2_W]; a.n2b = P[TPSPP_P_NORM2_B];
     a.wh = P[TPSPP_P_MLP_H_W]; a.ww = P[TPSPP_P_MLP_W_W]; a.wp = P[TPSPP_P_PROJ_W]; a.bp = P[TPSPP_P_PROJ_B];
     a.x1 = W(TPSPP_WS_X1); a.v = W(TPSPP_WS_V); a.H = h; a.F = d.F;
-    if ((h == 8 || h == 16) && d.F <= 32 && dgab_warp_smem(h, d.F) <= 220 * 1024) {      // warp-per-plane kernel
+    {      // warp-per-plane kernel (head_dims admits h = 8 or 16 and F <= 32 only)
+      TPSPP_REQUIRE((h == 8 || h == 16) && d.F <= 32 && dgab_warp_smem(h, d.F) <= 220 * 1024, "DGAB: unsupported geometry h=%d F=%d", h, d.F);
       const size_t smem = dgab_warp_smem(h, d.F);
       auto kern = h == 8 ? dgab_warp_kernel<8> : dgab_warp_kernel<16>;
       TPSPP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int grid = sm_count();
       if (grid > (B * 64 + DW_WARPS - 1) / DW_WARPS) grid = (B * 64 + DW_WARPS - 1) / DW_WARPS;
       kern<<<grid, DW_WARPS * 32, smem, st>>>(a, B * 64);
-    } else {
-      const size_t smem = dgab_plane_smem(h, d.F);
-      auto kern = h == 8 ? dgab_plane_kernel<2> : h == 16 ? dgab_plane_kernel<4> : h == 24 ? dgab_plane_kernel<6>
-                                                                                            : dgab_plane_kernel<8>;
-      TPSPP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = 0;
-      TPSPP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
-      if (per_sm < 1) per_sm = 1;
-      int grid = sm_count() * per_sm;
-      if (grid > B * 64) grid = B * 64;
-      kern<<<grid, 256, smem, st>>>(a, B * 64);
     }
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
