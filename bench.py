@@ -188,6 +188,31 @@ def _dist_env():
     return rank, world, local
 
 
+def _bind_to_gpu_cpus(local: int):
+    """Pin this rank (and, by first touch, its pinned host buffers) to the CPUs NVML reports as local to its GPU: with
+    several ranks per node the end-to-end path is bound by host memory / PCIe root traffic, and buffers that land on the
+    other socket cross the inter-socket link on every copy.  Returns a short description for the JSON line."""
+    if os.environ.get("TPSPP_BENCH_AFFINITY", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = None
+        if torch.cuda.is_available():
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode()) if uuid else pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "none"
+        os.sched_setaffinity(0, allowed)
+        return f"{len(allowed)} cpus local to the GPU ({allowed[0]}-{allowed[-1]})"
+    except Exception as e:  # noqa: BLE001 -- affinity is an optimisation, never a failure
+        return f"unavailable ({type(e).__name__})"
+
+
 def _cpu_reference(steps: int, warmup: int, batch: int):
     """The reference's CPU path (oracle port: same torch CPU ops the reference module calls,
     oracle/tpspp_oracle.py) on all host cores."""
@@ -273,6 +298,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the TPS++ hot path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # only with several ranks per node (at N = 1 the end-to-end path is not host-bound, and the CPU-baseline leg of this
+    # process must keep every core)
+    host_affinity = _bind_to_gpu_cpus(local) if world > 1 else "off (single rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N.device_info()     # fails loudly on a non-sm_100 device / missing library
@@ -519,7 +547,7 @@ def run_ours(args):
             "e2e": e2e_obj,
             "e2e_feature_boundary": feature_e2e,
             "from_image": image_obj,
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "host_affinity": host_affinity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
