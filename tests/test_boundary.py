@@ -164,3 +164,53 @@ def test_launch_profile_is_a_no_op_without_work(native_lib):
     assert native_lib.tpspp_launch_profile_read(None, 8, ctypes.byref(cnt)) != 0       # bad arguments are reported
     assert b"tpspp_launch_profile_read" in native_lib.tpspp_last_error()
 
+
+
+def test_every_cfg_struct_has_the_header_layout(tmp_path):
+    """sizeof / field offsets of the ctypes mirrors against include/tpspp.h compiled as plain C (the header must also BE plain C:
+    the reference-side bindings are cgo / ctypes style)."""
+    import ctypes
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = [("tpspp_warp_cfg", _native.WarpCfg), ("tpspp_head_cfg", _native.HeadCfg), ("tpspp_stage_cfg", _native.StageCfg),
+             ("tpspp_conv_cfg", _native.ConvCfg), ("tpspp_linear_cfg", _native.LinearCfg), ("tpspp_locnet_cfg", _native.LocnetCfg)]
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "tpspp.h"', "int main(void) {"]
+    for cname, mirror in pairs:
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for (cname, mirror), line in zip(pairs, out):
+        parts = line.split()
+        assert parts[0] == cname
+        assert int(parts[1]) == ctypes.sizeof(mirror), cname
+        offs = [int(v) for v in parts[2:]]
+        assert offs == [getattr(mirror, f[0]).offset for f in mirror._fields_], cname
+
+
+def test_training_and_locnet_workspace_queries_are_host_only(native_lib):
+    """tpspp_conv / tpspp_linear / tpspp_locnet workspace queries validate their cfg on the host (no GPU needed)."""
+    import ctypes
+    conv = _native.ConvCfg(8, 192, 16, 64, 3, 1, 1, 1, 3)
+    for i in range(3):
+        conv.up_h[i] = conv.up_w[i] = 1
+    assert native_lib.tpspp_conv_workspace_bytes(ctypes.byref(conv)) > 0
+    bad = _native.ConvCfg(8, 48, 16, 64, 3, 1, 1, 1, 1)
+    assert native_lib.tpspp_conv_workspace_bytes(ctypes.byref(bad)) == 0 and b"cin" in native_lib.tpspp_last_error()
+    lin = _native.LinearCfg(4096, 64, 256, 1)
+    assert native_lib.tpspp_linear_workspace_bytes(ctypes.byref(lin)) > 0
+    assert native_lib.tpspp_linear_workspace_bytes(ctypes.byref(_native.LinearCfg(100, 64, 256, 3))) == 0      # rows % batches
+    assert native_lib.tpspp_locnet_workspace_bytes(ctypes.byref(_native.LocnetCfg(4, 3, 64, 256, 20, 0))) > 0
+    assert native_lib.tpspp_locnet_workspace_bytes(ctypes.byref(_native.LocnetCfg(4, 1, 32, 100, 20, 0))) == 0  # 100 % 8
+    assert native_lib.tpspp_locnet_workspace_bytes(ctypes.byref(_native.LocnetCfg(4, 1, 32, 128, 20, 0))) == 0  # 4x16 map does not tile
+    assert b"not supported" in native_lib.tpspp_last_error()
+    assert native_lib.tpspp_locnet_workspace_bytes(ctypes.byref(_native.LocnetCfg(4, 2, 64, 256, 20, 0))) == 0  # 2 channels
