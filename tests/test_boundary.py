@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import tps_pp_b200 as T
-from tps_pp_b200 import _native, constants as K
+from tps_pp_b200 import _native, constants as K, functional as TF
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -214,3 +214,13 @@ def test_training_and_locnet_workspace_queries_are_host_only(native_lib):
     assert native_lib.tpspp_locnet_workspace_bytes(ctypes.byref(_native.LocnetCfg(4, 1, 32, 128, 20, 0))) == 0  # 4x16 map does not tile
     assert b"not supported" in native_lib.tpspp_last_error()
     assert native_lib.tpspp_locnet_workspace_bytes(ctypes.byref(_native.LocnetCfg(4, 2, 64, 256, 20, 0))) == 0  # 2 channels
+
+
+def test_locnet_param_table_matches_module():
+    """The 24-tensor table tpspp_locnet_fwd takes = the LocalizationNetwork slice of the reference state_dict order."""
+    m = T.TPSPreprocessor(num_fiducial=20, img_size=(64, 256), rectified_img_size=(64, 256), num_img_channel=3)
+    keys = [k for k in m.state_dict() if k.startswith("LocalizationNetwork.") and not k.endswith("num_batches_tracked")]
+    assert keys == ["LocalizationNetwork." + k for k in TF.locnet_param_keys()]
+    sd = m.state_dict()
+    assert [tuple(sd[k].shape) for k in keys] == TF.locnet_param_shapes(3, 20)
+    assert len(keys) == _native.LP_COUNT

@@ -303,6 +303,16 @@ def locnet_param_keys():
     return keys + ["localization_fc1.0.weight", "localization_fc1.0.bias", "localization_fc2.weight", "localization_fc2.bias"]
 
 
+def locnet_param_shapes(channels: int, num_fiducial: int):
+    """Shapes of the 24 tensors of :func:`locnet_param_keys` (tps_preprocessor.py:101-131)."""
+    shapes = []
+    chans = (channels, 64, 128, 256, 512)
+    for i in range(4):
+        shapes.append((chans[i + 1], chans[i], 3, 3))
+        shapes += [(chans[i + 1],)] * 4
+    return shapes + [(256, 512), (256,), (2 * num_fiducial, 256), (2 * num_fiducial,)]
+
+
 def locnet_supported(channels: int, height: int, width: int, num_fiducial: int) -> bool:
     """Whether the native localisation network takes this geometry (include/tpspp.h ``tpspp_locnet_cfg``)."""
     cfg = N.LocnetCfg(1, channels, height, width, num_fiducial, 0)
@@ -316,12 +326,16 @@ def locnet_forward(img: torch.Tensor, params, num_fiducial: int, workspace: Opti
     _require_cuda("img", img, torch.float32)
     if len(params) != N.LP_COUNT:
         raise RuntimeError(f"tps_pp_b200: the localisation network takes {N.LP_COUNT} parameter tensors, got {len(params)}")
-    for i, t in enumerate(params):
+    img = img.contiguous()
+    b, c, h, w = img.shape
+    # the kernels size every weight read from (channels, F): a module built for another configuration must fail here
+    for i, (t, shp) in enumerate(zip(params, locnet_param_shapes(c, num_fiducial))):
         _require_cuda(f"params[{i}]", t, torch.float32)
         if not t.is_contiguous():
             raise RuntimeError(f"tps_pp_b200: params[{i}] must be contiguous")
-    img = img.contiguous()
-    b, c, h, w = img.shape
+        if tuple(t.shape) != shp:
+            raise RuntimeError(f"tps_pp_b200: localisation-network params[{i}] has shape {tuple(t.shape)}, expected {shp} for "
+                               f"{c} image channels and {num_fiducial} control points")
     cfg = N.LocnetCfg(b, c, h, w, num_fiducial, 0)
     table = (ctypes.c_void_p * N.LP_COUNT)(*[t.data_ptr() for t in params])
     with torch.cuda.device(img.device):
