@@ -44,7 +44,9 @@ enum {
   TPSPP_E_NO_DEVICE = -4    /* no sm_100 device */
 };
 
-enum { TPSPP_F32 = 0, TPSPP_BF16 = 1 };
+/* TPSPP_SRC0_BF16: src0 is bf16, src1 and both outputs are fp32 -- the bf16 mode of the head hands its `feat_grid` to the
+ * warp this way (staged TPS++ kernel only, forward only). */
+enum { TPSPP_F32 = 0, TPSPP_BF16 = 1, TPSPP_SRC0_BF16 = 2 };
 
 /* Which Phi the grid generator uses. */
 enum {
@@ -76,7 +78,7 @@ typedef struct tpspp_warp_cfg {
   int32_t num_fiducial;   /* F                                                              */
   int32_t mode;           /* TPSPP_MODE_*                                                   */
   float theta;            /* 0.5 in the reference ("thela", tps_pp.py:341)                  */
-  int32_t feat_dtype;     /* TPSPP_F32 | TPSPP_BF16 (dtype of src0/src1/out0/out1)          */
+  int32_t feat_dtype;     /* TPSPP_F32 | TPSPP_BF16 (dtype of src0/src1/out0/out1) | TPSPP_SRC0_BF16 */
   int32_t variant;        /* TPSPP_VARIANT_*                                                */
 } tpspp_warp_cfg;
 
@@ -190,8 +192,10 @@ typedef struct tpspp_head_cfg {
  * the fused kernels (A/B measurements, tests).
  * TF32X3_CONV: run the 3x3 convolutions as all-tf32 3xTF32 (12 MMAs per 32-channel chunk) instead of the default tf32 main
  * term + bf16 correction terms (8 MMAs, same fp32-level accuracy) -- A/B measurements, tests. */
+/* FEATGRID_BF16 (precision TPSPP_HEAD_BF16 only): `feat_grid` is written as bf16 planes [B,64,2h,2w] (half the bytes of the
+ * buffer are used) -- pass it to tpspp_warp_fwd as src0 with feat_dtype = TPSPP_SRC0_BF16. */
 enum { TPSPP_HEAD_FLAG_WEIGHTS_CACHED = 1, TPSPP_HEAD_FLAG_UNFUSED_DOWN = 2, TPSPP_HEAD_FLAG_UNFUSED_SCORE = 4,
-       TPSPP_HEAD_FLAG_TF32X3_CONV = 8 };
+       TPSPP_HEAD_FLAG_TF32X3_CONV = 8, TPSPP_HEAD_FLAG_FEATGRID_BF16 = 16 };
 
 /* Index of each learnable tensor in the `params` pointer table = state_dict order of the
  * reference module (tps_pp.py:94-119,253-285,538-548).                      */

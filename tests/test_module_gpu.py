@@ -4,6 +4,7 @@ import pytest
 import torch
 
 import tps_pp_b200 as T
+from tps_pp_b200 import _native as N
 from oracle import tpspp_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -47,6 +48,27 @@ def test_tps_pp_forward_vs_reference_golden(golden, native_lib):
     print(f"output |ours-ref64|={e_o:.3e} (ref32-ref64 floor {floor_o:.3e}); mp_img {e_m:.3e} (floor {floor_m:.3e})")
     assert e_o <= max(1e-5, FLOOR_K * floor_o)
     assert e_m <= max(1e-5, FLOOR_K * floor_m)
+
+
+def test_tps_pp_bf16_mode_module_tolerance(golden, native_lib):
+    """The module in its bf16 mode (bf16 operands + bf16 storage in the 3x3 convolutions, bf16 feat_grid into the warp): stated
+    tolerance of the returned tensors against the reference's fp64 twin -- control points 1e-4, pc_score 0.15, the rectified
+    feature maps 6e-2 of their range (mp_img samples the fp32 x with a grid that is within 0.5 source px: SURVEY F7)."""
+    g = golden("tpspp_forward.npz")
+    sd = O.trained_like_state(int(g["state_seed"]))
+    m = T.TPS_PP().to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    m.head_precision = N.HEAD_BF16
+    x, o0, o1 = O.synthetic_tpspp_inputs(int(g["batch"]), int(g["input_seed"]))
+    with torch.no_grad():
+        r = m(torch.from_numpy(x).to(DEV), [torch.from_numpy(o0).to(DEV), torch.from_numpy(o1).to(DEV)])
+    assert r["output"].dtype == torch.float32 and r["mp_img"].dtype == torch.float32
+    assert mx(r["pc_score"], g["ref64_pc_score"]) <= 0.15
+    for key in ("output", "mp_img"):
+        ref = np.asarray(g["ref64_" + key])
+        err = mx(r[key], ref)
+        print(f"bf16 mode {key}: |ours - ref64| = {err:.3e} of range {float(np.abs(ref).max()):.2f}")
+        assert err <= 6e-2 * float(np.abs(ref).max())
 
 
 @pytest.mark.parametrize("weights", ["stock", "trained"])

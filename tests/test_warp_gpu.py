@@ -372,3 +372,23 @@ def test_staged_backward_equals_generic_full_geometry(consts):
     gs0, gs1, dC, ds = _oracle_bwd(fg[:2], x[:2], cp[:2], s[:2], c, go0[:2].cpu().numpy(), go1[:2].cpu().numpy())
     assert mx(a[0][:2], gs0) <= 2e-5 and mx(a[1][:2], gs1) <= 2e-5
     assert mx(a[2][:2], dC) <= 2e-4 * float(np.abs(dC).max())
+
+
+def test_src0_bf16_staged_warp(consts):
+    """TPSPP_SRC0_BF16 (bf16 feat_grid, fp32 x, fp32 outputs: the hand-over of the head's bf16 mode): the staged kernel on bf16
+    planes must equal the fp32 kernel on the same (bf16-rounded) values bit for bit; forward only; staged kernel only."""
+    c, hat, ph, P = consts
+    B = 37
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    fg = torch.randn((B, 64, 32, 128), device=DEV, generator=gen).bfloat16()
+    x = torch.randn((B, 64, 16, 64), device=DEV, generator=gen)
+    s = torch.tanh(0.5 * torch.randn((B, 1024, 32), device=DEV, generator=gen))
+    cp = cu(O.smooth_c_prime(O.tpspp_init_bias(), B, seed=3))
+    a0, a1 = TF.tps_warp(fg.float(), x, cp, s, ph, P, hat, (16, 64))
+    b0, b1 = TF.tps_warp(fg, x, cp, s, ph, P, hat, (16, 64))
+    assert b0.dtype == torch.float32 and b1.dtype == torch.float32
+    assert torch.equal(a0, b0) and torch.equal(a1, b1)
+    with pytest.raises(RuntimeError):                       # no generic / classical form of the mixed layout
+        TF.tps_warp(fg, x, cp, s, ph, P, hat, (16, 64), variant=N.VARIANT_GENERIC)
+    with pytest.raises(RuntimeError):                       # inference layout: no backward
+        TF.tps_warp(fg, x.clone().requires_grad_(), cp, s, ph, P, hat, (16, 64))

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TPSPP_LIB", os.path.join(_HERE, "libtpspp.so"))
 
 OK = 0
-F32, BF16 = 0, 1
+F32, BF16, SRC0_BF16 = 0, 1, 2
 MODE_ATTENTION, MODE_CLASSICAL = 0, 1
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_STAGED, VARIANT_TILED = 0, 1, 2, 3
 
@@ -68,6 +68,7 @@ HEAD_FLAG_WEIGHTS_CACHED = 1
 HEAD_FLAG_UNFUSED_DOWN = 2
 HEAD_FLAG_UNFUSED_SCORE = 4
 HEAD_FLAG_TF32X3_CONV = 8
+HEAD_FLAG_FEATGRID_BF16 = 16
 ABI_VERSION = 2
 P_COUNT = 58
 WS_NAMES = ("f0", "f1", "f2", "a0", "a1", "e0", "e1", "e2", "e3", "cbam", "d0", "d1", "d2", "de", "x1", "v", "de2", "p1", "wprep", "t1", "fs", "hid", "p1img")

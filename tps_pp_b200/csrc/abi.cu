@@ -69,8 +69,8 @@ int validate_cfg(const tpspp_warp_cfg* cfg) {
                 "num_fiducial must be in [1,125] (got %d)", cfg->num_fiducial);
   TPSPP_REQUIRE(cfg->mode == TPSPP_MODE_ATTENTION || cfg->mode == TPSPP_MODE_CLASSICAL,
                 "unknown mode %d", cfg->mode);
-  TPSPP_REQUIRE(cfg->feat_dtype == TPSPP_F32 || cfg->feat_dtype == TPSPP_BF16, "unknown feat_dtype %d",
-                cfg->feat_dtype);
+  TPSPP_REQUIRE(cfg->feat_dtype == TPSPP_F32 || cfg->feat_dtype == TPSPP_BF16 || cfg->feat_dtype == TPSPP_SRC0_BF16,
+                "unknown feat_dtype %d", cfg->feat_dtype);
   TPSPP_REQUIRE((long long)cfg->src0_h * cfg->src0_w < (1LL << 30) &&
                     (long long)cfg->out_h * cfg->out_w < (1LL << 30),
                 "plane too large");

@@ -999,7 +999,8 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   bool fused_down = false;
   if (tc && !(cfg->flags & TPSPP_HEAD_FLAG_UNFUSED_DOWN)) {
     rc = run_down_fused(x, o0, o1, wp[0], wp[1], wp[2], wp[5], P[TPSPP_P_DOWN0_B], P[TPSPP_P_DOWN1_B], P[TPSPP_P_DOWN2_B],
-                        P[TPSPP_P_DOWNFEAT_B], W(TPSPP_WS_F0), W(TPSPP_WS_F1), W(TPSPP_WS_F2), feat_grid, B, h, w, st, bf16 ? 1 : 0);
+                        P[TPSPP_P_DOWNFEAT_B], W(TPSPP_WS_F0), W(TPSPP_WS_F1), W(TPSPP_WS_F2), feat_grid, B, h, w, st, bf16 ? 1 : 0,
+                        (bf16 && (cfg->flags & TPSPP_HEAD_FLAG_FEATGRID_BF16)) ? 1 : 0);
     if (rc < 0) return rc;
     fused_down = rc == TPSPP_OK;
     TPSPP_REQUIRE(fused_down || !bf16, "head: the bf16 mode needs the fused down kernel's geometry (width 64, 16-byte aligned inputs)");

@@ -43,7 +43,7 @@ int run_mlp_fused(const float* v, const float* x1, const float* w1img, const flo
 // down0 + down1 + down2 + down_feat in one kernel (tps_pp.py:538-540,548,560-562,581-585); returns 1 if not applicable
 int run_down_fused(const float* x, const float* o0, const float* o1, const float* w0img, const float* w1img, const float* w2img,
                    const float* wfimg, const float* b0, const float* b1, const float* b2, const float* bf, float* f0, float* f1,
-                   float* f2, float* fg, int B, int h, int w, cudaStream_t st, int out_bf16 = 0);
+                   float* f2, float* fg, int B, int h, int w, cudaStream_t st, int out_bf16 = 0, int fg_bf16 = 0);
 // feat_linear.0 -> feat_linear.1 -> tanh(QK^T / 8) in one kernel (tps_pp.py:258-261,293-312); returns 1 if not applicable
 int run_score_fused(const float* de2, const float* w0img, const float* w1img, const float* p1img, const float* b0, const float* b1,
                     float* score, int B, int h, int w, int F, float scale, cudaStream_t st);

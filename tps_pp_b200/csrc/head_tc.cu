@@ -1750,7 +1750,8 @@ struct DownFusedArgs {
   const float *b0, *b1, *b2, *bf;
   float *f0, *f1, *f2, *fg;
   int B, h;                            // h = rows of x (the outs have 2h rows, 128 columns)
-  int out_bf16;                        // 1: f0 / f1 / f2 are stored as bf16 (feat_grid stays fp32: it is the warp's input)
+  int out_bf16;                        // 1: f0 / f1 / f2 are stored as [B,H,W,64] bf16
+  int fg_bf16;                         // 1: feat_grid is stored as bf16 planes [B,64,2h,128] (TPSPP_HEAD_FLAG_FEATGRID_BF16)
 };
 constexpr int DF_WARPS = 16;
 constexpr int DF_THREADS = (DF_WARPS + 2) * 32;
@@ -2047,8 +2048,20 @@ __global__ void __launch_bounds__(DF_THREADS, 1) down_fused_kernel(const __grid_
       if (lane == 0) mbar_arrive(d2_empty);
       if (it + 1 < n_my) block_epilogue(it + 1, 0, e0);
       const float4* bq = reinterpret_cast<const float4*>(bias_s + 3 * 64 + p * 16);
-      float* po = g.fg + (((size_t)img * 64 + p * 16) * H2 + (2 * r + ty)) * W2 + 64 * c0 + tx;
+      const size_t fo = (((size_t)img * 64 + p * 16) * H2 + (2 * r + ty)) * W2 + 64 * c0 + tx;
       const size_t plane = (size_t)H2 * W2;
+      if (g.fg_bf16) {            // bf16 mode: feat_grid as bf16 planes (the warp's TPSPP_SRC0_BF16 input)
+        __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(g.fg) + fo;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = bq[i >> 2];
+          pb[(size_t)i * plane] = __float2bfloat16_rn(fmaxf(acc[i] + (part[i] + b4.x), 0.f));
+          pb[(size_t)(i + 1) * plane] = __float2bfloat16_rn(fmaxf(acc[i + 1] + (part[i + 1] + b4.y), 0.f));
+          pb[(size_t)(i + 2) * plane] = __float2bfloat16_rn(fmaxf(acc[i + 2] + (part[i + 2] + b4.z), 0.f));
+          pb[(size_t)(i + 3) * plane] = __float2bfloat16_rn(fmaxf(acc[i + 3] + (part[i + 3] + b4.w), 0.f));
+        }
+      } else {
+      float* po = g.fg + fo;
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
         const float4 b4 = bq[i >> 2];
@@ -2056,6 +2069,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) down_fused_kernel(const __grid_
         po[(size_t)(i + 1) * plane] = fmaxf(acc[i + 1] + (part[i + 1] + b4.y), 0.f);
         po[(size_t)(i + 2) * plane] = fmaxf(acc[i + 2] + (part[i + 2] + b4.z), 0.f);
         po[(size_t)(i + 3) * plane] = fmaxf(acc[i + 3] + (part[i + 3] + b4.w), 0.f);
+      }
       }
     }
   }
@@ -2491,7 +2505,7 @@ int run_mlp_fused(const float* v, const float* x1, const float* w1img, const flo
 // separate convolutions instead: other widths, misaligned pointers)
 int run_down_fused(const float* x, const float* o0, const float* o1, const float* w0img, const float* w1img, const float* w2img,
                    const float* wfimg, const float* b0, const float* b1, const float* b2, const float* bf, float* f0, float* f1,
-                   float* f2, float* fg, int B, int h, int w, cudaStream_t st, int out_bf16) {
+                   float* f2, float* fg, int B, int h, int w, cudaStream_t st, int out_bf16, int fg_bf16) {
   if (w != 64 || h < 1 || B < 1) return 1;
   if ((((uintptr_t)x | (uintptr_t)o0 | (uintptr_t)o1 | (uintptr_t)w0img | (uintptr_t)w1img | (uintptr_t)w2img | (uintptr_t)wfimg) & 15) != 0)
     return 1;
@@ -2514,7 +2528,7 @@ int run_down_fused(const float* x, const float* o0, const float* o1, const float
   }
   g.w0img = w0img; g.w1img = w1img; g.w2img = w2img; g.wfimg = wfimg;
   g.b0 = b0; g.b1 = b1; g.b2 = b2; g.bf = bf;
-  g.f0 = f0; g.f1 = f1; g.f2 = f2; g.fg = fg; g.B = B; g.h = h; g.out_bf16 = out_bf16;
+  g.f0 = f0; g.f1 = f1; g.f2 = f2; g.fg = fg; g.B = B; g.h = h; g.out_bf16 = out_bf16; g.fg_bf16 = fg_bf16;
   static thread_local int df_dev = -1;
   int dev = 0;
   TPSPP_CHECK_CUDA(cudaGetDevice(&dev));

@@ -935,6 +935,7 @@ extern "C" int tpspp_warp_bwd(const tpspp_warp_cfg* cfg, const void* src0, const
   p.hatC = inv_delta_C; p.gout0 = gout0; p.gout1 = gout1; p.gsrc0 = gsrc0; p.gsrc1 = gsrc1;
   p.g_c_prime = g_c_prime; p.g_score = g_pc_score;
   TPSPP_REQUIRE(p.B <= 65535, "batch %d exceeds the backward kernels' grid.y limit (65535)", p.B);
+  TPSPP_REQUIRE(cfg->feat_dtype != TPSPP_SRC0_BF16, "tpspp_warp_bwd: TPSPP_SRC0_BF16 is a forward-only (inference) layout");
   if (cfg->feat_dtype == TPSPP_BF16) return launch_bwd_t<__nv_bfloat16>(cfg, p, workspace, (cudaStream_t)stream);
   return launch_bwd_t<float>(cfg, p, workspace, (cudaStream_t)stream);
 }

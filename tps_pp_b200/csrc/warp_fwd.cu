@@ -101,7 +101,9 @@ struct StagedSmemTail {   // lives after the stage ring and the grid
   uint64_t empty[ST_MAX_STAGES];
 };
 
-template <bool DUAL>
+// S0BF: the src0 planes are bf16 (TPSPP_SRC0_BF16: feat_grid of the head's bf16 mode) -- half the bytes per stage for the
+// larger source; src1 and both outputs stay fp32
+template <bool DUAL, bool S0BF = false>
 __global__ void __launch_bounds__(ST_THREADS, 2) warp_fwd_staged_kernel(StagedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const WarpParams& p = a.p;
@@ -222,8 +224,14 @@ __global__ void __launch_bounds__(ST_THREADS, 2) warp_fwd_staged_kernel(StagedAr
       float r0[ST_PPT], r1[ST_PPT];
 #pragma unroll
       for (int j = 0; j < ST_PPT; ++j) {
-        const float* q = s0 + t0[j].off;
-        r0[j] = blend4(q[0], q[t0[j].dx], q[t0[j].dy], q[t0[j].dy + t0[j].dx], t0[j].w);
+        if (S0BF) {
+          const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(s0) + t0[j].off;
+          r0[j] = blend4(__bfloat162float(q[0]), __bfloat162float(q[t0[j].dx]), __bfloat162float(q[t0[j].dy]),
+                         __bfloat162float(q[t0[j].dy + t0[j].dx]), t0[j].w);
+        } else {
+          const float* q = s0 + t0[j].off;
+          r0[j] = blend4(q[0], q[t0[j].dx], q[t0[j].dy], q[t0[j].dy + t0[j].dx], t0[j].w);
+        }
         if (DUAL) {
           const float* r = s1 + t1[j].off;
           r1[j] = blend4(r[0], r[t1[j].dx], r[t1[j].dy], r[t1[j].dy + t1[j].dx], t1[j].w);
@@ -252,11 +260,11 @@ static size_t staged_fixed_smem() { return (size_t)ST_MAX_N * sizeof(double2) + 
 // returns nstages (0 = not eligible)
 static int staged_plan(const tpspp_warp_cfg* cfg, uint32_t* s0, uint32_t* s1, uint32_t* stage) {
   if (cfg->mode != TPSPP_MODE_ATTENTION || cfg->num_fiducial != ST_F) return 0;
-  if (cfg->feat_dtype != TPSPP_F32) return 0;
+  if (cfg->feat_dtype != TPSPP_F32 && cfg->feat_dtype != TPSPP_SRC0_BF16) return 0;
   const int n = cfg->out_h * cfg->out_w;
   if (n > ST_MAX_N) return 0;
   if (cfg->channels1 != 0 && cfg->channels1 != cfg->channels0) return 0;
-  const size_t b0 = (size_t)cfg->src0_h * cfg->src0_w * 4;
+  const size_t b0 = (size_t)cfg->src0_h * cfg->src0_w * (cfg->feat_dtype == TPSPP_SRC0_BF16 ? 2 : 4);
   const size_t b1 = cfg->channels1 ? (size_t)cfg->src1_h * cfg->src1_w * 4 : 0;
   if (b0 % 16 || b1 % 16) return 0;
   const size_t st = (b0 + b1 + 127) / 128 * 128;
@@ -295,7 +303,9 @@ static int launch_staged(const tpspp_warp_cfg* cfg, const WarpParams& p, cudaStr
   a.planes_total = p.B * p.C0;
   const size_t smem = (size_t)a.nstages * a.stage_bytes + staged_fixed_smem();
   const bool dual = p.C1 > 0;
-  auto kern = dual ? warp_fwd_staged_kernel<true> : warp_fwd_staged_kernel<false>;
+  const bool s0bf = cfg->feat_dtype == TPSPP_SRC0_BF16;
+  auto kern = s0bf ? (dual ? warp_fwd_staged_kernel<true, true> : warp_fwd_staged_kernel<false, true>)
+                   : (dual ? warp_fwd_staged_kernel<true> : warp_fwd_staged_kernel<false>);
   TPSPP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int ctas_per_sm = 0;
   TPSPP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, ST_THREADS, smem));
@@ -484,6 +494,9 @@ static int launch_classical_tiled_t(const WarpParams& p, cudaStream_t stream) {
 }
 
 static int launch_generic(const tpspp_warp_cfg* cfg, const WarpParams& p, int mode, cudaStream_t stream) {
+  TPSPP_REQUIRE(cfg->feat_dtype != TPSPP_SRC0_BF16,
+                "TPSPP_SRC0_BF16 (bf16 src0 with fp32 src1 / outputs) exists for the staged TPS++ kernel only (attention mode, F = 32, "
+                "n <= 1024, 16-byte aligned tensors, grid_out NULL)");
   // an explicit TPSPP_VARIANT_GENERIC request keeps the plain kernel (tests compare the two)
   if (mode == 1 && cfg->variant == TPSPP_VARIANT_AUTO && classical_tiled_eligible(cfg, p)) {
     if (cfg->feat_dtype == TPSPP_BF16) return launch_classical_tiled_t<__nv_bfloat16>(p, stream);

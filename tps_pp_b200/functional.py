@@ -41,12 +41,17 @@ def _require_cuda(name: str, t: Optional[torch.Tensor], dtype=None):
 def _cfg(src0, src1, out_size, num_fiducial, mode, theta, variant) -> N.WarpCfg:
     if src0.dtype not in _DT:
         raise RuntimeError(f"tps_pp_b200: unsupported feature dtype {src0.dtype} (fp32 or bf16)")
+    dt = _DT[src0.dtype]
     if src1 is not None and src1.dtype != src0.dtype:
-        raise RuntimeError("tps_pp_b200: src0/src1 dtype mismatch")
+        # bf16 feat_grid + fp32 x: the hand-over of the head's bf16 mode (TPSPP_SRC0_BF16: fp32 outputs, staged kernel, inference)
+        if src0.dtype == torch.bfloat16 and src1.dtype == torch.float32:
+            dt = N.SRC0_BF16
+        else:
+            raise RuntimeError("tps_pp_b200: src0/src1 dtype mismatch")
     b, c0, h0, w0 = src0.shape
     c1, h1, w1 = (src1.shape[1:] if src1 is not None else (0, 0, 0))
     return N.WarpCfg(b, c0, h0, w0, c1, h1, w1, int(out_size[0]), int(out_size[1]), int(num_fiducial),
-                     int(mode), float(theta), _DT[src0.dtype], int(variant))
+                     int(mode), float(theta), dt, int(variant))
 
 
 class _TpsWarp(torch.autograd.Function):
@@ -79,7 +84,10 @@ class _TpsWarp(torch.autograd.Function):
             if P is None or P.shape != (n, 2):
                 raise RuntimeError(f"tps_pp_b200: P must be [{n},2]")
         cfg = _cfg(src0, src1, out_size, f, mode, theta, variant)
-        out0 = torch.empty((b, src0.shape[1], out_size[0], out_size[1]), dtype=src0.dtype, device=src0.device)
+        if cfg.feat_dtype == N.SRC0_BF16 and (src0.requires_grad or src1.requires_grad or c_prime.requires_grad):
+            raise RuntimeError("tps_pp_b200: the bf16-feat_grid / fp32-x warp is an inference layout (no backward)")
+        out0 = torch.empty((b, src0.shape[1], out_size[0], out_size[1]),
+                           dtype=torch.float32 if cfg.feat_dtype == N.SRC0_BF16 else src0.dtype, device=src0.device)
         out1 = (torch.empty((b, src1.shape[1], out_size[0], out_size[1]), dtype=src1.dtype, device=src1.device)
                 if src1 is not None else None)
         with torch.cuda.device(src0.device):
@@ -232,7 +240,8 @@ def head_forward(x: torch.Tensor, o0: torch.Tensor, o1: torch.Tensor, params, po
             weights_cached = False
         if weights_cached:
             cfg.flags |= N.HEAD_FLAG_WEIGHTS_CACHED
-        feat_grid = torch.empty((b, 64, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+        fg_bf16 = precision == N.HEAD_BF16 and (flags & N.HEAD_FLAG_FEATGRID_BF16) != 0
+        feat_grid = torch.empty((b, 64, 2 * h, 2 * w), dtype=torch.bfloat16 if fg_bf16 else torch.float32, device=x.device)
         c_prime = torch.empty((b, f, 2), dtype=torch.float32, device=x.device)
         score = torch.empty((b, h * w, f), dtype=torch.float32, device=x.device)
         N.check(N.lib().tpspp_head_fwd(ctypes.byref(cfg), _ptr(x), _ptr(o0), _ptr(o1), table, _ptr(feat_grid),

@@ -319,11 +319,16 @@ class TPS_PP(_BaseModule):
                                    f"{self.num_img_channel}) got batch_img {tuple(batch_img.shape)}")
             params = list(self.parameters())
             key = (batch_img.device.index, torch.cuda.current_stream(batch_img.device).cuda_stream)
-            stamp = (b, self.head_precision, self.head_flags, tuple((p.data_ptr(), p._version) for p in params))
+            flags = self.head_flags
+            if (self.head_precision == N.HEAD_BF16 and self.num_fiducial == 32 and c == 64
+                    and self.rectified_img_size[0] * self.rectified_img_size[1] <= 1024):
+                # bf16 mode: feat_grid goes to the (staged) warp as bf16 planes -- half the bytes of its larger source
+                flags |= N.HEAD_FLAG_FEATGRID_BF16
+            stamp = (b, self.head_precision, flags, tuple((p.data_ptr(), p._version) for p in params))
             ws, ws_stamp = self._head_ws.get(key, (None, None))
             fg, cp, sc, ws = TF.head_forward(batch_img, outs[0], outs[1], params, self.point_size, self.p_stride,
                                              self.head_precision, ws, weights_cached=(ws_stamp == stamp),
-                                             flags=self.head_flags)
+                                             flags=flags)
             if len(self._head_ws) >= 8 and key not in self._head_ws:
                 self._head_ws.clear()            # streams come and go: bound what the module pins
             self._head_ws[key] = (ws, stamp)
