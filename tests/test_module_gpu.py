@@ -253,3 +253,29 @@ def test_large_shard_is_batch_independent(native_lib):
             assert torch.equal(part["output"], out_full[lo:hi])
             assert torch.equal(part["pc_score"], sc_full[lo:hi])
     assert torch.isfinite(out_full).all()
+
+
+def test_training_step_launches_no_cudnn_or_cublas_kernel(native_lib):
+    """VERDICT r01 item 4's criterion, driver-visible: with the 14 ConvModules on tpspp_convcat_fwd/bwd and the 16 dense
+    layers on tpspp_linear_fwd/bwd, forward + backward of the rectifier launches no cuDNN / cuBLAS / CUTLASS kernel (CUPTI
+    kernel names of one step; what remains next to the tpspp:: kernels are ATen element-wise / reduction kernels)."""
+    from torch.profiler import profile, ProfilerActivity
+    sd = O.trained_like_state(3)
+    m = T.TPS_PP().to(DEV).train()
+    m.load_state_dict(sd, strict=True)
+    x, o0, o1 = O.synthetic_tpspp_inputs(4, 1)
+    tx = torch.from_numpy(x).to(DEV).requires_grad_()
+    t0, t1 = torch.from_numpy(o0).to(DEV).requires_grad_(), torch.from_numpy(o1).to(DEV).requires_grad_()
+    for _ in range(2):                                   # warm-up (lazy initialisations), then the profiled step
+        m(tx, [t0, t1])["output"].square().mean().backward()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        m(tx, [t0, t1])["output"].square().mean().backward()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages() if e.self_device_time_total > 0]
+    assert m.training_stages == {"convs_native": 14, "convs_library": 0, "linears_native": 16, "linears_library": 0}
+    ours = [n for n in names if "tpspp::" in n]
+    assert len(ours) >= 10, names
+    bad = [n for n in names if any(t in n.lower() for t in ("cudnn", "cublas", "cutlass", "gemm", "implicit_convolve", "wgrad2d", "dgrad"))
+           and "tpspp::" not in n]
+    assert not bad, bad
