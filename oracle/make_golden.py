@@ -256,6 +256,31 @@ def main():
     sdc = tp.state_dict()
     oc = O.classical_localization(sdc, torch.from_numpy(img))
     check("classical C'", _mx(oc, rc), 1e-6)
+
+    # ---- MORAN (moran.py:66-103): oracle restatement vs the unmodified reference class, fixture for the GPU test ----
+    print('MORAN.forward')
+    mo = rl.build_quiet(ref.MORAN, seed=0, num_img_channel=3, img_size=(32, 128), maxBatch=4).eval()
+    g = torch.Generator().manual_seed(21)
+    with torch.no_grad():
+        for name, buf in mo.named_buffers():          # BatchNorm statistics away from (0, 1)
+            if name.endswith('running_mean'):
+                buf.copy_(torch.randn(buf.shape, generator=g) * 0.1)
+            elif name.endswith('running_var'):
+                buf.copy_(0.5 + torch.rand(buf.shape, generator=g))
+        mo.get_parameter('cnn.16.weight').fill_(1.5)  # the last BatchNorm's gain: offsets large enough to matter
+    xm = np.random.RandomState(77).standard_normal((2, 3, 48, 160)).astype(np.float32)
+    sdm = {k: v.clone() for k, v in mo.state_dict().items()}
+    rms = {}
+    for enh in (0, 1):
+        with torch.no_grad():
+            rms[enh] = mo(torch.from_numpy(xm), enhance=enh)
+        om = O.moran_forward(sdm, torch.from_numpy(xm), (32, 128), enhance=enh)
+        check(f'MORAN forward (enhance={enh}) vs reference', _mx(om, rms[enh]), 1e-5)
+    check('MORAN identity grid', _mx(O.moran_grid((32, 128)), mo.grid[0]), 0.0)
+    if not args.check:
+        np.savez_compressed(os.path.join(GOLD, 'moran.npz'), x=xm, ref32_output=rms[0].numpy(), ref32_output_enhance1=rms[1].numpy(),
+                            state_keys=np.array(list(sdm.keys())),
+                            **{'sd.' + k: v.numpy() for k, v in sdm.items() if k != 'grid' and not k.endswith('num_batches_tracked')})
     nrtr_fixture(write=not args.check)
     backbone_fixture(write=not args.check)
     print('all oracle checks passed' + ('' if args.check else f'; fixtures written to {GOLD}'))

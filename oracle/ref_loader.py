@@ -148,7 +148,9 @@ def load_reference():
           "mmocr/models/textrecog/preprocessor/base_preprocessor.py")
     tpsp = _load("mmocr.models.textrecog.preprocessor.tps_preprocessor",
                  "mmocr/models/textrecog/preprocessor/tps_preprocessor.py")
+    moran = _load("mmocr.models.textrecog.preprocessor.moran", "mmocr/models/textrecog/preprocessor/moran.py")
     return types.SimpleNamespace(
+        MORAN=moran.MORAN,
         TPS_PP=tps_pp.TPS_PP,
         Attention_Enhanced_TPS=tps_pp.Attention_Enhanced_TPS,
         DGAB=dgab.DGAB,

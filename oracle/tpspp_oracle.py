@@ -458,6 +458,48 @@ def classical_localization(state, img, eps=1e-5):
     return x.view(x.shape[0], -1, 2)
 
 
+def moran_grid(target=(32, 128)) -> np.ndarray:
+    """The identity grid [H, W, 2] of moran.py:51-64 (x from the width axis, y from the height axis, align_corners)."""
+    h = np.arange(target[0]) * 2. / (target[0] - 1) - 1
+    w = np.arange(target[1]) * 2. / (target[1] - 1) - 1
+    g = np.stack(np.meshgrid(w, h, indexing='ij'), axis=-1)
+    return np.transpose(g, (1, 0, 2)).astype(np.float32)
+
+
+def moran_forward(state, x, target=(32, 128), enhance=0, eps=1e-5):
+    """moran.py:66-103, eval-mode BatchNorm: offset CNN on the bilinearly down-scaled image, MaxPool(2,1) of the positive
+    and negative parts, the offset map and then the image resampled with border padding / align_corners."""
+    dt = x.dtype
+    grid = torch.from_numpy(moran_grid(target)).to(dt)[None].repeat(x.shape[0], 1, 1, 1)
+    gx, gy = grid[..., 0:1], grid[..., 1:2]
+
+    def cnn(img):
+        y = F.max_pool2d(img, 2, 2)
+        for ci, pool, relu in ((1, True, True), (5, True, True), (9, False, True), (12, False, True), (15, False, False)):
+            y = F.conv2d(y, _t(state, f'cnn.{ci}.weight', dt), _t(state, f'cnn.{ci}.bias', dt), 1, 1)
+            q = f'cnn.{ci + 1}'
+            y = F.batch_norm(y, _t(state, q + '.running_mean', dt), _t(state, q + '.running_var', dt), _t(state, q + '.weight', dt),
+                             _t(state, q + '.bias', dt), False, 0.0, eps)
+            if relu:
+                y = F.relu(y)
+            if pool:
+                y = F.max_pool2d(y, 2, 2)
+        return y
+
+    def offsets_of(img):
+        off = cnn(img)
+        pooled = F.max_pool2d(F.relu(off), 2, 1) - F.max_pool2d(F.relu(-off), 2, 1)
+        return F.grid_sample(pooled, grid, padding_mode='border', align_corners=True).permute(0, 2, 3, 1)
+
+    small = F.interpolate(x, size=tuple(target), mode='bilinear', align_corners=True)
+    og = offsets_of(small)
+    out = F.grid_sample(x, torch.cat([gx, gy + og], 3), padding_mode='border', align_corners=True)
+    for _ in range(enhance):
+        og = og + offsets_of(out)
+        out = F.grid_sample(x, torch.cat([gx, gy + og], 3), padding_mode='border', align_corners=True)
+    return out
+
+
 # --------------------------------------------------------------------------
 # deterministic synthetic inputs (numpy legacy RNG: stable across versions) --
 # --------------------------------------------------------------------------

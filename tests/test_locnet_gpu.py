@@ -70,3 +70,36 @@ def test_locnet_module_forward_and_fallbacks(native_lib):
     with torch.no_grad():
         m2(torch.randn((2, 1, 32, 100), device=DEV))
     assert not m2._last_locnet_native
+
+
+def test_moran_drop_in_vs_reference_golden(native_lib, golden):
+    """MORAN (moran.py:13-103) with its two grid_sample calls on the native sampling core: state_dict keys of the reference,
+    output against the reference's own output (fixture written by oracle/make_golden.py) and against the fp64 oracle."""
+    g = golden("moran.npz")
+    m = T.MORAN(num_img_channel=3, img_size=(32, 128), maxBatch=4)
+    assert list(m.state_dict().keys()) == [str(k) for k in g["state_keys"]]
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    missing = m.load_state_dict(sd, strict=False)
+    assert set(missing.missing_keys) <= {"grid"} | {k for k in m.state_dict() if k.endswith("num_batches_tracked")}
+    assert not missing.unexpected_keys
+    m = m.to(DEV).eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    with torch.no_grad():
+        out0 = m(x)
+        assert m._last_sampler_native
+        out1 = m(x, enhance=1)
+    assert out0.shape == (2, 3, 32, 128)
+    # (a) the sampler itself: the same module with ATen's grid_sample (autograd recording) -- identical offsets, so the
+    #     difference is the native sampling core against ATen: a few fp32 ulps of the blend
+    out_grad = m(x.clone().requires_grad_())
+    assert not m._last_sampler_native
+    assert float((out_grad - out0).abs().max()) <= 5e-6
+    # (b) the whole module against the reference's own output and the fp64 oracle: the offset CNN is a cuDNN fp32 stack whose
+    #     ~1e-6 rounding differences from the reference's CPU convolutions are multiplied by the image gradient along y
+    #     (an N(0,1) noise image: O(1) per source pixel x 23.5 source pixels per unit offset)
+    assert float((out0.cpu() - torch.from_numpy(g["ref32_output"])).abs().max()) <= 2e-4
+    assert float((out1.cpu() - torch.from_numpy(g["ref32_output_enhance1"])).abs().max()) <= 4e-4
+    ref64 = O.moran_forward({k: v.double() for k, v in sd.items()}, torch.from_numpy(g["x"]).double(), (32, 128))
+    assert float((out0.cpu().double() - ref64).abs().max()) <= 2e-4
+    with pytest.raises(RuntimeError):
+        m.cpu()(torch.zeros(1, 3, 32, 128))

@@ -147,3 +147,13 @@ def test_backbone_stage_vs_reference(golden):
     assert mx(outs[0].numpy().reshape(-1)[::s], g["o0"]) < 2e-5
     assert mx(outs[1].numpy().reshape(-1)[::s], g["o1"]) < 2e-5
     assert tuple(x.shape) == (2, 64, 16, 64) and tuple(outs[0].shape) == tuple(outs[1].shape) == (2, 32, 32, 128)
+
+
+def test_moran_restatement_vs_reference(golden):
+    """oracle.moran_forward (moran.py:66-103) against the unmodified reference's output on the committed fixture."""
+    g = golden("moran.npz")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    x = torch.from_numpy(g["x"])
+    for enh, key in ((0, "ref32_output"), (1, "ref32_output_enhance1")):
+        out = O.moran_forward(sd, x, (32, 128), enhance=enh)
+        assert float((out - torch.from_numpy(g[key])).abs().max()) <= 1e-5

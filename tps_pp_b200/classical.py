@@ -15,8 +15,10 @@ otherwise -- training, or e.g. the 32x100 default of the recogniser configs -- i
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _native as N
 from . import constants as K
@@ -112,3 +114,67 @@ class TPSPreprocessor(BasePreprocessor):
         out, _ = TF.tps_warp(batch_img, None, c_prime.float(), None, gen.P_hat, None, gen.inv_delta_C,
                              self.rectified_img_size, N.MODE_CLASSICAL, 0.0, self.warp_variant)
         return out
+
+
+@PREPROCESSOR.register_module()
+class MORAN(BasePreprocessor):
+    """Drop-in MORAN rectifier (reference preprocessor/moran.py:13-103): a small offset CNN on the down-scaled image, the
+    offset map resampled to the target size and the image resampled along ``y + offset`` -- two
+    ``F.grid_sample(padding_mode='border', align_corners=True)`` calls per pass (``moran.py:89-103``), which run on the
+    native sampling core (``tpspp_sample_fwd``) whenever autograd is not recording; the offset CNN (five small
+    convolutions on a 16 x 64 map) stays a library stack.  Same ctor kwargs, ``cnn.*`` state_dict keys and ``grid`` buffer."""
+
+    def __init__(self, num_img_channel=3, img_size=(32, 128), maxBatch=256):
+        super().__init__()
+        self.targetH = img_size[0]
+        self.targetW = img_size[1]
+        self.maxBatch = maxBatch
+        self.cnn = nn.Sequential(
+            nn.MaxPool2d(2, 2),
+            nn.Conv2d(num_img_channel, 64, 3, 1, 1), nn.BatchNorm2d(64), nn.ReLU(True), nn.MaxPool2d(2, 2),
+            nn.Conv2d(64, 128, 3, 1, 1), nn.BatchNorm2d(128), nn.ReLU(True), nn.MaxPool2d(2, 2),
+            nn.Conv2d(128, 64, 3, 1, 1), nn.BatchNorm2d(64), nn.ReLU(True),
+            nn.Conv2d(64, 16, 3, 1, 1), nn.BatchNorm2d(16), nn.ReLU(True),
+            nn.Conv2d(16, 1, 3, 1, 1), nn.BatchNorm2d(1))
+        self.pool = nn.MaxPool2d(2, 1)
+        self.register_buffer("grid", torch.tensor(self.grid_process(maxBatch)).float())
+        self._last_sampler_native = None
+
+    def grid_process(self, maxBatch):
+        """The identity sampling grid [maxBatch, H, W, 2] (moran.py:51-64)."""
+        h_list = np.arange(self.targetH) * 2. / (self.targetH - 1) - 1
+        w_list = np.arange(self.targetW) * 2. / (self.targetW - 1) - 1
+        grid = np.stack(np.meshgrid(w_list, h_list, indexing="ij"), axis=-1)
+        grid = np.transpose(grid, (1, 0, 2))
+        return np.tile(np.expand_dims(grid, 0), [maxBatch, 1, 1, 1])
+
+    def _sample(self, src, grid):
+        if self._last_sampler_native:
+            return TF.grid_sample_border(src, grid)
+        return F.grid_sample(src, grid, padding_mode="border", align_corners=True)
+
+    def forward(self, x, test=None, enhance=0, debug=False):
+        if not x.is_cuda:
+            raise RuntimeError("tps_pp_b200.MORAN runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        assert x.size(0) <= self.maxBatch
+        self._last_sampler_native = (not torch.is_grad_enabled()) and x.dtype == torch.float32
+        b = x.size(0)
+        grid = self.grid[:b]
+        grid_x = grid[:, :, :, 0].unsqueeze(3)
+        grid_y = grid[:, :, :, 1].unsqueeze(3)
+        x_small = F.interpolate(x, size=(self.targetH, self.targetW), mode="bilinear", align_corners=True)
+
+        def offsets_of(img):
+            # the offset CNN feeds sampling coordinates: keep the library convolutions in true fp32 (cuDNN's default TF32
+            # moves the offsets by ~1e-3, i.e. the rectified pixels by the same order)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                off = self.cnn(img)
+            pooled = self.pool(F.relu(off)) - self.pool(F.relu(-off))
+            return self._sample(pooled.contiguous(), grid.contiguous()).permute(0, 2, 3, 1).contiguous()
+
+        offsets_grid = offsets_of(x_small)
+        x_rectified = self._sample(x, torch.cat([grid_x, grid_y + offsets_grid], 3))
+        for _ in range(enhance):
+            offsets_grid = offsets_grid + offsets_of(x_rectified)
+            x_rectified = self._sample(x, torch.cat([grid_x, grid_y + offsets_grid], 3))
+        return x_rectified
