@@ -314,8 +314,8 @@ TPSPP_API int tpspp_conv_bwd(const tpspp_conv_cfg* cfg, const float* x, const fl
  * autograd of the rectifier's dense layers runs on native kernels instead of cuBLAS.  Row-major fp32:
  *   y [rows, out] = x [rows, in] . w[out, in]^T + bias          (weight_batches == 1: nn.Linear)
  *   y_b = x_b . w_b^T for weight_batches equal groups of rows     (weight_batches  > 1: torch.bmm(x, w.transpose(1, 2)))
- * tcgen05 3xTF32 kernels when rows (per batch) % 128 == 0 and in/out features % 32 == 0 (out <= 256, and in <= 64 or out <= 64);
- * fp32 CUDA-core kernels for every other shape.  No activation: the caller applies it (and its derivative). */
+ * tcgen05 3xTF32 kernels when rows (per batch) % 128 == 0 and in/out features % 32 == 0 (the TMA-fed kernel for in <= 64 or
+ * out <= 64, the shared-memory-operand kernel for larger layers such as 512 -> 1536); fp32 CUDA-core kernels for every other shape.  No activation: the caller applies it (and its derivative). */
 typedef struct {
   int64_t rows;             /* product of the leading dimensions                                  */
   int32_t in_features, out_features;

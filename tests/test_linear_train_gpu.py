@@ -20,6 +20,9 @@ CASES = [
     ((4, 64), 48, 17, False, "DGAB mlp_h"),
     ((8, 4, 64, 16), 64, 256, True, "Mlp fc1, 32768 rows"),
     ((3, 37), 50, 7, True, "ragged"),
+    ((256,), 512, 512, True, "transformer-sized 512 -> 512 (shared-memory-operand tcgen05 kernel)"),
+    ((3, 128), 256, 1536, False, "fused QKV 256 -> 1536"),
+    ((128,), 512, 96, True, "512 -> 96 (32-column tiles)"),
 ]
 
 
@@ -42,8 +45,9 @@ def test_linear_fwd_bwd_vs_fp64(lead, k, n, bias, what):
     bd = b.detach().double().requires_grad_() if bias else None
     yd = torch.nn.functional.linear(xd, wd, bd)
     yd.backward(gy.double())
-    assert _rel(y.detach(), yd.detach()) <= 2e-6, what
-    assert _rel(x.grad, xd.grad) <= 2e-6, what
+    # fp32-level: 3xTF32 with fp32 accumulation -- the bound grows with the square root of the contraction length
+    assert _rel(y.detach(), yd.detach()) <= 2e-6 * max(1.0, (k / 256) ** 0.5), what
+    assert _rel(x.grad, xd.grad) <= 2e-6 * max(1.0, (n / 256) ** 0.5), what
     assert _rel(w.grad, wd.grad) <= 5e-6, what
     if bias:
         assert _rel(b.grad, bd.grad) <= 5e-6, what

@@ -103,9 +103,11 @@ __global__ void __launch_bounds__(256) lin_small_wgrad_kernel(const float* __res
 
 struct LinDims { long long R; int K, N, batches; long long rpb; bool tc_fwd, tc_dx, tc_wg; int nt_fwd, nt_dx; };
 static bool lin_tc_shape(long long R, int K, int N, long long rpb, int* NT) {
-  if (R % TC_TM || rpb % TC_TM || K % TC_KC || N % 32 || N > 256 || R > 0x7fffffffLL) return false;
+  if (R % TC_TM || rpb % TC_TM || K % TC_KC || N % 32 || N > 4096 || K > 4096 || R > 0x7fffffffLL) return false;
   *NT = N % 64 == 0 ? 64 : 32;
-  if (K > 64 && N != *NT) return false;       // lin_tma_plan: A stays in tensor memory across column blocks only for K <= 64
+  // K <= 64 (A stays in tensor memory across the column blocks) or a single column block: the TMA-fed lin_tma_kernel;
+  // anything else (transformer-sized layers, e.g. 512 -> 1536): run_conv_tc drops to the shared-memory-operand kernel with
+  // one CTA per (128-row tile, column block) -- still tcgen05 / 3xTF32, just without the TMA pipeline
   return true;
 }
 static int lin_dims(const tpspp_linear_cfg* c, LinDims* d) {
