@@ -335,6 +335,20 @@ TPSPP_API int tpspp_convcat_fwd(const tpspp_conv_cfg* cfg, const float* const* x
 TPSPP_API int tpspp_convcat_bwd(const tpspp_conv_cfg* cfg, const float* const* xs, const float* w, const float* y, const float* gy,
                                 float* const* gxs, float* gw, float* gb, void* workspace, tpspp_stream_t stream);
 
+/* ---- Single-query attention over a key/value cache: the per-step attention of NRTRDecoder.forward_test (reference
+ * decoders/nrtr_decoder.py:153-177; MultiHeadAttention / ScaledDotProductAttention, common/modules/transformer_module.py:
+ * 24-34,74-98) for a greedy decode that keeps the keys / values of earlier positions (the
+ * reference-side binding is tps_pp_b200/nrtr.py::NRTRDecoder.forward_test).
+ *   out[b,h,:] = sum_t softmax_t((q[b,h,:] / temperature) . K[b,t,h,:]) V[b,t,h,:],  t < kv_len (or kv_lens[b] when given)
+ * q / out [batch, heads*64] row-major fp32; k / v [batch, kv_capacity, heads*64]. */
+typedef struct {
+  int32_t batch, heads, head_dim;   /* head_dim = 64                                                        */
+  int32_t kv_len, kv_capacity;      /* keys used (all images) / rows allocated per image                    */
+  float temperature;                /* d_k ** 0.5 in the reference                                          */
+} tpspp_attn_cfg;
+TPSPP_API int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, const float* k, const float* v,
+                                const int32_t* kv_lens /* [batch] device pointer or NULL */, float* out, tpspp_stream_t stream);
+
 /* Number of kernel launches the most recent call on this host thread enqueued
  * (bench.py uses it to report gpu_launches). */
 TPSPP_API int tpspp_last_launch_count(void);

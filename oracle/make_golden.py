@@ -282,8 +282,64 @@ def main():
                             state_keys=np.array(list(sdm.keys())),
                             **{'sd.' + k: v.numpy() for k, v in sdm.items() if k != 'grid' and not k.endswith('num_batches_tracked')})
     nrtr_fixture(write=not args.check)
+    nrtr_decoder_fixture(write=not args.check)
     backbone_fixture(write=not args.check)
     print('all oracle checks passed' + ('' if args.check else f'; fixtures written to {GOLD}'))
+
+
+NRTR_DEC_SMALL = dict(n_layers=2, d_embedding=128, n_head=2, d_k=64, d_v=64, d_model=128, d_inner=64, n_position=64,
+                      num_classes=37, max_seq_len=12, start_idx=1, padding_idx=36)
+
+
+def nrtr_decoder_fixture(write: bool):
+    """the oracle's restatement of ``NRTRDecoder.forward_test`` (nrtr_decoder.py:153-177) against the
+    unmodified reference class -- on a reduced configuration whose weights fit a fixture (tests/golden/nrtr_decoder.npz, used
+    by the GPU test of the native incremental decode) and, seeded, on the full nrtr_tps++.py configuration; and the
+    reference's initial weights under ``torch.manual_seed`` for the drop-in's construction-order check."""
+    import contextlib
+    import io
+    from . import nrtr_loader as L
+    print('NRTRDecoder.forward_test')
+    ns = L.load_nrtr()
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(5)
+        dec = ns.NRTRDecoder(**NRTR_DEC_SMALL).eval()
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        dec.classifier.weight.mul_(12.0)                      # sharpen the random-init soft-max: decisive arg-maxes
+        for p_ in dec.parameters():
+            if p_.dim() == 1 and p_.numel() == 128:           # LayerNorm affines away from (1, 0)
+                p_.add_(torch.randn(p_.shape, generator=g) * 0.1)
+    out_enc = torch.randn((3, 20, 128), generator=g)
+    ratios = [1.0, 0.55, 0.8]
+    metas = [dict(valid_ratio=r) for r in ratios]
+    with torch.no_grad():
+        rp = dec.forward_test(None, out_enc, metas)
+    sd = {k: v.clone() for k, v in dec.state_dict().items()}
+    op = O.nrtr_forward_test(sd, out_enc, ratios, n_head=2, max_seq_len=12, start_idx=1, padding_idx=36)
+    check('NRTR decoder forward_test (reduced config): oracle vs reference', _mx(op, rp), 1e-6)
+    top2 = rp.topk(2, dim=-1).values
+    margin = float((top2[..., 0] - top2[..., 1]).min())
+    print(f'    min top-1 margin of the reference decode: {margin:.3e}; tokens {rp.argmax(-1)[0].tolist()}')
+    check('NRTR decoder fixture has decisive arg-maxes (margin > 1e-3)', 0.0 if margin > 1e-3 else 1.0, 0.0)
+    o64 = O.nrtr_forward_test({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}, out_enc.double(), ratios,
+                              n_head=2, max_seq_len=12, start_idx=1, padding_idx=36)
+    print(f'    reference fp32 vs oracle fp64 twin: {_mx(rp, o64):.3e}')
+    # full configuration, seeded: the drop-in must reproduce these initial weights from the same seed (digest only)
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(0)
+        full = ns.NRTRDecoder().eval()
+    digest = np.array([float(v.double().abs().sum()) for v in full.state_dict().values()])
+    fe = torch.randn((2, 16, 512), generator=g)
+    with torch.no_grad():
+        rf = full.forward_test(None, fe, None)
+    of = O.nrtr_forward_test(full.state_dict(), fe, None)
+    check('NRTR decoder forward_test (full config, seed 0): oracle vs reference', _mx(of, rf), 1e-6)
+    if write:
+        np.savez_compressed(os.path.join(GOLD, 'nrtr_decoder.npz'), out_enc=out_enc.numpy(), valid_ratios=np.array(ratios),
+                            ref32_probs=rp.numpy(), ref64_probs=o64.numpy(), min_margin=np.array(margin),
+                            full_state_keys=np.array(list(full.state_dict().keys())), full_init_digest=digest,
+                            **{'sd.' + k: v.numpy() for k, v in sd.items()})
 
 
 def nrtr_fixture(write: bool, batch: int = 2):

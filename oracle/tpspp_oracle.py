@@ -458,6 +458,69 @@ def classical_localization(state, img, eps=1e-5):
     return x.view(x.shape[0], -1, 2)
 
 
+def nrtr_decoder_attention(state, trg_seq, src, src_mask, n_head, padding_idx, dtype=torch.float32):
+    """NRTRDecoder._attention (nrtr_decoder.py:93-112) over pre-norm TFDecoderLayers (transformer_layers.py:152-165),
+    MultiHeadAttention / ScaledDotProductAttention (transformer_module.py:24-34,74-98), eval mode (dropout = identity)."""
+    emb = _t(state, 'trg_word_emb.weight', dtype)
+    d = emb.shape[1]
+    dk = d // n_head
+    x = emb[trg_seq] + _t(state, 'position_enc.position_table', dtype)[:, :trg_seq.shape[1]]
+    ls = trg_seq.shape[1]
+    causal = (1 - torch.triu(torch.ones((ls, ls)), diagonal=1)).unsqueeze(0).bool()
+    trg_mask = (trg_seq != padding_idx).unsqueeze(-2) & causal
+
+    def lin(prefix, v):
+        w = _t(state, prefix + '.weight', dtype)
+        b = _t(state, prefix + '.bias', dtype) if (prefix + '.bias') in state else None
+        return F.linear(v, w, b)
+
+    def mha(prefix, q, k, v, mask):
+        b, lq, lk = q.shape[0], q.shape[1], k.shape[1]
+        qq = lin(prefix + '.linear_q', q).view(b, lq, n_head, dk).transpose(1, 2)
+        kk = lin(prefix + '.linear_k', k).view(b, lk, n_head, dk).transpose(1, 2)
+        vv = lin(prefix + '.linear_v', v).view(b, lk, n_head, dk).transpose(1, 2)
+        a = torch.matmul(qq / dk ** 0.5, kk.transpose(2, 3))
+        if mask is not None:
+            m4 = mask.unsqueeze(1) if mask.dim() == 3 else mask.unsqueeze(1).unsqueeze(1)
+            a = a.masked_fill(m4 == 0, float('-inf'))
+        out = torch.matmul(F.softmax(a, dim=-1), vv).transpose(1, 2).contiguous().view(b, lq, n_head * dk)
+        return lin(prefix + '.fc', out)
+
+    i = 0
+    while f'layer_stack.{i}.norm1.weight' in state:
+        p = f'layer_stack.{i}.'
+        ln = lambda nm, v: F.layer_norm(v, (d,), _t(state, p + nm + '.weight', dtype), _t(state, p + nm + '.bias', dtype), 1e-5)
+        h = ln('norm1', x)
+        x = x + mha(p + 'self_attn', h, h, h, trg_mask)
+        x = x + mha(p + 'enc_attn', ln('norm2', x), src, src, src_mask)
+        x = x + lin(p + 'mlp.w_2', F.gelu(lin(p + 'mlp.w_1', ln('norm3', x))))
+        i += 1
+    return F.layer_norm(x, (d,), _t(state, 'layer_norm.weight', dtype), _t(state, 'layer_norm.bias', dtype), 1e-6)
+
+
+def nrtr_forward_test(state, out_enc, valid_ratios=None, n_head=8, max_seq_len=40, start_idx=1, padding_idx=92):
+    """NRTRDecoder.forward_test (nrtr_decoder.py:153-177): greedy decode that re-runs the decoder over the whole padded
+    sequence at every step; ``valid_ratios`` -> the source mask of ``_get_mask`` (:114-127).  Returns probabilities [N, T, C-1]."""
+    import math
+    dtype = out_enc.dtype
+    n, t, _ = out_enc.shape
+    src_mask = None
+    if valid_ratios is not None:
+        src_mask = torch.zeros((n, t), dtype=dtype)
+        for i, vr in enumerate(valid_ratios):
+            src_mask[i, :min(t, math.ceil(t * vr))] = 1
+    seq = torch.full((n, max_seq_len + 1), padding_idx, dtype=torch.long)
+    seq[:, 0] = start_idx
+    outs = []
+    for step in range(max_seq_len):
+        dec = nrtr_decoder_attention(state, seq, out_enc, src_mask, n_head, padding_idx, dtype)
+        logits = F.linear(dec[:, step, :], _t(state, 'classifier.weight', dtype), _t(state, 'classifier.bias', dtype))
+        probs = F.softmax(logits, dim=-1)
+        outs.append(probs)
+        seq[:, step + 1] = probs.argmax(dim=-1)
+    return torch.stack(outs, dim=1)
+
+
 def moran_grid(target=(32, 128)) -> np.ndarray:
     """The identity grid [H, W, 2] of moran.py:51-64 (x from the width axis, y from the height axis, align_corners)."""
     h = np.arange(target[0]) * 2. / (target[0] - 1) - 1

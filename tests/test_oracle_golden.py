@@ -1,6 +1,7 @@
 """CPU: the oracle restatement against the committed reference vectors (tests/golden, produced by
 oracle/make_golden.py from the unmodified reference in the build container)."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import tpspp_oracle as O
@@ -157,3 +158,24 @@ def test_moran_restatement_vs_reference(golden):
     for enh, key in ((0, "ref32_output"), (1, "ref32_output_enhance1")):
         out = O.moran_forward(sd, x, (32, 128), enhance=enh)
         assert float((out - torch.from_numpy(g[key])).abs().max()) <= 1e-5
+
+
+def test_nrtr_decoder_restatement_and_dropin_init(golden):
+    """oracle.nrtr_forward_test (nrtr_decoder.py:153-177) against the reference's own greedy decode on the committed
+    reduced-configuration fixture; the drop-in NRTRDecoder reproduces the reference's keys and seeded initial weights."""
+    import tps_pp_b200 as T
+    g = golden("nrtr_decoder.npz")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    probs = O.nrtr_forward_test(sd, torch.from_numpy(g["out_enc"]), [float(v) for v in g["valid_ratios"]], n_head=2,
+                                max_seq_len=12, start_idx=1, padding_idx=36)
+    assert float((probs - torch.from_numpy(g["ref32_probs"])).abs().max()) <= 1e-6
+    torch.manual_seed(0)
+    m = T.NRTRDecoder()
+    assert list(m.state_dict().keys()) == [str(k) for k in g["full_state_keys"]]
+    digest = np.array([float(v.double().abs().sum()) for v in m.state_dict().values()])
+    assert np.array_equal(digest, g["full_init_digest"])
+    small = T.NRTRDecoder(n_layers=2, d_embedding=128, n_head=2, d_model=128, d_inner=64, n_position=64, num_classes=37,
+                          max_seq_len=12, start_idx=1, padding_idx=36)
+    small.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError):
+        small.forward_test(None, torch.from_numpy(g["out_enc"]), None)        # CUDA only: no CPU fallback

@@ -57,6 +57,12 @@ class LocnetCfg(Structure):
 LP_COUNT = 24
 
 
+class AttnCfg(Structure):
+    """Mirror of ``tpspp_attn_cfg`` (include/tpspp.h)."""
+    _fields_ = [("batch", c_int32), ("heads", c_int32), ("head_dim", c_int32), ("kv_len", c_int32), ("kv_capacity", c_int32),
+                ("temperature", c_float)]
+
+
 class LinearCfg(Structure):
     """Mirror of ``tpspp_linear_cfg`` (include/tpspp.h)."""
     _fields_ = [("rows", ctypes.c_int64), ("in_features", c_int32), ("out_features", c_int32), ("weight_batches", c_int32)]
@@ -96,6 +102,7 @@ _SIGNATURES = {
     "tpspp_convcat_bwd": (c_int, [POINTER(ConvCfg), POINTER(c_void_p)] + [c_void_p] * 3 + [POINTER(c_void_p)] + [c_void_p] * 4),
     "tpspp_locnet_workspace_bytes": (c_size_t, [POINTER(LocnetCfg)]),
     "tpspp_locnet_fwd": (c_int, [POINTER(LocnetCfg), c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
+    "tpspp_attn_decode": (c_int, [POINTER(AttnCfg)] + [c_void_p] * 6),
     "tpspp_linear_workspace_bytes": (c_size_t, [POINTER(LinearCfg)]),
     "tpspp_linear_fwd": (c_int, [POINTER(LinearCfg)] + [c_void_p] * 6),
     "tpspp_linear_bwd": (c_int, [POINTER(LinearCfg)] + [c_void_p] * 8),

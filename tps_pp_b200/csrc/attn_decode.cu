@@ -1,0 +1,83 @@
+// Single-query multi-head attention over a key/value cache: the per-step attention of `NRTRDecoder.forward_test`
+// (reference decoders/nrtr_decoder.py:153-177 -> TFDecoderLayer -> MultiHeadAttention / ScaledDotProductAttention,
+// common/modules/transformer_module.py:24-34,74-98) when the greedy decode keeps the keys / values of earlier positions instead
+// of recomputing the whole prefix each step.
+//   out[b, h, :] = sum_t softmax_t((q[b,h,:] / temperature) . K[b,t,h,:]) V[b,t,h,:],   t < len(b)
+// q / out: [B, heads * 64] row-major; K / V: [B, capacity, heads * 64] (the self-attention cache, or the projected encoder
+// memory for enc_attn); len(b) = kv_len, or kv_lens[b] (the reference's valid_ratio source mask, nrtr_decoder.py:111-123).
+// One CTA per (image, head): four warps take every fourth key (lane = two of the 64 head dimensions, shuffle-reduced dot
+// product, online softmax in fp32), their partial (max, sum, accumulator) triples are merged through shared memory.
+#include "common.cuh"
+
+namespace tpspp {
+
+constexpr int AD_WARPS = 4, AD_DIM = 64;
+
+__global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                   const float* __restrict__ v, float* __restrict__ out,
+                                                                   const int* __restrict__ kv_lens, int kv_len, int capacity, int heads,
+                                                                   float inv_temperature) {
+  const int b = blockIdx.x, h = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = heads * AD_DIM;
+  int len = kv_lens != nullptr ? kv_lens[b] : kv_len;
+  len = len < 0 ? 0 : (len > capacity ? capacity : len);
+  const float2 qv = *reinterpret_cast<const float2*>(q + (size_t)b * D + h * AD_DIM + 2 * lane);
+  const float q0 = qv.x * inv_temperature, q1 = qv.y * inv_temperature;       // the reference scales q, then multiplies
+  const float* kb = k + (size_t)b * capacity * D + h * AD_DIM + 2 * lane;
+  const float* vb = v + (size_t)b * capacity * D + h * AD_DIM + 2 * lane;
+  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int t = warp; t < len; t += AD_WARPS) {
+    const float2 kv = __ldg(reinterpret_cast<const float2*>(kb + (size_t)t * D));
+    float s = q0 * kv.x + q1 * kv.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, s);
+    const float c = __expf(m - mn), p = __expf(s - mn);        // m = -inf on the first key: c = 0
+    const float2 vv = __ldg(reinterpret_cast<const float2*>(vb + (size_t)t * D));
+    l = l * c + p;
+    a0 = a0 * c + p * vv.x;
+    a1 = a1 * c + p * vv.y;
+    m = mn;
+  }
+  __shared__ float sm[AD_WARPS], sl[AD_WARPS], sa[AD_WARPS][AD_DIM];
+  if (lane == 0) { sm[warp] = m; sl[warp] = l; }
+  sa[warp][2 * lane] = a0; sa[warp][2 * lane + 1] = a1;
+  __syncthreads();
+  if (warp == 0) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < AD_WARPS; ++w) M = fmaxf(M, sm[w]);
+    float L = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < AD_WARPS; ++w) {
+      const float c = sm[w] == -INFINITY ? 0.f : __expf(sm[w] - M);
+      L += sl[w] * c;
+      o0 += sa[w][2 * lane] * c;
+      o1 += sa[w][2 * lane + 1] * c;
+    }
+    const float r = L > 0.f ? 1.f / L : 0.f;                    // an empty key set (len = 0) yields zeros
+    *reinterpret_cast<float2*>(out + (size_t)b * D + h * AD_DIM + 2 * lane) = make_float2(o0 * r, o1 * r);
+  }
+}
+
+}  // namespace tpspp
+
+using namespace tpspp;
+
+extern "C" int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, const float* k, const float* v, const int32_t* kv_lens,
+                                 float* out, tpspp_stream_t stream) {
+  reset_launch_count();
+  TPSPP_REQUIRE(cfg != nullptr, "attn cfg is NULL");
+  TPSPP_REQUIRE(cfg->batch >= 0 && cfg->heads > 0 && cfg->heads <= 65535, "attn: batch >= 0, 1 <= heads <= 65535");
+  TPSPP_REQUIRE(cfg->head_dim == AD_DIM, "attn: head_dim must be 64 (d_k = d_v = 64 in the NRTR configs), got %d", cfg->head_dim);
+  TPSPP_REQUIRE(cfg->kv_capacity > 0 && cfg->kv_len >= 0 && cfg->kv_len <= cfg->kv_capacity, "attn: 0 <= kv_len <= kv_capacity");
+  TPSPP_REQUIRE(cfg->temperature > 0.f, "attn: temperature must be positive");
+  if (cfg->batch == 0) return TPSPP_OK;
+  TPSPP_REQUIRE(q && k && v && out, "tpspp_attn_decode: null pointer");
+  TPSPP_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 7) == 0, "tpspp_attn_decode: buffers must be 8-byte aligned");
+  attn_decode_kernel<<<dim3(cfg->batch, cfg->heads), AD_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      q, k, v, out, kv_lens, cfg->kv_len, cfg->kv_capacity, cfg->heads, 1.f / cfg->temperature);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
+}

@@ -546,3 +546,25 @@ def bmm_nt(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """``torch.bmm(x, w.transpose(1, 2))`` -- x [B, rows, K], w [B, N, K] -> [B, rows, N] -- on the native kernels, differentiable
     (the einsum of ``atten_score``, tps_pp.py:293-299)."""
     return _Linear.apply(x, w, None)
+
+
+def attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kv_len: int, temperature: float,
+                kv_lens: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Single-query multi-head attention over a key/value cache (``tpspp_attn_decode``): q [B, heads*64], k / v
+    [B, capacity, heads*64] -> [B, heads*64]; keys ``t < kv_len`` (or ``kv_lens[b]``, int32 on the device).  Forward only."""
+    for nm, t in (("q", q), ("k", k), ("v", v)):
+        _require_cuda(nm, t, torch.float32)
+        if not t.is_contiguous():
+            raise RuntimeError(f"tps_pp_b200: attn_decode `{nm}` must be contiguous")
+    b, d = q.shape
+    if d != heads * 64 or k.shape[0] != b or k.shape[2] != d or v.shape != k.shape:
+        raise RuntimeError(f"tps_pp_b200: attn_decode shapes q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} heads {heads}")
+    if kv_lens is not None and (kv_lens.dtype != torch.int32 or not kv_lens.is_cuda or kv_lens.numel() != b):
+        raise RuntimeError("tps_pp_b200: kv_lens must be an int32 CUDA tensor with one entry per image")
+    if out is None:
+        out = torch.empty_like(q)
+    cfg = N.AttnCfg(b, heads, 64, int(kv_len), k.shape[1], float(temperature))
+    with torch.cuda.device(q.device):
+        N.check(N.lib().tpspp_attn_decode(ctypes.byref(cfg), _ptr(q), _ptr(k), _ptr(v), _ptr(kv_lens), _ptr(out), _stream(q)),
+                "tpspp_attn_decode")
+    return out

@@ -43,6 +43,7 @@ class Registry:
 
 BACKBONES = Registry("backbone")
 PREPROCESSOR = Registry("preprocessor")
+DECODERS = Registry("decoder")
 
 
 def build_backbone(cfg):
@@ -56,13 +57,18 @@ def build_preprocessor(cfg):
     return PREPROCESSOR.build(cfg)
 
 
+def build_decoder(cfg):
+    """reference mmocr/models/builder.py (``DECODERS``); used for ``decoder`` at recognizer/encode_decode_recognizer.py:60-66."""
+    return DECODERS.build(cfg)
+
+
 def register_into_mmocr(force: bool = True) -> bool:
     """Register the B200 modules into a real MMOCR install, replacing the stock classes."""
     try:
-        from mmocr.models.builder import BACKBONES as MB, PREPROCESSOR as MP  # type: ignore
+        from mmocr.models.builder import BACKBONES as MB, DECODERS as MD, PREPROCESSOR as MP  # type: ignore
     except Exception:
         return False
-    for reg, ours in ((MB, BACKBONES), (MP, PREPROCESSOR)):
+    for reg, ours in ((MB, BACKBONES), (MP, PREPROCESSOR), (MD, DECODERS)):
         for key, cls in ours.module_dict.items():
             reg.register_module(name=key, force=force, module=cls)
     return True
