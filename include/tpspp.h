@@ -320,7 +320,11 @@ typedef struct {
   int64_t rows;             /* product of the leading dimensions                                  */
   int32_t in_features, out_features;
   int32_t weight_batches;   /* 1, or the number of [out, in] weights (rows % weight_batches == 0)  */
+  int32_t flags;            /* TPSPP_LINEAR_FLAG_WEIGHTS_CACHED: `workspace` still holds the operand images of these weight VALUES
+                             * from an earlier tpspp_linear_fwd call with the same cfg (their re-layout launch is skipped; the
+                             * caller owns that invariant, as for TPSPP_HEAD_FLAG_WEIGHTS_CACHED) */
 } tpspp_linear_cfg;
+enum { TPSPP_LINEAR_FLAG_WEIGHTS_CACHED = 1 };
 TPSPP_API size_t tpspp_linear_workspace_bytes(const tpspp_linear_cfg* cfg);   /* covers both calls */
 TPSPP_API int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias /* or NULL */,
                                float* y, void* workspace, tpspp_stream_t stream);

@@ -65,7 +65,8 @@ class AttnCfg(Structure):
 
 class LinearCfg(Structure):
     """Mirror of ``tpspp_linear_cfg`` (include/tpspp.h)."""
-    _fields_ = [("rows", ctypes.c_int64), ("in_features", c_int32), ("out_features", c_int32), ("weight_batches", c_int32)]
+    _fields_ = [("rows", ctypes.c_int64), ("in_features", c_int32), ("out_features", c_int32), ("weight_batches", c_int32),
+                ("flags", c_int32)]
 
 
 SP_COUNT = 81
@@ -75,6 +76,7 @@ HEAD_FLAG_UNFUSED_DOWN = 2
 HEAD_FLAG_UNFUSED_SCORE = 4
 HEAD_FLAG_TF32X3_CONV = 8
 HEAD_FLAG_FEATGRID_BF16 = 16
+LINEAR_FLAG_WEIGHTS_CACHED = 1
 ABI_VERSION = 2
 P_COUNT = 58
 WS_NAMES = ("f0", "f1", "f2", "a0", "a1", "e0", "e1", "e2", "e3", "cbam", "d0", "d1", "d2", "de", "x1", "v", "de2", "p1", "wprep", "t1", "fs", "hid", "p1img")

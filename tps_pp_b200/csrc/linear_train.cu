@@ -179,10 +179,12 @@ extern "C" int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, con
   lin_offsets(d, off, &total);
   if (d.tc_fwd && !(((uintptr_t)x | (uintptr_t)y | (uintptr_t)workspace) & 15)) {
     float* img = reinterpret_cast<float*>((char*)workspace + off[LW_WFWD]);
-    const long long tot = (long long)((d.N + d.nt_fwd - 1) / d.nt_fwd * d.nt_fwd) * d.K * d.batches;
-    lin_wprep_kernel<<<(unsigned)min((tot + 255) / 256, 2048LL), 256, 0, st>>>(w, img, d.N, d.K, d.nt_fwd, 0, d.batches);
-    count_launch();
-    TPSPP_CHECK_CUDA(cudaGetLastError());
+    if (!(cfg->flags & TPSPP_LINEAR_FLAG_WEIGHTS_CACHED)) {
+      const long long tot = (long long)((d.N + d.nt_fwd - 1) / d.nt_fwd * d.nt_fwd) * d.K * d.batches;
+      lin_wprep_kernel<<<(unsigned)min((tot + 255) / 256, 2048LL), 256, 0, st>>>(w, img, d.N, d.K, d.nt_fwd, 0, d.batches);
+      count_launch();
+      TPSPP_CHECK_CUDA(cudaGetLastError());
+    }
     return lin_tc_run(x, img, bias, y, d, d.K, d.N, d.nt_fwd, st);
   }
   lin_small_fwd_kernel<<<dim3((d.N + 31) / 32, (unsigned)((d.rpb + 31) / 32), d.batches), 256, 0, st>>>(x, w, bias, y, d.K, d.N, d.rpb, 0);

@@ -504,7 +504,7 @@ class _Linear(torch.autograd.Function):
         weight = weight.contiguous()
         bias = bias.contiguous() if bias is not None else None
         rows = x2.numel() // k
-        cfg = N.LinearCfg(rows, k, n, batches)
+        cfg = N.LinearCfg(rows, k, n, batches, 0)
         y = torch.empty(x.shape[:-1] + (n,), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             nbytes = int(N.lib().tpspp_linear_workspace_bytes(ctypes.byref(cfg)))
@@ -522,7 +522,7 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x2, weight = ctx.saved_tensors
-        cfg = N.LinearCfg(*ctx.cfg)
+        cfg = N.LinearCfg(*ctx.cfg, 0)
         gy = gy.contiguous()
         need = ctx.needs_input_grad
         want_w = need[1] or (ctx.has_bias and need[2])
@@ -546,6 +546,38 @@ def bmm_nt(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """``torch.bmm(x, w.transpose(1, 2))`` -- x [B, rows, K], w [B, N, K] -> [B, rows, N] -- on the native kernels, differentiable
     (the einsum of ``atten_score``, tps_pp.py:293-299)."""
     return _Linear.apply(x, w, None)
+
+
+class PreparedLinear:
+    """Inference-side ``F.linear`` with a fixed weight: ``tpspp_linear_fwd`` on a persistent workspace, so the tensor-core
+    operand image of the weight is laid out once (``TPSPP_LINEAR_FLAG_WEIGHTS_CACHED`` afterwards) instead of at every call --
+    the NRTR decode calls each of its 43 dense layers 40 times per batch.  Forward only; rows fixed at construction."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], rows: int):
+        _require_cuda("weight", weight, torch.float32)
+        _require_cuda("bias", bias, torch.float32)
+        self.weight = weight.detach().contiguous()
+        self.bias = bias.detach().contiguous() if bias is not None else None
+        self.rows = int(rows)
+        self.n, self.k = self.weight.shape
+        self.cfg = N.LinearCfg(self.rows, self.k, self.n, 1, 0)
+        with torch.cuda.device(weight.device):
+            nbytes = int(N.lib().tpspp_linear_workspace_bytes(ctypes.byref(self.cfg)))
+        if nbytes == 0:
+            raise RuntimeError("tpspp_linear_workspace_bytes failed: " + N.last_error())
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+        self.prepared = False
+
+    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x.shape != (self.rows, self.k) or not x.is_contiguous() or x.dtype != torch.float32:
+            raise RuntimeError(f"tps_pp_b200: PreparedLinear expects a contiguous fp32 [{self.rows}, {self.k}] input, got {tuple(x.shape)}")
+        y = out if out is not None else torch.empty((self.rows, self.n), dtype=torch.float32, device=x.device)
+        self.cfg.flags = N.LINEAR_FLAG_WEIGHTS_CACHED if self.prepared else 0
+        with torch.cuda.device(x.device):
+            N.check(N.lib().tpspp_linear_fwd(ctypes.byref(self.cfg), _ptr(x), _ptr(self.weight), _ptr(self.bias), _ptr(y),
+                                             _ptr(self.ws), _stream(x)), "tpspp_linear_fwd")
+        self.prepared = True
+        return y
 
 
 def attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kv_len: int, temperature: float,

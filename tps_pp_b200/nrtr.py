@@ -76,6 +76,7 @@ class NRTRDecoder(_BaseModule):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
         self.classifier = nn.Linear(d_model, num_classes - 1)      # the padding class is never predicted (nrtr_decoder.py:77-78)
         self.last_test_native = None
+        self.decode_graph = True          # replay forward_test's launches from a CUDA graph (one per batch / source length)
 
     # ------------------------------------------------------------------ reference algorithm on torch ops
     def _attn_lib(self, att, q, k, v, mask):
@@ -138,9 +139,43 @@ class NRTRDecoder(_BaseModule):
     # ------------------------------------------------------------------ native incremental decode
     @torch.no_grad()
     def forward_test(self, feat, out_enc, img_metas):
+        """Greedy decode -> probabilities [N, max_seq_len, num_classes - 1] (nrtr_decoder.py:153-177).  The ~4000 small launches
+        of the 40 steps are replayed from one CUDA graph per (batch, source length) when ``self.decode_graph`` (default)."""
         if not out_enc.is_cuda:
             raise RuntimeError("tps_pp_b200.NRTRDecoder runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
         self.last_test_native = True
+        n, t_src, d = out_enc.shape
+        lens = None
+        if img_metas is not None:
+            lens = torch.tensor([min(t_src, math.ceil(t_src * m.get("valid_ratio", 1.0))) for m in img_metas], dtype=torch.int32,
+                                device=out_enc.device)
+        if not getattr(self, "decode_graph", True) or torch.cuda.is_current_stream_capturing():
+            return self._decode(out_enc, lens)
+        key = (n, t_src, out_enc.device.index, lens is not None, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        cache = self.__dict__.setdefault("_decode_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) >= 4:
+                cache.clear()
+            s_in = out_enc.detach().float().clone()
+            s_lens = lens.clone() if lens is not None else None
+            side = torch.cuda.Stream(device=out_enc.device)
+            side.wait_stream(torch.cuda.current_stream(out_enc.device))
+            with torch.cuda.stream(side):                      # lazy initialisations + allocator warm-up outside the capture
+                self._decode(s_in, s_lens)
+            torch.cuda.current_stream(out_enc.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                s_out = self._decode(s_in, s_lens)
+            ent = cache[key] = (graph, s_in, s_lens, s_out)
+        graph, s_in, s_lens, s_out = ent
+        s_in.copy_(out_enc)
+        if lens is not None:
+            s_lens.copy_(lens)
+        graph.replay()
+        return s_out.clone()
+
+    def _decode(self, out_enc, lens):
         n, t_src, d = out_enc.shape
         dev = out_enc.device
         temp = self.d_k ** 0.5
@@ -149,19 +184,29 @@ class NRTRDecoder(_BaseModule):
         mrows = (n * t_src + 127) // 128 * 128
         mem = torch.zeros((mrows, d), dtype=torch.float32, device=dev)
         mem[: n * t_src] = out_enc.reshape(n * t_src, d).float()
-        lens = None
-        if img_metas is not None:
-            lens = torch.tensor([min(t_src, math.ceil(t_src * m.get("valid_ratio", 1.0))) for m in img_metas], dtype=torch.int32, device=dev)
-        mem_k, mem_v, w_qkv = [], [], []
+        mem_k, mem_v, lin = [], [], []
         for lyr in self.layer_stack:
-            ea = lyr.enc_attn
+            ea, sa = lyr.enc_attn, lyr.self_attn
             kv = TF.linear(mem, torch.cat([ea.linear_k.weight, ea.linear_v.weight], 0),
                            None if ea.linear_k.bias is None else torch.cat([ea.linear_k.bias, ea.linear_v.bias], 0))
             mem_k.append(kv[: n * t_src, :d].reshape(n, t_src, d).contiguous())
             mem_v.append(kv[: n * t_src, d:].reshape(n, t_src, d).contiguous())
-            sa = lyr.self_attn
-            w_qkv.append((torch.cat([sa.linear_q.weight, sa.linear_k.weight, sa.linear_v.weight], 0),
-                          None if sa.linear_q.bias is None else torch.cat([sa.linear_q.bias, sa.linear_k.bias, sa.linear_v.bias], 0)))
+            # the layer's six dense operators with their operand images laid out once per decode (not once per step)
+            lin.append(dict(
+                qkv=TF.PreparedLinear(torch.cat([sa.linear_q.weight, sa.linear_k.weight, sa.linear_v.weight], 0),
+                                      None if sa.linear_q.bias is None else torch.cat([sa.linear_q.bias, sa.linear_k.bias, sa.linear_v.bias], 0), rows),
+                fc=TF.PreparedLinear(sa.fc.weight, sa.fc.bias, rows),
+                q=TF.PreparedLinear(ea.linear_q.weight, ea.linear_q.bias, rows),
+                efc=TF.PreparedLinear(ea.fc.weight, ea.fc.bias, rows),
+                w1=TF.PreparedLinear(lyr.mlp.w_1.weight, lyr.mlp.w_1.bias, rows),
+                w2=TF.PreparedLinear(lyr.mlp.w_2.weight, lyr.mlp.w_2.bias, rows)))
+        ncls = self.classifier.weight.shape[0]
+        npad = (ncls + 31) // 32 * 32                      # the tensor-core kernel takes output widths that are multiples of 32
+        wc = torch.zeros((npad, d), dtype=torch.float32, device=dev)
+        wc[:ncls] = self.classifier.weight
+        bc = torch.zeros((npad,), dtype=torch.float32, device=dev)
+        bc[:ncls] = self.classifier.bias
+        cls = TF.PreparedLinear(wc, bc, rows)
         cap = self.max_seq_len
         k_cache = [torch.zeros((n, cap, d), dtype=torch.float32, device=dev) for _ in self.layer_stack]
         v_cache = [torch.zeros((n, cap, d), dtype=torch.float32, device=dev) for _ in self.layer_stack]
@@ -173,18 +218,17 @@ class NRTRDecoder(_BaseModule):
         for step in range(self.max_seq_len):
             x[:n] = self.trg_word_emb(tok) + pos[step]
             for li, lyr in enumerate(self.layer_stack):
-                qkv = TF.linear(lyr.norm1(x), *w_qkv[li])
+                ops = lin[li]
+                qkv = ops["qkv"](lyr.norm1(x))
                 k_cache[li][:, step] = qkv[:n, d:2 * d]
                 v_cache[li][:, step] = qkv[:n, 2 * d:]
                 TF.attn_decode(qkv[:n, :d].contiguous(), k_cache[li], v_cache[li], self.n_head, step + 1, temp, out=att[:n])
-                x = x + TF.linear(att, lyr.self_attn.fc.weight, lyr.self_attn.fc.bias)
-                q = TF.linear(lyr.norm2(x), lyr.enc_attn.linear_q.weight, lyr.enc_attn.linear_q.bias)
+                x = x + ops["fc"](att)
+                q = ops["q"](lyr.norm2(x))
                 TF.attn_decode(q[:n], mem_k[li], mem_v[li], self.n_head, t_src, temp, kv_lens=lens, out=att[:n])
-                x = x + TF.linear(att, lyr.enc_attn.fc.weight, lyr.enc_attn.fc.bias)
-                hdn = F.gelu(TF.linear(lyr.norm3(x), lyr.mlp.w_1.weight, lyr.mlp.w_1.bias))
-                x = x + TF.linear(hdn, lyr.mlp.w_2.weight, lyr.mlp.w_2.bias)
-            logits = TF.linear(self.layer_norm(x), self.classifier.weight, self.classifier.bias)[:n]
-            probs = F.softmax(logits, dim=-1)
+                x = x + ops["efc"](att)
+                x = x + ops["w2"](F.gelu(ops["w1"](lyr.norm3(x))))
+            probs = F.softmax(cls(self.layer_norm(x))[:n, :ncls], dim=-1)
             outputs.append(probs)
             tok = probs.argmax(dim=-1)
         return torch.stack(outputs, dim=1)
