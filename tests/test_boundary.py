@@ -176,7 +176,8 @@ def test_every_cfg_struct_has_the_header_layout(tmp_path):
     if gcc is None:
         pytest.skip("gcc not available")
     pairs = [("tpspp_warp_cfg", _native.WarpCfg), ("tpspp_head_cfg", _native.HeadCfg), ("tpspp_stage_cfg", _native.StageCfg),
-             ("tpspp_conv_cfg", _native.ConvCfg), ("tpspp_linear_cfg", _native.LinearCfg), ("tpspp_locnet_cfg", _native.LocnetCfg)]
+             ("tpspp_conv_cfg", _native.ConvCfg), ("tpspp_linear_cfg", _native.LinearCfg), ("tpspp_locnet_cfg", _native.LocnetCfg),
+             ("tpspp_attn_cfg", _native.AttnCfg)]
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "tpspp.h"', "int main(void) {"]
     for cname, mirror in pairs:
         lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
