@@ -1242,6 +1242,8 @@ struct LinTmaArgs {
   ConvTcArgs t;
   CUtensorMap tmap;
   int rows_per_img;        // rows that share one weight image (per-image weights), else 0
+  int col_split;           // 1: K > 64 with several column blocks -- blockIdx.y owns ONE 64/32-column block of the output (the
+                           //    streamed-K path of this kernel handles a single block per CTA); 0: a CTA walks all blocks
 };
 constexpr int LN_WSTAGES = 4;
 __host__ __device__ constexpr int ln_smem_bytes() { return 2 * 16384 + LN_WSTAGES * TS_STAGE + 1536 + 1024; }
@@ -1286,7 +1288,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
     mbar_init(d_full, 1); mbar_init(d_empty, TC_PRODUCERS / 32);
     fence_barrier_init();
   }
-  for (int i = tid; i < a.Cout && i < 256; i += TC_THREADS) bias_s[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;
+  const int nb0 = g.col_split ? (int)blockIdx.y : 0;              // first column block of this CTA
+  for (int i = tid; i < (g.col_split ? NT : a.Cout) && i < 256; i += TC_THREADS)
+    bias_s[i] = a.bias != nullptr ? __ldg(a.bias + nb0 * NT + i) : 0.f;
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
@@ -1296,7 +1300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
   const long long R = (long long)a.B * a.Ho * a.Wo;
   const int ntiles = (int)(R / TC_TM);
   const int nchunks = a.Ctot / TC_KC;
-  const int nblocks = a.Cout / NT;
+  const int nblocks = g.col_split ? 1 : a.Cout / NT;
   const float* wbase = g.t.wprep;
   constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
 
@@ -1310,7 +1314,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
       const int st = wi_load & (LN_WSTAGES - 1);
       if (wi_load >= LN_WSTAGES) mbar_wait_bounded(&w_empty[st], (uint32_t)(((wi_load / LN_WSTAGES) - 1) & 1));
       const float* wsrc = wbase + (size_t)(g.rows_per_img > 0 ? ((long long)p_tile * TC_TM) / g.rows_per_img : 0) * (size_t)a.wimg_stride +
-                          (size_t)(p_nb * nchunks + p_ch) * (2 * NT * TC_KC);
+                          (size_t)((p_nb + nb0) * nchunks + p_ch) * (2 * NT * TC_KC);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&w_full[st], W_BYTES);
         bulk_g2s(wst + st * TS_STAGE, wsrc, W_BYTES, &w_full[st], policy_evict_last());
@@ -1413,7 +1417,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
       for (int nb = 0; nb < nblocks; ++nb, ++di) {
         mbar_wait_bounded(d_full, (uint32_t)(di & 1));
         tc_fence_after();
-        const int cb0 = nb * NT + kh * HC;                        // first output column of this thread's part
+        const int cbl = nb * NT + kh * HC;                        // ... within the columns this CTA owns (bias_s index)
+        const int cb0 = nb0 * NT + cbl;                           // first output column of this thread's part
         const size_t o0 = (size_t)m * a.Cout + cb0;
 #pragma unroll 1
         for (int pass = 0; pass < HC / 16; ++pass) {
@@ -1421,7 +1426,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
           const uint32_t taddr = lane_addr + (uint32_t)(kh * HC + pass * 16);
           tmem_ld_cols<16>(taddr, acc);
           tmem_ld_cols<16>(taddr + 64, part);
-          const int cb = cb0 + pass * 16;
+          const int cb = cbl + pass * 16;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             const float4 bs = *reinterpret_cast<const float4*>(bias_s + cb + j);      // shared memory, warp-uniform
@@ -2456,11 +2461,13 @@ static int launch_tc(const ConvTcArgs& t, dim3 grid, cudaStream_t st) {
 static bool lin_tma_plan(const ConvArgs& a, int NT, LinTmaArgs* g) {
   const ConvSrc& sc = a.src[0];
   if (!sc.nhwc || a.src[1].C != 0 || a.src[2].C != 0 || !a.out_nhwc || sc.uh != 1 || sc.uw != 1) return false;
-  if (a.sh != 1 || a.sw != 1 || a.pad != 0 || a.Ctot != sc.C || a.Ctot % TC_KC || a.Cout % NT || a.Cout > 256) return false;
+  if (a.sh != 1 || a.sw != 1 || a.pad != 0 || a.Ctot != sc.C || a.Ctot % TC_KC || a.Cout % NT) return false;
+  if (a.Cout > 256 && a.Ctot <= 2 * TC_KC) return false;      // the all-blocks-per-CTA form keeps <= 256 bias values in shared memory
   const long long R = (long long)a.B * a.Ho * a.Wo;
   if (R % TC_TM || R > 0x7fffffffLL || sc.H * sc.W * (long long)a.B != R) return false;
   const int nchunks = a.Ctot / TC_KC, nblocks = a.Cout / NT;
-  if (nchunks > 2 && nblocks != 1) return false;
+  g->col_split = (nchunks > 2 && nblocks != 1) ? 1 : 0;      // K > 64 and several column blocks: one block per blockIdx.y
+  if (g->col_split && (nblocks > 65535 || a.wimg_stride != 0)) return false;
   g->rows_per_img = 0;
   if (a.wimg_stride != 0) {
     const long long per = (long long)a.Ho * a.Wo;
@@ -2654,7 +2661,8 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
       TPSPP_CHECK_CUDA(cudaFuncSetAttribute(lin_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes()));
       lin_dev = dev;
     }
-    dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()));
+    dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()), lg.col_split ? (unsigned)(a.Cout / NT) : 1u);
+    if (lg.col_split) pgrid.x = (unsigned)min((long long)grid.x, max(1LL, 2LL * sm_count() / pgrid.y));
     if (NT == 64) lin_tma_kernel<64><<<pgrid, TC_THREADS, ln_smem_bytes(), st>>>(lg);
     else lin_tma_kernel<32><<<pgrid, TC_THREADS, ln_smem_bytes(), st>>>(lg);
     count_launch();
