@@ -27,6 +27,8 @@ struct ConvArgs {
   int out_cstride;       // channels per image of the out / skip tensors when this launch writes a channel slice (0: = Cout)
   int zi;                // 1: up-sampled sources are ZERO-INSERTED instead of nearest (data gradient of a strided convolution)
   int out_bf16, skip_bf16; // 1: out / skip are stored as bf16 (bf16 mode of the head, 3x3 TMA kernel only)
+  int splitk;              // row-major linear layers only (lin_tma_kernel): > 1 = the K chunks are split over blockIdx.z and `out` is a
+                           // partial buffer [splitk][rows][Cout] (no bias / activation / skip: the caller reduces)
 };
 enum { CONV_ACT_RELU = 0, CONV_ACT_NONE = 1, CONV_ACT_GELU = 2, CONV_ACT_TANH = 3 };
 // operand mode of a tensor-core convolution (head_tc.cu): 3xTF32 | single-pass bf16 | tf32 main term + bf16 corrections

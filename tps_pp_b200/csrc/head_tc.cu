@@ -1299,7 +1299,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
 
   const long long R = (long long)a.B * a.Ho * a.Wo;
   const int ntiles = (int)(R / TC_TM);
-  const int nchunks = a.Ctot / TC_KC;
+  // split-K (a.splitk > 1, small-row GEMMs such as the NRTR decode steps: a launch is a few dozen CTAs that would each walk all
+  // of K serially at ~1 us per chunk): blockIdx.z owns nchunks consecutive chunks and writes its own partial output
+  const int ksp = a.splitk > 1 ? a.splitk : 1;
+  const int nchunks_total = a.Ctot / TC_KC;
+  const int nchunks = nchunks_total / ksp;
+  const int ch0 = (int)blockIdx.z * nchunks;
   const int nblocks = g.col_split ? 1 : a.Cout / NT;
   const float* wbase = g.t.wprep;
   constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
@@ -1314,7 +1319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
       const int st = wi_load & (LN_WSTAGES - 1);
       if (wi_load >= LN_WSTAGES) mbar_wait_bounded(&w_empty[st], (uint32_t)(((wi_load / LN_WSTAGES) - 1) & 1));
       const float* wsrc = wbase + (size_t)(g.rows_per_img > 0 ? ((long long)p_tile * TC_TM) / g.rows_per_img : 0) * (size_t)a.wimg_stride +
-                          (size_t)((p_nb + nb0) * nchunks + p_ch) * (2 * NT * TC_KC);
+                          (size_t)((p_nb + nb0) * nchunks_total + ch0 + p_ch) * (2 * NT * TC_KC);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&w_full[st], W_BYTES);
         bulk_g2s(wst + st * TS_STAGE, wsrc, W_BYTES, &w_full[st], policy_evict_last());
@@ -1334,7 +1339,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
       if (t_idx >= 2) mbar_wait_bounded(&t_empty[tb], (uint32_t)(((t_idx >> 1) - 1) & 1));
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&t_full[tb], 16384);
-        tma_load_2d(tiles + tb * 16384, &g.tmap, t_ch * TC_KC, t_tile * TC_TM, &t_full[tb], policy_evict_first());
+        tma_load_2d(tiles + tb * 16384, &g.tmap, (ch0 + t_ch) * TC_KC, t_tile * TC_TM, &t_full[tb], policy_evict_first());
       }
       __syncwarp();
       ++t_idx;
@@ -1419,7 +1424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
         tc_fence_after();
         const int cbl = nb * NT + kh * HC;                        // ... within the columns this CTA owns (bias_s index)
         const int cb0 = nb0 * NT + cbl;                           // first output column of this thread's part
-        const size_t o0 = (size_t)m * a.Cout + cb0;
+        const size_t o0 = (size_t)m * a.Cout + cb0 + (size_t)blockIdx.z * (size_t)R * a.Cout;
 #pragma unroll 1
         for (int pass = 0; pass < HC / 16; ++pass) {
           float acc[16], part[16];
@@ -2468,6 +2473,9 @@ static bool lin_tma_plan(const ConvArgs& a, int NT, LinTmaArgs* g) {
   const int nchunks = a.Ctot / TC_KC, nblocks = a.Cout / NT;
   g->col_split = (nchunks > 2 && nblocks != 1) ? 1 : 0;      // K > 64 and several column blocks: one block per blockIdx.y
   if (g->col_split && (nblocks > 65535 || a.wimg_stride != 0)) return false;
+  if (a.splitk > 1 && (nchunks % a.splitk || nchunks / a.splitk < 1 || !(g->col_split || nblocks == 1) || a.wimg_stride != 0 ||
+                       a.bias != nullptr || a.skip != nullptr || a.act != CONV_ACT_NONE || a.splitk > 64))
+    return false;
   g->rows_per_img = 0;
   if (a.wimg_stride != 0) {
     const long long per = (long long)a.Ho * a.Wo;
@@ -2651,7 +2659,9 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
   }
   TPSPP_REQUIRE(mode == CM_TF32X3, "conv_tc: the bf16 / mixed operand modes exist for the NCHW-source convolutions only");
   LinTmaArgs lg;
-  if (KS == 1 && nhwc && lin_tma_plan(a, NT, &lg)) {
+  const bool lin_ok = KS == 1 && nhwc && lin_tma_plan(a, NT, &lg);
+  TPSPP_REQUIRE(a.splitk <= 1 || lin_ok, "conv_tc: split-K exists for the TMA-fed row-major linear kernel only");
+  if (lin_ok) {
     lg.t = t;
     int dev = 0;
     TPSPP_CHECK_CUDA(cudaGetDevice(&dev));
@@ -2663,6 +2673,7 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
     }
     dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()), lg.col_split ? (unsigned)(a.Cout / NT) : 1u);
     if (lg.col_split) pgrid.x = (unsigned)min((long long)grid.x, max(1LL, 2LL * sm_count() / pgrid.y));
+    if (a.splitk > 1) pgrid.z = (unsigned)a.splitk;
     if (NT == 64) lin_tma_kernel<64><<<pgrid, TC_THREADS, ln_smem_bytes(), st>>>(lg);
     else lin_tma_kernel<32><<<pgrid, TC_THREADS, ln_smem_bytes(), st>>>(lg);
     count_launch();

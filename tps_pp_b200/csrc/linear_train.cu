@@ -101,7 +101,20 @@ __global__ void __launch_bounds__(256) lin_small_wgrad_kernel(const float* __res
   }
 }
 
-struct LinDims { long long R; int K, N, batches; long long rpb; bool tc_fwd, tc_dx, tc_wg; int nt_fwd, nt_dx; };
+struct LinDims { long long R; int K, N, batches; long long rpb; bool tc_fwd, tc_dx, tc_wg; int nt_fwd, nt_dx, sk_fwd; };
+
+// y[r][n] = sum_s part[s][r][n] + bias[n]: the reduction of a split-K forward (fixed order: deterministic)
+__global__ void __launch_bounds__(256) lin_splitk_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ bias,
+                                                                float4* __restrict__ y, long long total4, int n4, int splits) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total4; i += (long long)gridDim.x * 256) {
+    float4 acc = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias) + (i % n4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 p = __ldg(part + (size_t)s * total4 + i);
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    y[i] = acc;
+  }
+}
 static bool lin_tc_shape(long long R, int K, int N, long long rpb, int* NT) {
   if (R % TC_TM || rpb % TC_TM || K % TC_KC || N % 32 || N > 4096 || K > 4096 || R > 0x7fffffffLL) return false;
   *NT = N % 64 == 0 ? 64 : 32;
@@ -122,16 +135,26 @@ static int lin_dims(const tpspp_linear_cfg* c, LinDims* d) {
   d->nt_fwd = d->nt_dx = 64;
   d->tc_fwd = d->R > 0 && lin_tc_shape(d->R, d->K, d->N, d->rpb, &d->nt_fwd);
   d->tc_dx = d->R > 0 && lin_tc_shape(d->R, d->N, d->K, d->rpb, &d->nt_dx);
+  // split-K of the forward: few row tiles (inference steps of a transformer decoder) and a long K
+  d->sk_fwd = 1;
+  if (d->tc_fwd && d->batches == 1 && d->K >= 256) {
+    const long long ctas = (d->R / TC_TM) * ((d->N + d->nt_fwd - 1) / d->nt_fwd);
+    const int chunks = d->K / TC_KC;
+    int sk = 1;
+    while (sk < 4 && ctas * sk * 2 <= 2LL * sm_count() && chunks % (sk * 2) == 0 && chunks / (sk * 2) >= 2) sk *= 2;
+    d->sk_fwd = sk;
+  }
   d->tc_wg = d->R >= 2048 && d->rpb % 32 == 0 && d->K <= 1024 && d->N <= 1024 && (d->batches == 1 || d->rpb >= 256);
   return TPSPP_OK;
 }
-enum { LW_WFWD = 0, LW_WDX, LW_WG, LW_COUNT };
+enum { LW_WFWD = 0, LW_WDX, LW_WG, LW_SPLITK, LW_COUNT };
 static void lin_offsets(const LinDims& d, size_t* off, size_t* total) {
   size_t sz[LW_COUNT];
   const int npf = (d.N + d.nt_fwd - 1) / d.nt_fwd * d.nt_fwd, npx = (d.K + d.nt_dx - 1) / d.nt_dx * d.nt_dx;
   sz[LW_WFWD] = d.tc_fwd ? (size_t)2 * npf * d.K * d.batches : 0;
   sz[LW_WDX] = d.tc_dx ? (size_t)2 * npx * d.N * d.batches : 0;
   sz[LW_WG] = d.tc_wg ? wgrad_rows_ws_floats(d.R, d.K, d.N, d.batches) : 0;
+  sz[LW_SPLITK] = d.sk_fwd > 1 ? (size_t)d.sk_fwd * d.R * d.N : 0;
   size_t cur = 0;
   for (int i = 0; i < LW_COUNT; ++i) {
     off[i] = cur;
@@ -142,7 +165,7 @@ static void lin_offsets(const LinDims& d, size_t* off, size_t* total) {
 
 // out[R, Nn] = in[R, Kk] . img^T (+ bias) through the tcgen05 row-major linear kernel
 static int lin_tc_run(const float* in, const float* wimg, const float* bias, float* out, const LinDims& d, int Kk, int Nn, int NT,
-                      cudaStream_t st) {
+                      cudaStream_t st, int splitk = 1, float* part = nullptr) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.src[0].ptr = in; a.src[0].C = Kk; a.src[0].H = 1; a.src[0].W = (int)d.rpb; a.src[0].uh = a.src[0].uw = 1; a.src[0].nhwc = 1;
@@ -150,6 +173,17 @@ static int lin_tc_run(const float* in, const float* wimg, const float* bias, flo
   a.bias = bias; a.out = out; a.B = d.batches; a.Ho = 1; a.Wo = (int)d.rpb; a.Ctot = Kk; a.sh = a.sw = 1; a.pad = 0;
   a.out_nhwc = 1; a.act = CONV_ACT_NONE; a.act_scale = 1.f; a.Cout = Nn;
   a.wimg_stride = d.batches > 1 ? (long long)2 * ((Nn + NT - 1) / NT * NT) * Kk : 0;
+  if (splitk > 1 && part != nullptr && ((uintptr_t)out & 15) == 0 && (bias == nullptr || ((uintptr_t)bias & 15) == 0) && Nn % 4 == 0) {
+    a.bias = nullptr; a.out = part; a.splitk = splitk;
+    const int rc = run_conv_tc(1, a, wimg, NT, st, CM_TF32X3);
+    if (rc != TPSPP_OK) return rc;
+    const long long total4 = d.R * Nn / 4;
+    lin_splitk_reduce_kernel<<<(unsigned)min((total4 + 255) / 256, 4LL * sm_count()), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(part), bias, reinterpret_cast<float4*>(out), total4, Nn / 4, splitk);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+    return TPSPP_OK;
+  }
   return run_conv_tc(1, a, wimg, NT, st, CM_TF32X3);
 }
 
@@ -185,7 +219,7 @@ extern "C" int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, con
       count_launch();
       TPSPP_CHECK_CUDA(cudaGetLastError());
     }
-    return lin_tc_run(x, img, bias, y, d, d.K, d.N, d.nt_fwd, st);
+    return lin_tc_run(x, img, bias, y, d, d.K, d.N, d.nt_fwd, st, d.sk_fwd, reinterpret_cast<float*>((char*)workspace + off[LW_SPLITK]));
   }
   lin_small_fwd_kernel<<<dim3((d.N + 31) / 32, (unsigned)((d.rpb + 31) / 32), d.batches), 256, 0, st>>>(x, w, bias, y, d.K, d.N, d.rpb, 0);
   count_launch();
