@@ -328,6 +328,11 @@ enum { TPSPP_LINEAR_FLAG_WEIGHTS_CACHED = 1 };
 TPSPP_API size_t tpspp_linear_workspace_bytes(const tpspp_linear_cfg* cfg);   /* covers both calls */
 TPSPP_API int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias /* or NULL */,
                                float* y, void* workspace, tpspp_stream_t stream);
+/* y = act(x w^T + bias) + residual: the inference form with the epilogue a transformer layer needs (residual [rows, out] or
+ * NULL; act = TPSPP_ACT_NONE | TPSPP_ACT_GELU (erf form)); weight_batches must be 1. */
+enum { TPSPP_ACT_NONE = 0, TPSPP_ACT_GELU = 1 };
+TPSPP_API int tpspp_linear_fwd_ex(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias, const float* residual,
+                                  int32_t act, float* y, void* workspace, tpspp_stream_t stream);
 /* gx [rows, in] (or NULL), gw [batches, out, in] (or NULL), gb [out] (or NULL; needs gw) from gy [rows, out] */
 TPSPP_API int tpspp_linear_bwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* gy, float* gx,
                                float* gw, float* gb, void* workspace, tpspp_stream_t stream);
@@ -349,9 +354,14 @@ typedef struct {
   int32_t batch, heads, head_dim;   /* head_dim = 64                                                        */
   int32_t kv_len, kv_capacity;      /* keys used (all images) / rows allocated per image                    */
   float temperature;                /* d_k ** 0.5 in the reference                                          */
+  int32_t q_stride, new_stride;     /* floats between consecutive images' rows of q and of k_new / v_new (0 = heads*64): lets q, k_new,
+                                       v_new be column slices of one fused q|k|v projection                                     */
 } tpspp_attn_cfg;
-TPSPP_API int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, const float* k, const float* v,
-                                const int32_t* kv_lens /* [batch] device pointer or NULL */, float* out, tpspp_stream_t stream);
+/* k_new / v_new (or NULL): this step's key / value rows; the kernel stores them at cache position kv_len - 1 (kv_lens[b] - 1)
+ * before it attends, so the caller needs no separate cache-append copy. */
+TPSPP_API int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, float* k, float* v,
+                                const int32_t* kv_lens /* [batch] device pointer or NULL */, const float* k_new, const float* v_new,
+                                float* out, tpspp_stream_t stream);
 
 /* Number of kernel launches the most recent call on this host thread enqueued
  * (bench.py uses it to report gpu_launches). */

@@ -76,3 +76,26 @@ def test_linear_rejects_cpu_tensors():
     from tps_pp_b200 import functional as TF
     with pytest.raises(RuntimeError):
         TF.linear(torch.zeros(4, 8), torch.zeros(3, 8), None)
+
+
+@pytest.mark.parametrize("rows,k,n", [(256, 512, 512), (1024, 512, 256), (256, 256, 512), (128, 64, 64)], ids=["split-K", "unsplit", "K=256", "small"])
+def test_prepared_linear_residual_gelu(rows, k, n):
+    """The inference form a transformer layer needs: act(x w^T + b) + residual in the dense kernel's epilogue (or in the split-K
+    reduction), cached operand images, in-place residual."""
+    from tps_pp_b200 import functional as TF
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(rows + k + n)
+    x = torch.randn((rows, k), device=dev, generator=g)
+    w = torch.randn((n, k), device=dev, generator=g) / k ** 0.5
+    b = torch.randn((n,), device=dev, generator=g)
+    r = torch.randn((rows, n), device=dev, generator=g)
+    op = TF.PreparedLinear(w, b, rows)
+    for gelu in (False, True):
+        lin = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        ref = (torch.nn.functional.gelu(lin) if gelu else lin) + r.double()
+        for _ in range(2):                                   # second call: cached operand image
+            y = op(x, residual=r, gelu=gelu)
+            assert _rel(y, ref) <= 3e-6 * max(1.0, (k / 256) ** 0.5)
+        inplace = r.clone()
+        op(x, out=inplace, residual=inplace, gelu=gelu)
+        assert torch.equal(inplace, y)

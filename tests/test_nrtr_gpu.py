@@ -32,6 +32,15 @@ def test_attn_decode_vs_torch(native_lib, b, heads, cap, length):
         a = a.masked_fill(t >= limit, float("-inf"))
         ref = torch.matmul(torch.softmax(a, -1), vv).transpose(1, 2).reshape(b, d)
         assert float((out.double() - ref).abs().max()) <= 2e-6 * float(ref.abs().max().clamp_min(1.0))
+    # append form: q / k_new / v_new as column slices of one fused projection; the kernel writes the step's rows into the cache
+    fused = torch.randn((b, 3 * d), device=DEV, generator=g)
+    kc, vc = k.clone(), v.clone()
+    out = TF.attn_decode(fused[:, :d], kc, vc, heads, length, 8.0, k_new=fused[:, d:2 * d], v_new=fused[:, 2 * d:])
+    k2, v2 = k.clone(), v.clone()
+    k2[:, length - 1] = fused[:, d:2 * d]
+    v2[:, length - 1] = fused[:, 2 * d:]
+    assert torch.equal(kc, k2) and torch.equal(vc, v2)
+    assert torch.equal(out, TF.attn_decode(fused[:, :d].contiguous(), k2, v2, heads, length, 8.0))
 
 
 def test_nrtr_decoder_native_decode_vs_reference_golden(native_lib, golden):

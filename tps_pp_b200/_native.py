@@ -60,7 +60,7 @@ LP_COUNT = 24
 class AttnCfg(Structure):
     """Mirror of ``tpspp_attn_cfg`` (include/tpspp.h)."""
     _fields_ = [("batch", c_int32), ("heads", c_int32), ("head_dim", c_int32), ("kv_len", c_int32), ("kv_capacity", c_int32),
-                ("temperature", c_float)]
+                ("temperature", c_float), ("q_stride", c_int32), ("new_stride", c_int32)]
 
 
 class LinearCfg(Structure):
@@ -77,6 +77,7 @@ HEAD_FLAG_UNFUSED_SCORE = 4
 HEAD_FLAG_TF32X3_CONV = 8
 HEAD_FLAG_FEATGRID_BF16 = 16
 LINEAR_FLAG_WEIGHTS_CACHED = 1
+ACT_NONE, ACT_GELU = 0, 1
 ABI_VERSION = 2
 P_COUNT = 58
 WS_NAMES = ("f0", "f1", "f2", "a0", "a1", "e0", "e1", "e2", "e3", "cbam", "d0", "d1", "d2", "de", "x1", "v", "de2", "p1", "wprep", "t1", "fs", "hid", "p1img")
@@ -104,7 +105,8 @@ _SIGNATURES = {
     "tpspp_convcat_bwd": (c_int, [POINTER(ConvCfg), POINTER(c_void_p)] + [c_void_p] * 3 + [POINTER(c_void_p)] + [c_void_p] * 4),
     "tpspp_locnet_workspace_bytes": (c_size_t, [POINTER(LocnetCfg)]),
     "tpspp_locnet_fwd": (c_int, [POINTER(LocnetCfg), c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
-    "tpspp_attn_decode": (c_int, [POINTER(AttnCfg)] + [c_void_p] * 6),
+    "tpspp_attn_decode": (c_int, [POINTER(AttnCfg)] + [c_void_p] * 8),
+    "tpspp_linear_fwd_ex": (c_int, [POINTER(LinearCfg)] + [c_void_p] * 4 + [c_int32] + [c_void_p] * 3),
     "tpspp_linear_workspace_bytes": (c_size_t, [POINTER(LinearCfg)]),
     "tpspp_linear_fwd": (c_int, [POINTER(LinearCfg)] + [c_void_p] * 6),
     "tpspp_linear_bwd": (c_int, [POINTER(LinearCfg)] + [c_void_p] * 8),

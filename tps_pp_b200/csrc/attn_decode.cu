@@ -13,27 +13,39 @@ namespace tpspp {
 
 constexpr int AD_WARPS = 4, AD_DIM = 64;
 
-__global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float* __restrict__ q, const float* __restrict__ k,
-                                                                   const float* __restrict__ v, float* __restrict__ out,
-                                                                   const int* __restrict__ kv_lens, int kv_len, int capacity, int heads,
-                                                                   float inv_temperature) {
+__global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float* __restrict__ q, float* __restrict__ k, float* __restrict__ v,
+                                                                   float* __restrict__ out, const int* __restrict__ kv_lens, int kv_len,
+                                                                   int capacity, int heads, float inv_temperature, int q_stride,
+                                                                   const float* __restrict__ k_new, const float* __restrict__ v_new,
+                                                                   int new_stride) {
   const int b = blockIdx.x, h = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = heads * AD_DIM;
   int len = kv_lens != nullptr ? kv_lens[b] : kv_len;
   len = len < 0 ? 0 : (len > capacity ? capacity : len);
-  const float2 qv = *reinterpret_cast<const float2*>(q + (size_t)b * D + h * AD_DIM + 2 * lane);
+  if (k_new != nullptr && len > 0) {
+    // append: this step's key / value rows (e.g. slices of a fused q|k|v projection) become cache position len - 1.  A CTA
+    // touches only its own (image, head) slice, so the write needs no ordering against other CTAs.
+    if (warp == 0) {
+      const size_t dst = ((size_t)b * capacity + (len - 1)) * D + h * AD_DIM + 2 * lane;
+      const size_t src = (size_t)b * new_stride + h * AD_DIM + 2 * lane;
+      *reinterpret_cast<float2*>(k + dst) = *reinterpret_cast<const float2*>(k_new + src);
+      *reinterpret_cast<float2*>(v + dst) = *reinterpret_cast<const float2*>(v_new + src);
+    }
+    __syncthreads();
+  }
+  const float2 qv = *reinterpret_cast<const float2*>(q + (size_t)b * q_stride + h * AD_DIM + 2 * lane);
   const float q0 = qv.x * inv_temperature, q1 = qv.y * inv_temperature;       // the reference scales q, then multiplies
   const float* kb = k + (size_t)b * capacity * D + h * AD_DIM + 2 * lane;
   const float* vb = v + (size_t)b * capacity * D + h * AD_DIM + 2 * lane;
   float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
   for (int t = warp; t < len; t += AD_WARPS) {
-    const float2 kv = __ldg(reinterpret_cast<const float2*>(kb + (size_t)t * D));
+    const float2 kv = *reinterpret_cast<const float2*>(kb + (size_t)t * D);      // (plain loads: the cache may just have been appended to)
     float s = q0 * kv.x + q1 * kv.y;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mn = fmaxf(m, s);
     const float c = __expf(m - mn), p = __expf(s - mn);        // m = -inf on the first key: c = 0
-    const float2 vv = __ldg(reinterpret_cast<const float2*>(vb + (size_t)t * D));
+    const float2 vv = *reinterpret_cast<const float2*>(vb + (size_t)t * D);
     l = l * c + p;
     a0 = a0 * c + p * vv.x;
     a1 = a1 * c + p * vv.y;
@@ -64,8 +76,8 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float*
 
 using namespace tpspp;
 
-extern "C" int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, const float* k, const float* v, const int32_t* kv_lens,
-                                 float* out, tpspp_stream_t stream) {
+extern "C" int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, float* k, float* v, const int32_t* kv_lens,
+                                 const float* k_new, const float* v_new, float* out, tpspp_stream_t stream) {
   reset_launch_count();
   TPSPP_REQUIRE(cfg != nullptr, "attn cfg is NULL");
   TPSPP_REQUIRE(cfg->batch >= 0 && cfg->heads > 0 && cfg->heads <= 65535, "attn: batch >= 0, 1 <= heads <= 65535");
@@ -74,9 +86,14 @@ extern "C" int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, cons
   TPSPP_REQUIRE(cfg->temperature > 0.f, "attn: temperature must be positive");
   if (cfg->batch == 0) return TPSPP_OK;
   TPSPP_REQUIRE(q && k && v && out, "tpspp_attn_decode: null pointer");
-  TPSPP_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 7) == 0, "tpspp_attn_decode: buffers must be 8-byte aligned");
+  TPSPP_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out | (uintptr_t)k_new | (uintptr_t)v_new) & 7) == 0,
+                "tpspp_attn_decode: buffers must be 8-byte aligned");
+  const int D = cfg->heads * AD_DIM;
+  const int qs = cfg->q_stride > 0 ? cfg->q_stride : D, ns = cfg->new_stride > 0 ? cfg->new_stride : D;
+  TPSPP_REQUIRE(qs >= D && ns >= D && qs % 2 == 0 && ns % 2 == 0, "tpspp_attn_decode: row strides must be even and >= heads * 64");
+  TPSPP_REQUIRE((k_new == nullptr) == (v_new == nullptr), "tpspp_attn_decode: k_new and v_new come together");
   attn_decode_kernel<<<dim3(cfg->batch, cfg->heads), AD_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      q, k, v, out, kv_lens, cfg->kv_len, cfg->kv_capacity, cfg->heads, 1.f / cfg->temperature);
+      q, k, v, out, kv_lens, cfg->kv_len, cfg->kv_capacity, cfg->heads, 1.f / cfg->temperature, qs, k_new, v_new, ns);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;

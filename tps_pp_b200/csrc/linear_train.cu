@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(256) lin_wprep_kernel(const float* __restrict_
 // (coalesced global reads for either weight orientation), thread = one column x four rows
 __global__ void __launch_bounds__(256) lin_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, float* __restrict__ y, int K, int N,
-                                                            long long rows_per_batch, int transposed) {
+                                                            long long rows_per_batch, int transposed,
+                                                            const float* __restrict__ residual = nullptr, int gelu = 0) {
   // transposed = 0: y = x w^T (w [N][K]);  1: y = x w (w [K][N], the data gradient with K/N swapped by the caller)
   __shared__ float Xs[32][33], Ws[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -71,7 +72,13 @@ __global__ void __launch_bounds__(256) lin_small_fwd_kernel(const float* __restr
   const float bv = bias != nullptr ? __ldg(bias + n0 + tx) : 0.f;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    if (r0 + ty + 8 * j < rend) y[(size_t)(r0 + ty + 8 * j) * N + n0 + tx] = acc[j] + bv;
+    if (r0 + ty + 8 * j < rend) {
+      const size_t o = (size_t)(r0 + ty + 8 * j) * N + n0 + tx;
+      float v = acc[j] + bv;
+      if (gelu) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+      if (residual != nullptr) v += residual[o];
+      y[o] = v;
+    }
 }
 // gw[b][n][k] = sum over the batch's rows of gy[r][n] x[r][k]; gb[n] = sum_r gy[r][n] (column K of the same grid).
 // block = 32 features (k) x 8 row lanes for one output feature n; fixed summation order (deterministic)
@@ -104,13 +111,20 @@ __global__ void __launch_bounds__(256) lin_small_wgrad_kernel(const float* __res
 struct LinDims { long long R; int K, N, batches; long long rpb; bool tc_fwd, tc_dx, tc_wg; int nt_fwd, nt_dx, sk_fwd; };
 
 // y[r][n] = sum_s part[s][r][n] + bias[n]: the reduction of a split-K forward (fixed order: deterministic)
+__device__ __forceinline__ float lin_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __global__ void __launch_bounds__(256) lin_splitk_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ bias,
-                                                                float4* __restrict__ y, long long total4, int n4, int splits) {
+                                                                const float4* __restrict__ residual, float4* __restrict__ y,
+                                                                long long total4, int n4, int splits, int gelu) {
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total4; i += (long long)gridDim.x * 256) {
     float4 acc = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias) + (i % n4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < splits; ++s) {
       const float4 p = __ldg(part + (size_t)s * total4 + i);
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    if (gelu) { acc.x = lin_gelu(acc.x); acc.y = lin_gelu(acc.y); acc.z = lin_gelu(acc.z); acc.w = lin_gelu(acc.w); }
+    if (residual != nullptr) {
+      const float4 r = residual[i];            // may alias y (x = x + f(x)): read, then write the same element
+      acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
     }
     y[i] = acc;
   }
@@ -165,7 +179,7 @@ static void lin_offsets(const LinDims& d, size_t* off, size_t* total) {
 
 // out[R, Nn] = in[R, Kk] . img^T (+ bias) through the tcgen05 row-major linear kernel
 static int lin_tc_run(const float* in, const float* wimg, const float* bias, float* out, const LinDims& d, int Kk, int Nn, int NT,
-                      cudaStream_t st, int splitk = 1, float* part = nullptr) {
+                      cudaStream_t st, int splitk = 1, float* part = nullptr, const float* residual = nullptr, int gelu = 0) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.src[0].ptr = in; a.src[0].C = Kk; a.src[0].H = 1; a.src[0].W = (int)d.rpb; a.src[0].uh = a.src[0].uw = 1; a.src[0].nhwc = 1;
@@ -173,17 +187,22 @@ static int lin_tc_run(const float* in, const float* wimg, const float* bias, flo
   a.bias = bias; a.out = out; a.B = d.batches; a.Ho = 1; a.Wo = (int)d.rpb; a.Ctot = Kk; a.sh = a.sw = 1; a.pad = 0;
   a.out_nhwc = 1; a.act = CONV_ACT_NONE; a.act_scale = 1.f; a.Cout = Nn;
   a.wimg_stride = d.batches > 1 ? (long long)2 * ((Nn + NT - 1) / NT * NT) * Kk : 0;
-  if (splitk > 1 && part != nullptr && ((uintptr_t)out & 15) == 0 && (bias == nullptr || ((uintptr_t)bias & 15) == 0) && Nn % 4 == 0) {
+  if (splitk > 1 && part != nullptr && ((uintptr_t)out & 15) == 0 && (bias == nullptr || ((uintptr_t)bias & 15) == 0) &&
+      ((uintptr_t)residual & 15) == 0 && Nn % 4 == 0) {
     a.bias = nullptr; a.out = part; a.splitk = splitk;
     const int rc = run_conv_tc(1, a, wimg, NT, st, CM_TF32X3);
     if (rc != TPSPP_OK) return rc;
     const long long total4 = d.R * Nn / 4;
     lin_splitk_reduce_kernel<<<(unsigned)min((total4 + 255) / 256, 4LL * sm_count()), 256, 0, st>>>(
-        reinterpret_cast<const float4*>(part), bias, reinterpret_cast<float4*>(out), total4, Nn / 4, splitk);
+        reinterpret_cast<const float4*>(part), bias, reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), total4,
+        Nn / 4, splitk, gelu);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
     return TPSPP_OK;
   }
+  // unsplit: the kernel's own epilogue applies the activation (branch-free erf GELU, |error| <= 4.7e-7) and adds the residual
+  a.skip = residual; a.skip_pre = 0;
+  if (gelu) a.act = CONV_ACT_GELU;
   return run_conv_tc(1, a, wimg, NT, st, CM_TF32X3);
 }
 
@@ -201,7 +220,15 @@ extern "C" size_t tpspp_linear_workspace_bytes(const tpspp_linear_cfg* cfg) {
 
 extern "C" int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias, float* y,
                                 void* workspace, tpspp_stream_t stream) {
+  return tpspp_linear_fwd_ex(cfg, x, w, bias, nullptr, TPSPP_ACT_NONE, y, workspace, stream);
+}
+
+extern "C" int tpspp_linear_fwd_ex(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias, const float* residual,
+                                   int32_t act, float* y, void* workspace, tpspp_stream_t stream) {
   reset_launch_count();
+  TPSPP_REQUIRE(act == TPSPP_ACT_NONE || act == TPSPP_ACT_GELU, "tpspp_linear_fwd_ex: unknown activation %d", act);
+  TPSPP_REQUIRE(cfg == nullptr || cfg->weight_batches <= 1 || (residual == nullptr && act == TPSPP_ACT_NONE),
+                "tpspp_linear_fwd_ex: batched weights (bmm) take no residual / activation");
   LinDims d;
   int rc = lin_dims(cfg, &d);
   if (rc != TPSPP_OK) return rc;
@@ -219,9 +246,11 @@ extern "C" int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, con
       count_launch();
       TPSPP_CHECK_CUDA(cudaGetLastError());
     }
-    return lin_tc_run(x, img, bias, y, d, d.K, d.N, d.nt_fwd, st, d.sk_fwd, reinterpret_cast<float*>((char*)workspace + off[LW_SPLITK]));
+    return lin_tc_run(x, img, bias, y, d, d.K, d.N, d.nt_fwd, st, d.sk_fwd, reinterpret_cast<float*>((char*)workspace + off[LW_SPLITK]),
+                      residual, act == TPSPP_ACT_GELU ? 1 : 0);
   }
-  lin_small_fwd_kernel<<<dim3((d.N + 31) / 32, (unsigned)((d.rpb + 31) / 32), d.batches), 256, 0, st>>>(x, w, bias, y, d.K, d.N, d.rpb, 0);
+  lin_small_fwd_kernel<<<dim3((d.N + 31) / 32, (unsigned)((d.rpb + 31) / 32), d.batches), 256, 0, st>>>(x, w, bias, y, d.K, d.N, d.rpb, 0,
+                                                                                                         residual, act == TPSPP_ACT_GELU ? 1 : 0);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;

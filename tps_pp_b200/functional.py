@@ -568,35 +568,51 @@ class PreparedLinear:
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
         self.prepared = False
 
-    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                 gelu: bool = False) -> torch.Tensor:
+        """``act(x w^T + b) + residual`` (``tpspp_linear_fwd_ex``); ``out`` may be ``residual`` itself (x = x + f(.) in place)."""
         if x.shape != (self.rows, self.k) or not x.is_contiguous() or x.dtype != torch.float32:
             raise RuntimeError(f"tps_pp_b200: PreparedLinear expects a contiguous fp32 [{self.rows}, {self.k}] input, got {tuple(x.shape)}")
         y = out if out is not None else torch.empty((self.rows, self.n), dtype=torch.float32, device=x.device)
+        for nm, t in (("out", y), ("residual", residual)):
+            if t is not None and (t.shape != (self.rows, self.n) or not t.is_contiguous() or t.dtype != torch.float32 or not t.is_cuda):
+                raise RuntimeError(f"tps_pp_b200: PreparedLinear `{nm}` must be a contiguous fp32 CUDA [{self.rows}, {self.n}] tensor")
         self.cfg.flags = N.LINEAR_FLAG_WEIGHTS_CACHED if self.prepared else 0
         with torch.cuda.device(x.device):
-            N.check(N.lib().tpspp_linear_fwd(ctypes.byref(self.cfg), _ptr(x), _ptr(self.weight), _ptr(self.bias), _ptr(y),
-                                             _ptr(self.ws), _stream(x)), "tpspp_linear_fwd")
+            N.check(N.lib().tpspp_linear_fwd_ex(ctypes.byref(self.cfg), _ptr(x), _ptr(self.weight), _ptr(self.bias), _ptr(residual),
+                                                N.ACT_GELU if gelu else N.ACT_NONE, _ptr(y), _ptr(self.ws), _stream(x)),
+                    "tpspp_linear_fwd_ex")
         self.prepared = True
         return y
 
 
 def attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kv_len: int, temperature: float,
-                kv_lens: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                kv_lens: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Single-query multi-head attention over a key/value cache (``tpspp_attn_decode``): q [B, heads*64], k / v
-    [B, capacity, heads*64] -> [B, heads*64]; keys ``t < kv_len`` (or ``kv_lens[b]``, int32 on the device).  Forward only."""
-    for nm, t in (("q", q), ("k", k), ("v", v)):
+    [B, capacity, heads*64] -> [B, heads*64]; keys ``t < kv_len`` (or ``kv_lens[b]``, int32 on the device).  ``k_new`` / ``v_new``
+    [B, heads*64]: this step's rows, stored at cache position ``kv_len - 1`` by the kernel before it attends.  ``q`` / ``k_new`` /
+    ``v_new`` may be column slices of one fused projection (unit stride along the features).  Forward only."""
+    for nm, t in (("k", k), ("v", v)):
         _require_cuda(nm, t, torch.float32)
         if not t.is_contiguous():
             raise RuntimeError(f"tps_pp_b200: attn_decode `{nm}` must be contiguous")
     b, d = q.shape
+    for nm, t in (("q", q), ("k_new", k_new), ("v_new", v_new)):
+        _require_cuda(nm, t, torch.float32)
+        if t is not None and (t.dim() != 2 or t.shape != (b, d) or t.stride(1) != 1):
+            raise RuntimeError(f"tps_pp_b200: attn_decode `{nm}` must be [B, heads*64] with unit stride along the features")
+    if (k_new is None) != (v_new is None) or (k_new is not None and k_new.stride(0) != v_new.stride(0)):
+        raise RuntimeError("tps_pp_b200: attn_decode k_new / v_new come together, with the same row stride")
     if d != heads * 64 or k.shape[0] != b or k.shape[2] != d or v.shape != k.shape:
         raise RuntimeError(f"tps_pp_b200: attn_decode shapes q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} heads {heads}")
     if kv_lens is not None and (kv_lens.dtype != torch.int32 or not kv_lens.is_cuda or kv_lens.numel() != b):
         raise RuntimeError("tps_pp_b200: kv_lens must be an int32 CUDA tensor with one entry per image")
     if out is None:
-        out = torch.empty_like(q)
-    cfg = N.AttnCfg(b, heads, 64, int(kv_len), k.shape[1], float(temperature))
+        out = torch.empty((b, d), dtype=torch.float32, device=q.device)
+    cfg = N.AttnCfg(b, heads, 64, int(kv_len), k.shape[1], float(temperature), int(q.stride(0)) if b > 1 else d,
+                    (int(k_new.stride(0)) if b > 1 else d) if k_new is not None else 0)
     with torch.cuda.device(q.device):
-        N.check(N.lib().tpspp_attn_decode(ctypes.byref(cfg), _ptr(q), _ptr(k), _ptr(v), _ptr(kv_lens), _ptr(out), _stream(q)),
-                "tpspp_attn_decode")
+        N.check(N.lib().tpspp_attn_decode(ctypes.byref(cfg), _ptr(q), _ptr(k), _ptr(v), _ptr(kv_lens), _ptr(k_new), _ptr(v_new),
+                                          _ptr(out), _stream(q)), "tpspp_attn_decode")
     return out

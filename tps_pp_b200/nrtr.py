@@ -220,14 +220,14 @@ class NRTRDecoder(_BaseModule):
             for li, lyr in enumerate(self.layer_stack):
                 ops = lin[li]
                 qkv = ops["qkv"](lyr.norm1(x))
-                k_cache[li][:, step] = qkv[:n, d:2 * d]
-                v_cache[li][:, step] = qkv[:n, 2 * d:]
-                TF.attn_decode(qkv[:n, :d].contiguous(), k_cache[li], v_cache[li], self.n_head, step + 1, temp, out=att[:n])
-                x = x + ops["fc"](att)
+                # q, and this step's k / v rows, are column slices of the fused projection; the kernel appends k / v to the cache
+                TF.attn_decode(qkv[:n, :d], k_cache[li], v_cache[li], self.n_head, step + 1, temp, out=att[:n],
+                               k_new=qkv[:n, d:2 * d], v_new=qkv[:n, 2 * d:])
+                ops["fc"](att, out=x, residual=x)                                   # x += fc(att), in the dense layer's epilogue
                 q = ops["q"](lyr.norm2(x))
                 TF.attn_decode(q[:n], mem_k[li], mem_v[li], self.n_head, t_src, temp, kv_lens=lens, out=att[:n])
-                x = x + ops["efc"](att)
-                x = x + ops["w2"](F.gelu(ops["w1"](lyr.norm3(x))))
+                ops["efc"](att, out=x, residual=x)
+                ops["w2"](ops["w1"](lyr.norm3(x), gelu=True), out=x, residual=x)   # x += w_2(GELU(w_1(LN(x))))
             probs = F.softmax(cls(self.layer_norm(x))[:n, :ncls], dim=-1)
             outputs.append(probs)
             tok = probs.argmax(dim=-1)
