@@ -356,6 +356,7 @@ typedef struct {
   float temperature;                /* d_k ** 0.5 in the reference                                          */
   int32_t q_stride, new_stride;     /* floats between consecutive images' rows of q and of k_new / v_new (0 = heads*64): lets q, k_new,
                                        v_new be column slices of one fused q|k|v projection                                     */
+  int32_t kv_head_major;            /* 0: k / v are [batch, kv_capacity, heads*64]; 1: [batch, heads, kv_capacity, 64] (contiguous per head) */
 } tpspp_attn_cfg;
 /* k_new / v_new (or NULL): this step's key / value rows; the kernel stores them at cache position kv_len - 1 (kv_lens[b] - 1)
  * before it attends, so the caller needs no separate cache-append copy. */

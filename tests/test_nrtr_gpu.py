@@ -41,6 +41,12 @@ def test_attn_decode_vs_torch(native_lib, b, heads, cap, length):
     v2[:, length - 1] = fused[:, 2 * d:]
     assert torch.equal(kc, k2) and torch.equal(vc, v2)
     assert torch.equal(out, TF.attn_decode(fused[:, :d].contiguous(), k2, v2, heads, length, 8.0))
+    # head-major caches [B, heads, capacity, 64]: same arithmetic, contiguous per (image, head)
+    kh = k.view(b, cap, heads, 64).permute(0, 2, 1, 3).contiguous()
+    vh = v.view(b, cap, heads, 64).permute(0, 2, 1, 3).contiguous()
+    outh = TF.attn_decode(fused[:, :d], kh, vh, heads, length, 8.0, k_new=fused[:, d:2 * d], v_new=fused[:, 2 * d:], head_major=True)
+    assert torch.equal(outh, out)
+    assert torch.equal(kh.permute(0, 2, 1, 3).reshape(b, cap, d), k2)
 
 
 def test_nrtr_decoder_native_decode_vs_reference_golden(native_lib, golden):

@@ -60,7 +60,7 @@ LP_COUNT = 24
 class AttnCfg(Structure):
     """Mirror of ``tpspp_attn_cfg`` (include/tpspp.h)."""
     _fields_ = [("batch", c_int32), ("heads", c_int32), ("head_dim", c_int32), ("kv_len", c_int32), ("kv_capacity", c_int32),
-                ("temperature", c_float), ("q_stride", c_int32), ("new_stride", c_int32)]
+                ("temperature", c_float), ("q_stride", c_int32), ("new_stride", c_int32), ("kv_head_major", c_int32)]
 
 
 class LinearCfg(Structure):

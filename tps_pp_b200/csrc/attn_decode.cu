@@ -3,10 +3,11 @@
 // common/modules/transformer_module.py:24-34,74-98) when the greedy decode keeps the keys / values of earlier positions instead
 // of recomputing the whole prefix each step.
 //   out[b, h, :] = sum_t softmax_t((q[b,h,:] / temperature) . K[b,t,h,:]) V[b,t,h,:],   t < len(b)
-// q / out: [B, heads * 64] row-major; K / V: [B, capacity, heads * 64] (the self-attention cache, or the projected encoder
-// memory for enc_attn); len(b) = kv_len, or kv_lens[b] (the reference's valid_ratio source mask, nrtr_decoder.py:111-123).
-// One CTA per (image, head): four warps take every fourth key (lane = two of the 64 head dimensions, shuffle-reduced dot
-// product, online softmax in fp32), their partial (max, sum, accumulator) triples are merged through shared memory.
+// q / out: [B, heads * 64] row-major; K / V: [B, capacity, heads * 64], or head-major [B, heads, capacity, 64]
+// (cfg.kv_head_major) -- the self-attention cache, or the projected encoder memory for enc_attn; len(b) = kv_len, or kv_lens[b] (the reference's valid_ratio source mask, nrtr_decoder.py:111-123).
+// One CTA per (image, head): four warps stride the keys in groups of four (lane = two of the 64 head dimensions,
+// shuffle-reduced dot products, online softmax in fp32), their partial (max, sum, accumulator) triples are merged through
+// shared memory.
 #include "common.cuh"
 
 namespace tpspp {
@@ -17,7 +18,7 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float*
                                                                    float* __restrict__ out, const int* __restrict__ kv_lens, int kv_len,
                                                                    int capacity, int heads, float inv_temperature, int q_stride,
                                                                    const float* __restrict__ k_new, const float* __restrict__ v_new,
-                                                                   int new_stride) {
+                                                                   int new_stride, int head_major) {
   const int b = blockIdx.x, h = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = heads * AD_DIM;
   int len = kv_lens != nullptr ? kv_lens[b] : kv_len;
@@ -26,7 +27,8 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float*
     // append: this step's key / value rows (e.g. slices of a fused q|k|v projection) become cache position len - 1.  A CTA
     // touches only its own (image, head) slice, so the write needs no ordering against other CTAs.
     if (warp == 0) {
-      const size_t dst = ((size_t)b * capacity + (len - 1)) * D + h * AD_DIM + 2 * lane;
+      const size_t dst = head_major ? (((size_t)b * heads + h) * capacity + (len - 1)) * AD_DIM + 2 * lane
+                                    : ((size_t)b * capacity + (len - 1)) * D + h * AD_DIM + 2 * lane;
       const size_t src = (size_t)b * new_stride + h * AD_DIM + 2 * lane;
       *reinterpret_cast<float2*>(k + dst) = *reinterpret_cast<const float2*>(k_new + src);
       *reinterpret_cast<float2*>(v + dst) = *reinterpret_cast<const float2*>(v_new + src);
@@ -35,21 +37,42 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float*
   }
   const float2 qv = *reinterpret_cast<const float2*>(q + (size_t)b * q_stride + h * AD_DIM + 2 * lane);
   const float q0 = qv.x * inv_temperature, q1 = qv.y * inv_temperature;       // the reference scales q, then multiplies
-  const float* kb = k + (size_t)b * capacity * D + h * AD_DIM + 2 * lane;
-  const float* vb = v + (size_t)b * capacity * D + h * AD_DIM + 2 * lane;
+  // key t of this (image, head): head_major [B, heads, capacity, 64] -- one contiguous 256-byte row per key, 16 KB per CTA for
+  // 64 keys (the [B, capacity, heads*64] layout interleaves the eight heads: 256-byte pieces 2 KB apart)
+  const size_t tstride = head_major ? AD_DIM : D;
+  const size_t base = head_major ? ((size_t)b * heads + h) * capacity * AD_DIM + 2 * lane : (size_t)b * capacity * D + h * AD_DIM + 2 * lane;
+  const float* kb = k + base;
+  const float* vb = v + base;
   float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
-  for (int t = warp; t < len; t += AD_WARPS) {
-    const float2 kv = *reinterpret_cast<const float2*>(kb + (size_t)t * D);      // (plain loads: the cache may just have been appended to)
-    float s = q0 * kv.x + q1 * kv.y;
+  // four keys per warp step: their key / value rows are loaded together and the four shuffle reductions interleave (one key
+  // per step left a warp waiting on one 256-byte load and five dependent shuffles at a time: 16 us per call at B = 256)
+  constexpr int U = 4;
+  for (int t0 = warp * U; t0 < len; t0 += AD_WARPS * U) {
+    float2 kv[U], vv[U];
+    float s[U];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mn = fmaxf(m, s);
-    const float c = __expf(m - mn), p = __expf(s - mn);        // m = -inf on the first key: c = 0
-    const float2 vv = *reinterpret_cast<const float2*>(vb + (size_t)t * D);
-    l = l * c + p;
-    a0 = a0 * c + p * vv.x;
-    a1 = a1 * c + p * vv.y;
-    m = mn;
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u < len ? t0 + u : len - 1;                 // clamp: a valid row is loaded, its score is masked below
+      kv[u] = *reinterpret_cast<const float2*>(kb + (size_t)t * tstride);      // (plain loads: the cache may just have been appended to)
+      vv[u] = *reinterpret_cast<const float2*>(vb + (size_t)t * tstride);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) s[u] = q0 * kv[u].x + q1 * kv[u].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (t0 + u < len) {
+        const float mn = fmaxf(m, s[u]);
+        const float c = __expf(m - mn), p = __expf(s[u] - mn);          // m = -inf on the first key: c = 0
+        l = l * c + p;
+        a0 = a0 * c + p * vv[u].x;
+        a1 = a1 * c + p * vv[u].y;
+        m = mn;
+      }
+    }
   }
   __shared__ float sm[AD_WARPS], sl[AD_WARPS], sa[AD_WARPS][AD_DIM];
   if (lane == 0) { sm[warp] = m; sl[warp] = l; }
@@ -93,7 +116,8 @@ extern "C" int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, floa
   TPSPP_REQUIRE(qs >= D && ns >= D && qs % 2 == 0 && ns % 2 == 0, "tpspp_attn_decode: row strides must be even and >= heads * 64");
   TPSPP_REQUIRE((k_new == nullptr) == (v_new == nullptr), "tpspp_attn_decode: k_new and v_new come together");
   attn_decode_kernel<<<dim3(cfg->batch, cfg->heads), AD_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      q, k, v, out, kv_lens, cfg->kv_len, cfg->kv_capacity, cfg->heads, 1.f / cfg->temperature, qs, k_new, v_new, ns);
+      q, k, v, out, kv_lens, cfg->kv_len, cfg->kv_capacity, cfg->heads, 1.f / cfg->temperature, qs, k_new, v_new, ns,
+      cfg->kv_head_major != 0);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;

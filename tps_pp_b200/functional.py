@@ -588,9 +588,9 @@ class PreparedLinear:
 
 def attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kv_len: int, temperature: float,
                 kv_lens: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None) -> torch.Tensor:
+                k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None, head_major: bool = False) -> torch.Tensor:
     """Single-query multi-head attention over a key/value cache (``tpspp_attn_decode``): q [B, heads*64], k / v
-    [B, capacity, heads*64] -> [B, heads*64]; keys ``t < kv_len`` (or ``kv_lens[b]``, int32 on the device).  ``k_new`` / ``v_new``
+    [B, capacity, heads*64] (or, with ``head_major``, [B, heads, capacity, 64]) -> [B, heads*64]; keys ``t < kv_len`` (or ``kv_lens[b]``, int32 on the device).  ``k_new`` / ``v_new``
     [B, heads*64]: this step's rows, stored at cache position ``kv_len - 1`` by the kernel before it attends.  ``q`` / ``k_new`` /
     ``v_new`` may be column slices of one fused projection (unit stride along the features).  Forward only."""
     for nm, t in (("k", k), ("v", v)):
@@ -604,14 +604,17 @@ def attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, k
             raise RuntimeError(f"tps_pp_b200: attn_decode `{nm}` must be [B, heads*64] with unit stride along the features")
     if (k_new is None) != (v_new is None) or (k_new is not None and k_new.stride(0) != v_new.stride(0)):
         raise RuntimeError("tps_pp_b200: attn_decode k_new / v_new come together, with the same row stride")
-    if d != heads * 64 or k.shape[0] != b or k.shape[2] != d or v.shape != k.shape:
-        raise RuntimeError(f"tps_pp_b200: attn_decode shapes q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} heads {heads}")
+    want = (b, heads, k.shape[2] if k.dim() == 4 else 0, 64) if head_major else (b, k.shape[1], d)
+    if d != heads * 64 or tuple(k.shape) != want or v.shape != k.shape:
+        raise RuntimeError(f"tps_pp_b200: attn_decode shapes q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} heads {heads} "
+                           f"(head_major={head_major})")
     if kv_lens is not None and (kv_lens.dtype != torch.int32 or not kv_lens.is_cuda or kv_lens.numel() != b):
         raise RuntimeError("tps_pp_b200: kv_lens must be an int32 CUDA tensor with one entry per image")
     if out is None:
         out = torch.empty((b, d), dtype=torch.float32, device=q.device)
-    cfg = N.AttnCfg(b, heads, 64, int(kv_len), k.shape[1], float(temperature), int(q.stride(0)) if b > 1 else d,
-                    (int(k_new.stride(0)) if b > 1 else d) if k_new is not None else 0)
+    cfg = N.AttnCfg(b, heads, 64, int(kv_len), k.shape[2] if head_major else k.shape[1], float(temperature),
+                    int(q.stride(0)) if b > 1 else d, (int(k_new.stride(0)) if b > 1 else d) if k_new is not None else 0,
+                    1 if head_major else 0)
     with torch.cuda.device(q.device):
         N.check(N.lib().tpspp_attn_decode(ctypes.byref(cfg), _ptr(q), _ptr(k), _ptr(v), _ptr(kv_lens), _ptr(k_new), _ptr(v_new),
                                           _ptr(out), _stream(q)), "tpspp_attn_decode")

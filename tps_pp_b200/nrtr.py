@@ -189,8 +189,9 @@ class NRTRDecoder(_BaseModule):
             ea, sa = lyr.enc_attn, lyr.self_attn
             kv = TF.linear(mem, torch.cat([ea.linear_k.weight, ea.linear_v.weight], 0),
                            None if ea.linear_k.bias is None else torch.cat([ea.linear_k.bias, ea.linear_v.bias], 0))
-            mem_k.append(kv[: n * t_src, :d].reshape(n, t_src, d).contiguous())
-            mem_v.append(kv[: n * t_src, d:].reshape(n, t_src, d).contiguous())
+            # head-major [n, heads, t_src, 64]: every (image, head) attention CTA then reads one contiguous block
+            mem_k.append(kv[: n * t_src, :d].reshape(n, t_src, self.n_head, 64).permute(0, 2, 1, 3).contiguous())
+            mem_v.append(kv[: n * t_src, d:].reshape(n, t_src, self.n_head, 64).permute(0, 2, 1, 3).contiguous())
             # the layer's six dense operators with their operand images laid out once per decode (not once per step)
             lin.append(dict(
                 qkv=TF.PreparedLinear(torch.cat([sa.linear_q.weight, sa.linear_k.weight, sa.linear_v.weight], 0),
@@ -208,8 +209,8 @@ class NRTRDecoder(_BaseModule):
         bc[:ncls] = self.classifier.bias
         cls = TF.PreparedLinear(wc, bc, rows)
         cap = self.max_seq_len
-        k_cache = [torch.zeros((n, cap, d), dtype=torch.float32, device=dev) for _ in self.layer_stack]
-        v_cache = [torch.zeros((n, cap, d), dtype=torch.float32, device=dev) for _ in self.layer_stack]
+        k_cache = [torch.zeros((n, self.n_head, cap, 64), dtype=torch.float32, device=dev) for _ in self.layer_stack]
+        v_cache = [torch.zeros((n, self.n_head, cap, 64), dtype=torch.float32, device=dev) for _ in self.layer_stack]
         tok = torch.full((n,), self.start_idx, dtype=torch.long, device=dev)
         x = torch.zeros((rows, d), dtype=torch.float32, device=dev)
         att = torch.zeros((rows, d), dtype=torch.float32, device=dev)
@@ -222,10 +223,10 @@ class NRTRDecoder(_BaseModule):
                 qkv = ops["qkv"](lyr.norm1(x))
                 # q, and this step's k / v rows, are column slices of the fused projection; the kernel appends k / v to the cache
                 TF.attn_decode(qkv[:n, :d], k_cache[li], v_cache[li], self.n_head, step + 1, temp, out=att[:n],
-                               k_new=qkv[:n, d:2 * d], v_new=qkv[:n, 2 * d:])
+                               k_new=qkv[:n, d:2 * d], v_new=qkv[:n, 2 * d:], head_major=True)
                 ops["fc"](att, out=x, residual=x)                                   # x += fc(att), in the dense layer's epilogue
                 q = ops["q"](lyr.norm2(x))
-                TF.attn_decode(q[:n], mem_k[li], mem_v[li], self.n_head, t_src, temp, kv_lens=lens, out=att[:n])
+                TF.attn_decode(q[:n], mem_k[li], mem_v[li], self.n_head, t_src, temp, kv_lens=lens, out=att[:n], head_major=True)
                 ops["efc"](att, out=x, residual=x)
                 ops["w2"](ops["w1"](lyr.norm3(x), gelu=True), out=x, residual=x)   # x += w_2(GELU(w_1(LN(x))))
             probs = F.softmax(cls(self.layer_norm(x))[:n, :ncls], dim=-1)
