@@ -513,6 +513,37 @@ def run_ours(args):
                          "stage_gflop_per_img": STAGE_GFLOP_PER_IMG}
         else:
             e2e_obj, image_obj = feature_e2e, None
+        # SURVEY 8f rank 2 / BASELINE configs[4] "+ NRTR inference": the recogniser's greedy decode behind the rectifier, as the
+        # native incremental decode (tps_pp_b200.NRTRDecoder.forward_test) and as the reference's full-prefix recompute on
+        # torch / cuBLAS fp32 ops -- same module, same random-init weights, same batch as the headline line; outside the timed region
+        nrtr_obj = None
+        if world == 1 and args.head == "tc" and not args.no_cpu_baseline:
+            try:
+                torch.manual_seed(0)
+                dec = T.NRTRDecoder().to(dev).eval()
+                enc = torch.randn((B, 64, 512), device=dev)         # 4 x 16 feature map of a 32 x 128 image after layer5
+
+                def _time(fn, n_it):
+                    fn(); fn()
+                    torch.cuda.synchronize()
+                    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    q0.record()
+                    for _ in range(n_it):
+                        out_ = fn()
+                    q1.record()
+                    torch.cuda.synchronize()
+                    return q0.elapsed_time(q1) / n_it, out_
+                with torch.no_grad():
+                    nat_ms, p_nat = _time(lambda: dec.forward_test(None, enc, None), 5)
+                    lib_ms, p_lib = _time(lambda: dec.forward_test_library(None, enc, None), 1)
+                nrtr_obj = {"what": "NRTRDecoder greedy decode, 6 layers x 512 x 8 heads, 40 steps, 64 source tokens, batch %d" % B,
+                            "native_ms": nat_ms, "native_img_per_s": B / (nat_ms * 1e-3),
+                            "reference_algorithm_on_cublas_fp32_ms": lib_ms, "speedup": lib_ms / nat_ms,
+                            "argmax_agreement": float((p_nat.argmax(-1) == p_lib.argmax(-1)).float().mean()),
+                            "native_path": "KV-cache incremental decode: tpspp_linear_fwd_ex (tcgen05 3xTF32, split-K) + tpspp_attn_decode, one CUDA graph"}
+                del dec, enc, p_nat, p_lib
+            except Exception as e:  # noqa: BLE001 -- a secondary figure must not take the headline line down
+                nrtr_obj = {"error": f"{type(e).__name__}: {e}"}
         line = {
             "metric": "tps_pp_rectified_img_per_s", "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -549,6 +580,7 @@ def run_ours(args):
             "e2e": e2e_obj,
             "e2e_feature_boundary": feature_e2e,
             "from_image": image_obj,
+            "nrtr_decode": nrtr_obj,
             "gpu_launches": launches, "clocks": clocks, "host_affinity": host_affinity,
         }
         print(json.dumps(line), flush=True)
