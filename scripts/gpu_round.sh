@@ -13,6 +13,10 @@ echo "== bench global batch 2048 (configs[4] shard at N=1)"; timeout 900 python 
 echo "== training step (native, CUDA graph) + per-kernel table; library arm"
 timeout 600 python scripts/train_step_bench.py --profile 2>&1 | grep -v Warning | tail -75 > gpurun_out/train_kernels.txt; tail -1 gpurun_out/train_kernels.txt > gpurun_out/train_native.json
 timeout 600 python scripts/train_step_bench.py --library-convs 2>&1 | tail -1 > gpurun_out/train_library.json
+echo "== NRTR greedy decode (native incremental decode vs the reference's algorithm on cuBLAS fp32)"
+timeout 600 python scripts/nrtr_decode_bench.py 256 64 2>&1 | tail -1 > gpurun_out/nrtr_decode.json
+timeout 600 python scripts/nrtr_decode_bench.py 1024 64 2>&1 | tail -1 > gpurun_out/nrtr_decode_b1024.json
+echo "== warp backward per kernel"; timeout 300 python scripts/warp_bwd_profile.py 2>&1 | grep -v Warn | tail -8 > gpurun_out/warp_bwd_kernels.txt
 echo "== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
