@@ -1,4 +1,5 @@
 // Host-side plumbing of the C ABI: error string, launch counter, device info, cfg validation.
+#include <stdlib.h>
 #include "common.cuh"
 
 #include <string.h>
@@ -7,6 +8,7 @@ namespace tpspp {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
+static thread_local bool g_pdl = false;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -42,6 +44,12 @@ void count_launch(int n) {
   if (g_prof_on && g_prof_n > 0) prof_record();
 }
 void reset_launch_count() { g_launches = 0; }
+static bool pdl_env() {
+  static const bool on = [] { const char* e = getenv("TPSPP_PDL"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
+bool pdl_on() { return g_pdl && !g_prof_on; }      // per-launch timing (events between launches) wants the grids serialised
+void pdl_scope(bool on) { g_pdl = on && pdl_env(); }
 
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;

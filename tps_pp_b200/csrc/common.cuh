@@ -20,6 +20,32 @@ void count_launch(int n = 1);
 void prof_begin(cudaStream_t st);      // no-op unless tpspp_launch_profile(1) was called on this thread
 void reset_launch_count();
 int sm_count();
+// Programmatic dependent launch along one ABI call's kernel chain (tpspp_head_fwd, tpspp_stage_fwd): while pdl_scope is
+// on, launch_k() sets cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs are scheduled, run their
+// prologue (barrier init, TMEM allocation) and park in pdl_wait() while the previous grid drains.  Only kernels whose every
+// CTA executes pdl_wait() before it touches activations may be launched through launch_k (a grid that completes without
+// having waited would break the chain's transitivity); TMEM kernels call pdl_trigger() only AFTER their own allocation, so a
+// parked dependent can never hold the columns a still-unallocated CTA of the grid it waits for needs.  TPSPP_PDL=0 turns it off.
+bool pdl_on();
+void pdl_scope(bool on);
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_on() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 #define TPSPP_CHECK_CUDA(expr)                                                        \
   do {                                                                                \

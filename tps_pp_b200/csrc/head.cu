@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(256) cbam_kernel(const float* __restrict__ x, 
                                                     const float* __restrict__ w0, const float* __restrict__ w2,
                                                     const float* __restrict__ spw, const float* __restrict__ spb,
                                                     int py, int px) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float xs[64][65];
   __shared__ float avg[64], mxv[64], hid[2][4], gate[64];
   __shared__ float spm[2][66];   // [mean|max][p]
@@ -256,6 +258,8 @@ struct LocArgs {
 };
 
 __global__ void __launch_bounds__(256) loc_p1_kernel(LocArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int F = a.F, b = blockIdx.x, tid = threadIdx.x;
   float* en = sm;                 // [F][65]
@@ -408,6 +412,8 @@ constexpr int DG_MAXH = 32;
 constexpr int DW_WARPS = 16;
 template <int H>
 __global__ void __launch_bounds__(DW_WARPS * 32, 1) dgab_warp_kernel(DgabArgs a, int nplanes) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float dsm[];
   constexpr int n = H * 64, E = 2 * H;             // E elements per lane: idx = lane + 32 i  ->  h = i >> 1, w = lane + 32 (i & 1)
   const int F = a.F, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -953,6 +959,7 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   rc = head_attrs_once();
   if (rc != TPSPP_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  struct PdlScope { PdlScope(bool on) { pdl_scope(on); } ~PdlScope() { pdl_scope(false); } } pdl_guard(cfg->precision != TPSPP_HEAD_FP32);
   size_t off[TPSPP_WS_COUNT], total;
   head_offsets(d, off, &total);
   auto W = [&](int i) { return reinterpret_cast<float*>((char*)workspace + off[i]); };
@@ -1027,8 +1034,8 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
   RUN(3, mk_src(W(TPSPP_WS_E1), 64, d.h1, d.w1, NCHW), none, none, P[TPSPP_P_ENC2_W], P[TPSPP_P_ENC2_B], nullptr, W(TPSPP_WS_E2), NCHW, B, d.h2, d.w2, d.ps, d.ps, st, wp[8], cmode[8]);
   RUN(3, mk_src(W(TPSPP_WS_E2), 64, d.h2, d.w2, NCHW), none, none, P[TPSPP_P_ENC3_W], P[TPSPP_P_ENC3_B], nullptr, W(TPSPP_WS_E3), NCHW, B, d.py, d.px, 2, 1, st, wp[9], cmode[9]);
   // CBAM on the deepest map (tps_pp.py:163)
-  cbam_kernel<<<B, 256, 0, st>>>(W(TPSPP_WS_E3), W(TPSPP_WS_CBAM), P[TPSPP_P_CBAM_MLP0_W], P[TPSPP_P_CBAM_MLP2_W],
-                                 P[TPSPP_P_CBAM_SP_W], P[TPSPP_P_CBAM_SP_B], d.py, d.px);
+  launch_k(cbam_kernel, dim3(B), dim3(256), 0, st, (const float*)W(TPSPP_WS_E3), W(TPSPP_WS_CBAM), P[TPSPP_P_CBAM_MLP0_W], P[TPSPP_P_CBAM_MLP2_W],
+           P[TPSPP_P_CBAM_SP_W], P[TPSPP_P_CBAM_SP_B], d.py, d.px);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   // decoder (tps_pp.py:165-168): upsample + conv + skip
@@ -1047,7 +1054,7 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
     a.c_prime = c_prime; a.p1 = W(TPSPP_WS_P1); a.F = d.F;
     a.p1img = (tc && d.F == 32) ? W(TPSPP_WS_P1IMG) : nullptr;
     const size_t smem = (size_t)(d.F * 65 + d.F * 256 + 2 * d.F + d.F * 33) * sizeof(float);
-    loc_p1_kernel<<<B, 256, smem, st>>>(a);
+    launch_k(loc_p1_kernel, dim3(B), dim3(256), smem, st, a);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
   }
@@ -1065,7 +1072,7 @@ extern "C" int tpspp_head_fwd(const tpspp_head_cfg* cfg, const float* x, const f
       TPSPP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int grid = sm_count();
       if (grid > (B * 64 + DW_WARPS - 1) / DW_WARPS) grid = (B * 64 + DW_WARPS - 1) / DW_WARPS;
-      kern<<<grid, DW_WARPS * 32, smem, st>>>(a, B * 64);
+      launch_k(kern, dim3(grid), dim3(DW_WARPS * 32), smem, st, a, B * 64);
     }
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());

@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(ConvTcArgs t) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_trigger();          // this CTA holds its tensor memory: the next grid of the chain may be scheduled behind it
+  pdl_wait();             // ... and nothing below runs before the previous grid has completed (no-op in a plain launch)
 
   const int HoWo = a.Ho * a.Wo;
   const long long Mtot = (long long)a.B * HoWo;
@@ -456,6 +458,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_ts_kernel(ConvTcArgs t) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_trigger();          // this CTA holds its tensor memory: the next grid of the chain may be scheduled behind it
+  pdl_wait();             // ... and nothing below runs before the previous grid has completed (no-op in a plain launch)
 
   const int HoWo = a.Ho * a.Wo;
   const long long Mtot = (long long)a.B * HoWo;
@@ -774,6 +778,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_trigger();          // this CTA holds its tensor memory: the next grid of the chain may be scheduled behind it
+  pdl_wait();             // ... and nothing below runs before the previous grid has completed (no-op in a plain launch)
 
   const int HoWo = a.Ho * a.Wo;
   const int ntiles = (int)(((long long)a.B * HoWo) / TC_TM);
@@ -1296,6 +1302,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) lin_tma_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_trigger();          // this CTA holds its tensor memory: the next grid of the chain may be scheduled behind it
+  pdl_wait();             // ... and nothing below runs before the previous grid has completed (no-op in a plain launch)
 
   const long long R = (long long)a.B * a.Ho * a.Wo;
   const int ntiles = (int)(R / TC_TM);
@@ -1524,6 +1532,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_trigger();          // this CTA holds its tensor memory: the next grid of the chain may be scheduled behind it
+  pdl_wait();             // ... and nothing below runs before the previous grid has completed (no-op in a plain launch)
   const int ntiles = (int)(g.R / TC_TM);
   const int n_my = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   constexpr uint32_t IDESC = umma_instr_desc(TC_TM, NT, 2);
@@ -1816,6 +1826,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) down_fused_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_trigger();          // this CTA holds its tensor memory: the next grid of the chain may be scheduled behind it
+  pdl_wait();             // ... and nothing below runs before the previous grid has completed (no-op in a plain launch)
   const int tiles_per_img = g.h * 2;
   const int ntiles = g.B * tiles_per_img;
   const int n_my = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -2175,6 +2187,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) score_fused_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_trigger();          // this CTA holds its tensor memory: the next grid of the chain may be scheduled behind it
+  pdl_wait();             // ... and nothing below runs before the previous grid has completed (no-op in a plain launch)
   const int tiles_per_img = g.h / 2;
   const int ntiles = g.B * tiles_per_img;
   const int n_my = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -2510,7 +2524,7 @@ int run_mlp_fused(const float* v, const float* x1, const float* w1img, const flo
   }
   const long long ntiles = R / TC_TM;
   dim3 grid((unsigned)min(ntiles, (long long)sm_count()));
-  mlp_fused_kernel<<<grid, MF_THREADS, MF_SMEM, st>>>(g);
+  launch_k(mlp_fused_kernel, grid, dim3(MF_THREADS), MF_SMEM, st, g);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;
@@ -2553,7 +2567,7 @@ int run_down_fused(const float* x, const float* o0, const float* o1, const float
   }
   const long long ntiles = (long long)B * h * 2;
   dim3 grid((unsigned)min(ntiles, (long long)sm_count()));
-  down_fused_kernel<<<grid, DF_THREADS, DF_SMEM, st>>>(g);
+  launch_k(down_fused_kernel, grid, dim3(DF_THREADS), DF_SMEM, st, g);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;
@@ -2581,7 +2595,7 @@ int run_score_fused(const float* de2, const float* w0img, const float* w1img, co
   }
   const long long ntiles = (long long)B * (h / 2);
   dim3 grid((unsigned)min(ntiles, (long long)sm_count()));
-  score_fused_kernel<<<grid, SF_THREADS, SF_SMEM, st>>>(g);
+  launch_k(score_fused_kernel, grid, dim3(SF_THREADS), SF_SMEM, st, g);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;
@@ -2625,15 +2639,15 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
       dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()));
       if (NT == 32) {       // 32-channel layers of the backbone stage: half the weight bytes and half the B-operand reads per chunk
         TPSPP_REQUIRE((KS == 1 && mode == CM_TF32X3) || (KS == 3 && mode == CM_MIX), "conv_tc: the 32-column tile exists for 1x1/3xTF32 and 3x3/mixed only");
-        if (KS == 1) conv_tma_kernel<1, CM_TF32X3, 32><<<pgrid, TM_THREADS, tm_smem_bytes(1), st>>>(g);
-        else conv_tma_kernel<3, CM_MIX, 32><<<pgrid, TM_THREADS, tm_smem_bytes(3), st>>>(g);
+        if (KS == 1) launch_k(conv_tma_kernel<1, CM_TF32X3, 32>, pgrid, dim3(TM_THREADS), tm_smem_bytes(1), st, g);
+        else launch_k(conv_tma_kernel<3, CM_MIX, 32>, pgrid, dim3(TM_THREADS), tm_smem_bytes(3), st, g);
         count_launch();
         TPSPP_CHECK_CUDA(cudaGetLastError());
         return TPSPP_OK;
       }
       auto kern = KS == 1 ? (mode == CM_BF16 ? conv_tma_kernel<1, CM_BF16> : mode == CM_MIX ? conv_tma_kernel<1, CM_MIX> : conv_tma_kernel<1, CM_TF32X3>)
                           : (mode == CM_BF16 ? conv_tma_kernel<3, CM_BF16> : mode == CM_MIX ? conv_tma_kernel<3, CM_MIX> : conv_tma_kernel<3, CM_TF32X3>);
-      kern<<<pgrid, TM_THREADS, tm_smem_bytes(KS), st>>>(g);
+      launch_k(kern, pgrid, dim3(TM_THREADS), tm_smem_bytes(KS), st, g);
       count_launch();
       TPSPP_CHECK_CUDA(cudaGetLastError());
       return TPSPP_OK;
@@ -2652,7 +2666,7 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
     }
     auto kern = KS == 1 ? (mode == CM_BF16 ? conv_ts_kernel<1, CM_BF16> : mode == CM_MIX ? conv_ts_kernel<1, CM_MIX> : conv_ts_kernel<1, CM_TF32X3>)
                         : (mode == CM_BF16 ? conv_ts_kernel<3, CM_BF16> : mode == CM_MIX ? conv_ts_kernel<3, CM_MIX> : conv_ts_kernel<3, CM_TF32X3>);
-    kern<<<grid, TC_THREADS, TS_SMEM, st>>>(t);
+    launch_k(kern, grid, dim3(TC_THREADS), TS_SMEM, st, t);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
     return TPSPP_OK;

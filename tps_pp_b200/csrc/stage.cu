@@ -44,6 +44,8 @@ struct StemArgs {
   int B, H, W;
 };
 __global__ void __launch_bounds__(256) stem_kernel(StemArgs a) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float ws[27 * 32];      // [k = cin*9 + tap][cout]
   __shared__ __align__(16) float bs[32];
   for (int i = threadIdx.x; i < 27 * 32; i += 256) {
@@ -166,6 +168,7 @@ extern "C" int tpspp_stage_fwd(const tpspp_stage_cfg* cfg, const float* img, con
     TPSPP_REQUIRE(((uintptr_t)P[i] & 3) == 0, "tpspp_stage_fwd: params[%d] is not a float pointer", i);
   }
   cudaStream_t st = (cudaStream_t)stream;
+  struct PdlScope { PdlScope() { pdl_scope(true); } ~PdlScope() { pdl_scope(false); } } pdl_guard;
   size_t off[SW_COUNT], total;
   stage_offsets(d, off, &total);
   auto W = [&](int i) { return reinterpret_cast<float*>((char*)workspace + off[i]); };
@@ -207,7 +210,7 @@ extern "C" int tpspp_stage_fwd(const tpspp_stage_cfg* cfg, const float* img, con
     const long long total_px = (long long)d.B * d.H * d.W;
     long long blocks = (total_px + 255) / 256;
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
-    stem_kernel<<<(unsigned)blocks, 256, 0, st>>>(sa);
+    launch_k(stem_kernel, dim3((unsigned)blocks), dim3(256), 0, st, sa);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
   }

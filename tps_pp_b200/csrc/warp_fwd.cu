@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(ST_THREADS, 2) warp_fwd_staged_kernel(StagedAr
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_trigger();          // chained behind the head's last kernel (programmatic dependent launch, common.cuh): barriers are
+  pdl_wait();             // set up while that grid drains; no-op in a plain launch
 
   if (warp == ST_CONSUMER_WARPS) {
     // ===== producer: one lane streams whole planes through the ring =====
@@ -315,7 +317,9 @@ static int launch_staged(const tpspp_warp_cfg* cfg, const WarpParams& p, cudaStr
   }
   int grid = sm_count() * ctas_per_sm;
   if (grid > a.planes_total) grid = a.planes_total;
-  kern<<<grid, ST_THREADS, smem, stream>>>(a);
+  pdl_scope(true);
+  launch_k(kern, dim3(grid), dim3(ST_THREADS), smem, stream, a);
+  pdl_scope(false);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;
