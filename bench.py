@@ -540,7 +540,7 @@ def run_ours(args):
                             "native_ms": nat_ms, "native_img_per_s": B / (nat_ms * 1e-3),
                             "reference_algorithm_on_cublas_fp32_ms": lib_ms, "speedup": lib_ms / nat_ms,
                             "argmax_agreement": float((p_nat.argmax(-1) == p_lib.argmax(-1)).float().mean()),
-                            "native_path": "KV-cache incremental decode: tpspp_linear_fwd_ex (tcgen05 3xTF32, split-K) + tpspp_attn_decode, one CUDA graph"}
+                            "native_path": "KV-cache incremental decode: tpspp_linear_ln_fwd (tcgen05 3xTF32, split-K, residual / GELU / next LayerNorm in the epilogue) + tpspp_attn_decode, one CUDA graph"}
                 del dec, enc, p_nat, p_lib
             except Exception as e:  # noqa: BLE001 -- a secondary figure must not take the headline line down
                 nrtr_obj = {"error": f"{type(e).__name__}: {e}"}

@@ -333,6 +333,13 @@ TPSPP_API int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, cons
 enum { TPSPP_ACT_NONE = 0, TPSPP_ACT_GELU = 1 };
 TPSPP_API int tpspp_linear_fwd_ex(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias, const float* residual,
                                   int32_t act, float* y, void* workspace, tpspp_stream_t stream);
+/* ... and with the NEXT sub-layer's LayerNorm attached (a pre-norm transformer layer, nrtr_decoder.py / tf_layers: x = x + f(.)
+ * is followed at once by LN(x)): y as above, y_ln = LayerNorm(y; ln_weight, ln_bias or NULL, ln_eps) [rows, out] -- computed by the
+ * kernel that finishes y (the split-K reduction), one warp per row.  y_ln == NULL: exactly tpspp_linear_fwd_ex.  With y_ln:
+ * act must be TPSPP_ACT_NONE, out_features % 128 == 0 and <= 1024, y_ln must not alias x / y / residual, 16-byte aligned pointers. */
+TPSPP_API int tpspp_linear_ln_fwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias, const float* residual,
+                                  int32_t act, float* y, const float* ln_weight, const float* ln_bias, float ln_eps, float* y_ln,
+                                  void* workspace, tpspp_stream_t stream);
 /* gx [rows, in] (or NULL), gw [batches, out, in] (or NULL), gb [out] (or NULL; needs gw) from gy [rows, out] */
 TPSPP_API int tpspp_linear_bwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* gy, float* gx,
                                float* gw, float* gb, void* workspace, tpspp_stream_t stream);

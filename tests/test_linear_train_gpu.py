@@ -99,3 +99,39 @@ def test_prepared_linear_residual_gelu(rows, k, n):
         inplace = r.clone()
         op(x, out=inplace, residual=inplace, gelu=gelu)
         assert torch.equal(inplace, y)
+
+
+@pytest.mark.parametrize("rows,k,n", [(256, 512, 512), (1024, 512, 256), (256, 256, 128), (64, 48, 128)],
+                         ids=["split-K", "unsplit", "K=256", "cuda-core"])
+def test_prepared_linear_with_layernorm_output(rows, k, n):
+    """``tpspp_linear_ln_fwd``: y = x w^T + b + residual and LN(y) for the next sub-layer from the kernel that finishes y
+    (split-K reduction, or a warp-per-row pass behind the unsplit kernel); in-place residual; y itself unchanged by the LN."""
+    from tps_pp_b200 import functional as TF
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(7 * rows + k + n)
+    x = torch.randn((rows, k), device=dev, generator=g)
+    w = torch.randn((n, k), device=dev, generator=g) / k ** 0.5
+    b = torch.randn((n,), device=dev, generator=g)
+    r = torch.randn((rows, n), device=dev, generator=g)
+    ln = torch.nn.LayerNorm(n, eps=1e-6).to(dev)
+    with torch.no_grad():
+        ln.weight.copy_(1.0 + 0.1 * torch.randn((n,), device=dev, generator=g))
+        ln.bias.copy_(0.1 * torch.randn((n,), device=dev, generator=g))
+    op = TF.PreparedLinear(w, b, rows)
+    plain = op(x, residual=r)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double()) + r.double()
+    ref_ln = torch.nn.functional.layer_norm(ref, (n,), ln.weight.double(), ln.bias.double(), 1e-6)
+    for _ in range(2):
+        hn = torch.full((rows, n), float("nan"), device=dev)
+        y = op(x, residual=r, ln=ln, ln_out=hn)
+        assert torch.equal(y, plain)                       # same reduction order with or without the LayerNorm output
+        assert _rel(hn, ref_ln) <= 4e-6 * max(1.0, (k / 256) ** 0.5)
+        assert (hn - torch.nn.functional.layer_norm(y, (n,), ln.weight, ln.bias, 1e-6)).abs().max().item() <= 2e-6
+    inplace = r.clone()
+    hn2 = torch.empty_like(hn)
+    op(x, out=inplace, residual=inplace, ln=ln, ln_out=hn2)
+    assert torch.equal(inplace, plain) and torch.equal(hn2, hn)
+    with pytest.raises(RuntimeError):
+        op(x, residual=r, ln=ln, ln_out=None)
+    with pytest.raises(RuntimeError):
+        op(x, residual=r, gelu=True, ln=ln, ln_out=hn)      # LayerNorm output with an activation: rejected by the library

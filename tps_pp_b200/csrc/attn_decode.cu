@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float*
                                                                    int capacity, int heads, float inv_temperature, int q_stride,
                                                                    const float* __restrict__ k_new, const float* __restrict__ v_new,
                                                                    int new_stride, int head_major) {
+  pdl_trigger();          // no-ops in the plain launches the decode uses; they keep the kernel legal behind launch_k
+  pdl_wait();
   const int b = blockIdx.x, h = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = heads * AD_DIM;
   int len = kv_lens != nullptr ? kv_lens[b] : kv_len;
@@ -115,9 +117,10 @@ extern "C" int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, floa
   const int qs = cfg->q_stride > 0 ? cfg->q_stride : D, ns = cfg->new_stride > 0 ? cfg->new_stride : D;
   TPSPP_REQUIRE(qs >= D && ns >= D && qs % 2 == 0 && ns % 2 == 0, "tpspp_attn_decode: row strides must be even and >= heads * 64");
   TPSPP_REQUIRE((k_new == nullptr) == (v_new == nullptr), "tpspp_attn_decode: k_new and v_new come together");
-  attn_decode_kernel<<<dim3(cfg->batch, cfg->heads), AD_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      q, k, v, out, kv_lens, cfg->kv_len, cfg->kv_capacity, cfg->heads, 1.f / cfg->temperature, qs, k_new, v_new, ns,
-      cfg->kv_head_major != 0);
+  // (plain launch: inside the decode's CUDA graph programmatic edges bought nothing at batch 256 and cost 7 % at 1024)
+  launch_k(attn_decode_kernel, dim3(cfg->batch, cfg->heads), dim3(AD_WARPS * 32), 0, (cudaStream_t)stream,
+           q, k, v, out, kv_lens, cfg->kv_len, cfg->kv_capacity, cfg->heads, 1.f / cfg->temperature, qs, k_new, v_new, ns,
+           (int)(cfg->kv_head_major != 0));
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
   return TPSPP_OK;

@@ -2688,8 +2688,8 @@ int run_conv_tc(int KS, const ConvArgs& a, const float* wprep, int NT, cudaStrea
     dim3 pgrid((unsigned)min((long long)grid.x, 2LL * sm_count()), lg.col_split ? (unsigned)(a.Cout / NT) : 1u);
     if (lg.col_split) pgrid.x = (unsigned)min((long long)grid.x, max(1LL, 2LL * sm_count() / pgrid.y));
     if (a.splitk > 1) pgrid.z = (unsigned)a.splitk;
-    if (NT == 64) lin_tma_kernel<64><<<pgrid, TC_THREADS, ln_smem_bytes(), st>>>(lg);
-    else lin_tma_kernel<32><<<pgrid, TC_THREADS, ln_smem_bytes(), st>>>(lg);
+    if (NT == 64) launch_k(lin_tma_kernel<64>, pgrid, dim3(TC_THREADS), ln_smem_bytes(), st, lg);
+    else launch_k(lin_tma_kernel<32>, pgrid, dim3(TC_THREADS), ln_smem_bytes(), st, lg);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
     return TPSPP_OK;

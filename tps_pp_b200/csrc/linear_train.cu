@@ -115,8 +115,11 @@ __device__ __forceinline__ float lin_gelu(float x) { return 0.5f * x * (1.f + er
 __global__ void __launch_bounds__(256) lin_splitk_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ bias,
                                                                 const float4* __restrict__ residual, float4* __restrict__ y,
                                                                 long long total4, int n4, int splits, int gelu) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total4; i += (long long)gridDim.x * 256) {
     float4 acc = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias) + (i % n4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int s = 0; s < splits; ++s) {
       const float4 p = __ldg(part + (size_t)s * total4 + i);
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
@@ -128,6 +131,102 @@ __global__ void __launch_bounds__(256) lin_splitk_reduce_kernel(const float4* __
     }
     y[i] = acc;
   }
+}
+// The same reduction with the NEXT sub-layer's LayerNorm attached (a pre-norm transformer layer reads LN(x) right after
+// x += f(.)): one warp per row keeps the row in registers -- y = sum_s part[s] + bias + residual, y_ln = LN(y) * w + b
+// (two-pass mean / variance in fp32, biased variance like torch).  splits == 0: y is already complete (unsplit linear), LN only.
+constexpr int LRL_WARPS = 4;
+// PER = float4 per lane the row is unrolled for (>= N / 128), SPLITS = partial sums (compile-time: every load of a row --
+// partials, bias, residual, LayerNorm parameters -- is issued before the first add: one L2 round trip instead of one per split)
+template <int PER, int SPLITS>
+__global__ void __launch_bounds__(LRL_WARPS * 32) lin_reduce_ln_kernel(const float4* __restrict__ part, const float* __restrict__ bias,
+                                                                       const float4* __restrict__ residual, float4* __restrict__ y,
+                                                                       const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                                       float eps, float4* __restrict__ y_ln, long long R, int N) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int n4 = N >> 2, per = n4 >> 5;            // float4 per lane (N % 128 == 0)
+  const long long total4 = R * n4;
+  const float inv_n = 1.f / (float)N;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = (long long)blockIdx.x * LRL_WARPS + (threadIdx.x >> 5); r < R; r += (long long)gridDim.x * LRL_WARPS) {
+    const long long i0 = r * n4 + lane;
+    float4 v[PER], w[PER], b[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if (j < per) {
+        w[j] = __ldg(reinterpret_cast<const float4*>(ln_w) + j * 32 + lane);
+        b[j] = ln_b != nullptr ? __ldg(reinterpret_cast<const float4*>(ln_b) + j * 32 + lane) : zero4;
+      }
+    }
+    if (SPLITS > 0) {
+      float4 res[PER], p[SPLITS > 0 ? SPLITS : 1][PER];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        if (j < per) {
+          v[j] = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias) + j * 32 + lane) : zero4;
+          res[j] = residual != nullptr ? residual[i0 + j * 32] : zero4;      // may alias y: read before the write below
+#pragma unroll
+          for (int s = 0; s < SPLITS; ++s) p[s][j] = __ldg(part + (size_t)s * total4 + i0 + j * 32);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        if (j < per) {
+#pragma unroll
+          for (int s = 0; s < SPLITS; ++s) { v[j].x += p[s][j].x; v[j].y += p[s][j].y; v[j].z += p[s][j].z; v[j].w += p[s][j].w; }   // bias, split 0, 1, ...: the order of lin_splitk_reduce_kernel
+          if (residual != nullptr) { v[j].x += res[j].x; v[j].y += res[j].y; v[j].z += res[j].z; v[j].w += res[j].w; }
+          y[i0 + j * 32] = v[j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < PER; ++j)
+        if (j < per) v[j] = y[i0 + j * 32];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+      if (j < per) sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_n;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if (j < per) {
+        const float a0 = v[j].x - mean, a1 = v[j].y - mean, a2 = v[j].z - mean, a3 = v[j].w - mean;
+        sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_n + eps);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if (j < per) {
+        float4 o4;
+        o4.x = (v[j].x - mean) * rstd * w[j].x + b[j].x; o4.y = (v[j].y - mean) * rstd * w[j].y + b[j].y;
+        o4.z = (v[j].z - mean) * rstd * w[j].z + b[j].z; o4.w = (v[j].w - mean) * rstd * w[j].w + b[j].w;
+        y_ln[i0 + j * 32] = o4;
+      }
+    }
+  }
+}
+// splits in {0, 1, 2, 4} (what lin_dims produces; 0 = y already complete)
+static void launch_reduce_ln(const float4* part, const float* bias, const float4* residual, float4* y, const float* ln_w, const float* ln_b,
+                             float eps, float4* y_ln, long long R, int N, int splits, cudaStream_t st) {
+  const dim3 grid((unsigned)min((R + LRL_WARPS - 1) / LRL_WARPS, 8LL * sm_count())), block(LRL_WARPS * 32);
+  const int per = N / 128;
+#define TPSPP_LRL(PER, SP) launch_k(lin_reduce_ln_kernel<PER, SP>, grid, block, 0, st, part, bias, residual, y, ln_w, ln_b, eps, y_ln, R, N)
+#define TPSPP_LRL_S(PER) do { if (splits == 0) TPSPP_LRL(PER, 0); else if (splits == 1) TPSPP_LRL(PER, 1); else if (splits == 2) TPSPP_LRL(PER, 2); \
+                              else TPSPP_LRL(PER, 4); } while (0)
+  if (per <= 2) TPSPP_LRL_S(2);
+  else if (per <= 4) TPSPP_LRL_S(4);
+  else TPSPP_LRL_S(8);
+#undef TPSPP_LRL_S
+#undef TPSPP_LRL
 }
 static bool lin_tc_shape(long long R, int K, int N, long long rpb, int* NT) {
   if (R % TC_TM || rpb % TC_TM || K % TC_KC || N % 32 || N > 4096 || K > 4096 || R > 0x7fffffffLL) return false;
@@ -179,7 +278,8 @@ static void lin_offsets(const LinDims& d, size_t* off, size_t* total) {
 
 // out[R, Nn] = in[R, Kk] . img^T (+ bias) through the tcgen05 row-major linear kernel
 static int lin_tc_run(const float* in, const float* wimg, const float* bias, float* out, const LinDims& d, int Kk, int Nn, int NT,
-                      cudaStream_t st, int splitk = 1, float* part = nullptr, const float* residual = nullptr, int gelu = 0) {
+                      cudaStream_t st, int splitk = 1, float* part = nullptr, const float* residual = nullptr, int gelu = 0,
+                      const float* ln_w = nullptr, const float* ln_b = nullptr, float ln_eps = 0.f, float* y_ln = nullptr) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.src[0].ptr = in; a.src[0].C = Kk; a.src[0].H = 1; a.src[0].W = (int)d.rpb; a.src[0].uh = a.src[0].uw = 1; a.src[0].nhwc = 1;
@@ -193,9 +293,13 @@ static int lin_tc_run(const float* in, const float* wimg, const float* bias, flo
     const int rc = run_conv_tc(1, a, wimg, NT, st, CM_TF32X3);
     if (rc != TPSPP_OK) return rc;
     const long long total4 = d.R * Nn / 4;
-    lin_splitk_reduce_kernel<<<(unsigned)min((total4 + 255) / 256, 4LL * sm_count()), 256, 0, st>>>(
-        reinterpret_cast<const float4*>(part), bias, reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), total4,
-        Nn / 4, splitk, gelu);
+    if (y_ln != nullptr)
+      launch_reduce_ln(reinterpret_cast<const float4*>(part), bias, reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out),
+                       ln_w, ln_b, ln_eps, reinterpret_cast<float4*>(y_ln), d.R, Nn, splitk, st);
+    else
+      launch_k(lin_splitk_reduce_kernel, dim3((unsigned)min((total4 + 255) / 256, 4LL * sm_count())), dim3(256), 0, st,
+               reinterpret_cast<const float4*>(part), bias, reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), total4,
+               Nn / 4, splitk, gelu);
     count_launch();
     TPSPP_CHECK_CUDA(cudaGetLastError());
     return TPSPP_OK;
@@ -203,7 +307,12 @@ static int lin_tc_run(const float* in, const float* wimg, const float* bias, flo
   // unsplit: the kernel's own epilogue applies the activation (branch-free erf GELU, |error| <= 4.7e-7) and adds the residual
   a.skip = residual; a.skip_pre = 0;
   if (gelu) a.act = CONV_ACT_GELU;
-  return run_conv_tc(1, a, wimg, NT, st, CM_TF32X3);
+  const int rc = run_conv_tc(1, a, wimg, NT, st, CM_TF32X3);
+  if (rc != TPSPP_OK || y_ln == nullptr) return rc;
+  launch_reduce_ln(nullptr, nullptr, nullptr, reinterpret_cast<float4*>(out), ln_w, ln_b, ln_eps, reinterpret_cast<float4*>(y_ln), d.R, Nn, 0, st);
+  count_launch();
+  TPSPP_CHECK_CUDA(cudaGetLastError());
+  return TPSPP_OK;
 }
 
 }  // namespace tpspp
@@ -225,8 +334,22 @@ extern "C" int tpspp_linear_fwd(const tpspp_linear_cfg* cfg, const float* x, con
 
 extern "C" int tpspp_linear_fwd_ex(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias, const float* residual,
                                    int32_t act, float* y, void* workspace, tpspp_stream_t stream) {
+  return tpspp_linear_ln_fwd(cfg, x, w, bias, residual, act, y, nullptr, nullptr, 0.f, nullptr, workspace, stream);
+}
+
+extern "C" int tpspp_linear_ln_fwd(const tpspp_linear_cfg* cfg, const float* x, const float* w, const float* bias, const float* residual,
+                                   int32_t act, float* y, const float* ln_weight, const float* ln_bias, float ln_eps, float* y_ln,
+                                   void* workspace, tpspp_stream_t stream) {
   reset_launch_count();
-  TPSPP_REQUIRE(act == TPSPP_ACT_NONE || act == TPSPP_ACT_GELU, "tpspp_linear_fwd_ex: unknown activation %d", act);
+  if (y_ln != nullptr) {
+    TPSPP_REQUIRE(cfg != nullptr && ln_weight != nullptr && act == TPSPP_ACT_NONE && cfg->weight_batches == 1,
+                  "tpspp_linear_ln_fwd: the LayerNorm output needs ln_weight, no activation and a single weight");
+    TPSPP_REQUIRE(cfg->out_features % 128 == 0 && cfg->out_features <= 1024, "tpspp_linear_ln_fwd: out_features must be a multiple of 128, at most 1024");
+    TPSPP_REQUIRE(y_ln != y && y_ln != residual && y_ln != x, "tpspp_linear_ln_fwd: y_ln must not alias x, y or residual");
+    TPSPP_REQUIRE((((uintptr_t)y_ln | (uintptr_t)ln_weight | (uintptr_t)ln_bias | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)residual) & 15) == 0,
+                  "tpspp_linear_ln_fwd: y, y_ln, bias, residual and the LayerNorm parameters must be 16-byte aligned");
+  }
+  TPSPP_REQUIRE(act == TPSPP_ACT_NONE || act == TPSPP_ACT_GELU, "tpspp_linear_fwd: unknown activation %d", act);
   TPSPP_REQUIRE(cfg == nullptr || cfg->weight_batches <= 1 || (residual == nullptr && act == TPSPP_ACT_NONE),
                 "tpspp_linear_fwd_ex: batched weights (bmm) take no residual / activation");
   LinDims d;
@@ -247,12 +370,17 @@ extern "C" int tpspp_linear_fwd_ex(const tpspp_linear_cfg* cfg, const float* x, 
       TPSPP_CHECK_CUDA(cudaGetLastError());
     }
     return lin_tc_run(x, img, bias, y, d, d.K, d.N, d.nt_fwd, st, d.sk_fwd, reinterpret_cast<float*>((char*)workspace + off[LW_SPLITK]),
-                      residual, act == TPSPP_ACT_GELU ? 1 : 0);
+                      residual, act == TPSPP_ACT_GELU ? 1 : 0, ln_weight, ln_bias, ln_eps, y_ln);
   }
   lin_small_fwd_kernel<<<dim3((d.N + 31) / 32, (unsigned)((d.rpb + 31) / 32), d.batches), 256, 0, st>>>(x, w, bias, y, d.K, d.N, d.rpb, 0,
                                                                                                          residual, act == TPSPP_ACT_GELU ? 1 : 0);
   count_launch();
   TPSPP_CHECK_CUDA(cudaGetLastError());
+  if (y_ln != nullptr) {
+    launch_reduce_ln(nullptr, nullptr, nullptr, reinterpret_cast<float4*>(y), ln_weight, ln_bias, ln_eps, reinterpret_cast<float4*>(y_ln), d.R, d.N, 0, st);
+    count_launch();
+    TPSPP_CHECK_CUDA(cudaGetLastError());
+  }
   return TPSPP_OK;
 }
 

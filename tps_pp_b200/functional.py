@@ -569,19 +569,30 @@ class PreparedLinear:
         self.prepared = False
 
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-                 gelu: bool = False) -> torch.Tensor:
-        """``act(x w^T + b) + residual`` (``tpspp_linear_fwd_ex``); ``out`` may be ``residual`` itself (x = x + f(.) in place)."""
+                 gelu: bool = False, ln: Optional[torch.nn.LayerNorm] = None, ln_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``act(x w^T + b) + residual`` (``tpspp_linear_ln_fwd``); ``out`` may be ``residual`` itself (x = x + f(.) in place).
+        With ``ln`` (an ``nn.LayerNorm`` over the output features) and ``ln_out`` [rows, out]: ``ln_out = ln(result)`` is written by
+        the kernel that finishes the result -- the LayerNorm a pre-norm transformer layer applies next, without its own launch."""
         if x.shape != (self.rows, self.k) or not x.is_contiguous() or x.dtype != torch.float32:
             raise RuntimeError(f"tps_pp_b200: PreparedLinear expects a contiguous fp32 [{self.rows}, {self.k}] input, got {tuple(x.shape)}")
         y = out if out is not None else torch.empty((self.rows, self.n), dtype=torch.float32, device=x.device)
         for nm, t in (("out", y), ("residual", residual)):
             if t is not None and (t.shape != (self.rows, self.n) or not t.is_contiguous() or t.dtype != torch.float32 or not t.is_cuda):
                 raise RuntimeError(f"tps_pp_b200: PreparedLinear `{nm}` must be a contiguous fp32 CUDA [{self.rows}, {self.n}] tensor")
+        lw = lb = None
+        eps = 0.0
+        if ln is not None:
+            if ln_out is None or ln_out.shape != (self.rows, self.n) or not ln_out.is_contiguous() or ln_out.dtype != torch.float32 or not ln_out.is_cuda:
+                raise RuntimeError(f"tps_pp_b200: PreparedLinear `ln_out` must be a contiguous fp32 CUDA [{self.rows}, {self.n}] tensor")
+            if tuple(ln.normalized_shape) != (self.n,) or ln.weight is None:
+                raise RuntimeError(f"tps_pp_b200: PreparedLinear `ln` must be an affine LayerNorm over the {self.n} output features")
+            lw, lb, eps = ln.weight.detach(), (ln.bias.detach() if ln.bias is not None else None), float(ln.eps)
         self.cfg.flags = N.LINEAR_FLAG_WEIGHTS_CACHED if self.prepared else 0
         with torch.cuda.device(x.device):
-            N.check(N.lib().tpspp_linear_fwd_ex(ctypes.byref(self.cfg), _ptr(x), _ptr(self.weight), _ptr(self.bias), _ptr(residual),
-                                                N.ACT_GELU if gelu else N.ACT_NONE, _ptr(y), _ptr(self.ws), _stream(x)),
-                    "tpspp_linear_fwd_ex")
+            N.check(N.lib().tpspp_linear_ln_fwd(ctypes.byref(self.cfg), _ptr(x), _ptr(self.weight), _ptr(self.bias), _ptr(residual),
+                                                N.ACT_GELU if gelu else N.ACT_NONE, _ptr(y), _ptr(lw), _ptr(lb), eps,
+                                                _ptr(ln_out) if ln is not None else None, _ptr(self.ws), _stream(x)),
+                    "tpspp_linear_ln_fwd")
         self.prepared = True
         return y
 

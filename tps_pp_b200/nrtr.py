@@ -10,7 +10,8 @@ Same constructor kwargs, sub-module names and ``state_dict`` keys (``trg_word_em
 reference re-runs all six layers over the whole 41-token padded sequence at each of its 40 steps (54 of the recogniser's
 60 GFLOP per image); here the keys / values of earlier positions and the projected encoder memory are kept, each step
 processes ONE token per image -- dense layers on the tcgen05 3xTF32 kernels (``tpspp_linear_fwd``), attention over the
-caches in ``tpspp_attn_decode``; LayerNorm, GELU, the embedding gather and the soft-max are torch element-wise ops.
+caches in ``tpspp_attn_decode``; residual adds, GELU and the LayerNorm in front of the next sub-layer run in the dense layers'
+epilogues (``tpspp_linear_ln_fwd``); the embedding gather, the first LayerNorm of a step and the soft-max are torch ops.
 Position ``t`` of the causal, pad-masked reference attends exactly to tokens ``0..t``, so the results are the reference's
 up to fp32 summation order.  ``forward_train`` and ``forward_test_library`` (the reference's algorithm, for A/B) run torch ops.
 """
@@ -216,20 +217,25 @@ class NRTRDecoder(_BaseModule):
         att = torch.zeros((rows, d), dtype=torch.float32, device=dev)
         pos = self.position_enc.position_table[0]
         outputs = []
+        hn = torch.zeros((rows, d), dtype=torch.float32, device=dev)     # LN(x) for the next sub-layer, written by the dense layer before it
+        layers = list(self.layer_stack)
         for step in range(self.max_seq_len):
             x[:n] = self.trg_word_emb(tok) + pos[step]
-            for li, lyr in enumerate(self.layer_stack):
+            hn[:n] = layers[0].norm1(x[:n])
+            for li, lyr in enumerate(layers):
                 ops = lin[li]
-                qkv = ops["qkv"](lyr.norm1(x))
+                qkv = ops["qkv"](hn)
                 # q, and this step's k / v rows, are column slices of the fused projection; the kernel appends k / v to the cache
                 TF.attn_decode(qkv[:n, :d], k_cache[li], v_cache[li], self.n_head, step + 1, temp, out=att[:n],
                                k_new=qkv[:n, d:2 * d], v_new=qkv[:n, 2 * d:], head_major=True)
-                ops["fc"](att, out=x, residual=x)                                   # x += fc(att), in the dense layer's epilogue
-                q = ops["q"](lyr.norm2(x))
+                # x += fc(att) and hn = norm2(x): residual and the next LayerNorm in the kernel that finishes the dense layer
+                ops["fc"](att, out=x, residual=x, ln=lyr.norm2, ln_out=hn)
+                q = ops["q"](hn)
                 TF.attn_decode(q[:n], mem_k[li], mem_v[li], self.n_head, t_src, temp, kv_lens=lens, out=att[:n], head_major=True)
-                ops["efc"](att, out=x, residual=x)
-                ops["w2"](ops["w1"](lyr.norm3(x), gelu=True), out=x, residual=x)   # x += w_2(GELU(w_1(LN(x))))
-            probs = F.softmax(cls(self.layer_norm(x))[:n, :ncls], dim=-1)
+                ops["efc"](att, out=x, residual=x, ln=lyr.norm3, ln_out=hn)
+                nxt = layers[li + 1].norm1 if li + 1 < len(layers) else self.layer_norm
+                ops["w2"](ops["w1"](hn, gelu=True), out=x, residual=x, ln=nxt, ln_out=hn)   # x += w_2(GELU(w_1(LN(x))))
+            probs = F.softmax(cls(hn)[:n, :ncls], dim=-1)
             outputs.append(probs)
             tok = probs.argmax(dim=-1)
         return torch.stack(outputs, dim=1)
