@@ -107,3 +107,54 @@ def test_image_to_rectified_features_vs_oracle(native_lib):
     err = mx(r["img_ref"], r64["output"])
     print(f"img -> output: |ours - ref64| = {err:.3e}, reference's own |ref32 - ref64| = {floor:.3e}")
     assert err <= max(1e-5, 1.5 * floor)
+
+
+def test_pipelined_streams_match_serial(native_lib):
+    """The end-to-end pattern of bench.py: uploads on a copy stream into two device buffer sets, compute on the main stream behind
+    an event, downloads on a third stream.  The chain's kernels are launched with programmatic stream serialization (next grid's
+    prologue overlaps the previous grid's drain, csrc/common.cuh); cross-stream event dependencies must stay full dependencies --
+    every pipelined step has to reproduce the serial result of ITS OWN input bit for bit."""
+    m, _ = _backbone()
+    tps = T.TPS_PP().to(DEV).eval()
+    tps.load_state_dict(O.trained_like_state(3), strict=True)
+    steps, batch = 8, 24
+    host_in = [torch.from_numpy(O.synthetic_images(batch, 500 + i)).pin_memory() for i in range(steps)]
+    with torch.no_grad():
+        serial = []
+        for h in host_in:
+            xx, outs = m.stage(h.to(DEV))
+            serial.append(tps(xx, outs)["output"].cpu())
+            torch.cuda.synchronize()
+        dev = torch.device(DEV)
+        dbuf = [torch.empty((batch, 3, 32, 128), device=dev) for _ in range(2)]
+        s_in, s_out, main = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.current_stream(dev)
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        host_out = [torch.empty_like(serial[0]).pin_memory() for _ in range(steps)]
+        for k in range(2):
+            ev_free[k].record(main)
+
+        def upload(i):
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_free[i & 1])
+                dbuf[i & 1].copy_(host_in[i], non_blocking=True)
+                ev_in[i & 1].record(s_in)
+
+        upload(0)
+        for i in range(steps):
+            k = i & 1
+            if i + 1 < steps:
+                upload(i + 1)
+            main.wait_event(ev_in[k])
+            xx, outs = m.stage(dbuf[k])
+            out = tps(xx, outs)["output"]
+            done = torch.cuda.Event()
+            done.record(main)
+            ev_free[k].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                host_out[i].copy_(out, non_blocking=True)
+            out.record_stream(s_out)
+        torch.cuda.synchronize()
+    for i in range(steps):
+        assert torch.equal(host_out[i], serial[i]), f"pipelined step {i} differs from its serial result"
