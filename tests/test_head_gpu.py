@@ -316,3 +316,50 @@ def test_fused_score_chain_equals_separate_launches(native_lib):
           f"|separate-ref64| {e_u:.2e}")
     assert mx(res[0][0], res[N.HEAD_FLAG_UNFUSED_SCORE][0]) <= 5e-6
     assert e_f <= 2e-4 and e_f <= 1.25 * e_u + 2e-6
+
+
+def test_head_back_to_back_calls_and_graph_capture(native_lib):
+    """The head's 17 launches are chained with programmatic dependent launches (the next grid's prologue overlaps the previous
+    grid's drain, csrc/common.cuh).  Calls issued back to back with DIFFERENT inputs on one workspace, on a non-default stream,
+    must each reproduce their own serial result bit for bit, and the chain must be capturable into a CUDA graph and replay
+    correctly on new input values."""
+    sd = O.trained_like_state(3)
+    m = T.TPS_PP().to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    params = list(m.parameters())
+    B, reps = 48, 6
+    g = torch.Generator(device=DEV).manual_seed(23)
+    ins = [(torch.randn((B, 64, 16, 64), device=DEV, generator=g), torch.randn((B, 32, 32, 128), device=DEV, generator=g),
+            torch.randn((B, 32, 32, 128), device=DEV, generator=g)) for _ in range(reps)]
+    with torch.no_grad():
+        serial = []
+        for x, o0, o1 in ins:
+            fg, cp, sc, _ = TF.head_forward(x, o0, o1, params, (2, 16), 2, N.HEAD_TC)
+            torch.cuda.synchronize()
+            serial.append((fg.clone(), cp.clone(), sc.clone()))
+        s = torch.cuda.Stream(device=DEV)
+        s.wait_stream(torch.cuda.current_stream())
+        outs, ws = [], None
+        with torch.cuda.stream(s):
+            for x, o0, o1 in ins:                      # no synchronisation between the calls, one shared workspace
+                fg, cp, sc, ws = TF.head_forward(x, o0, o1, params, (2, 16), 2, N.HEAD_TC, ws)
+                outs.append((fg.clone(), cp.clone(), sc.clone()))
+        s.synchronize()
+        for i, (a, b) in enumerate(zip(outs, serial)):
+            for u, v, nm in zip(a, b, ("feat_grid", "c_prime", "pc_score")):
+                assert torch.equal(u, v), f"call {i}: {nm}"
+        # CUDA graph: capture one call, replay it on new input values
+        x, o0, o1 = (t.clone() for t in ins[0])
+        with torch.cuda.stream(s):
+            fg, cp, sc, ws = TF.head_forward(x, o0, o1, params, (2, 16), 2, N.HEAD_TC, ws)      # warm (weight images cached)
+        s.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            fg, cp, sc, ws = TF.head_forward(x, o0, o1, params, (2, 16), 2, N.HEAD_TC, ws)
+        for i in (3, 1):
+            for dst, src in zip((x, o0, o1), ins[i]):
+                dst.copy_(src)
+            graph.replay()
+            torch.cuda.synchronize()
+            for u, v, nm in zip((fg, cp, sc), serial[i], ("feat_grid", "c_prime", "pc_score")):
+                assert torch.equal(u, v), f"graph replay of input {i}: {nm}"
