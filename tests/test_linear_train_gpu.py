@@ -101,8 +101,8 @@ def test_prepared_linear_residual_gelu(rows, k, n):
         assert torch.equal(inplace, y)
 
 
-@pytest.mark.parametrize("rows,k,n", [(256, 512, 512), (1024, 512, 256), (256, 256, 128), (64, 48, 128)],
-                         ids=["split-K", "unsplit", "K=256", "cuda-core"])
+@pytest.mark.parametrize("rows,k,n", [(256, 512, 512), (1024, 512, 256), (256, 256, 128), (64, 48, 128), (256, 512, 1024), (128, 1024, 768)],
+                         ids=["split-K", "unsplit", "K=256", "cuda-core", "N=1024", "N=768"])
 def test_prepared_linear_with_layernorm_output(rows, k, n):
     """``tpspp_linear_ln_fwd``: y = x w^T + b + residual and LN(y) for the next sub-layer from the kernel that finishes y
     (split-K reduction, or a warp-per-row pass behind the unsplit kernel); in-place residual; y itself unchanged by the LN."""

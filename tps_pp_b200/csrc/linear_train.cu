@@ -161,21 +161,37 @@ __global__ void __launch_bounds__(LRL_WARPS * 32) lin_reduce_ln_kernel(const flo
       }
     }
     if (SPLITS > 0) {
-      float4 res[PER], p[SPLITS > 0 ? SPLITS : 1][PER];
+      // SB splits of the whole row are in flight at a time (all of them unless that would take more than 16 float4 per lane)
+      constexpr int SP = SPLITS > 0 ? SPLITS : 1, SB = PER * SP > 16 ? (16 / PER > 0 ? 16 / PER : 1) : SP;
+      float4 res[PER];
 #pragma unroll
       for (int j = 0; j < PER; ++j) {
         if (j < per) {
           v[j] = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias) + j * 32 + lane) : zero4;
           res[j] = residual != nullptr ? residual[i0 + j * 32] : zero4;      // may alias y: read before the write below
-#pragma unroll
-          for (int s = 0; s < SPLITS; ++s) p[s][j] = __ldg(part + (size_t)s * total4 + i0 + j * 32);
         }
+      }
+#pragma unroll
+      for (int s0 = 0; s0 < SP; s0 += SB) {
+        float4 p[SB][PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+          if (j < per) {
+#pragma unroll
+            for (int s = 0; s < SB; ++s)
+              if (s0 + s < SP) p[s][j] = __ldg(part + (size_t)(s0 + s) * total4 + i0 + j * 32);
+          }
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+          if (j < per) {
+#pragma unroll
+            for (int s = 0; s < SB; ++s)       // bias, split 0, 1, ...: the order of lin_splitk_reduce_kernel
+              if (s0 + s < SP) { v[j].x += p[s][j].x; v[j].y += p[s][j].y; v[j].z += p[s][j].z; v[j].w += p[s][j].w; }
+          }
       }
 #pragma unroll
       for (int j = 0; j < PER; ++j) {
         if (j < per) {
-#pragma unroll
-          for (int s = 0; s < SPLITS; ++s) { v[j].x += p[s][j].x; v[j].y += p[s][j].y; v[j].z += p[s][j].z; v[j].w += p[s][j].w; }   // bias, split 0, 1, ...: the order of lin_splitk_reduce_kernel
           if (residual != nullptr) { v[j].x += res[j].x; v[j].y += res[j].y; v[j].z += res[j].z; v[j].w += res[j].w; }
           y[i0 + j * 32] = v[j];
         }
