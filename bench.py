@@ -436,7 +436,7 @@ def run_ours(args):
         # (2) at the image boundary: img -> native stem + layer1 + layer2 (tpspp_stage_fwd) -> rectifier.
         # 49 KB per image go up instead of 1.31 MB; the step does MORE work (0.6 GFLOP/img of backbone convolutions).
         image = None
-        if args.head in ("tc", "tc3x"):
+        if args.head in ("tc", "tc3x", "bf16"):
             bb = T.ResNetABI_v2_large(arch_settings=[3, 4, 6, 6, 3], strides=[1, 2, 2, 1, 2]).to(dev).eval()
             _trained_like_backbone_(bb)
             img = torch.randn((B, 3, 32, 128), device=dev, generator=gen)
