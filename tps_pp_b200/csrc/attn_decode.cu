@@ -14,6 +14,7 @@ namespace tpspp {
 
 constexpr int AD_WARPS = 4, AD_DIM = 64;
 
+template <bool STREAM>
 __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float* __restrict__ q, float* __restrict__ k, float* __restrict__ v,
                                                                    float* __restrict__ out, const int* __restrict__ kv_lens, int kv_len,
                                                                    int capacity, int heads, float inv_temperature, int q_stride,
@@ -55,8 +56,17 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const float*
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int t = t0 + u < len ? t0 + u : len - 1;                 // clamp: a valid row is loaded, its score is masked below
-      kv[u] = *reinterpret_cast<const float2*>(kb + (size_t)t * tstride);      // (plain loads: the cache may just have been appended to)
-      vv[u] = *reinterpret_cast<const float2*>(vb + (size_t)t * tstride);
+      // coherent loads (the cache may just have been appended to).  STREAM = this call alone reads more keys / values than the L2
+      // holds (126 MB; the encoder memory at batch 1024: 268 MB per call): evict-first, so the dense layers' weight images stay
+      // in L2 while it streams by (44.5 -> 43.3 ms per decode at batch 1024).  Below that size the hint costs time (batch 256,
+      // 67 MB per call: 22.6 -> 23.8 ms), so smaller calls keep plain loads
+      if (STREAM) {
+        kv[u] = __ldcs(reinterpret_cast<const float2*>(kb + (size_t)t * tstride));
+        vv[u] = __ldcs(reinterpret_cast<const float2*>(vb + (size_t)t * tstride));
+      } else {
+        kv[u] = *reinterpret_cast<const float2*>(kb + (size_t)t * tstride);
+        vv[u] = *reinterpret_cast<const float2*>(vb + (size_t)t * tstride);
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) s[u] = q0 * kv[u].x + q1 * kv[u].y;
@@ -118,7 +128,8 @@ extern "C" int tpspp_attn_decode(const tpspp_attn_cfg* cfg, const float* q, floa
   TPSPP_REQUIRE(qs >= D && ns >= D && qs % 2 == 0 && ns % 2 == 0, "tpspp_attn_decode: row strides must be even and >= heads * 64");
   TPSPP_REQUIRE((k_new == nullptr) == (v_new == nullptr), "tpspp_attn_decode: k_new and v_new come together");
   // (plain launch: inside the decode's CUDA graph programmatic edges bought nothing at batch 256 and cost 7 % at 1024)
-  launch_k(attn_decode_kernel, dim3(cfg->batch, cfg->heads), dim3(AD_WARPS * 32), 0, (cudaStream_t)stream,
+  const bool stream_kv = (long long)cfg->batch * cfg->heads * cfg->kv_len * (2LL * AD_DIM * 4) > (126LL << 20);
+  launch_k(stream_kv ? attn_decode_kernel<true> : attn_decode_kernel<false>, dim3(cfg->batch, cfg->heads), dim3(AD_WARPS * 32), 0, (cudaStream_t)stream,
            q, k, v, out, kv_lens, cfg->kv_len, cfg->kv_capacity, cfg->heads, 1.f / cfg->temperature, qs, k_new, v_new, ns,
            (int)(cfg->kv_head_major != 0));
   count_launch();
