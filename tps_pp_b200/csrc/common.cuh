@@ -40,7 +40,13 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_on() ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...) != cudaSuccess && cfg.numAttrs != 0) {
+    // the attribute was refused (a tool or driver without programmatic launch): the plain launch is always valid -- every chained
+    // kernel's griddepcontrol instructions are no-ops in it.  A genuine launch error repeats here and is reported by the caller.
+    cudaGetLastError();
+    cfg.numAttrs = 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  }
 }
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
